@@ -1,0 +1,122 @@
+"""WGAN-GP algorithm plugin: the reference's train-step interface over the CUDA engine.
+
+Mirrors gan/algorithms/wgan_gp.py:9-95: `train(inputs)` runs n_critic critic updates on the
+same batch plus one generator update and returns (gen_loss, dis_loss, gradient_penalty,
+metrics). Optional keyword arguments inject the random draws (noise, interpolation alpha,
+phase-shuffle shifts) so the step can be checked against the reference semantics.
+
+Data parallelism (no reference counterpart): with torch.distributed initialised,
+each rank runs its batch shard; the flat fp32 gradient buffer is all-reduced over NCCL before
+the fused Adam (which folds in 1/world_size). PhaseShuffle shifts are per-call scalars shared
+by the whole batch, so all ranks draw them from the same seeded stream.
+"""
+import numpy as np
+import torch
+
+from .registry import register
+from .gan import GAN, metrics_from_scalars
+from .. import _lib as L
+
+
+def _dist():
+  import torch.distributed as dist
+  return dist if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 else None
+
+
+@register('wgan-gp')
+class WGAN_GP(GAN):
+
+  def __init__(self, hparams, generator, discriminator, summary=None):
+    super().__init__(hparams, generator, discriminator, summary)
+
+    self.penalty = hparams.gradient_penalty
+    self.n_critic = hparams.n_critic
+    self.conv2d = getattr(hparams, 'conv2d', False)
+    if self.n_critic != self.engine.cfg.n_critic:
+      raise ValueError('n_critic changed after the models were built')
+
+  # ------------------------------------------------------------------ losses (wgan_gp.py:19-62)
+  def generator_loss(self, fake_output):
+    return -torch.mean(fake_output)
+
+  def interpolation(self, real, fake, alpha=None):
+    real, fake = self.engine.to_device(real), self.engine.to_device(fake)
+    if alpha is None:
+      alpha = torch.rand((real.shape[0], 1, 1), device=real.device)
+    alpha = self.engine.to_device(alpha).reshape(-1, 1, 1)
+    return (alpha * real) + ((1 - alpha) * fake)
+
+  def gradient_penalty(self, real, fake, training=True, alpha=None, shifts=None):
+    interpolated = self.interpolation(real, fake, alpha)
+    if shifts is None:
+      m = self.engine.cfg.phase_m
+      shifts = np.random.randint(-m, m + 1, size=4)
+    _, sumsq = self.engine.gp_debug(interpolated, shifts)
+    return torch.mean(torch.square(torch.sqrt(sumsq) - 1.0))
+
+  def discriminator_loss(self, real_output, fake_output, real=None, fake=None, training=True):
+    real_loss = -torch.mean(real_output)
+    fake_loss = torch.mean(fake_output)
+    gradient_penalty = self.gradient_penalty(real, fake, training=training)
+    loss = real_loss + fake_loss + self.penalty * gradient_penalty
+    return loss, gradient_penalty
+
+  # ------------------------------------------------------------------ steps (wgan_gp.py:22-36,64-95)
+  def _train_discriminator(self, inputs, noise=None, alpha=None, shifts=None):
+    dist = _dist()
+    if dist is None:
+      s = self.engine.critic_step(inputs, noise, alpha, shifts, update=True)
+    else:
+      s = self.engine.critic_step(inputs, noise, alpha, shifts, update=False)
+      dist.all_reduce(self.engine.grad_tensor(L.DISCRIMINATOR))
+      self.dis_optimizer.update()
+    return float(s[L.S_DIS_LOSS]), float(s[L.S_GP])
+
+  def _train_generator(self, inputs, noise=None, shifts=None):
+    dist = _dist()
+    if dist is None:
+      s = self.engine.generator_step(inputs, noise, shifts, update=True)
+    else:
+      s = self.engine.generator_step(inputs, noise, shifts, update=False)
+      dist.all_reduce(self.engine.grad_tensor(L.GENERATOR))
+      self.gen_optimizer.update()
+    return float(s[L.S_GEN_LOSS]), metrics_from_scalars(s)
+
+  def train(self, inputs, noise=None, alpha=None, shifts=None):
+    """wgan_gp.py:82-95. noise (n_critic+1, B, nd), alpha (n_critic, B), shifts (12*n_critic+4,)."""
+    dist = _dist()
+    if dist is None:
+      s = self.engine.train_step(inputs, noise, alpha, shifts)
+      return (float(s[L.S_GEN_LOSS]), float(s[L.S_DIS_LOSS]), float(s[L.S_GP]), metrics_from_scalars(s))
+    return self._train_dp(dist, inputs, noise, alpha, shifts)
+
+  def _train_dp(self, dist, inputs, noise, alpha, shifts):
+    eng, nc = self.engine, self.n_critic
+    real = eng.to_device(inputs)
+    shifts = None if shifts is None else np.asarray(shifts, np.int32).reshape(-1)
+    hist = torch.zeros((nc + 1, L.NUM_SCALARS), device=eng.device)
+    scal = eng.scalars_tensor()
+    gd, gg = eng.grad_tensor(L.DISCRIMINATOR), eng.grad_tensor(L.GENERATOR)
+    for i in range(nc):
+      eng.critic_step(real, None if noise is None else noise[i], None if alpha is None else alpha[i],
+                      None if shifts is None else shifts[12 * i:12 * i + 12], update=False, sync=False)
+      hist[i].copy_(scal)
+      dist.all_reduce(gd)
+      eng.apply_update(L.DISCRIMINATOR)
+    eng.generator_step(real, None if noise is None else noise[nc],
+                       None if shifts is None else shifts[12 * nc:12 * nc + 4], update=False, sync=False)
+    hist[nc].copy_(scal)
+    dist.all_reduce(gg)
+    eng.apply_update(L.GENERATOR)
+    out = torch.zeros(L.NUM_SCALARS, device=eng.device)
+    out[L.S_DIS_LOSS] = hist[:nc, L.S_DIS_LOSS].mean()
+    out[L.S_GP] = hist[:nc, L.S_GP].mean()
+    out[L.S_GEN_LOSS:] = hist[nc, L.S_GEN_LOSS:]
+    dist.all_reduce(out)
+    s = (out / dist.get_world_size()).cpu().numpy()
+    return (float(s[L.S_GEN_LOSS]), float(s[L.S_DIS_LOSS]), float(s[L.S_GP]), metrics_from_scalars(s))
+
+  def validate(self, inputs, noise=None, alpha=None, shifts=None):
+    """gan.py:87-90 -> (fake, gen_loss, dis_loss, gradient_penalty, metrics)."""
+    fake, s = self.engine.validate(inputs, noise, alpha, shifts)
+    return (fake, float(s[L.S_GEN_LOSS]), float(s[L.S_DIS_LOSS]), float(s[L.S_GP]), metrics_from_scalars(s))

@@ -1,0 +1,12 @@
+#!/usr/bin/env bash
+# Build libcalciumgan_b200.so in-tree for sm_100a (cross-compiles without a GPU).
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/../libcalciumgan_b200.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+"$NVCC" -std=c++17 -O3 -lineinfo \
+  -gencode arch=compute_100a,code=sm_100a \
+  -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function \
+  ${CG_PTXAS_V:+-Xptxas -v} \
+   -shared -o "$OUT" "$HERE/cg_engine.cu"
+echo "built $OUT"

@@ -1,0 +1,108 @@
+// Shared definitions for the calciumgan_b200 CUDA engine (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CG_LRELU_ALPHA 0.3f   // tf.keras.layers.LeakyReLU() default (reference gan/models/utils.py:7)
+#define CG_LN_EPS 1e-3f       // tf.keras.layers.LayerNormalization() default (gan/models/calciumgan.py:45)
+#define CG_CPAD 64            // channel padding granule (one 128-byte swizzled TMA row of bf16)
+#define CG_MAX_SEG 64         // max taps (kernel_size)
+
+typedef __nv_bfloat16 bf16;
+
+// ---- element conversion ------------------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  static __device__ __forceinline__ float to_f(float x) { return x; }
+  static __device__ __forceinline__ float from_f(float x) { return x; }
+};
+template <> struct Elem<bf16> {
+  static __device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
+  static __device__ __forceinline__ bf16 from_f(float x) { return __float2bfloat16_rn(x); }
+};
+
+// load 4 consecutive elements as floats (pointer must be 4-element aligned); nullptr -> zeros
+template <typename T> __device__ __forceinline__ void load4(const T* p, float (&v)[4]);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+  if (p) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+  }
+}
+template <> __device__ __forceinline__ void load4<bf16>(const bf16* p, float (&v)[4]) {
+  if (p) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+  } else {
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+  }
+}
+
+__device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : CG_LRELU_ALPHA * x; }
+__device__ __forceinline__ float lrelu_slope(float h) { return h > 0.f ? 1.f : CG_LRELU_ALPHA; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// PhaseShuffle index map (reference gan/models/calciumgan.py:117-138, closed form SURVEY §8a):
+// out[:, t, :] = x[:, ps_index(t, shift, w), :].  int32, bit-exact.
+__host__ __device__ __forceinline__ int ps_index(int t, int shift, int w) {
+  int j = t + shift;
+  j = j < 0 ? -j : j;
+  if (j > w - 1) j = 2 * (w - 1) - j;
+  return j;
+}
+
+// ---- implicit-GEMM operand addressing ("row-shift GEMM") -----------------------------------
+// out[b, q, phase*o_phase_col + n] = epi( sum_{seg in phase} sum_{c<Kc}
+//        A[b, q + shift(seg), acol(seg) + c] * W[n, wk(seg) + c] )      (rows outside [0,a_rows) read 0)
+struct SegTable {
+  int nphase;
+  int nseg[2];
+  short shift[2][CG_MAX_SEG];
+  int acol[2][CG_MAX_SEG];
+  int wk[2][CG_MAX_SEG];
+};
+
+enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_LRELU = 2, EPI_MASK = 3, EPI_BIAS_SIGMOID = 4 };
+
+struct RsParams {
+  const void* A; long long a_bs; int a_rs; int a_rows;
+  const void* W; int w_ld;
+  void* out; long long o_bs; int o_rs; int o_phase_col;
+  float* out32; long long o32_bs; int o32_rs;      // optional unpadded fp32 copy (n < n_real)
+  const float* bias;                               // fp32, n_real entries
+  const void* mask;                                // EPI_MASK: same indexing as out
+  int B, Q, N, n_real, Kc, epi;
+  SegTable seg;
+};
+
+// dW[seg][m][n] += sum_{b,q} S[b, q + shift(seg), scol(seg) + m] * P[b, q, n]
+struct WgParams {
+  const void* S; long long s_bs; int s_rs; int s_rows;
+  const void* P; long long p_bs; int p_rs;
+  float* dW; int m_real, n_real;
+  int B, Q, Mp, Np;
+  int nseg;
+  int rows_per_split;
+  short shift[CG_MAX_SEG];
+  int scol[CG_MAX_SEG];
+};

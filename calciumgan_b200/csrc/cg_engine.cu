@@ -1,0 +1,1004 @@
+// calciumgan_b200 engine: context, device arena, step orchestration and the C ABI
+// declared in include/calciumgan_b200.h.  Replaces TensorFlow underneath the reference's
+// gan/algorithms/wgan_gp.py + gan/models/calciumgan.py (paths relative to /root/reference).
+//
+// Data layout in HBM (one arena per context):
+//   activations   channels-last (batch, time, Cp), Cp = channels rounded up to 64, pad == 0
+//   critic batch  the three critic calls of one sub-step (real, fake, xhat) are ONE batch of 3B
+//                 samples ("groups"), each group with its own 4 PhaseShuffle shifts
+//   weights       fp32 master in Keras get_weights() order (flat), Adam m/v alongside, plus
+//                 packed T copies [N][tap*Cp + c] for the forward and data-gradient GEMMs
+//   gradients     flat fp32 in the same order as the master weights (all-reduced in place by DP)
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/calciumgan_b200.h"
+#include "cg_kernels_simt.cuh"
+#include "cg_kernels_tc.cuh"
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int set_err(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CU(x)                                                                              \
+  do {                                                                                     \
+    cudaError_t e_ = (x);                                                                  \
+    if (e_ != cudaSuccess)                                                                 \
+      return set_err("%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_));    \
+  } while (0)
+#define CK(x)              \
+  do {                     \
+    int r_ = (x);          \
+    if (r_) return r_;     \
+  } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+static const int NL = 5;   // conv layers per network (calciumgan.py: 5 x Conv1DTranspose / 5 x Conv1D)
+
+struct ParamInfo {
+  int64_t shape[4];
+  int ndim;
+  int64_t offset, size;
+};
+
+struct Model {
+  std::vector<ParamInfo> params;
+  int64_t total = 0;
+  float *w = nullptr, *m = nullptr, *v = nullptr, *g = nullptr;   // flat fp32
+  int64_t steps = 0;                                               // optimizer.iterations
+  void add(std::initializer_list<int64_t> shp) {
+    ParamInfo p{};
+    p.ndim = (int)shp.size();
+    int i = 0;
+    p.size = 1;
+    for (auto s : shp) { p.shape[i++] = s; p.size *= s; }
+    p.offset = total;
+    total += p.size;
+    params.push_back(p);
+  }
+};
+
+struct cg_ctx {
+  cg_config cfg;
+  bool bf;          // bf16 activations
+  bool use_tc;      // tcgen05 implicit-GEMM kernels
+  int esz;
+  cudaStream_t stream = 0;
+  int64_t launches = 0;
+  int64_t dev_bytes = 0;
+  std::vector<void*> allocs;
+
+  int L, C, nd, nu, K, w0, Bmax;
+  int gc[NL + 1], gcp[NL + 1], gl[NL + 1];   // generator channels / padded / lengths
+  int dc[NL + 1], dcp[NL + 1], dl[NL + 1];   // critic
+  Model gen, dis;
+  int g_k[NL + 1], g_b[NL + 1], g_gam[NL + 1], g_bet[NL + 1], g_d1k, g_d1b;   // param indices
+  // packed weights (T)
+  void *Wf_d[NL + 1], *Wb_d[NL + 1];     // critic conv: forward [Cout][K*Cin_p], dgrad [Cin][K*Cout_p]
+  void *Wf_g[NL + 1], *Wb_g[NL + 1];     // generator convT: forward [Cout][K*Cin_p], bwd-data [Cin][K*Cout_p]
+  void *Wf_d1, *Wb_d1;                   // generator output dense: [C][Cp], transposed
+  // critic activations (capacity 3*Bmax)
+  void *X[NL + 1], *H[NL + 1], *DX[NL + 1], *DA[NL + 1];
+  float *scores, *coef, *sumsq, *ucoef, *norms;
+  // generator activations (capacity Bmax)
+  float* Z;
+  void *HG[NL + 1], *AG[NL + 1], *DHG[NL + 1], *DAG[NL + 1], *DO;
+  float *MU[NL + 1], *RSTD[NL + 1];
+  float* FAKE32;
+  float *alpha_buf, *noise_buf;
+  float* d_scal;        // [n_critic+1][CG_NUM_SCALARS]
+  float* h_scal;        // pinned
+  uint64_t seed = 1234, rng_counter = 0;
+  TcState tc;
+};
+
+// ------------------------------------------------------------------------------------------ arena
+static int dalloc(cg_ctx* c, void** p, size_t bytes) {
+  bytes = (bytes + 1023) / 1024 * 1024;
+  CU(cudaMalloc(p, bytes));
+  CU(cudaMemsetAsync(*p, 0, bytes, c->stream));
+  c->allocs.push_back(*p);
+  c->dev_bytes += (int64_t)bytes;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ seg tables
+static int floor_div2(int d) { return d >= 0 ? d / 2 : -((-d + 1) / 2); }
+
+// strided-conv form: A viewed as (B, Lin/2, 2*Cp); tap k -> row shift j, column offset p*Cp
+static SegTable seg_strided(int K, int Cp) {
+  SegTable s;
+  memset(&s, 0, sizeof(s));
+  const int padL = (K - 2) / 2;
+  s.nphase = 1;
+  s.nseg[0] = K;
+  for (int k = 0; k < K; ++k) {
+    const int d = k - padL, j = floor_div2(d), p = d - 2 * j;
+    s.shift[0][k] = (short)j;
+    s.acol[0][k] = p * Cp;
+    s.wk[0][k] = k * Cp;
+  }
+  return s;
+}
+// transposed form: out[b, 2q+r] = sum_{k : (r+padL-k) even} A[b, q + (r+padL-k)/2] * W[k]
+static SegTable seg_transposed(int K, int Cp) {
+  SegTable s;
+  memset(&s, 0, sizeof(s));
+  const int padL = (K - 2) / 2;
+  s.nphase = 2;
+  for (int r = 0; r < 2; ++r) {
+    int n = 0;
+    for (int k = 0; k < K; ++k) {
+      const int e = r + padL - k;
+      if (e & 1) continue;
+      s.shift[r][n] = (short)(e / 2);
+      s.acol[r][n] = 0;
+      s.wk[r][n] = k * Cp;
+      ++n;
+    }
+    s.nseg[r] = n;
+  }
+  return s;
+}
+static SegTable seg_dense() {
+  SegTable s;
+  memset(&s, 0, sizeof(s));
+  s.nphase = 1;
+  s.nseg[0] = 1;
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+#define DISPATCH_T(c, ...)                    \
+  do {                                        \
+    if ((c)->bf) { using T = bf16; __VA_ARGS__; } \
+    else { using T = float; __VA_ARGS__; }    \
+  } while (0)
+
+static int post_launch(cg_ctx* c, const char* what) {
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err("launch %s failed: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+static int launch_rsgemm(cg_ctx* c, const RsParams& p) {
+  if (c->use_tc && tc_rsgemm_supported(p)) {
+    CK(tc_rsgemm_launch(&c->tc, p, c->stream));
+    return post_launch(c, "rsgemm_tc");
+  }
+  const long long M = (long long)p.B * p.Q;
+  dim3 grid((unsigned)((M + 63) / 64), (unsigned)(p.N / 64), (unsigned)p.seg.nphase);
+  DISPATCH_T(c, rsgemm_simt_kernel<T><<<grid, 256, 0, c->stream>>>(p));
+  return post_launch(c, "rsgemm_simt");
+}
+
+static int launch_wgrad(cg_ctx* c, WgParams p) {
+  if (c->use_tc && tc_wgrad_supported(p)) {
+    CK(tc_wgrad_launch(&c->tc, p, c->stream));
+    return post_launch(c, "wgrad_tc");
+  }
+  const long long R = (long long)p.B * p.Q;
+  const int tiles = (p.Mp / 64) * (p.Np / 64) * p.nseg;
+  int splits = (148 * 8 + tiles - 1) / tiles;
+  long long max_splits = (R + 255) / 256;
+  if (splits > max_splits) splits = (int)max_splits;
+  if (splits < 1) splits = 1;
+  long long rps = (R + splits - 1) / splits;
+  rps = (rps + 15) / 16 * 16;
+  splits = (int)((R + rps - 1) / rps);
+  p.rows_per_split = (int)rps;
+  dim3 grid((unsigned)((p.Mp / 64) * (p.Np / 64)), (unsigned)p.nseg, (unsigned)splits);
+  DISPATCH_T(c, wgrad_simt_kernel<T><<<grid, 256, 0, c->stream>>>(p));
+  return post_launch(c, "wgrad_simt");
+}
+
+static int launch_pack(cg_ctx* c, const float* src, void* dst, int N, int n_real, int nseg, int Cp, int c_real,
+                       long long sk, long long sn, long long sc) {
+  const long long total = (long long)N * nseg * Cp;
+  DISPATCH_T(c, pack_weight_kernel<T><<<grid_for(total), 256, 0, c->stream>>>(src, (T*)dst, N, n_real, nseg, Cp,
+                                                                              c_real, sk, sn, sc));
+  return post_launch(c, "pack");
+}
+
+// refresh packed T copies of one model's GEMM weights from the fp32 master
+static int repack(cg_ctx* c, int which) {
+  const int K = c->K;
+  if (which == CG_DISCRIMINATOR) {
+    for (int l = 1; l <= NL; ++l) {
+      const float* w = c->dis.w + c->dis.params[2 * (l - 1)].offset;   // (K, Cin, Cout)
+      const int ci = c->dc[l - 1], co = c->dc[l], cip = c->dcp[l - 1], cop = c->dcp[l];
+      CK(launch_pack(c, w, c->Wf_d[l], cop, co, K, cip, ci, (long long)ci * co, 1, co));
+      CK(launch_pack(c, w, c->Wb_d[l], cip, ci, K, cop, co, (long long)ci * co, co, 1));
+    }
+  } else {
+    for (int i = 1; i <= NL; ++i) {
+      const float* w = c->gen.w + c->gen.params[c->g_k[i]].offset;     // (K, 1, Cout, Cin)
+      const int ci = c->gc[i - 1], co = c->gc[i], cip = c->gcp[i - 1], cop = c->gcp[i];
+      CK(launch_pack(c, w, c->Wf_g[i], cop, co, K, cip, ci, (long long)ci * co, ci, 1));
+      CK(launch_pack(c, w, c->Wb_g[i], cip, ci, K, cop, co, (long long)ci * co, 1, ci));
+    }
+    const float* w1 = c->gen.w + c->gen.params[c->g_d1k].offset;       // (C_in, C_out)
+    const int C = c->C, Cp = c->gcp[NL];
+    CK(launch_pack(c, w1, c->Wf_d1, Cp, C, 1, Cp, C, 0, 1, C));        // [n=out][c=in]
+    CK(launch_pack(c, w1, c->Wb_d1, Cp, C, 1, Cp, C, 0, C, 1));        // [n=in][c=out]
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ create
+extern "C" int cg_version(void) { return CG_VERSION; }
+extern "C" const char* cg_last_error(void) { return g_err.c_str(); }
+
+extern "C" void cg_destroy(cg_ctx* c) {
+  if (!c) return;
+  cudaDeviceSynchronize();
+  tc_destroy(&c->tc);
+  for (void* p : c->allocs) cudaFree(p);
+  if (c->h_scal) cudaFreeHost(c->h_scal);
+  delete c;
+}
+
+extern "C" int cg_create(const cg_config* cfg, cg_ctx** out) {
+  if (!cfg || !out) return set_err("cg_create: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_err("cg_create: no CUDA device (this library has no CPU fallback)");
+  if (cfg->strides != 2) return set_err("cg_create: only strides == 2 is implemented (got %d)", cfg->strides);
+  if (cfg->kernel_size < 2 || cfg->kernel_size > CG_MAX_SEG)
+    return set_err("cg_create: kernel_size must be in [2, %d]", CG_MAX_SEG);
+  if (cfg->seq_len % 32 != 0 || cfg->seq_len < 32)
+    return set_err("Conv1D: w %g is not an integer.", cfg->seq_len / 32.0);   // calciumgan.py:17-18
+  if (cfg->max_batch < 1 || cfg->channels < 1 || cfg->noise_dim < 1 || cfg->num_units < 1)
+    return set_err("cg_create: bad sizes");
+  if (cfg->phase_m < 0 || cfg->phase_m > cfg->seq_len / 32 * 2 - 1)
+    return set_err("cg_create: phase shuffle m=%d too large for the shortest layer", cfg->phase_m);
+
+  cg_ctx* c = new cg_ctx();
+  c->cfg = *cfg;
+  if (c->cfg.world_size < 1) c->cfg.world_size = 1;
+  if (c->cfg.n_critic < 1) c->cfg.n_critic = 1;
+  c->bf = cfg->precision == CG_BF16;
+  c->esz = c->bf ? 2 : 4;
+  c->use_tc = c->bf && !cfg->force_simt;
+  c->L = cfg->seq_len; c->C = cfg->channels; c->nd = cfg->noise_dim; c->nu = cfg->num_units;
+  c->K = cfg->kernel_size; c->w0 = c->L / 32; c->Bmax = cfg->max_batch;
+  const int nu = c->nu;
+  const int gcs[NL + 1] = {c->nd, nu * 5, nu * 4, nu * 3, nu * 2, c->C};
+  const int dcs[NL + 1] = {c->C, nu, nu * 2, nu * 3, nu * 4, nu * 5};
+  for (int i = 0; i <= NL; ++i) {
+    c->gc[i] = gcs[i]; c->gcp[i] = round_up(gcs[i], CG_CPAD); c->gl[i] = c->w0 << i;
+    c->dc[i] = dcs[i]; c->dcp[i] = round_up(dcs[i], CG_CPAD); c->dl[i] = c->L >> i;
+  }
+  // ---- parameter tables in Keras get_weights() order
+  Model& G = c->gen;
+  Model& D = c->dis;
+  G.add({c->nd, (int64_t)c->w0 * c->nd}); G.add({(int64_t)c->w0 * c->nd});
+  for (int i = 1; i <= NL; ++i) {
+    c->g_k[i] = (int)G.params.size(); G.add({c->K, 1, c->gc[i], c->gc[i - 1]});
+    c->g_b[i] = (int)G.params.size(); G.add({c->gc[i]});
+    if (cfg->layer_norm) {
+      c->g_gam[i] = (int)G.params.size(); G.add({c->gc[i]});
+      c->g_bet[i] = (int)G.params.size(); G.add({c->gc[i]});
+    }
+  }
+  c->g_d1k = (int)G.params.size(); G.add({c->C, c->C});
+  c->g_d1b = (int)G.params.size(); G.add({c->C});
+  for (int l = 1; l <= NL; ++l) { D.add({c->K, c->dc[l - 1], c->dc[l]}); D.add({c->dc[l]}); }
+  D.add({(int64_t)c->dl[NL] * c->dc[NL], 1}); D.add({1});
+
+#define DA_(ptr, bytes)                                          \
+  do {                                                           \
+    if (dalloc(c, (void**)&(ptr), (size_t)(bytes))) { cg_destroy(c); return 1; } \
+  } while (0)
+  for (Model* m : {&G, &D}) {
+    DA_(m->w, m->total * 4); DA_(m->m, m->total * 4); DA_(m->v, m->total * 4); DA_(m->g, m->total * 4);
+  }
+  const size_t es = c->esz;
+  const size_t Bt = 3 * (size_t)c->Bmax, Bm = c->Bmax;
+  for (int l = 1; l <= NL; ++l) {
+    DA_(c->Wf_d[l], (size_t)c->dcp[l] * c->K * c->dcp[l - 1] * es);
+    DA_(c->Wb_d[l], (size_t)c->dcp[l - 1] * c->K * c->dcp[l] * es);
+    DA_(c->Wf_g[l], (size_t)c->gcp[l] * c->K * c->gcp[l - 1] * es);
+    DA_(c->Wb_g[l], (size_t)c->gcp[l - 1] * c->K * c->gcp[l] * es);
+  }
+  DA_(c->Wf_d1, (size_t)c->gcp[NL] * c->gcp[NL] * es);
+  DA_(c->Wb_d1, (size_t)c->gcp[NL] * c->gcp[NL] * es);
+  DA_(c->X[0], Bt * c->dl[0] * c->dcp[0] * es);
+  DA_(c->DX[0], Bm * c->dl[0] * c->dcp[0] * es);
+  c->H[0] = nullptr; c->DA[0] = nullptr;
+  for (int l = 1; l <= NL; ++l) {
+    const size_t n = Bt * c->dl[l] * c->dcp[l] * es;
+    DA_(c->H[l], n); DA_(c->DA[l], n);
+    if (l < NL) { DA_(c->X[l], n); DA_(c->DX[l], n); } else { c->X[l] = c->H[l]; c->DX[l] = nullptr; }
+  }
+  DA_(c->scores, Bt * 4); DA_(c->coef, Bt * 4); DA_(c->sumsq, Bm * 4); DA_(c->ucoef, Bm * 4); DA_(c->norms, Bm * 4);
+  DA_(c->Z, Bm * c->nd * 4);
+  for (int i = 0; i <= NL; ++i) {
+    const size_t n = Bm * c->gl[i] * c->gcp[i] * es;
+    DA_(c->HG[i], n); DA_(c->DHG[i], n);
+    if (i >= 1) {
+      DA_(c->AG[i], n); DA_(c->DAG[i], n);
+      DA_(c->MU[i], Bm * c->gl[i] * 4); DA_(c->RSTD[i], Bm * c->gl[i] * 4);
+    } else { c->AG[i] = c->DAG[i] = nullptr; c->MU[i] = c->RSTD[i] = nullptr; }
+  }
+  DA_(c->DO, Bm * c->L * c->gcp[NL] * es);
+  DA_(c->FAKE32, Bm * c->L * c->C * 4);
+  DA_(c->alpha_buf, (size_t)c->cfg.n_critic * Bm * 4);
+  DA_(c->noise_buf, (size_t)(c->cfg.n_critic + 1) * Bm * c->nd * 4);
+  DA_(c->d_scal, (size_t)(c->cfg.n_critic + 1) * CG_NUM_SCALARS * 4);
+#undef DA_
+  if (cudaMallocHost((void**)&c->h_scal, (size_t)(c->cfg.n_critic + 1) * CG_NUM_SCALARS * 4) != cudaSuccess) {
+    cg_destroy(c);
+    return set_err("cudaMallocHost failed");
+  }
+  if (c->use_tc && tc_init(&c->tc)) { cg_destroy(c); return 1; }
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) { cg_destroy(c); return set_err("arena init failed"); }
+  *out = c;
+  return 0;
+}
+
+extern "C" int cg_set_stream(cg_ctx* c, void* s) { c->stream = (cudaStream_t)s; return 0; }
+extern "C" int cg_synchronize(cg_ctx* c) { CU(cudaStreamSynchronize(c->stream)); return 0; }
+extern "C" int64_t cg_launch_count(cg_ctx* c) { return c->launches; }
+extern "C" int64_t cg_device_bytes(cg_ctx* c) { return c->dev_bytes; }
+extern "C" void* cg_fake_ptr(cg_ctx* c) { return c->FAKE32; }
+extern "C" void* cg_scores_ptr(cg_ctx* c) { return c->scores; }
+extern "C" void* cg_scalars_ptr(cg_ctx* c) { return c->d_scal; }
+
+static Model* model_of(cg_ctx* c, int which) { return which == CG_GENERATOR ? &c->gen : &c->dis; }
+extern "C" int64_t cg_num_params(cg_ctx* c, int which) { return model_of(c, which)->total; }
+extern "C" int cg_num_tensors(cg_ctx* c, int which) { return (int)model_of(c, which)->params.size(); }
+extern "C" int cg_tensor_info(cg_ctx* c, int which, int idx, int64_t shape[4], int* ndim, int64_t* offset) {
+  Model* m = model_of(c, which);
+  if (idx < 0 || idx >= (int)m->params.size()) return set_err("cg_tensor_info: index %d out of range", idx);
+  for (int i = 0; i < 4; ++i) shape[i] = m->params[idx].shape[i];
+  *ndim = m->params[idx].ndim;
+  *offset = m->params[idx].offset;
+  return 0;
+}
+extern "C" int cg_set_weights(cg_ctx* c, int which, const float* host) {
+  Model* m = model_of(c, which);
+  CU(cudaMemcpyAsync(m->w, host, m->total * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(repack(c, which));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int cg_get_weights(cg_ctx* c, int which, float* host) {
+  Model* m = model_of(c, which);
+  CU(cudaMemcpyAsync(host, m->w, m->total * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int cg_get_grads(cg_ctx* c, int which, float* host) {
+  Model* m = model_of(c, which);
+  CU(cudaMemcpyAsync(host, m->g, m->total * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" void* cg_grad_ptr(cg_ctx* c, int which) { return model_of(c, which)->g; }
+extern "C" int cg_get_opt_state(cg_ctx* c, int which, float* hm, float* hv, int64_t* step) {
+  Model* m = model_of(c, which);
+  if (hm) CU(cudaMemcpyAsync(hm, m->m, m->total * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (hv) CU(cudaMemcpyAsync(hv, m->v, m->total * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (step) *step = m->steps;
+  return 0;
+}
+extern "C" int cg_set_opt_state(cg_ctx* c, int which, const float* hm, const float* hv, int64_t step) {
+  Model* m = model_of(c, which);
+  if (hm) CU(cudaMemcpyAsync(m->m, hm, m->total * 4, cudaMemcpyHostToDevice, c->stream));
+  if (hv) CU(cudaMemcpyAsync(m->v, hv, m->total * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  m->steps = step;
+  return 0;
+}
+extern "C" int cg_seed(cg_ctx* c, uint64_t seed) { c->seed = seed; c->rng_counter = 0; return 0; }
+
+static uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// Keras glorot-uniform / zeros / LN (1,0) init on the host, then upload
+extern "C" int cg_init_weights(cg_ctx* c, uint64_t seed) {
+  uint64_t st = splitmix64(seed);
+  auto uni = [&]() { st = splitmix64(st); return (double)(st >> 11) * (1.0 / 9007199254740992.0); };
+  for (int which = 0; which < 2; ++which) {
+    Model* m = model_of(c, which);
+    std::vector<float> h((size_t)m->total, 0.f);
+    for (size_t i = 0; i < m->params.size(); ++i) {
+      const ParamInfo& p = m->params[i];
+      double fan_in = 0, fan_out = 0;
+      if (p.ndim == 2) { fan_in = (double)p.shape[0]; fan_out = (double)p.shape[1]; }
+      else if (p.ndim == 3) { fan_in = (double)p.shape[0] * p.shape[1]; fan_out = (double)p.shape[0] * p.shape[2]; }
+      else if (p.ndim == 4) { fan_in = (double)p.shape[0] * p.shape[3]; fan_out = (double)p.shape[0] * p.shape[2]; }
+      if (p.ndim >= 2) {
+        const double lim = std::sqrt(6.0 / (fan_in + fan_out));
+        for (int64_t j = 0; j < p.size; ++j) h[p.offset + j] = (float)((2.0 * uni() - 1.0) * lim);
+      }
+    }
+    if (which == CG_GENERATOR && c->cfg.layer_norm)
+      for (int i = 1; i <= NL; ++i) {
+        const ParamInfo& p = m->params[c->g_gam[i]];
+        for (int64_t j = 0; j < p.size; ++j) h[p.offset + j] = 1.f;
+      }
+    CK(cg_set_weights(c, which, h.data()));
+    CU(cudaMemsetAsync(m->m, 0, m->total * 4, c->stream));
+    CU(cudaMemsetAsync(m->v, 0, m->total * 4, c->stream));
+    m->steps = 0;
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ generator
+static float* gparam(cg_ctx* c, int idx) { return c->gen.w + c->gen.params[idx].offset; }
+static float* ggrad(cg_ctx* c, int idx) { return c->gen.g + c->gen.params[idx].offset; }
+static float* dparam(cg_ctx* c, int idx) { return c->dis.w + c->dis.params[idx].offset; }
+static float* dgrad(cg_ctx* c, int idx) { return c->dis.g + c->dis.params[idx].offset; }
+
+// calciumgan.py:22-103. noise (B, nd) fp32 device. Writes FAKE32 (B, L, C).
+static int g_forward(cg_ctx* c, const float* noise, int B) {
+  DISPATCH_T(c, dense0_forward_kernel<T><<<grid_for((long long)B * c->w0 * c->gcp[0]), 256, 0, c->stream>>>(
+                    noise, gparam(c, 0), gparam(c, 1), (T*)c->HG[0], B, c->nd, c->w0, c->gcp[0]));
+  CK(post_launch(c, "dense0_fwd"));
+  for (int i = 1; i <= NL; ++i) {
+    RsParams p;
+    memset(&p, 0, sizeof(p));
+    p.A = c->HG[i - 1]; p.a_bs = (long long)c->gl[i - 1] * c->gcp[i - 1]; p.a_rs = c->gcp[i - 1]; p.a_rows = c->gl[i - 1];
+    p.W = c->Wf_g[i]; p.w_ld = c->K * c->gcp[i - 1];
+    p.out = c->AG[i]; p.o_bs = (long long)c->gl[i] * c->gcp[i]; p.o_rs = 2 * c->gcp[i]; p.o_phase_col = c->gcp[i];
+    p.bias = gparam(c, c->g_b[i]);
+    p.B = B; p.Q = c->gl[i - 1]; p.N = c->gcp[i]; p.n_real = c->gc[i]; p.Kc = c->gcp[i - 1];
+    p.epi = EPI_BIAS;
+    p.seg = seg_transposed(c->K, c->gcp[i - 1]);
+    CK(launch_rsgemm(c, p));
+    const long long rows = (long long)B * c->gl[i];
+    if (c->cfg.layer_norm) {
+      DISPATCH_T(c, ln_lrelu_forward_kernel<T><<<grid_for(rows * 32), 256, 0, c->stream>>>(
+                        (const T*)c->AG[i], gparam(c, c->g_gam[i]), gparam(c, c->g_bet[i]), (T*)c->HG[i], c->MU[i],
+                        c->RSTD[i], rows, c->gc[i], c->gcp[i]));
+      CK(post_launch(c, "ln_fwd"));
+    } else {
+      DISPATCH_T(c, lrelu_kernel<T><<<grid_for(rows * c->gcp[i]), 256, 0, c->stream>>>((const T*)c->AG[i],
+                                                                                      (T*)c->HG[i], rows * c->gcp[i]));
+      CK(post_launch(c, "lrelu"));
+    }
+  }
+  RsParams p;
+  memset(&p, 0, sizeof(p));
+  const int Cp = c->gcp[NL];
+  p.A = c->HG[NL]; p.a_bs = (long long)c->L * Cp; p.a_rs = Cp; p.a_rows = c->L;
+  p.W = c->Wf_d1; p.w_ld = Cp;
+  p.out = nullptr;
+  p.out32 = c->FAKE32; p.o32_bs = (long long)c->L * c->C; p.o32_rs = c->C;
+  p.o_bs = (long long)c->L * Cp; p.o_rs = Cp;
+  p.bias = gparam(c, c->g_d1b);
+  p.B = B; p.Q = c->L; p.N = Cp; p.n_real = c->C; p.Kc = Cp;
+  p.epi = c->cfg.normalize ? EPI_BIAS_SIGMOID : EPI_BIAS;
+  p.seg = seg_dense();
+  CK(launch_rsgemm(c, p));
+  return 0;
+}
+
+static int launch_colsum(cg_ctx* c, const void* X, float* out, long long rows, int Cp, int c_real) {
+  int gx = (int)((rows + 3) / 4);
+  if (gx > 148 * 4) gx = 148 * 4;
+  dim3 grid(gx, (c_real + 63) / 64), block(64, 4);
+  DISPATCH_T(c, colsum_kernel<T><<<grid, block, 0, c->stream>>>((const T*)X, out, rows, Cp, c_real));
+  return post_launch(c, "colsum");
+}
+
+// backward of the generator given DX[0] = dLoss/dfake (B, L, dcp0); accumulates into gen.g
+static int g_backward(cg_ctx* c, int B) {
+  const int Cp = c->gcp[NL];
+  const long long rowsL = (long long)B * c->L;
+  DISPATCH_T(c, sigmoid_backward_kernel<T><<<grid_for(rowsL * Cp), 256, 0, c->stream>>>(
+                    (const T*)c->DX[0], c->FAKE32, (T*)c->DO, rowsL, c->C, Cp, c->cfg.normalize));
+  CK(post_launch(c, "sigmoid_bwd"));
+  {  // output dense: dW1[c_in][c_out] = sum_rows HG5[row,c_in] * DO[row,c_out]
+    WgParams w;
+    memset(&w, 0, sizeof(w));
+    w.S = c->HG[NL]; w.s_bs = (long long)c->L * Cp; w.s_rs = Cp; w.s_rows = c->L;
+    w.P = c->DO; w.p_bs = (long long)c->L * Cp; w.p_rs = Cp;
+    w.dW = ggrad(c, c->g_d1k); w.m_real = c->C; w.n_real = c->C;
+    w.B = B; w.Q = c->L; w.Mp = Cp; w.Np = Cp; w.nseg = 1;
+    CK(launch_wgrad(c, w));
+    CK(launch_colsum(c, c->DO, ggrad(c, c->g_d1b), rowsL, Cp, c->C));
+    RsParams p;
+    memset(&p, 0, sizeof(p));
+    p.A = c->DO; p.a_bs = (long long)c->L * Cp; p.a_rs = Cp; p.a_rows = c->L;
+    p.W = c->Wb_d1; p.w_ld = Cp;
+    p.out = c->DHG[NL]; p.o_bs = (long long)c->L * Cp; p.o_rs = Cp;
+    p.B = B; p.Q = c->L; p.N = Cp; p.n_real = c->C; p.Kc = Cp; p.epi = EPI_NONE;
+    p.seg = seg_dense();
+    CK(launch_rsgemm(c, p));
+  }
+  for (int i = NL; i >= 1; --i) {
+    const long long rows = (long long)B * c->gl[i];
+    if (c->cfg.layer_norm) {
+      int blocks = grid_for(rows * 32, 256, 148 * 4);
+      DISPATCH_T(c, ln_lrelu_backward_kernel<T><<<blocks, 256, 2 * c->gc[i] * sizeof(float), c->stream>>>(
+                        (const T*)c->DHG[i], (const T*)c->AG[i], (const T*)c->HG[i], c->MU[i], c->RSTD[i],
+                        gparam(c, c->g_gam[i]), (T*)c->DAG[i], ggrad(c, c->g_gam[i]), ggrad(c, c->g_bet[i]), rows,
+                        c->gc[i], c->gcp[i]));
+      CK(post_launch(c, "ln_bwd"));
+    } else {
+      DISPATCH_T(c, mask_mul_kernel<T><<<grid_for(rows * c->gcp[i]), 256, 0, c->stream>>>(
+                        (const T*)c->DHG[i], (const T*)c->HG[i], (T*)c->DAG[i], rows * c->gcp[i]));
+      CK(post_launch(c, "mask_mul"));
+    }
+    // dWt[k][co][ci] = sum_{b,q} DAG[b, 2q + k - padL, co] * HG[i-1][b, q, ci]
+    WgParams w;
+    memset(&w, 0, sizeof(w));
+    const SegTable st = seg_strided(c->K, c->gcp[i]);
+    w.S = c->DAG[i]; w.s_bs = (long long)c->gl[i] * c->gcp[i]; w.s_rs = 2 * c->gcp[i]; w.s_rows = c->gl[i] / 2;
+    w.P = c->HG[i - 1]; w.p_bs = (long long)c->gl[i - 1] * c->gcp[i - 1]; w.p_rs = c->gcp[i - 1];
+    w.dW = ggrad(c, c->g_k[i]); w.m_real = c->gc[i]; w.n_real = c->gc[i - 1];
+    w.B = B; w.Q = c->gl[i - 1]; w.Mp = c->gcp[i]; w.Np = c->gcp[i - 1]; w.nseg = c->K;
+    for (int k = 0; k < c->K; ++k) { w.shift[k] = st.shift[0][k]; w.scol[k] = st.acol[0][k]; }
+    CK(launch_wgrad(c, w));
+    CK(launch_colsum(c, c->DAG[i], ggrad(c, c->g_b[i]), rows, c->gcp[i], c->gc[i]));
+    // dHG[i-1][b,q,ci] = sum_k DAG[b, 2q+k-padL, co] * Wt[k][co][ci]   (strided-conv form)
+    RsParams p;
+    memset(&p, 0, sizeof(p));
+    p.A = c->DAG[i]; p.a_bs = (long long)c->gl[i] * c->gcp[i]; p.a_rs = 2 * c->gcp[i]; p.a_rows = c->gl[i] / 2;
+    p.W = c->Wb_g[i]; p.w_ld = c->K * c->gcp[i];
+    p.out = c->DHG[i - 1]; p.o_bs = (long long)c->gl[i - 1] * c->gcp[i - 1]; p.o_rs = c->gcp[i - 1];
+    p.B = B; p.Q = c->gl[i - 1]; p.N = c->gcp[i - 1]; p.n_real = c->gc[i - 1]; p.Kc = c->gcp[i]; p.epi = EPI_NONE;
+    p.seg = st;
+    CK(launch_rsgemm(c, p));
+  }
+  const int tot = (c->nd + 1) * c->w0 * c->nd;
+  DISPATCH_T(c, dense0_backward_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
+                    c->Z, (const T*)c->DHG[0], (const T*)c->HG[0], ggrad(c, 0), ggrad(c, 1), B, c->nd, c->w0,
+                    c->gcp[0]));
+  CK(post_launch(c, "dense0_bwd"));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ critic
+static void* off(cg_ctx* c, void* base, long long elems) { return (char*)base + elems * c->esz; }
+
+static GroupShifts group_shifts(const int32_t* sh, int groups, int layer /*1..4*/) {
+  GroupShifts g;
+  for (int i = 0; i < 4; ++i) g.s[i] = i < groups ? sh[i * 4 + (layer - 1)] : 0;
+  return g;
+}
+
+static RsParams conv_fwd_params(cg_ctx* c, int l, const void* A, void* out, int Bt, int epi, const void* mask) {
+  RsParams p;
+  memset(&p, 0, sizeof(p));
+  p.A = A; p.a_bs = (long long)c->dl[l - 1] * c->dcp[l - 1]; p.a_rs = 2 * c->dcp[l - 1]; p.a_rows = c->dl[l - 1] / 2;
+  p.W = c->Wf_d[l]; p.w_ld = c->K * c->dcp[l - 1];
+  p.out = out; p.o_bs = (long long)c->dl[l] * c->dcp[l]; p.o_rs = c->dcp[l];
+  p.bias = dparam(c, 2 * (l - 1) + 1);
+  p.mask = mask;
+  p.B = Bt; p.Q = c->dl[l]; p.N = c->dcp[l]; p.n_real = c->dc[l]; p.Kc = c->dcp[l - 1]; p.epi = epi;
+  p.seg = seg_strided(c->K, c->dcp[l - 1]);
+  return p;
+}
+
+// calciumgan.py:141-192 on X[0][0:Bt]; groups of B samples share PhaseShuffle shifts sh[g*4 + layer-1]
+static int d_forward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh) {
+  for (int l = 1; l <= NL; ++l) {
+    CK(launch_rsgemm(c, conv_fwd_params(c, l, c->X[l - 1], c->H[l], Bt, EPI_BIAS_LRELU, nullptr)));
+    if (l < NL) {
+      const long long tot = (long long)Bt * c->dl[l] * c->dcp[l] / (16 / c->esz);
+      DISPATCH_T(c, ps_gather_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
+                        (const T*)c->H[l], (T*)c->X[l], Bt, B, c->dl[l], c->dcp[l], group_shifts(sh, groups, l)));
+      CK(post_launch(c, "ps_gather"));
+    }
+  }
+  DISPATCH_T(c, head_forward_kernel<T><<<Bt, 256, 0, c->stream>>>((const T*)c->X[NL], dparam(c, 10), dparam(c, 11),
+                                                                  c->scores, c->dl[NL], c->dc[NL], c->dcp[NL]));
+  return post_launch(c, "head_fwd");
+}
+
+// data-gradient of conv layer l: DA[l] (rows dl[l]) -> out (rows dl[l-1]) for samples [b0, b0+nb)
+static int d_dgrad_layer(cg_ctx* c, int l, int b0, int nb, void* out) {
+  RsParams p;
+  memset(&p, 0, sizeof(p));
+  p.A = off(c, c->DA[l], (long long)b0 * c->dl[l] * c->dcp[l]);
+  p.a_bs = (long long)c->dl[l] * c->dcp[l]; p.a_rs = c->dcp[l]; p.a_rows = c->dl[l];
+  p.W = c->Wb_d[l]; p.w_ld = c->K * c->dcp[l];
+  p.out = out; p.o_bs = (long long)c->dl[l - 1] * c->dcp[l - 1]; p.o_rs = 2 * c->dcp[l - 1]; p.o_phase_col = c->dcp[l - 1];
+  p.B = nb; p.Q = c->dl[l]; p.N = c->dcp[l - 1]; p.n_real = c->dc[l - 1]; p.Kc = c->dcp[l]; p.epi = EPI_NONE;
+  p.seg = seg_transposed(c->K, c->dcp[l]);
+  return launch_rsgemm(c, p);
+}
+
+// backward chain of sum_b coef[b]*D(x)_b down to DA[1] (and DX[0] for samples [dx0_b0, dx0_b0+dx0_nb))
+static int d_backward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh, int dx0_b0, int dx0_nb) {
+  DISPATCH_T(c, head_backward_kernel<T><<<grid_for((long long)Bt * c->dl[NL] * c->dcp[NL]), 256, 0, c->stream>>>(
+                    (const T*)c->H[NL], dparam(c, 10), c->coef, (T*)c->DA[NL], Bt, c->dl[NL], c->dc[NL], c->dcp[NL]));
+  CK(post_launch(c, "head_bwd"));
+  for (int l = NL; l >= 2; --l) {
+    CK(d_dgrad_layer(c, l, 0, Bt, c->DX[l - 1]));
+    const long long tot = (long long)Bt * c->dl[l - 1] * c->dcp[l - 1];
+    DISPATCH_T(c, ps_scatter_mask_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
+                      (const T*)c->DX[l - 1], (const T*)c->H[l - 1], (T*)c->DA[l - 1], Bt, B, c->dl[l - 1],
+                      c->dcp[l - 1], group_shifts(sh, groups, l - 1)));
+    CK(post_launch(c, "ps_scatter_mask"));
+  }
+  if (dx0_nb > 0) CK(d_dgrad_layer(c, 1, dx0_b0, dx0_nb, c->DX[0]));
+  return 0;
+}
+
+// all critic weight gradients from X[l-1] x DA[l] over Bt samples; biases from the first nb_bias samples
+static int d_wgrad(cg_ctx* c, int Bt, int nb_bias) {
+  for (int l = 1; l <= NL; ++l) {
+    WgParams w;
+    memset(&w, 0, sizeof(w));
+    const SegTable st = seg_strided(c->K, c->dcp[l - 1]);
+    w.S = c->X[l - 1]; w.s_bs = (long long)c->dl[l - 1] * c->dcp[l - 1]; w.s_rs = 2 * c->dcp[l - 1]; w.s_rows = c->dl[l - 1] / 2;
+    w.P = c->DA[l]; w.p_bs = (long long)c->dl[l] * c->dcp[l]; w.p_rs = c->dcp[l];
+    w.dW = dgrad(c, 2 * (l - 1)); w.m_real = c->dc[l - 1]; w.n_real = c->dc[l];
+    w.B = Bt; w.Q = c->dl[l]; w.Mp = c->dcp[l - 1]; w.Np = c->dcp[l]; w.nseg = c->K;
+    for (int k = 0; k < c->K; ++k) { w.shift[k] = st.shift[0][k]; w.scol[k] = st.acol[0][k]; }
+    CK(launch_wgrad(c, w));
+    if (nb_bias > 0)
+      CK(launch_colsum(c, c->DA[l], dgrad(c, 2 * (l - 1) + 1), (long long)nb_bias * c->dl[l], c->dcp[l], c->dc[l]));
+  }
+  const int tot = c->dl[NL] * c->dc[NL];
+  DISPATCH_T(c, head_wgrad_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
+                    (const T*)c->X[NL], c->coef, dgrad(c, 10), dgrad(c, 11), Bt, nb_bias, c->dl[NL], c->dc[NL], c->dcp[NL]));
+  return post_launch(c, "head_wgrad");
+}
+
+// ------------------------------------------------------------------------------------------ rng
+static int draw(cg_ctx* c, float* out, long long n, int mode) {
+  const uint64_t stream = (c->rng_counter++) * 2654435761ull + (uint64_t)(c->cfg.rank + 1) * 0x100000001B3ull;
+  rng_fill_kernel<<<grid_for((n + 3) / 4), 256, 0, c->stream>>>(out, n, c->seed, stream, mode);
+  return post_launch(c, "rng_fill");
+}
+static void draw_shifts(cg_ctx* c, int32_t* out, int n) {   // identical on every rank (shared per-call scalars)
+  const int m = c->cfg.phase_m;
+  for (int i = 0; i < n; ++i) {
+    const uint64_t r = splitmix64(c->seed * 0x9E3779B97F4A7C15ull + 0xABCDull + (c->rng_counter++));
+    out[i] = (int32_t)(r % (uint64_t)(2 * m + 1)) - m;
+  }
+}
+
+static int check_batch(cg_ctx* c, int B) {
+  if (B < 1 || B > c->Bmax) return set_err("batch %d outside [1, max_batch=%d]", B, c->Bmax);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ Adam
+extern "C" int cg_apply_update(cg_ctx* c, int which) {
+  Model* m = model_of(c, which);
+  m->steps += 1;
+  const double t = (double)m->steps, b1 = 0.9, b2 = 0.999;
+  const float lr_t = (float)(c->cfg.learning_rate * std::sqrt(1.0 - std::pow(b2, t)) / (1.0 - std::pow(b1, t)));
+  adam_kernel<<<grid_for(m->total), 256, 0, c->stream>>>(m->w, m->m, m->v, m->g, m->total, lr_t, 0.9f, 0.999f, 1e-7f,
+                                                        1.0f / (float)c->cfg.world_size);
+  CK(post_launch(c, "adam"));
+  return repack(c, which);
+}
+
+static int fetch_scalars(cg_ctx* c, int slot, int flags, float* scalars_host) {
+  if (flags & CG_FLAG_NO_SYNC) return 0;
+  CU(cudaMemcpyAsync(c->h_scal, c->d_scal + (size_t)slot * CG_NUM_SCALARS, CG_NUM_SCALARS * 4, cudaMemcpyDeviceToHost,
+                     c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (scalars_host) memcpy(scalars_host, c->h_scal, CG_NUM_SCALARS * 4);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ critic step
+// forward part shared by cg_critic_step and cg_validate: fake, D on [real; fake; xhat], dgrad chain, GP scalars
+static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
+                             const int32_t* sh, int slot) {
+  CK(g_forward(c, noise, B));
+  const long long tot = (long long)B * c->L * c->dcp[0];
+  DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(real, c->FAKE32, alpha, (T*)c->X[0], B,
+                                                                           c->L, c->C, c->dcp[0], 0));
+  CK(post_launch(c, "assemble_x0"));
+  CK(d_forward(c, 3 * B, B, 3, sh));
+  fill_coef_kernel<<<(3 * B + 255) / 256, 256, 0, c->stream>>>(c->coef, B, 3, 0.f);
+  CK(post_launch(c, "fill_coef"));
+  CK(d_backward(c, 3 * B, B, 3, sh, 2 * B, B));
+  CU(cudaMemsetAsync(c->sumsq, 0, (size_t)B * 4, c->stream));
+  const long long per = (long long)c->L * c->dcp[0];
+  const int chunks = 8;
+  DISPATCH_T(c, sumsq_kernel<T><<<B * chunks, 256, 0, c->stream>>>((const T*)c->DX[0], c->sumsq, per, chunks));
+  CK(post_launch(c, "sumsq"));
+  critic_scalars_kernel<<<1, 256, 0, c->stream>>>(c->scores, c->sumsq, c->ucoef, c->norms,
+                                                  c->d_scal + (size_t)slot * CG_NUM_SCALARS, B, c->cfg.gp_lambda);
+  return post_launch(c, "critic_scalars");
+}
+
+static int critic_step_impl(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
+                            const int32_t* sh, int flags, int slot) {
+  CK(critic_forward_gp(c, real, B, noise, alpha, sh, slot));
+  // GP second-order term without the second-order graph: v0 = u = d(lambda*GP)/dg
+  const long long per = (long long)c->L * c->dcp[0];
+  DISPATCH_T(c, scale_rows_kernel<T><<<grid_for(per * B), 256, 0, c->stream>>>(
+                    (const T*)c->DX[0], c->ucoef, (T*)off(c, c->X[0], 2 * B * per), per, per * B));
+  CK(post_launch(c, "scale_rows"));
+  const int32_t* sh2 = sh + 8;
+  for (int l = 1; l <= NL; ++l) {
+    const long long gin = 2LL * B * c->dl[l - 1] * c->dcp[l - 1], gout = 2LL * B * c->dl[l] * c->dcp[l];
+    void* dst = l < NL ? off(c, c->DX[l], gout) : off(c, c->X[l], gout);
+    CK(launch_rsgemm(c, conv_fwd_params(c, l, off(c, c->X[l - 1], gin), dst, B, EPI_MASK, off(c, c->H[l], gout))));
+    if (l < NL) {
+      const long long tot = (long long)B * c->dl[l] * c->dcp[l] / (16 / c->esz);
+      GroupShifts g; g.s[0] = sh2[l - 1]; g.s[1] = g.s[2] = g.s[3] = 0;
+      DISPATCH_T(c, ps_gather_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
+                        (const T*)dst, (T*)off(c, c->X[l], gout), B, B, c->dl[l], c->dcp[l], g));
+      CK(post_launch(c, "ps_gather_lin"));
+    }
+  }
+  CU(cudaMemsetAsync(c->dis.g, 0, c->dis.total * 4, c->stream));
+  CK(d_wgrad(c, 3 * B, 2 * B));
+  if (!(flags & CG_FLAG_NO_UPDATE)) CK(cg_apply_update(c, CG_DISCRIMINATOR));
+  return 0;
+}
+
+static int prep_random(cg_ctx* c, int B, const float*& noise, const float** alpha, const int32_t*& sh, int32_t* shbuf,
+                       int nsh) {
+  if (!noise) {
+    CK(draw(c, c->noise_buf, (long long)B * c->nd, 0));
+    noise = c->noise_buf;
+  }
+  if (alpha && !*alpha) {
+    CK(draw(c, c->alpha_buf, B, 1));
+    *alpha = c->alpha_buf;
+  }
+  if (!sh) {
+    draw_shifts(c, shbuf, nsh);
+    sh = shbuf;
+  }
+  for (int i = 0; i < nsh; ++i)
+    if (sh[i] < -c->cfg.phase_m || sh[i] > c->cfg.phase_m)
+      return set_err("phase-shuffle shift %d outside [-m, m] (m=%d)", sh[i], c->cfg.phase_m);
+  return 0;
+}
+
+extern "C" int cg_critic_step(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
+                              const int32_t* sh, int flags, float* scalars_host) {
+  CK(check_batch(c, B));
+  int32_t shbuf[12];
+  CK(prep_random(c, B, noise, &alpha, sh, shbuf, 12));
+  CK(critic_step_impl(c, real, B, noise, alpha, sh, flags, 0));
+  return fetch_scalars(c, 0, flags, scalars_host);
+}
+
+// ------------------------------------------------------------------------------------------ generator step
+static int generator_step_impl(cg_ctx* c, const float* real, int B, const float* noise, const int32_t* sh, int flags,
+                               int slot) {
+  CU(cudaMemcpyAsync(c->Z, noise, (size_t)B * c->nd * 4, cudaMemcpyDeviceToDevice, c->stream));
+  CK(g_forward(c, c->Z, B));
+  const long long tot = (long long)B * c->L * c->dcp[0];
+  DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(c->FAKE32, nullptr, nullptr, (T*)c->X[0],
+                                                                           B, c->L, c->C, c->dcp[0], 1));
+  CK(post_launch(c, "assemble_x0_fake"));
+  CK(d_forward(c, B, B, 1, sh));
+  float* scal = c->d_scal + (size_t)slot * CG_NUM_SCALARS;
+  gen_loss_kernel<<<1, 256, 0, c->stream>>>(c->scores, scal, B);
+  CK(post_launch(c, "gen_loss"));
+  fill_coef_kernel<<<(B + 255) / 256, 256, 0, c->stream>>>(c->coef, B, 1, -1.f / B);
+  CK(post_launch(c, "fill_coef"));
+  CK(d_backward(c, B, B, 1, sh, 0, B));
+  CU(cudaMemsetAsync(c->gen.g, 0, c->gen.total * 4, c->stream));
+  CK(g_backward(c, B));
+  if (real) {
+    CU(cudaMemsetAsync(scal + CG_S_MET_MIN, 0, 4 * 4, c->stream));
+    const long long rows = (long long)B * c->L;
+    metrics_kernel<<<grid_for(rows * 32, 256, 148 * 4), 256, 0, c->stream>>>(
+        real, c->FAKE32, scal + CG_S_MET_MIN, rows, c->C, c->cfg.signals_min, c->cfg.signals_max, c->cfg.normalize);
+    CK(post_launch(c, "metrics"));
+  }
+  if (!(flags & CG_FLAG_NO_UPDATE)) CK(cg_apply_update(c, CG_GENERATOR));
+  return 0;
+}
+
+extern "C" int cg_generator_step(cg_ctx* c, const float* real, int B, const float* noise, const int32_t* sh, int flags,
+                                 float* scalars_host) {
+  CK(check_batch(c, B));
+  int32_t shbuf[4];
+  CK(prep_random(c, B, noise, nullptr, sh, shbuf, 4));
+  CK(generator_step_impl(c, real, B, noise, sh, flags, 0));
+  return fetch_scalars(c, 0, flags, scalars_host);
+}
+
+// wgan_gp.py:82-95
+extern "C" int cg_train_step(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
+                             const int32_t* sh, float* scalars_host) {
+  CK(check_batch(c, B));
+  const int nc = c->cfg.n_critic;
+  std::vector<int32_t> shbuf(12 * nc + 4);
+  if (!noise) { CK(draw(c, c->noise_buf, (long long)(nc + 1) * B * c->nd, 0)); noise = c->noise_buf; }
+  if (!alpha) { CK(draw(c, c->alpha_buf, (long long)nc * B, 1)); alpha = c->alpha_buf; }
+  if (!sh) { draw_shifts(c, shbuf.data(), 12 * nc + 4); sh = shbuf.data(); }
+  for (int i = 0; i < 12 * nc + 4; ++i)
+    if (sh[i] < -c->cfg.phase_m || sh[i] > c->cfg.phase_m) return set_err("phase-shuffle shift out of range");
+  for (int i = 0; i < nc; ++i)
+    CK(critic_step_impl(c, real, B, noise + (size_t)i * B * c->nd, alpha + (size_t)i * B, sh + 12 * i, 0, i));
+  CK(generator_step_impl(c, real, B, noise + (size_t)nc * B * c->nd, sh + 12 * nc, 0, nc));
+  CU(cudaMemcpyAsync(c->h_scal, c->d_scal, (size_t)(nc + 1) * CG_NUM_SCALARS * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (scalars_host) {
+    memset(scalars_host, 0, CG_NUM_SCALARS * 4);
+    double dl = 0, gp = 0;
+    for (int i = 0; i < nc; ++i) { dl += c->h_scal[i * CG_NUM_SCALARS + CG_S_DIS_LOSS]; gp += c->h_scal[i * CG_NUM_SCALARS + CG_S_GP]; }
+    scalars_host[CG_S_DIS_LOSS] = (float)(dl / nc);
+    scalars_host[CG_S_GP] = (float)(gp / nc);
+    const float* g = c->h_scal + (size_t)nc * CG_NUM_SCALARS;
+    for (int i = CG_S_GEN_LOSS; i <= CG_S_MET_STD; ++i) scalars_host[i] = g[i];
+  }
+  return 0;
+}
+
+// gan.py:58-70,87-90 with the WGAN-GP losses; no parameter update
+extern "C" int cg_validate(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
+                           const int32_t* sh, float* fake_out, float* scalars_host) {
+  CK(check_batch(c, B));
+  int32_t shbuf[12];
+  CK(prep_random(c, B, noise, &alpha, sh, shbuf, 12));
+  CK(critic_forward_gp(c, real, B, noise, alpha, sh, 0));
+  float* scal = c->d_scal;
+  gen_loss_kernel<<<1, 256, 0, c->stream>>>(c->scores + B, scal, B);   // -mean D(fake)
+  CK(post_launch(c, "gen_loss"));
+  CU(cudaMemsetAsync(scal + CG_S_MET_MIN, 0, 4 * 4, c->stream));
+  const long long rows = (long long)B * c->L;
+  metrics_kernel<<<grid_for(rows * 32, 256, 148 * 4), 256, 0, c->stream>>>(
+      real, c->FAKE32, scal + CG_S_MET_MIN, rows, c->C, c->cfg.signals_min, c->cfg.signals_max, c->cfg.normalize);
+  CK(post_launch(c, "metrics"));
+  if (fake_out) CU(cudaMemcpyAsync(fake_out, c->FAKE32, (size_t)rows * c->C * 4, cudaMemcpyDeviceToDevice, c->stream));
+  return fetch_scalars(c, 0, 0, scalars_host);
+}
+
+extern "C" int cg_generate(cg_ctx* c, const float* noise, int B, int denorm, float* out) {
+  CK(check_batch(c, B));
+  if (!noise || !out) return set_err("cg_generate: null pointer");
+  CK(g_forward(c, noise, B));
+  const long long tot = (long long)B * c->L * c->C;
+  if (denorm) {
+    denorm_kernel<<<grid_for(tot), 256, 0, c->stream>>>(c->FAKE32, out, tot, c->cfg.signals_min, c->cfg.signals_max);
+    CK(post_launch(c, "denorm"));
+  } else {
+    CU(cudaMemcpyAsync(out, c->FAKE32, (size_t)tot * 4, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ debug taps
+extern "C" int cg_debug_critic_forward(cg_ctx* c, const float* x, int B, const int32_t* sh, float* scores_dev) {
+  CK(check_batch(c, B));
+  if (!x || !sh || !scores_dev) return set_err("cg_debug_critic_forward: null pointer");
+  const long long tot = (long long)B * c->L * c->dcp[0];
+  DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(x, nullptr, nullptr, (T*)c->X[0], B, c->L,
+                                                                           c->C, c->dcp[0], 1));
+  CK(post_launch(c, "assemble_x0"));
+  CK(d_forward(c, B, B, 1, sh));
+  CU(cudaMemcpyAsync(scores_dev, c->scores, (size_t)B * 4, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int cg_debug_gp(cg_ctx* c, const float* xhat, int B, const int32_t* sh, float* grad_dev, float* norms_dev) {
+  CK(check_batch(c, B));
+  if (!xhat || !sh) return set_err("cg_debug_gp: null pointer");
+  const long long tot = (long long)B * c->L * c->dcp[0];
+  DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(xhat, nullptr, nullptr, (T*)c->X[0], B,
+                                                                           c->L, c->C, c->dcp[0], 1));
+  CK(post_launch(c, "assemble_x0"));
+  CK(d_forward(c, B, B, 1, sh));
+  fill_coef_kernel<<<(B + 255) / 256, 256, 0, c->stream>>>(c->coef, B, 1, 1.f);
+  CK(post_launch(c, "fill_coef"));
+  CK(d_backward(c, B, B, 1, sh, 0, B));
+  if (grad_dev) {
+    DISPATCH_T(c, unpad_kernel<T><<<grid_for((long long)B * c->L * c->C), 256, 0, c->stream>>>(
+                      (const T*)c->DX[0], grad_dev, (long long)B * c->L, c->C, c->dcp[0]));
+    CK(post_launch(c, "unpad"));
+  }
+  if (norms_dev) {
+    CU(cudaMemsetAsync(c->sumsq, 0, (size_t)B * 4, c->stream));
+    DISPATCH_T(c, sumsq_kernel<T><<<B * 8, 256, 0, c->stream>>>((const T*)c->DX[0], c->sumsq, (long long)c->L * c->dcp[0], 8));
+    CK(post_launch(c, "sumsq"));
+    CU(cudaMemcpyAsync(norms_dev, c->sumsq, (size_t)B * 4, cudaMemcpyDeviceToDevice, c->stream));   // squared norms
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int cg_phase_shuffle_index(int w, int shift, int32_t* idx) {
+  if (w < 1 || !idx) return set_err("cg_phase_shuffle_index: bad arguments");
+  if (shift > w - 1 || shift < -(w - 1)) return set_err("cg_phase_shuffle_index: |shift| must be < w");
+  for (int t = 0; t < w; ++t) idx[t] = ps_index(t, shift, w);
+  return 0;
+}
+
+extern "C" int cg_debug_phase_shuffle(cg_ctx* c, const float* x, int B, int w, int ch, int shift, float* out) {
+  if (!x || !out || B < 1 || w < 1 || ch < 4 || ch % 4) return set_err("cg_debug_phase_shuffle: bad arguments");
+  if (shift > w - 1 || shift < -(w - 1)) return set_err("cg_debug_phase_shuffle: |shift| must be < w");
+  GroupShifts g; g.s[0] = shift; g.s[1] = g.s[2] = g.s[3] = 0;
+  ps_gather_kernel<float><<<grid_for((long long)B * w * ch / 4), 256, 0, c->stream>>>(x, out, B, B, w, ch, g);
+  CK(post_launch(c, "ps_gather_debug"));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ microbench hook
+extern "C" int cg_bench_layer(cg_ctx* c, int which, int layer, int pass, int B, int iters, float* ms_out,
+                              double* flops_out) {
+  if (layer < 1 || layer > NL) return set_err("cg_bench_layer: layer must be 1..5");
+  if (iters < 1) iters = 1;
+  int Bt = B;
+  if (which == CG_DISCRIMINATOR) { if (Bt < 1 || Bt > 3 * c->Bmax) return set_err("cg_bench_layer: batch out of range"); }
+  else CK(check_batch(c, B));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  double macs = 0;
+  for (int it = -1; it < iters; ++it) {
+    if (it == 0) CU(cudaEventRecord(e0, c->stream));
+    if (which == CG_DISCRIMINATOR) {
+      const int l = layer;
+      macs = (double)Bt * c->dl[l] * c->K * c->dc[l - 1] * c->dc[l];
+      if (pass == 0) CK(launch_rsgemm(c, conv_fwd_params(c, l, c->X[l - 1], c->H[l], Bt, EPI_BIAS_LRELU, nullptr)));
+      else if (pass == 1) CK(d_dgrad_layer(c, l, 0, l == 1 ? (Bt > c->Bmax ? c->Bmax : Bt) : Bt, l == 1 ? c->DX[0] : c->DX[l - 1]));
+      else {
+        WgParams w;
+        memset(&w, 0, sizeof(w));
+        const SegTable st = seg_strided(c->K, c->dcp[l - 1]);
+        w.S = c->X[l - 1]; w.s_bs = (long long)c->dl[l - 1] * c->dcp[l - 1]; w.s_rs = 2 * c->dcp[l - 1]; w.s_rows = c->dl[l - 1] / 2;
+        w.P = c->DA[l]; w.p_bs = (long long)c->dl[l] * c->dcp[l]; w.p_rs = c->dcp[l];
+        w.dW = dgrad(c, 2 * (l - 1)); w.m_real = c->dc[l - 1]; w.n_real = c->dc[l];
+        w.B = Bt; w.Q = c->dl[l]; w.Mp = c->dcp[l - 1]; w.Np = c->dcp[l]; w.nseg = c->K;
+        for (int k = 0; k < c->K; ++k) { w.shift[k] = st.shift[0][k]; w.scol[k] = st.acol[0][k]; }
+        CK(launch_wgrad(c, w));
+      }
+      if (pass == 1 && l == 1 && Bt > c->Bmax) macs = (double)c->Bmax * c->dl[l] * c->K * c->dc[l - 1] * c->dc[l];
+    } else {
+      const int i = layer;
+      macs = (double)B * c->gl[i - 1] * c->K * c->gc[i - 1] * c->gc[i];
+      if (pass != 0) return set_err("cg_bench_layer: generator supports pass 0 only");
+      RsParams p;
+      memset(&p, 0, sizeof(p));
+      p.A = c->HG[i - 1]; p.a_bs = (long long)c->gl[i - 1] * c->gcp[i - 1]; p.a_rs = c->gcp[i - 1]; p.a_rows = c->gl[i - 1];
+      p.W = c->Wf_g[i]; p.w_ld = c->K * c->gcp[i - 1];
+      p.out = c->AG[i]; p.o_bs = (long long)c->gl[i] * c->gcp[i]; p.o_rs = 2 * c->gcp[i]; p.o_phase_col = c->gcp[i];
+      p.bias = gparam(c, c->g_b[i]);
+      p.B = B; p.Q = c->gl[i - 1]; p.N = c->gcp[i]; p.n_real = c->gc[i]; p.Kc = c->gcp[i - 1]; p.epi = EPI_BIAS;
+      p.seg = seg_transposed(c->K, c->gcp[i - 1]);
+      CK(launch_rsgemm(c, p));
+    }
+  }
+  CU(cudaEventRecord(e1, c->stream));
+  CU(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms_out) *ms_out = ms / iters;
+  if (flops_out) *flops_out = 2.0 * macs;
+  return 0;
+}

@@ -1,0 +1,730 @@
+// CUDA-core kernels of the calciumgan_b200 engine: the fp32 path (reference non-mixed-precision
+// mode, parity rel <= 1e-4) and every memory-bound glue op of both precisions.
+// All tensors are channels-last (batch, time, channels_padded); T = float | bf16.
+#pragma once
+#include "cg_common.cuh"
+
+// =============================================================================================
+// Row-shift implicit GEMM on CUDA cores (fp32 accumulate). 64x64 tile, 256 threads, 4x4/thread.
+// Used for: strided Conv1D fwd (reference calciumgan.py:145-185), Conv1DTranspose fwd
+// (models/utils.py:79-89), their data gradients, the GP linearised forward, per-timestep Dense.
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) rsgemm_simt_kernel(const __grid_constant__ RsParams p) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int phase = blockIdx.z;
+  const long long M = (long long)p.B * p.Q;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  const int lrow = tid >> 2;
+  const int lc = (tid & 3) * 4;
+  const long long r = m0 + lrow;
+  const bool rvalid = r < M;
+  const int lb = rvalid ? (int)(r / p.Q) : 0;
+  const int lq = rvalid ? (int)(r % p.Q) : 0;
+  const T* Ab = reinterpret_cast<const T*>(p.A) + (long long)lb * p.a_bs;
+  const T* Wr = reinterpret_cast<const T*>(p.W) + (long long)(n0 + lrow) * p.w_ld;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int nseg = p.seg.nseg[phase];
+
+  for (int s = 0; s < nseg; ++s) {
+    const int srow = lq + p.seg.shift[phase][s];
+    const bool av = rvalid && srow >= 0 && srow < p.a_rows;
+    const T* ap = Ab + (long long)srow * p.a_rs + p.seg.acol[phase][s];
+    const T* wp = Wr + p.seg.wk[phase][s];
+    for (int c0 = 0; c0 < p.Kc; c0 += BK) {
+      float a4[4], w4[4];
+      load4<T>(av ? ap + c0 + lc : nullptr, a4);
+      load4<T>(wp + c0 + lc, w4);
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        As[lc + i][lrow] = a4[i];
+        Bs[lc + i][lrow] = w4[i];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        const float4 av4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 bv4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float a[4] = {av4.x, av4.y, av4.z, av4.w};
+        const float b[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+    }
+  }
+
+  T* out = reinterpret_cast<T*>(p.out);
+  const T* mask = reinterpret_cast<const T*>(p.mask);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long rr = m0 + ty * 4 + i;
+    if (rr >= M) continue;
+    const int b = (int)(rr / p.Q), q = (int)(rr % p.Q);
+    const long long obase = (long long)b * p.o_bs + (long long)q * p.o_rs + phase * p.o_phase_col;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      float v = acc[i][j];
+      const bool real = n < p.n_real;
+      if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_LRELU || p.epi == EPI_BIAS_SIGMOID)
+        v += real ? p.bias[n] : 0.f;
+      if (p.epi == EPI_BIAS_LRELU) v = lrelu(v);
+      if (p.epi == EPI_BIAS_SIGMOID) v = 1.f / (1.f + __expf(-v));
+      if (p.epi == EPI_MASK) v *= lrelu_slope(Elem<T>::to_f(mask[obase + n]));
+      if (!real) v = 0.f;
+      if (out) out[obase + n] = Elem<T>::from_f(v);
+      if (p.out32 && real) p.out32[(long long)b * p.o32_bs + (long long)q * p.o32_rs + n] = v;
+    }
+  }
+}
+
+// =============================================================================================
+// Weight gradient on CUDA cores: dW[seg][m][n] += sum_rows S[row + shift, scol + m] * P[row, n].
+// grid: x = mtiles*ntiles, y = seg, z = row split; fp32 atomics into the flat gradient buffer.
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) wgrad_simt_kernel(const __grid_constant__ WgParams p) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int ntiles = p.Np / BN;
+  const int m0 = (blockIdx.x / ntiles) * BM;
+  const int n0 = (blockIdx.x % ntiles) * BN;
+  const int seg = blockIdx.y;
+  const long long R = (long long)p.B * p.Q;
+  const long long r_begin = (long long)blockIdx.z * p.rows_per_split;
+  long long r_end = r_begin + p.rows_per_split;
+  if (r_end > R) r_end = R;
+  const int shift = p.shift[seg];
+  const int scol = p.scol[seg];
+
+  const int lr = tid >> 4;
+  const int lc = (tid & 15) * 4;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const T* S = reinterpret_cast<const T*>(p.S);
+  const T* P = reinterpret_cast<const T*>(p.P);
+  for (long long r0 = r_begin; r0 < r_end; r0 += BK) {
+    const long long r = r0 + lr;
+    float a4[4], b4[4];
+    const T* sp = nullptr;
+    const T* pp = nullptr;
+    if (r < r_end) {
+      const int b = (int)(r / p.Q), q = (int)(r % p.Q);
+      const int srow = q + shift;
+      if (srow >= 0 && srow < p.s_rows) sp = S + (long long)b * p.s_bs + (long long)srow * p.s_rs + scol + m0 + lc;
+      pp = P + (long long)b * p.p_bs + (long long)q * p.p_rs + n0 + lc;
+    }
+    load4<T>(sp, a4);
+    load4<T>(pp, b4);
+    __syncthreads();
+    *reinterpret_cast<float4*>(&As[lr][lc]) = make_float4(a4[0], a4[1], a4[2], a4[3]);
+    *reinterpret_cast<float4*>(&Bs[lr][lc]) = make_float4(b4[0], b4[1], b4[2], b4[3]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 av4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {av4.x, av4.y, av4.z, av4.w};
+      const float b[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+  float* dW = p.dW + (long long)seg * p.m_real * p.n_real;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.m_real) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < p.n_real) atomicAdd(&dW[(long long)m * p.n_real + n], acc[i][j]);
+    }
+  }
+}
+
+// =============================================================================================
+// Weight packing: fp32 Keras-layout master -> T [N][nseg*Cp + c] (K-major rows, zero padded).
+// dst[n][k*Cp + c] = src[k*sk + n*sn + c*sc] for n < n_real, c < c_real.
+// =============================================================================================
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int n_real,
+                                   int nseg, int Cp, int c_real, long long sk, long long sn, long long sc) {
+  const long long total = (long long)N * nseg * Cp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    const int k = (int)((i / Cp) % nseg);
+    const int n = (int)(i / ((long long)Cp * nseg));
+    float v = 0.f;
+    if (n < n_real && c < c_real) v = src[k * sk + n * sn + c * sc];
+    dst[i] = Elem<T>::from_f(v);
+  }
+}
+
+// =============================================================================================
+// PhaseShuffle gather (calciumgan.py:117-138): X[b,t,:] = H[b, ps_index(t, shift[group(b)]), :].
+// 16-byte vectors; shifts are per call-group (one scalar per layer per critic call).
+// =============================================================================================
+struct GroupShifts { int s[4]; };   // up to 3 groups used
+
+template <typename T>
+__global__ void ps_gather_kernel(const T* __restrict__ H, T* __restrict__ X, int Bt, int group_b, int w,
+                                 int Cp, GroupShifts sh) {
+  constexpr int V = 16 / sizeof(T);
+  const int cv = Cp / V;
+  const long long total = (long long)Bt * w * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    const int t = (int)((i / cv) % w);
+    const int b = (int)(i / ((long long)cv * w));
+    const int j = ps_index(t, sh.s[b / group_b], w);
+    const uint4 v = *reinterpret_cast<const uint4*>(H + ((long long)b * w + j) * Cp + c * V);
+    *reinterpret_cast<uint4*>(X + ((long long)b * w + t) * Cp + c * V) = v;
+  }
+}
+
+// Adjoint of the gather fused with the LeakyReLU slope of the layer below:
+// DA[b,j,:] = slope(H[b,j,:]) * sum_{t : ps_index(t)=j} DX[b,t,:]      (at most 2 contributors)
+template <typename T>
+__global__ void ps_scatter_mask_kernel(const T* __restrict__ DX, const T* __restrict__ H, T* __restrict__ DA,
+                                       int Bt, int group_b, int w, int Cp, GroupShifts sh) {
+  const long long total = (long long)Bt * w * Cp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    const int j = (int)((i / Cp) % w);
+    const int b = (int)(i / ((long long)Cp * w));
+    const int s = sh.s[b / group_b];
+    const T* dx = DX + (long long)b * w * Cp + c;
+    float acc = 0.f;
+    const int t0 = j - s;                 // direct: t + s = j
+    if (t0 >= 0 && t0 < w) acc += Elem<T>::to_f(dx[(long long)t0 * Cp]);
+    if (s > 0) {                          // reflected at the end: t + s > w-1, j = 2(w-1) - (t+s)
+      const int t1 = 2 * (w - 1) - j - s;
+      if (t1 >= 0 && t1 < w && t1 + s > w - 1) acc += Elem<T>::to_f(dx[(long long)t1 * Cp]);
+    } else if (s < 0) {                   // reflected at the front: t + s < 0, j = -(t+s)
+      const int t1 = -j - s;
+      if (t1 >= 0 && t1 < w && t1 + s < 0) acc += Elem<T>::to_f(dx[(long long)t1 * Cp]);
+    }
+    DA[i] = Elem<T>::from_f(acc * lrelu_slope(Elem<T>::to_f(H[i])));
+  }
+}
+
+// DA = DH * slope(H) (no PhaseShuffle / no layer-norm case)
+template <typename T>
+__global__ void mask_mul_kernel(const T* __restrict__ DH, const T* __restrict__ H, T* __restrict__ DA,
+                                long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    DA[i] = Elem<T>::from_f(Elem<T>::to_f(DH[i]) * lrelu_slope(Elem<T>::to_f(H[i])));
+}
+
+// H = lrelu(A) (generator without layer-norm)
+template <typename T>
+__global__ void lrelu_kernel(const T* __restrict__ A, T* __restrict__ H, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    H[i] = Elem<T>::from_f(lrelu(Elem<T>::to_f(A[i])));
+}
+
+// =============================================================================================
+// Critic input assembly + interpolation (wgan_gp.py:38-41): fp32 (B,L,C) -> T (B,L,Cp) groups.
+// mode 0: X0[g0]=real, X0[g1]=fake, X0[g2]=alpha*real+(1-alpha)*fake ; mode 1: X0[g0]=src only.
+// =============================================================================================
+template <typename T>
+__global__ void assemble_x0_kernel(const float* __restrict__ real, const float* __restrict__ fake,
+                                   const float* __restrict__ alpha, T* __restrict__ X0, int B, int L, int C,
+                                   int Cp, int mode) {
+  const long long per = (long long)L * Cp;
+  const long long total = (long long)B * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    const long long bt = i / Cp;
+    const int b = (int)(bt / L);
+    if (mode == 1) {
+      X0[i] = Elem<T>::from_f(c < C ? real[bt * C + c] : 0.f);
+      continue;
+    }
+    float r = 0.f, f = 0.f, x = 0.f;
+    if (c < C) {
+      r = real[bt * C + c];
+      f = fake[bt * C + c];
+      const float a = alpha[b];
+      x = a * r + (1.f - a) * f;
+    }
+    X0[i] = Elem<T>::from_f(r);
+    X0[total + i] = Elem<T>::from_f(f);
+    X0[2 * total + i] = Elem<T>::from_f(x);
+  }
+}
+
+// unpad + cast: T (B,L,Cp) -> fp32 (B,L,C)
+template <typename T>
+__global__ void unpad_kernel(const T* __restrict__ src, float* __restrict__ dst, long long rows, int C, int Cp) {
+  const long long total = rows * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    dst[i] = Elem<T>::to_f(src[(i / C) * Cp + c]);
+  }
+}
+
+// =============================================================================================
+// Critic head (calciumgan.py:188-190): scores[b] = <X5[b], wd> + bd ; one block per sample.
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) head_forward_kernel(const T* __restrict__ X5, const float* __restrict__ wd,
+                                                           const float* __restrict__ bd, float* __restrict__ scores,
+                                                           int w5, int c5, int Cp) {
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  const T* x = X5 + (long long)b * w5 * Cp;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < w5 * Cp; i += blockDim.x) {
+    const int c = i % Cp, t = i / Cp;
+    if (c < c5) acc += Elem<T>::to_f(x[i]) * wd[t * c5 + c];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) scores[b] = v + bd[0];
+  }
+}
+
+// DA5[b,t,c] = slope(H5) * coef[b] * wd[t*c5+c]
+template <typename T>
+__global__ void head_backward_kernel(const T* __restrict__ H5, const float* __restrict__ wd,
+                                     const float* __restrict__ coef, T* __restrict__ DA5, int Bt, int w5, int c5,
+                                     int Cp) {
+  const long long per = (long long)w5 * Cp;
+  const long long total = (long long)Bt * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    const int t = (int)((i / Cp) % w5);
+    const int b = (int)(i / per);
+    float v = 0.f;
+    if (c < c5) v = lrelu_slope(Elem<T>::to_f(H5[i])) * coef[b] * wd[t * c5 + c];
+    DA5[i] = Elem<T>::from_f(v);
+  }
+}
+
+// dwd[t*c5+c] += sum_b coef[b] * X5[b,t,c];  dbd += sum_{b<nb_bias} coef[b]
+template <typename T>
+__global__ void head_wgrad_kernel(const T* __restrict__ X5, const float* __restrict__ coef, float* __restrict__ dwd,
+                                  float* __restrict__ dbd, int Bt, int nb_bias, int w5, int c5, int Cp) {
+  const int total = w5 * c5;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % c5, t = i / c5;
+    float acc = 0.f;
+    for (int b = 0; b < Bt; ++b) acc += coef[b] * Elem<T>::to_f(X5[((long long)b * w5 + t) * Cp + c]);
+    dwd[i] += acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int b = 0; b < nb_bias; ++b) s += coef[b];
+    dbd[0] += s;
+  }
+}
+
+// =============================================================================================
+// column sums (bias gradients): out[c] += sum_rows X[row, c], c < c_real. grid-strided rows.
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, float* __restrict__ out, long long rows,
+                                                     int Cp, int c_real) {
+  // blockDim = (64, 4): x over channels chunk, y over rows
+  const int c = blockIdx.y * 64 + threadIdx.x;
+  float acc = 0.f;
+  if (c < c_real)
+    for (long long r = (long long)blockIdx.x * 4 + threadIdx.y; r < rows; r += (long long)gridDim.x * 4)
+      acc += Elem<T>::to_f(X[r * Cp + c]);
+  __shared__ float red[4][64];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < c_real) {
+    const float s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    atomicAdd(&out[c], s);
+  }
+}
+
+// =============================================================================================
+// Generator layer-norm + LeakyReLU (calciumgan.py:45-46): one warp per (b,t) row, channels C of Cp.
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) ln_lrelu_forward_kernel(const T* __restrict__ A, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, T* __restrict__ H,
+                                                               float* __restrict__ mu_out, float* __restrict__ rstd_out,
+                                                               long long rows, int C, int Cp) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const T* a = A + r * Cp;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += Elem<T>::to_f(a[c]);
+    const float mu = warp_sum(s) / C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float d = Elem<T>::to_f(a[c]) - mu;
+      v += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(v) / C + CG_LN_EPS);
+    T* h = H + r * Cp;
+    for (int c = lane; c < Cp; c += 32) {
+      float o = 0.f;
+      if (c < C) o = lrelu((Elem<T>::to_f(a[c]) - mu) * rstd * gamma[c] + beta[c]);
+      h[c] = Elem<T>::from_f(o);
+    }
+    if (lane == 0) {
+      mu_out[r] = mu;
+      rstd_out[r] = rstd;
+    }
+  }
+}
+
+// backward of LN + LeakyReLU: DA, dgamma, dbeta. Shared-memory partials then global atomics.
+template <typename T>
+__global__ void __launch_bounds__(256) ln_lrelu_backward_kernel(
+    const T* __restrict__ DH, const T* __restrict__ A, const T* __restrict__ H, const float* __restrict__ mu_in,
+    const float* __restrict__ rstd_in, const float* __restrict__ gamma, T* __restrict__ DA,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C, int Cp) {
+  extern __shared__ float sm[];   // [2*C]
+  float* sg = sm;
+  float* sb = sm + C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const T* a = A + r * Cp;
+    const T* dh = DH + r * Cp;
+    const T* h = H + r * Cp;
+    const float mu = mu_in[r], rstd = rstd_in[r];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (Elem<T>::to_f(a[c]) - mu) * rstd;
+      const float dn = Elem<T>::to_f(dh[c]) * lrelu_slope(Elem<T>::to_f(h[c]));
+      const float gd = gamma[c] * dn;
+      s1 += gd;
+      s2 += gd * xh;
+      atomicAdd(&sg[c], dn * xh);
+      atomicAdd(&sb[c], dn);
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+    T* da = DA + r * Cp;
+    for (int c = lane; c < Cp; c += 32) {
+      float o = 0.f;
+      if (c < C) {
+        const float xh = (Elem<T>::to_f(a[c]) - mu) * rstd;
+        const float dn = Elem<T>::to_f(dh[c]) * lrelu_slope(Elem<T>::to_f(h[c]));
+        o = rstd * (gamma[c] * dn - s1 - xh * s2);
+      }
+      da[c] = Elem<T>::from_f(o);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(&dgamma[i], sg[i]);
+    atomicAdd(&dbeta[i], sb[i]);
+  }
+}
+
+// =============================================================================================
+// Generator first Dense (calciumgan.py:32-34): HG0[b,t,c] = lrelu(z[b,:] . W0[:, t*nd+c] + b0), pad -> 0
+// =============================================================================================
+template <typename T>
+__global__ void dense0_forward_kernel(const float* __restrict__ z, const float* __restrict__ W0,
+                                      const float* __restrict__ b0, T* __restrict__ HG0, int B, int nd, int w0,
+                                      int Cp) {
+  const long long total = (long long)B * w0 * Cp;
+  const int nout = w0 * nd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    const int t = (int)((i / Cp) % w0);
+    const int b = (int)(i / ((long long)Cp * w0));
+    float v = 0.f;
+    if (c < nd) {
+      const int j = t * nd + c;
+      float acc = b0[j];
+      for (int k = 0; k < nd; ++k) acc = fmaf(z[b * nd + k], W0[(long long)k * nout + j], acc);
+      v = lrelu(acc);
+    }
+    HG0[i] = Elem<T>::from_f(v);
+  }
+}
+
+// dW0[k][j] += sum_b z[b,k]*dpre[b,j] ; db0[j] += sum_b dpre[b,j] ; dpre = DHG0 * slope(HG0)
+template <typename T>
+__global__ void dense0_backward_kernel(const float* __restrict__ z, const T* __restrict__ DHG0,
+                                       const T* __restrict__ HG0, float* __restrict__ dW0, float* __restrict__ db0,
+                                       int B, int nd, int w0, int Cp) {
+  const int nout = w0 * nd;
+  const int total = (nd + 1) * nout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i % nout, k = i / nout;   // k == nd -> bias row
+    const int t = j / nd, c = j % nd;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const long long idx = ((long long)b * w0 + t) * Cp + c;
+      const float dp = Elem<T>::to_f(DHG0[idx]) * lrelu_slope(Elem<T>::to_f(HG0[idx]));
+      acc += (k < nd ? z[b * nd + k] : 1.f) * dp;
+    }
+    if (k < nd) dW0[(long long)k * nout + j] += acc;
+    else db0[j] += acc;
+  }
+}
+
+// DO[b,t,c] = DX0[b,t,c] * f(1-f) with f = fake32[b,t,c] (sigmoid head backward); pad -> 0
+template <typename T>
+__global__ void sigmoid_backward_kernel(const T* __restrict__ DX0, const float* __restrict__ fake, T* __restrict__ DO,
+                                        long long rows, int C, int Cp, int normalize) {
+  const long long total = rows * Cp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    float v = 0.f;
+    if (c < C) {
+      v = Elem<T>::to_f(DX0[i]);
+      if (normalize) {
+        const float f = fake[(i / Cp) * C + c];
+        v *= f * (1.f - f);
+      }
+    }
+    DO[i] = Elem<T>::from_f(v);
+  }
+}
+
+// =============================================================================================
+// Gradient-penalty scalars (wgan_gp.py:49-50,58-62)
+// =============================================================================================
+// sumsq[b] = sum g[b,:]^2 ; one block per (sample, chunk), atomics into sumsq (zeroed before)
+template <typename T>
+__global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ G, float* __restrict__ sumsq,
+                                                    long long per_sample, int chunks) {
+  __shared__ float red[8];
+  const int b = blockIdx.x / chunks, ch = blockIdx.x % chunks;
+  const long long len = (per_sample + chunks - 1) / chunks;
+  const long long beg = (long long)ch * len;
+  long long end = beg + len;
+  if (end > per_sample) end = per_sample;
+  const T* g = G + (long long)b * per_sample;
+  float acc = 0.f;
+  for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    const float v = Elem<T>::to_f(g[i]);
+    acc = fmaf(v, v, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(&sumsq[b], v);
+  }
+}
+
+// single block: losses + per-sample coefficient of u = d(lambda*GP)/dg
+// scal[0]=dis_loss scal[1]=gp scal[2]=real_loss scal[3]=fake_loss ; norms[b] = ||g_b||
+__global__ void critic_scalars_kernel(const float* __restrict__ scores, const float* __restrict__ sumsq,
+                                      float* __restrict__ ucoef, float* __restrict__ norms, float* __restrict__ scal,
+                                      int B, float lambda) {
+  __shared__ float red[3][32];
+  float sr = 0.f, sf = 0.f, sg = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    sr += scores[b];
+    sf += scores[B + b];
+    const float n = sqrtf(sumsq[b]);
+    norms[b] = n;
+    sg += (n - 1.f) * (n - 1.f);
+    ucoef[b] = lambda * (2.f / B) * (n - 1.f) / n;   // no epsilon: tf.norm (wgan_gp.py:49)
+  }
+  sr = warp_sum(sr); sf = warp_sum(sf); sg = warp_sum(sg);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = sr; red[1][threadIdx.x >> 5] = sf; red[2][threadIdx.x >> 5] = sg;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b2 = 0.f, c = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) { a += red[0][i]; b2 += red[1][i]; c += red[2][i]; }
+    const float real_loss = -a / B, fake_loss = b2 / B, gp = c / B;
+    scal[0] = real_loss + fake_loss + lambda * gp;
+    scal[1] = gp;
+    scal[2] = real_loss;
+    scal[3] = fake_loss;
+  }
+}
+
+// gen_loss = -mean(scores[0:B]) -> scal[4]
+__global__ void gen_loss_kernel(const float* __restrict__ scores, float* __restrict__ scal, int B) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) s += scores[b];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) a += red[i];
+    scal[4] = -a / B;
+  }
+}
+
+// coef for the concatenated critic batch: [-1/B]*B, [+1/B]*B, [1]*B   (or a constant for 1 group)
+__global__ void fill_coef_kernel(float* coef, int B, int groups, float single) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * groups) return;
+  if (groups == 1) coef[i] = single;
+  else coef[i] = i < B ? -1.f / B : (i < 2 * B ? 1.f / B : 1.f);
+}
+
+// V0[b] = ucoef[b] * G[b]
+template <typename T>
+__global__ void scale_rows_kernel(const T* __restrict__ G, const float* __restrict__ ucoef, T* __restrict__ V,
+                                  long long per_sample, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    V[i] = Elem<T>::from_f(Elem<T>::to_f(G[i]) * ucoef[i / per_sample]);
+}
+
+// =============================================================================================
+// Signal metrics (gan.py:32-41, signals_metrics.py:9-28): warp per (b,t) row over C neurons.
+// acc[0..3] += squared diff of min / max / mean / std (population). Finalised by /rows on host side kernel.
+// =============================================================================================
+__global__ void __launch_bounds__(256) metrics_kernel(const float* __restrict__ real, const float* __restrict__ fake,
+                                                      float* __restrict__ acc, long long rows, int C, float smin,
+                                                      float smax, int normalize) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float sc = normalize ? (smax - smin) : 1.f, of = normalize ? smin : 0.f;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (long long r = warp; r < rows; r += nwarps) {
+    float st[2][4];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const float* x = (w == 0 ? real : fake) + r * C;
+      float mn = INFINITY, mx = -INFINITY, s = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float v = x[c] * sc + of;
+        mn = fminf(mn, v); mx = fmaxf(mx, v); s += v;
+      }
+      mn = warp_min(mn); mx = warp_max(mx);
+      const float mean = warp_sum(s) / C;
+      float q = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float d = x[c] * sc + of - mean;
+        q += d * d;
+      }
+      st[w][0] = mn; st[w][1] = mx; st[w][2] = mean; st[w][3] = sqrtf(warp_sum(q) / C);
+    }
+    a0 += (st[0][0] - st[1][0]) * (st[0][0] - st[1][0]);
+    a1 += (st[0][1] - st[1][1]) * (st[0][1] - st[1][1]);
+    a2 += (st[0][2] - st[1][2]) * (st[0][2] - st[1][2]);
+    a3 += (st[0][3] - st[1][3]) * (st[0][3] - st[1][3]);
+  }
+  if (lane == 0) {
+    const float inv = 1.f / (float)rows;
+    atomicAdd(&acc[0], a0 * inv); atomicAdd(&acc[1], a1 * inv);
+    atomicAdd(&acc[2], a2 * inv); atomicAdd(&acc[3], a3 * inv);
+  }
+}
+
+// out = x*(max-min)+min (gan/utils/utils.py:30-32)
+__global__ void denorm_kernel(const float* __restrict__ x, float* __restrict__ out, long long total, float smin,
+                              float smax) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = x[i] * (smax - smin) + smin;
+}
+
+// =============================================================================================
+// Fused Adam (Keras form, optimizer.py:9,34): fp32 master weights + moments, gradient pre-scaled.
+// =============================================================================================
+__global__ void adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
+                            const float* __restrict__ g, long long n, float lr_t, float b1, float b2, float eps,
+                            float gscale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+// =============================================================================================
+// Philox4x32-10 counter RNG for noise (gan.py:29-30) and interpolation alpha (wgan_gp.py:40).
+// =============================================================================================
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ void philox4x32(uint64_t seed, uint64_t stream, uint64_t idx, uint32_t (&c)[4]) {
+  c[0] = (uint32_t)idx; c[1] = (uint32_t)(idx >> 32); c[2] = (uint32_t)stream; c[3] = (uint32_t)(stream >> 32);
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+// mode 0: standard normal (Box-Muller); mode 1: uniform [0,1)
+__global__ void rng_fill_kernel(float* __restrict__ out, long long n, uint64_t seed, uint64_t stream, int mode) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i * 4 < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    uint32_t c[4];
+    philox4x32(seed, stream, (uint64_t)i, c);
+    float u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = (c[j] >> 8) * (1.0f / 16777216.0f);   // [0,1)
+    float r[4];
+    if (mode == 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = u[j];
+    } else {
+      const float ra = sqrtf(-2.f * logf(1.f - u[0])), rb = sqrtf(-2.f * logf(1.f - u[2]));
+      r[0] = ra * cospif(2.f * u[1]); r[1] = ra * sinpif(2.f * u[1]);
+      r[2] = rb * cospif(2.f * u[3]); r[3] = rb * sinpif(2.f * u[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (i * 4 + j < n) out[i * 4 + j] = r[j];
+  }
+}

@@ -1,0 +1,316 @@
+"""Host-side handle on one cg_ctx: device buffers, streams and tensor marshalling.
+
+PyTorch is used here for device memory, streams and DLPack interchange only; every
+arithmetic operation of the hot path runs inside libcalciumgan_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def hparams_to_config(hparams, max_batch=None, world_size=1, rank=0, force_simt=False):
+  """Map the reference's hparams Namespace (main.py:229-261 + dataset_helper.py:84-91) to cg_config."""
+  if getattr(hparams, 'batch_norm', False):
+    raise NotImplementedError('--batch_norm couples samples and is out of scope (SURVEY §3.6-6)')
+  if getattr(hparams, 'activation', 'leakyrelu') != 'leakyrelu':
+    raise NotImplementedError('only --activation leakyrelu is implemented')
+  if getattr(hparams, 'conv2d', False):
+    raise NotImplementedError('conv2d signals are out of scope')
+  cfg = L.CgConfig()
+  cfg.seq_len = int(hparams.signal_shape[0])
+  cfg.channels = int(getattr(hparams, 'num_channels', hparams.signal_shape[-1]))
+  cfg.noise_dim = int(hparams.noise_dim)
+  cfg.num_units = int(hparams.num_units)
+  cfg.kernel_size = int(hparams.kernel_size)
+  cfg.strides = int(hparams.strides)
+  cfg.phase_m = int(hparams.m)
+  cfg.layer_norm = int(bool(getattr(hparams, 'layer_norm', False)))
+  cfg.normalize = int(bool(getattr(hparams, 'normalize', True)))
+  cfg.max_batch = int(max_batch if max_batch is not None else hparams.batch_size)
+  cfg.n_critic = int(getattr(hparams, 'n_critic', 5))
+  cfg.precision = L.BF16 if getattr(hparams, 'mixed_precision', False) else L.FP32
+  cfg.gp_lambda = float(getattr(hparams, 'gradient_penalty', 10.0))
+  cfg.learning_rate = float(getattr(hparams, 'learning_rate', 1e-4))
+  cfg.signals_min = float(getattr(hparams, 'signals_min', 0.0))
+  cfg.signals_max = float(getattr(hparams, 'signals_max', 1.0))
+  cfg.world_size = int(world_size)
+  cfg.rank = int(rank)
+  cfg.force_simt = int(bool(force_simt))
+  return cfg
+
+
+class _DevArray(object):
+  """Expose a raw device pointer through __cuda_array_interface__ so torch can wrap it."""
+
+  def __init__(self, ptr, n, typestr='<f4'):
+    self.__cuda_array_interface__ = {
+        'shape': (int(n),), 'typestr': typestr, 'data': (int(ptr), False), 'version': 2}
+
+
+def phase_shuffle_index(w, shift):
+  """Host copy of the kernels' PhaseShuffle index map (int32)."""
+  idx = np.empty(w, np.int32)
+  L.check(L.load().cg_phase_shuffle_index(int(w), int(shift), idx.ctypes.data_as(C.POINTER(C.c_int32))))
+  return idx
+
+
+class Engine(object):
+  """One cg_ctx on the current CUDA device."""
+
+  def __init__(self, cfg):
+    self.lib = L.load()
+    if not torch.cuda.is_available():
+      raise RuntimeError('calciumgan_b200 needs a CUDA device (no CPU fallback)')
+    self.device = torch.device('cuda', torch.cuda.current_device())
+    torch.cuda.init()
+    torch.zeros(1, device=self.device)   # make sure the primary context exists
+    self.cfg = cfg
+    ctx = C.c_void_p()
+    L.check(self.lib.cg_create(C.byref(cfg), C.byref(ctx)))
+    self.ctx = ctx
+    self._scal = (C.c_float * L.NUM_SCALARS)()
+    self._grad_views = {}
+
+  def close(self):
+    if getattr(self, 'ctx', None):
+      self.lib.cg_destroy(self.ctx)
+      self.ctx = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+  # ---------------------------------------------------------------- marshalling
+  def _use_stream(self):
+    L.check(self.lib.cg_set_stream(self.ctx, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+  def to_device(self, x, shape=None):
+    """numpy / torch / DLPack-able -> contiguous fp32 CUDA tensor."""
+    if x is None:
+      return None
+    if not isinstance(x, torch.Tensor):
+      if hasattr(x, '__dlpack__') and not isinstance(x, np.ndarray):
+        x = torch.from_dlpack(x)
+      else:
+        x = torch.as_tensor(np.asarray(x))
+    x = x.to(device=self.device, dtype=torch.float32).contiguous()
+    if shape is not None and tuple(x.shape) != tuple(shape):
+      raise ValueError('expected shape %s, got %s' % (tuple(shape), tuple(x.shape)))
+    return x
+
+  @staticmethod
+  def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+  @staticmethod
+  def _shifts(shifts, n):
+    if shifts is None:
+      return None
+    a = np.ascontiguousarray(np.asarray(shifts, dtype=np.int32).reshape(-1))
+    if a.size != n:
+      raise ValueError('expected %d phase-shuffle shifts, got %d' % (n, a.size))
+    return a.ctypes.data_as(C.POINTER(C.c_int32)), a
+
+  def signal_shape(self, batch):
+    return (batch, self.cfg.seq_len, self.cfg.channels)
+
+  # ---------------------------------------------------------------- parameters
+  def tensor_infos(self, which):
+    out = []
+    for i in range(self.lib.cg_num_tensors(self.ctx, which)):
+      shape = (C.c_int64 * 4)()
+      ndim, off = C.c_int(), C.c_int64()
+      L.check(self.lib.cg_tensor_info(self.ctx, which, i, shape, C.byref(ndim), C.byref(off)))
+      out.append((tuple(int(shape[j]) for j in range(ndim.value)), int(off.value)))
+    return out
+
+  def num_params(self, which):
+    return int(self.lib.cg_num_params(self.ctx, which))
+
+  def _split(self, which, flat):
+    return [flat[o:o + int(np.prod(s))].reshape(s).copy() for s, o in self.tensor_infos(which)]
+
+  def _join(self, which, arrays):
+    infos = self.tensor_infos(which)
+    if len(arrays) != len(infos):
+      raise ValueError('expected %d arrays, got %d' % (len(infos), len(arrays)))
+    flat = np.empty(self.num_params(which), np.float32)
+    for a, (s, o) in zip(arrays, infos):
+      a = np.asarray(a, dtype=np.float32)
+      if tuple(a.shape) != tuple(s):
+        raise ValueError('weight shape mismatch: expected %s, got %s' % (s, a.shape))
+      flat[o:o + a.size] = a.reshape(-1)
+    return flat
+
+  def get_weights(self, which):
+    self._use_stream()
+    flat = np.empty(self.num_params(which), np.float32)
+    L.check(self.lib.cg_get_weights(self.ctx, which, flat.ctypes.data_as(C.c_void_p)))
+    return self._split(which, flat)
+
+  def set_weights(self, which, arrays):
+    self._use_stream()
+    flat = self._join(which, arrays)
+    L.check(self.lib.cg_set_weights(self.ctx, which, flat.ctypes.data_as(C.c_void_p)))
+
+  def get_grads(self, which):
+    self._use_stream()
+    flat = np.empty(self.num_params(which), np.float32)
+    L.check(self.lib.cg_get_grads(self.ctx, which, flat.ctypes.data_as(C.c_void_p)))
+    return self._split(which, flat)
+
+  def grad_tensor(self, which):
+    """Flat fp32 CUDA tensor aliasing the library's gradient buffer (for the NCCL all-reduce)."""
+    if which not in self._grad_views:
+      ptr = self.lib.cg_grad_ptr(self.ctx, which)
+      self._grad_views[which] = torch.as_tensor(_DevArray(ptr, self.num_params(which)), device=self.device)
+    return self._grad_views[which]
+
+  def init_weights(self, seed):
+    self._use_stream()
+    L.check(self.lib.cg_init_weights(self.ctx, C.c_uint64(int(seed))))
+
+  def seed(self, seed):
+    L.check(self.lib.cg_seed(self.ctx, C.c_uint64(int(seed))))
+
+  def get_opt_state(self, which):
+    n = self.num_params(which)
+    m, v, step = np.empty(n, np.float32), np.empty(n, np.float32), C.c_int64()
+    L.check(self.lib.cg_get_opt_state(self.ctx, which, m.ctypes.data_as(C.c_void_p),
+                                      v.ctypes.data_as(C.c_void_p), C.byref(step)))
+    return m, v, int(step.value)
+
+  def set_opt_state(self, which, m=None, v=None, step=0):
+    mp = np.ascontiguousarray(m, np.float32).ctypes.data_as(C.c_void_p) if m is not None else C.c_void_p(0)
+    vp = np.ascontiguousarray(v, np.float32).ctypes.data_as(C.c_void_p) if v is not None else C.c_void_p(0)
+    L.check(self.lib.cg_set_opt_state(self.ctx, which, mp, vp, C.c_int64(int(step))))
+
+  def get_step(self, which):
+    step = C.c_int64()
+    L.check(self.lib.cg_get_opt_state(self.ctx, which, C.c_void_p(0), C.c_void_p(0), C.byref(step)))
+    return int(step.value)
+
+  def set_step(self, which, step):
+    self.set_opt_state(which, None, None, step)
+
+  # ---------------------------------------------------------------- hot path
+  def critic_step(self, real, noise=None, alpha=None, shifts=None, update=True, sync=True):
+    self._use_stream()
+    real = self.to_device(real)
+    B = real.shape[0]
+    noise = self.to_device(noise, (B, self.cfg.noise_dim)) if noise is not None else None
+    alpha = self.to_device(alpha).reshape(-1) if alpha is not None else None
+    sh = self._shifts(shifts, 12)
+    flags = (0 if update else L.FLAG_NO_UPDATE) | (0 if sync else L.FLAG_NO_SYNC)
+    L.check(self.lib.cg_critic_step(self.ctx, self._ptr(real), B, self._ptr(noise), self._ptr(alpha),
+                                    sh[0] if sh else None, flags, self._scal))
+    return np.array(self._scal[:], np.float32) if sync else None
+
+  def generator_step(self, real, noise=None, shifts=None, update=True, sync=True):
+    self._use_stream()
+    real = self.to_device(real)
+    B = real.shape[0]
+    noise = self.to_device(noise, (B, self.cfg.noise_dim)) if noise is not None else None
+    sh = self._shifts(shifts, 4)
+    flags = (0 if update else L.FLAG_NO_UPDATE) | (0 if sync else L.FLAG_NO_SYNC)
+    L.check(self.lib.cg_generator_step(self.ctx, self._ptr(real), B, self._ptr(noise),
+                                       sh[0] if sh else None, flags, self._scal))
+    return np.array(self._scal[:], np.float32) if sync else None
+
+  def apply_update(self, which):
+    self._use_stream()
+    L.check(self.lib.cg_apply_update(self.ctx, which))
+
+  def train_step(self, real, noises=None, alphas=None, shifts=None):
+    self._use_stream()
+    real = self.to_device(real)
+    B, nc = real.shape[0], self.cfg.n_critic
+    noises = self.to_device(noises, (nc + 1, B, self.cfg.noise_dim)) if noises is not None else None
+    alphas = self.to_device(alphas, (nc, B)) if alphas is not None else None
+    sh = self._shifts(shifts, 12 * nc + 4)
+    L.check(self.lib.cg_train_step(self.ctx, self._ptr(real), B, self._ptr(noises), self._ptr(alphas),
+                                   sh[0] if sh else None, self._scal))
+    return np.array(self._scal[:], np.float32)
+
+  def validate(self, real, noise=None, alpha=None, shifts=None):
+    self._use_stream()
+    real = self.to_device(real)
+    B = real.shape[0]
+    noise = self.to_device(noise, (B, self.cfg.noise_dim)) if noise is not None else None
+    alpha = self.to_device(alpha).reshape(-1) if alpha is not None else None
+    sh = self._shifts(shifts, 12)
+    fake = torch.empty(self.signal_shape(B), device=self.device, dtype=torch.float32)
+    L.check(self.lib.cg_validate(self.ctx, self._ptr(real), B, self._ptr(noise), self._ptr(alpha),
+                                 sh[0] if sh else None, self._ptr(fake), self._scal))
+    return fake, np.array(self._scal[:], np.float32)
+
+  def generate(self, noise, denorm=False):
+    self._use_stream()
+    noise = self.to_device(noise)
+    B = noise.shape[0]
+    out = torch.empty(self.signal_shape(B), device=self.device, dtype=torch.float32)
+    L.check(self.lib.cg_generate(self.ctx, self._ptr(noise), B, int(bool(denorm)), self._ptr(out)))
+    return out
+
+  def critic_forward(self, x, shifts):
+    self._use_stream()
+    x = self.to_device(x)
+    B = x.shape[0]
+    sh = self._shifts(shifts, 4)
+    out = torch.empty((B,), device=self.device, dtype=torch.float32)
+    L.check(self.lib.cg_debug_critic_forward(self.ctx, self._ptr(x), B, sh[0], self._ptr(out)))
+    return out.reshape(B, 1)
+
+  def gp_debug(self, xhat, shifts):
+    """returns (dD/dxhat (B,L,C), squared norms (B,))"""
+    self._use_stream()
+    x = self.to_device(xhat)
+    B = x.shape[0]
+    sh = self._shifts(shifts, 4)
+    g = torch.empty(self.signal_shape(B), device=self.device, dtype=torch.float32)
+    n2 = torch.empty((B,), device=self.device, dtype=torch.float32)
+    L.check(self.lib.cg_debug_gp(self.ctx, self._ptr(x), B, sh[0], self._ptr(g), self._ptr(n2)))
+    return g, n2
+
+  def phase_shuffle(self, x, shift):
+    self._use_stream()
+    x = self.to_device(x)
+    B, w, ch = x.shape
+    out = torch.empty_like(x)
+    L.check(self.lib.cg_debug_phase_shuffle(self.ctx, self._ptr(x), B, w, ch, int(shift), self._ptr(out)))
+    return out
+
+  def fake(self, batch):
+    """fp32 CUDA tensor aliasing the generator output of the last step."""
+    ptr = self.lib.cg_fake_ptr(self.ctx)
+    n = batch * self.cfg.seq_len * self.cfg.channels
+    return torch.as_tensor(_DevArray(ptr, n), device=self.device).reshape(self.signal_shape(batch))
+
+  def scores(self, n):
+    ptr = self.lib.cg_scores_ptr(self.ctx)
+    return torch.as_tensor(_DevArray(ptr, n), device=self.device)
+
+  def scalars_tensor(self):
+    """CUDA view of the scalars the last step wrote (slot 0), valid on the engine stream."""
+    ptr = self.lib.cg_scalars_ptr(self.ctx)
+    return torch.as_tensor(_DevArray(ptr, L.NUM_SCALARS), device=self.device)
+
+  def launch_count(self):
+    return int(self.lib.cg_launch_count(self.ctx))
+
+  def device_bytes(self):
+    return int(self.lib.cg_device_bytes(self.ctx))
+
+  def synchronize(self):
+    L.check(self.lib.cg_synchronize(self.ctx))
+
+  def bench_layer(self, which, layer, pass_, batch, iters=10):
+    self._use_stream()
+    ms, fl = C.c_float(), C.c_double()
+    L.check(self.lib.cg_bench_layer(self.ctx, which, layer, pass_, batch, iters, C.byref(ms), C.byref(fl)))
+    return float(ms.value), float(fl.value)

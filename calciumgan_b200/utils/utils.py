@@ -1,0 +1,72 @@
+"""Checkpoint + small helpers with the reference's names and on-disk layout
+(gan/utils/utils.py:30-32,116-152): `output_dir/checkpoints/epoch-%03d.pkl` holding
+{'epoch', 'gen_weights', 'dis_weights', 'gen_steps', 'dis_steps'} with fp32 numpy arrays in
+Keras get_weights() order. The reference pickles tf.Variable step counters; plain ints are
+written here (its loader assigns whatever it finds). Adam moments, which the reference does
+not save, go under extra keys the reference's loader ignores."""
+import os
+import pickle
+from glob import glob
+
+import numpy as np
+
+from .. import _lib as L
+
+
+def normalize(x, x_min, x_max):
+  ''' scale x to be between 0 and 1 '''
+  return (x - x_min) / (x_max - x_min)
+
+
+def denormalize(x, x_min, x_max):
+  ''' re-scale signals back to its original range '''
+  return x * (x_max - x_min) + x_min
+
+
+def save_models(hparams, gan, epoch, save_optimizer_state=True):
+  if not hasattr(hparams, 'ckpt_dir'):
+    hparams.ckpt_dir = os.path.join(hparams.output_dir, 'checkpoints')
+  if not os.path.exists(hparams.ckpt_dir):
+    os.makedirs(hparams.ckpt_dir)
+  filename = os.path.join(hparams.ckpt_dir, 'epoch-{:03d}.pkl'.format(epoch))
+
+  with open(filename, 'wb') as file:
+    content = {
+        'epoch': epoch,
+        'gen_weights': gan.generator.get_weights(),
+        'dis_weights': gan.discriminator.get_weights(),
+        'gen_steps': int(gan.gen_optimizer.iterations),
+        'dis_steps': int(gan.dis_optimizer.iterations)
+    }
+    if save_optimizer_state:
+      gm, gv, _ = gan.engine.get_opt_state(L.GENERATOR)
+      dm, dv, _ = gan.engine.get_opt_state(L.DISCRIMINATOR)
+      content['b200_adam'] = {'gen_m': gm, 'gen_v': gv, 'dis_m': dm, 'dis_v': dv}
+    pickle.dump(content, file)
+
+  if getattr(hparams, 'verbose', 0):
+    print('Saved checkpoint to {}'.format(filename))
+
+
+def load_models(hparams, gan):
+  if not hasattr(hparams, 'ckpt_dir'):
+    hparams.ckpt_dir = os.path.join(hparams.output_dir, 'checkpoints')
+
+  hparams.start_epoch = 0
+  filenames = glob(os.path.join(hparams.ckpt_dir, 'epoch-*'))
+  if filenames:
+    filename = sorted(filenames)[-1]
+    with open(filename, 'rb') as file:
+      ckpt = pickle.load(file)
+    hparams.start_epoch = ckpt['epoch'] + 1
+    gan.generator.set_weights(ckpt['gen_weights'])
+    gan.discriminator.set_weights(ckpt['dis_weights'])
+    adam = ckpt.get('b200_adam')
+    if adam is not None:   # the reference restarts the moments from zero (utils.py:126-127,148-149)
+      gan.engine.set_opt_state(L.GENERATOR, adam['gen_m'], adam['gen_v'], 0)
+      gan.engine.set_opt_state(L.DISCRIMINATOR, adam['dis_m'], adam['dis_v'], 0)
+    gan.gen_optimizer.iterations = ckpt['gen_steps']
+    gan.dis_optimizer.iterations = ckpt['dis_steps']
+
+    if getattr(hparams, 'verbose', 0):
+      print('\n\nRestored checkpoint at {}\n\n'.format(filename))

@@ -1,0 +1,166 @@
+/* calciumgan_b200 — C ABI of the B200-native WGAN-GP training step.
+ *
+ * This is the boundary that replaces TensorFlow 2.3.1 underneath the reference's
+ * `gan/algorithms/wgan_gp.py` + `gan/models/calciumgan.py` (reference paths relative to
+ * /root/reference).  Plain pointers and sizes only; no torch / DLPack types in signatures
+ * (the Python host resolves DLPack capsules to device pointers before calling).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; cg_last_error() returns a
+ *     thread-local message.  A CUDA error is never swallowed and there is no CPU fallback.
+ *   - one context per process/GPU; a context is not thread-safe.
+ *   - "dev" pointers are device pointers on the context's device, "host" pointers are host.
+ *   - all kernels are launched on the stream set by cg_set_stream (default: stream 0).
+ *   - signals cross as fp32 NWC (batch, seq_len, channels), exactly what `gan.train(signal)`
+ *     receives at main.py:49.
+ *   - weights cross as one flat fp32 array per model in Keras get_weights() order and layout
+ *     (gan/utils/utils.py:116-152): generator = [dense k(nd, w*nd), b] + 5 x [convT k(K,1,Cout,Cin),
+ *     b, (LN gamma, beta)] + [dense k(C,C), b];  critic = 5 x [conv k(K,Cin,Cout), b] + [dense k(w5*5nu,1), b].
+ */
+#ifndef CALCIUMGAN_B200_H_
+#define CALCIUMGAN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CG_VERSION 100
+
+enum { CG_GENERATOR = 0, CG_DISCRIMINATOR = 1 };
+enum { CG_FP32 = 0, CG_BF16 = 1 };
+
+/* Hyper-parameters: the hparams fields read by gan/models/calciumgan.py:23-27,38-45,96-98,142-151,
+ * gan/algorithms/wgan_gp.py:15-17, gan/algorithms/gan.py:18-22 and gan/algorithms/optimizer.py:8-9. */
+typedef struct cg_config {
+  int32_t seq_len;        /* hparams.signal_shape[0]                          */
+  int32_t channels;       /* hparams.num_channels                              */
+  int32_t noise_dim;      /* --noise_dim                                       */
+  int32_t num_units;      /* --num_units                                       */
+  int32_t kernel_size;    /* --kernel_size                                     */
+  int32_t strides;        /* --strides (only 2 is implemented)                 */
+  int32_t phase_m;        /* --m, PhaseShuffle range                           */
+  int32_t layer_norm;     /* --layer_norm                                      */
+  int32_t normalize;      /* hparams.normalize -> sigmoid head + denormalised metrics */
+  int32_t max_batch;      /* largest per-call batch (smaller batches accepted) */
+  int32_t n_critic;       /* --n_critic                                        */
+  int32_t precision;      /* CG_FP32 | CG_BF16 (--mixed_precision)             */
+  float gp_lambda;        /* --gradient_penalty                                */
+  float learning_rate;    /* --learning_rate                                   */
+  float signals_min;      /* hparams.signals_min                               */
+  float signals_max;      /* hparams.signals_max                               */
+  int32_t world_size;     /* data-parallel ranks (gradients are scaled 1/world_size in cg_apply_update) */
+  int32_t rank;
+  int32_t force_simt;     /* debug: run the CUDA-core kernels even in bf16 mode */
+  int32_t reserved[7];
+} cg_config;
+
+typedef struct cg_ctx cg_ctx;
+
+/* scalars written by the step functions (host float arrays) */
+enum {
+  CG_S_DIS_LOSS = 0, CG_S_GP = 1, CG_S_REAL_LOSS = 2, CG_S_FAKE_LOSS = 3,   /* critic step  */
+  CG_S_GEN_LOSS = 4,                                                         /* generator step */
+  CG_S_MET_MIN = 5, CG_S_MET_MAX = 6, CG_S_MET_MEAN = 7, CG_S_MET_STD = 8,  /* gan.py:36-41 */
+  CG_NUM_SCALARS = 16
+};
+
+/* flags for the step functions */
+enum {
+  CG_FLAG_NO_UPDATE = 1,   /* leave gradients in the flat buffer, do not run Adam (DP host allreduces first) */
+  CG_FLAG_NO_SYNC = 2      /* do not copy scalars back / synchronise (scalars_host may be NULL) */
+};
+
+int cg_version(void);
+const char* cg_last_error(void);
+
+int cg_create(const cg_config* cfg, cg_ctx** out);
+void cg_destroy(cg_ctx* ctx);
+int cg_set_stream(cg_ctx* ctx, void* cuda_stream);
+int cg_synchronize(cg_ctx* ctx);
+
+/* ---- parameters: Keras get_weights()/set_weights() (gan/utils/utils.py:124-125,146-147) ---- */
+int64_t cg_num_params(cg_ctx* ctx, int which);
+int cg_num_tensors(cg_ctx* ctx, int which);
+/* shape (up to 4 dims, unused = 0) and flat offset of tensor `idx` in checkpoint order */
+int cg_tensor_info(cg_ctx* ctx, int which, int idx, int64_t shape[4], int* ndim, int64_t* offset);
+int cg_set_weights(cg_ctx* ctx, int which, const float* host_flat);
+int cg_get_weights(cg_ctx* ctx, int which, float* host_flat);
+int cg_init_weights(cg_ctx* ctx, uint64_t seed);            /* glorot-uniform / zeros / LN (1, 0) */
+/* per-parameter gradients of the last step, before Adam (north_star parity check) */
+int cg_get_grads(cg_ctx* ctx, int which, float* host_flat);
+/* device pointer of the flat fp32 gradient buffer (the DP host all-reduces it in place) */
+void* cg_grad_ptr(cg_ctx* ctx, int which);
+/* Adam moments + iteration counter (optimizer.py:15-21; extra checkpoint keys) */
+int cg_get_opt_state(cg_ctx* ctx, int which, float* host_m, float* host_v, int64_t* step);
+int cg_set_opt_state(cg_ctx* ctx, int which, const float* host_m, const float* host_v, int64_t step);
+int cg_seed(cg_ctx* ctx, uint64_t seed);                    /* noise / alpha / shift streams */
+
+/* ---- the hot path ----
+ * real_dev  : (batch, seq_len, channels) fp32 device pointer
+ * noise_dev : (batch, noise_dim) fp32 or NULL (drawn on device, gan.py:29-30)
+ * alpha_dev : (batch) fp32 or NULL (drawn on device, wgan_gp.py:40)
+ * shifts    : host int32 PhaseShuffle draws in call order or NULL (drawn on host, calciumgan.py:121-124)
+ */
+
+/* wgan_gp.py:64-80 `_train_discriminator`. shifts_host[12]: D(real), D(fake), D(xhat). */
+int cg_critic_step(cg_ctx* ctx, const float* real_dev, int batch, const float* noise_dev,
+                   const float* alpha_dev, const int32_t* shifts_host, int flags, float* scalars_host);
+
+/* wgan_gp.py:22-36 `_train_generator` (+ gan.py:32-41 metrics). shifts_host[4]. */
+int cg_generator_step(cg_ctx* ctx, const float* real_dev, int batch, const float* noise_dev,
+                      const int32_t* shifts_host, int flags, float* scalars_host);
+
+/* optimizer.py:31-34 `Optimizer.update` tail: Adam on the flat gradient buffer (scaled by
+ * 1/world_size) and refresh of the packed low-precision weight copies. */
+int cg_apply_update(cg_ctx* ctx, int which);
+
+/* wgan_gp.py:82-95 `train`: n_critic critic updates on the same batch + one generator update.
+ * noise_dev (n_critic+1, batch, noise_dim) | NULL, alpha_dev (n_critic, batch) | NULL,
+ * shifts_host[12*n_critic+4] | NULL.  scalars: gen_loss, mean dis_loss, mean gp, 4 metrics. */
+int cg_train_step(cg_ctx* ctx, const float* real_dev, int batch, const float* noise_dev,
+                  const float* alpha_dev, const int32_t* shifts_host, float* scalars_host);
+
+/* gan.py:87-90 `validate` (= _step(training=False) with WGAN-GP losses). shifts_host[12].
+ * fake_out_dev (batch, seq_len, channels) fp32 or NULL. */
+int cg_validate(cg_ctx* ctx, const float* real_dev, int batch, const float* noise_dev,
+                const float* alpha_dev, const int32_t* shifts_host, float* fake_out_dev,
+                float* scalars_host);
+
+/* gan.py:92-97 `generate(noise, denorm)`. out_dev (batch, seq_len, channels) fp32. */
+int cg_generate(cg_ctx* ctx, const float* noise_dev, int batch, int denorm, float* out_dev);
+
+/* ---- parity / debug taps ---- */
+/* critic forward on arbitrary input: scores_dev (batch) fp32. shifts_host[4]. */
+int cg_debug_critic_forward(cg_ctx* ctx, const float* x_dev, int batch, const int32_t* shifts_host,
+                            float* scores_dev);
+/* gradient penalty of the critic at xhat: grad_dev (batch, seq_len, channels) fp32 | NULL,
+ * norms_dev (batch) fp32 | NULL. shifts_host[4]. */
+int cg_debug_gp(cg_ctx* ctx, const float* xhat_dev, int batch, const int32_t* shifts_host,
+                float* grad_dev, float* norms_dev);
+/* PhaseShuffle alone (calciumgan.py:117-138) on a fp32 (batch, w, ch) device tensor, ch % 4 == 0;
+ * bit-exact index arithmetic. cg_phase_shuffle_index fills host idx[w] with the source row of each
+ * output row (no GPU needed). */
+int cg_debug_phase_shuffle(cg_ctx* ctx, const float* x_dev, int batch, int w, int ch, int shift, float* out_dev);
+int cg_phase_shuffle_index(int w, int shift, int32_t* idx_host);
+/* device pointer to the generator output (batch, seq_len, channels) fp32 of the last step */
+void* cg_fake_ptr(cg_ctx* ctx);
+/* device pointer to the critic scores of the last critic forward (groups x batch) fp32 */
+void* cg_scores_ptr(cg_ctx* ctx);
+/* device pointer to the CG_NUM_SCALARS floats the last step wrote (valid with CG_FLAG_NO_SYNC) */
+void* cg_scalars_ptr(cg_ctx* ctx);
+/* number of kernels this library launched since creation (bench "gpu_launches") */
+int64_t cg_launch_count(cg_ctx* ctx);
+/* bytes of device memory owned by the context */
+int64_t cg_device_bytes(cg_ctx* ctx);
+/* microbenchmark hook: time `iters` launches of one conv layer kernel with CUDA events on the
+ * context stream. which/layer: CG_DISCRIMINATOR conv 1..5 or CG_GENERATOR convT 1..5; pass: 0 fwd,
+ * 1 dgrad, 2 wgrad. Writes avg milliseconds and the algorithmic FLOPs of one launch. */
+int cg_bench_layer(cg_ctx* ctx, int which, int layer, int pass, int batch, int iters,
+                   float* ms_out, double* flops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CALCIUMGAN_B200_H_ */

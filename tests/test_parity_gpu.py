@@ -1,0 +1,255 @@
+"""Parity of the CUDA path against the CPU oracle through the reference-facing plugin API and
+the C ABI (north_star: generator output, critic scores, GP value and per-parameter gradients
+after one step; rel <= 1e-4 in fp32, <= 2e-2 in bf16; PhaseShuffle bit-exact).
+
+The oracle is an fp64 restatement ("parity unpinned" - see oracle/calciumgan_oracle.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import calciumgan_oracle as O
+from tests.util import namespace_from_oracle, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4   # north_star
+BF16_TOL = 2e-2   # north_star
+GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'tiny_step.npz')
+
+
+def build(hp, batch, mixed=False, **kw):
+  from calciumgan_b200.algorithms.registry import get_algorithm
+  from calciumgan_b200.models.registry import get_models
+  ns = namespace_from_oracle(hp, batch, mixed_precision=mixed, **kw)
+  g, d = get_models(ns, None)
+  gan = get_algorithm(ns, g, d, None)
+  assert type(gan).__name__ == 'WGAN_GP'
+  return ns, gan
+
+
+def check_list(got, ref, tol, what):
+  assert len(got) == len(ref)
+  worst = 0.0
+  for i, (a, b) in enumerate(zip(got, ref)):
+    b = b.numpy() if hasattr(b, 'numpy') else b
+    assert a.shape == tuple(b.shape), (what, i, a.shape, b.shape)
+    if float(np.abs(b).max()) == 0.0:
+      assert float(np.abs(a).max()) <= 1e-6, (what, i, 'expected exact zeros', float(np.abs(a).max()))
+      continue
+    e = rel_err(a, b)
+    worst = max(worst, e)
+    assert e <= tol, '%s[%d] shape %s rel err %.3e > %.1e' % (what, i, a.shape, e, tol)
+  return worst
+
+
+# ------------------------------------------------------------------------------------------ golden (fp32)
+def test_tiny_golden_critic_step_fp32():
+  import tests.golden.make_golden as mk
+  gold = np.load(GOLD)
+  hp = mk.tiny_hp()
+  ns, gan = build(hp, mk.BATCH)
+  gan.generator.set_weights([gold['gen_w%02d' % i] for i in range(24)])
+  gan.discriminator.set_weights([gold['dis_w%02d' % i] for i in range(12)])
+  s = gan.engine.critic_step(gold['real'], gold['noises'][0], gold['alphas'][0], gold['shifts'][:12], update=False)
+  assert rel_err(gan.engine.fake(mk.BATCH).cpu().numpy(), gold['c_fake']) <= FP32_TOL
+  sc = gan.engine.scores(3 * mk.BATCH).cpu().numpy()
+  assert rel_err(sc[:mk.BATCH], gold['c_real_out'].ravel()) <= FP32_TOL
+  assert rel_err(sc[mk.BATCH:2 * mk.BATCH], gold['c_fake_out'].ravel()) <= FP32_TOL
+  assert abs(s[0] - gold['c_scalars'][0]) <= FP32_TOL * max(1.0, abs(gold['c_scalars'][0]))
+  assert abs(s[1] - gold['c_scalars'][1]) <= FP32_TOL * max(1.0, abs(gold['c_scalars'][1]))
+  grads = gan.engine.get_grads(1)
+  check_list(grads, [gold['c_grad%02d' % i] for i in range(12)], FP32_TOL, 'critic grad')
+
+
+def test_tiny_golden_generator_step_fp32():
+  import tests.golden.make_golden as mk
+  gold = np.load(GOLD)
+  hp = mk.tiny_hp()
+  ns, gan = build(hp, mk.BATCH)
+  gan.generator.set_weights([gold['gen_w%02d' % i] for i in range(24)])
+  gan.discriminator.set_weights([gold['dis_w%02d' % i] for i in range(12)])
+  nc = mk.N_CRITIC
+  s = gan.engine.generator_step(gold['real'], gold['noises'][nc], gold['shifts'][12 * nc:12 * nc + 4], update=False)
+  assert abs(s[4] - gold['g_scalars'][0]) <= FP32_TOL * max(1.0, abs(gold['g_scalars'][0]))
+  # metrics sorted: max, mean, min, std  (C enum order: min, max, mean, std)
+  np.testing.assert_allclose([s[6], s[7], s[5], s[8]], gold['g_scalars'][1:], rtol=1e-3, atol=1e-7)
+  check_list(gan.engine.get_grads(0), [gold['g_grad%02d' % i] for i in range(24)], FP32_TOL, 'generator grad')
+
+
+def test_tiny_golden_full_train_step_fp32():
+  import tests.golden.make_golden as mk
+  gold = np.load(GOLD)
+  hp = mk.tiny_hp()
+  ns, gan = build(hp, mk.BATCH)
+  gan.generator.set_weights([gold['gen_w%02d' % i] for i in range(24)])
+  gan.discriminator.set_weights([gold['dis_w%02d' % i] for i in range(12)])
+  gen_loss, dis_loss, gp, metrics = gan.train(gold['real'], noise=gold['noises'], alpha=gold['alphas'],
+                                              shifts=gold['shifts'])
+  t = gold['t_scalars']
+  assert abs(gen_loss - t[0]) <= 1e-3 * max(1.0, abs(t[0]))
+  assert abs(dis_loss - t[1]) <= 1e-3 * max(1.0, abs(t[1]))
+  assert abs(gp - t[2]) <= 1e-3 * max(1.0, abs(t[2]))
+  assert set(metrics) == {'signals_metrics/min', 'signals_metrics/max', 'signals_metrics/mean', 'signals_metrics/std'}
+  # after n_critic Adam steps + 1: weights moved by ~lr per step; compare the *update* not the weight
+  w0 = [gold['dis_w%02d' % i] for i in range(12)]
+  w1 = [gold['t_dis_w%02d' % i] for i in range(12)]
+  got = gan.discriminator.get_weights()
+  for i in range(12):
+    ref_upd, got_upd = w1[i] - w0[i], got[i] - w0[i]
+    if np.abs(ref_upd).max() == 0:
+      continue
+    assert rel_err(got_upd, ref_upd) <= 5e-2, ('dis update', i, rel_err(got_upd, ref_upd))
+  g0 = [gold['gen_w%02d' % i] for i in range(24)]
+  g1 = [gold['t_gen_w%02d' % i] for i in range(24)]
+  got = gan.generator.get_weights()
+  for i in range(24):
+    assert rel_err(got[i] - g0[i], g1[i] - g0[i]) <= 5e-2, ('gen update', i)
+  assert gan.gen_optimizer.iterations == 1 and gan.dis_optimizer.iterations == mk.N_CRITIC
+
+
+# ------------------------------------------------------------------------------------------ PhaseShuffle bit-exact
+@pytest.mark.parametrize('w', [4, 64, 1024])
+def test_phase_shuffle_gather_bit_exact(w):
+  hp = O.HParams(signal_shape=(64, 6), noise_dim=4, num_units=4, kernel_size=6, m=2, n_critic=1)
+  ns, gan = build(hp, 2)
+  rng = np.random.RandomState(0)
+  x = rng.standard_normal((3, w, 8)).astype(np.float32)
+  m = min(10, w - 1)
+  for shift in range(-m, m + 1):
+    got = gan.engine.phase_shuffle(x, shift).cpu().numpy()
+    np.testing.assert_array_equal(got, O.phase_shuffle_literal(x, shift))
+
+
+# ------------------------------------------------------------------------------------------ seeded medium configs
+def _medium_hp(**kw):
+  d = dict(signal_shape=(256, 20), noise_dim=8, num_units=16, kernel_size=24, m=3, n_critic=1)
+  d.update(kw)
+  return O.HParams(**d)
+
+
+def _run_both(hp, batch, mixed, seed=7, force_simt=False):
+  ns, gan = build(hp, batch, mixed=mixed, force_simt=force_simt)
+  gw, dw = O.init_weights(hp, seed=seed)
+  gw, dw = O.randomize_weights(gw, seed + 1), O.randomize_weights(dw, seed + 2)
+  gan.generator.set_weights(gw)
+  gan.discriminator.set_weights(dw)
+  real, noises, alphas, shifts = O.synthetic_batch(hp, batch, seed=seed + 3, n_critic=1)
+  ref_c = O.critic_step(gw, dw, real, noises[0], alphas[0], shifts[:12].reshape(3, 4), hp)
+  s = gan.engine.critic_step(real, noises[0], alphas[0], shifts[:12], update=False)
+  got_c = dict(scal=s, fake=gan.engine.fake(batch).cpu().numpy(), scores=gan.engine.scores(3 * batch).cpu().numpy(),
+               grads=gan.engine.get_grads(1))
+  ref_g = O.generator_step(gw, dw, real, noises[1], shifts[12:16], hp)
+  s = gan.engine.generator_step(real, noises[1], shifts[12:16], update=False)
+  got_g = dict(scal=s, grads=gan.engine.get_grads(0))
+  return ref_c, got_c, ref_g, got_g, gan
+
+
+@pytest.mark.parametrize('layer_norm', [True, False])
+@pytest.mark.parametrize('K', [24, 5])
+def test_medium_fp32(layer_norm, K):
+  hp = _medium_hp(layer_norm=layer_norm, kernel_size=K)
+  ref_c, got_c, ref_g, got_g, _ = _run_both(hp, 4, mixed=False)
+  B = 4
+  assert rel_err(got_c['fake'], ref_c['fake'].numpy()) <= FP32_TOL
+  assert rel_err(got_c['scores'][:B], ref_c['real_out'].numpy().ravel()) <= FP32_TOL
+  assert rel_err(got_c['scores'][B:2 * B], ref_c['fake_out'].numpy().ravel()) <= FP32_TOL
+  assert abs(got_c['scal'][1] - ref_c['gradient_penalty']) <= FP32_TOL * max(1.0, ref_c['gradient_penalty'])
+  assert abs(got_c['scal'][0] - ref_c['dis_loss']) <= FP32_TOL * max(1.0, abs(ref_c['dis_loss']))
+  check_list(got_c['grads'], ref_c['grads'], FP32_TOL, 'critic grad')
+  assert abs(got_g['scal'][4] - ref_g['gen_loss']) <= FP32_TOL * max(1.0, abs(ref_g['gen_loss']))
+  check_list(got_g['grads'], ref_g['grads'], FP32_TOL, 'generator grad')
+
+
+@pytest.mark.parametrize('force_simt', [True, False])
+def test_medium_bf16(force_simt):
+  hp = _medium_hp(signal_shape=(512, 102), num_units=32)
+  B = 8
+  ref_c, got_c, ref_g, got_g, _ = _run_both(hp, B, mixed=True, force_simt=force_simt)
+  assert rel_err(got_c['fake'], ref_c['fake'].numpy()) <= BF16_TOL
+  assert rel_err(got_c['scores'][:B], ref_c['real_out'].numpy().ravel()) <= BF16_TOL
+  assert rel_err(got_c['scores'][B:2 * B], ref_c['fake_out'].numpy().ravel()) <= BF16_TOL
+  assert abs(got_c['scal'][1] - ref_c['gradient_penalty']) <= BF16_TOL * max(1.0, ref_c['gradient_penalty'])
+  check_list(got_c['grads'], ref_c['grads'], BF16_TOL, 'critic grad')
+  check_list(got_g['grads'], ref_g['grads'], BF16_TOL, 'generator grad')
+
+
+def test_gp_debug_tap_fp32():
+  hp = _medium_hp()
+  ns, gan = build(hp, 4)
+  gw, dw = O.init_weights(hp, seed=3)
+  dw = O.randomize_weights(dw, 4)
+  gan.discriminator.set_weights(dw)
+  real, _, _, _ = O.synthetic_batch(hp, 4, seed=5, n_critic=1)
+  sh = [3, -2, 0, 1]
+  gp, g, _ = O.gp_four_pass(dw, real, sh, hp)
+  got_g, sumsq = gan.engine.gp_debug(real, sh)
+  assert rel_err(got_g.cpu().numpy(), g.numpy()) <= FP32_TOL
+  n = np.sqrt(sumsq.cpu().numpy())
+  assert abs(float(np.mean((n - 1) ** 2)) - float(gp)) <= FP32_TOL * max(1.0, float(gp))
+  out = gan.discriminator(real, shifts=sh)
+  ref = O.discriminator_forward([torch.tensor(a, dtype=torch.float64) for a in dw],
+                                torch.tensor(real, dtype=torch.float64), sh, hp)
+  assert rel_err(out.cpu().numpy(), ref.numpy()) <= FP32_TOL
+
+
+def test_validate_and_generate_fp32():
+  hp = _medium_hp()
+  B = 4
+  ns, gan = build(hp, B)
+  gw, dw = O.init_weights(hp, seed=11)
+  gw, dw = O.randomize_weights(gw, 12), O.randomize_weights(dw, 13)
+  gan.generator.set_weights(gw)
+  gan.discriminator.set_weights(dw)
+  real, noises, alphas, shifts = O.synthetic_batch(hp, B, seed=14, n_critic=1)
+  fake, gen_loss, dis_loss, gp, metrics = O.validate_step(gw, dw, real, noises[0], alphas[0],
+                                                          shifts[:12].reshape(3, 4), hp)
+  f2, gl2, dl2, gp2, m2 = gan.validate(real, noise=noises[0], alpha=alphas[0], shifts=shifts[:12])
+  assert rel_err(f2.cpu().numpy(), fake.numpy()) <= FP32_TOL
+  assert abs(gl2 - gen_loss) <= FP32_TOL * max(1, abs(gen_loss))
+  assert abs(dl2 - dis_loss) <= FP32_TOL * max(1, abs(dis_loss))
+  assert abs(gp2 - gp) <= FP32_TOL * max(1, abs(gp))
+  for k in metrics:
+    assert abs(m2[k] - metrics[k]) <= 1e-3 * max(1e-3, abs(metrics[k])), k
+  w_before = gan.discriminator.get_weights()
+  out = gan.generate(noises[0])
+  assert rel_err(out.cpu().numpy(), fake.numpy()) <= FP32_TOL
+  den = gan.generate(noises[0], denorm=True)
+  np.testing.assert_allclose(den.cpu().numpy(), out.cpu().numpy() * (hp.signals_max - hp.signals_min) + hp.signals_min,
+                             rtol=1e-6)
+  for a, b in zip(w_before, gan.discriminator.get_weights()):
+    np.testing.assert_array_equal(a, b)     # validate/generate never update
+
+
+def test_ragged_last_batch_and_errors():
+  hp = _medium_hp()
+  ns, gan = build(hp, 4)
+  real, noises, alphas, shifts = O.synthetic_batch(hp, 3, seed=2, n_critic=1)
+  out = gan.train(real)    # smaller last batch of an epoch, library-drawn randomness
+  assert np.isfinite(out[0]) and np.isfinite(out[1]) and np.isfinite(out[2])
+  from calciumgan_b200._lib import CgError
+  big, _, _, _ = O.synthetic_batch(hp, 5, seed=2, n_critic=1)
+  with pytest.raises(CgError, match='max_batch'):
+    gan.train(big)
+  with pytest.raises(CgError, match='outside'):
+    gan.engine.critic_step(real, noises[0], alphas[0], [99] * 12, update=False)
+
+
+def test_checkpoint_roundtrip(tmp_path):
+  from calciumgan_b200.utils import utils
+  hp = _medium_hp()
+  ns, gan = build(hp, 2, output_dir=str(tmp_path))
+  real, _, _, _ = O.synthetic_batch(hp, 2, seed=2, n_critic=1)
+  gan.train(real)
+  ns.ckpt_dir = os.path.join(str(tmp_path), 'checkpoints')
+  utils.save_models(ns, gan, epoch=3)
+  gw, dw = gan.generator.get_weights(), gan.discriminator.get_weights()
+  ns2, gan2 = build(hp, 2, output_dir=str(tmp_path), seed=99)
+  utils.load_models(ns2, gan2)
+  assert ns2.start_epoch == 4
+  for a, b in zip(gw, gan2.generator.get_weights()):
+    np.testing.assert_array_equal(a, b)
+  for a, b in zip(dw, gan2.discriminator.get_weights()):
+    np.testing.assert_array_equal(a, b)
+  assert gan2.gen_optimizer.iterations == 1 and gan2.dis_optimizer.iterations == 1
