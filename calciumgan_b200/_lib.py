@@ -57,12 +57,14 @@ SIGNATURES = {
     'cg_generate': (_I, [_P, _P, _I, _I, _P]),
     'cg_debug_critic_forward': (_I, [_P, _P, _I, _I32P, _P]),
     'cg_debug_gp': (_I, [_P, _P, _I, _I32P, _P, _P]),
+    'cg_debug_layer': (_I, [_P, _I, _I, _I, _P, _P, _I, _P]),
     'cg_debug_phase_shuffle': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'cg_phase_shuffle_index': (_I, [_I, _I, _I32P]),
     'cg_fake_ptr': (_P, [_P]),
     'cg_scores_ptr': (_P, [_P]),
     'cg_scalars_ptr': (_P, [_P]),
     'cg_launch_count': (_I64, [_P]),
+    'cg_tc_launch_count': (_I64, [_P]),
     'cg_device_bytes': (_I64, [_P]),
     'cg_bench_layer': (_I, [_P, _I, _I, _I, _I, _I, _F, C.POINTER(C.c_double)]),
 }

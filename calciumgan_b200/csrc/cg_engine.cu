@@ -34,6 +34,7 @@ static int set_err(const char* fmt, ...) {
   g_err = buf;
   return 1;
 }
+int cg_tc_set_err(const char* msg) { return set_err("%s", msg); }
 #define CU(x)                                                                              \
   do {                                                                                     \
     cudaError_t e_ = (x);                                                                  \
@@ -86,6 +87,7 @@ struct cg_ctx {
   int esz;
   cudaStream_t stream = 0;
   int64_t launches = 0;
+  int64_t tc_launches = 0;
   int64_t dev_bytes = 0;
   std::vector<void*> allocs;
 
@@ -186,6 +188,7 @@ static int post_launch(cg_ctx* c, const char* what) {
 static int launch_rsgemm(cg_ctx* c, const RsParams& p) {
   if (c->use_tc && tc_rsgemm_supported(p)) {
     CK(tc_rsgemm_launch(&c->tc, p, c->stream));
+    c->tc_launches++;
     return post_launch(c, "rsgemm_tc");
   }
   const long long M = (long long)p.B * p.Q;
@@ -197,6 +200,7 @@ static int launch_rsgemm(cg_ctx* c, const RsParams& p) {
 static int launch_wgrad(cg_ctx* c, WgParams p) {
   if (c->use_tc && tc_wgrad_supported(p)) {
     CK(tc_wgrad_launch(&c->tc, p, c->stream));
+    c->tc_launches++;
     return post_launch(c, "wgrad_tc");
   }
   const long long R = (long long)p.B * p.Q;
@@ -362,6 +366,7 @@ extern "C" int cg_create(const cg_config* cfg, cg_ctx** out) {
 extern "C" int cg_set_stream(cg_ctx* c, void* s) { c->stream = (cudaStream_t)s; return 0; }
 extern "C" int cg_synchronize(cg_ctx* c) { CU(cudaStreamSynchronize(c->stream)); return 0; }
 extern "C" int64_t cg_launch_count(cg_ctx* c) { return c->launches; }
+extern "C" int64_t cg_tc_launch_count(cg_ctx* c) { return c->tc_launches; }
 extern "C" int64_t cg_device_bytes(cg_ctx* c) { return c->dev_bytes; }
 extern "C" void* cg_fake_ptr(cg_ctx* c) { return c->FAKE32; }
 extern "C" void* cg_scores_ptr(cg_ctx* c) { return c->scores; }
@@ -461,22 +466,50 @@ static float* ggrad(cg_ctx* c, int idx) { return c->gen.g + c->gen.params[idx].o
 static float* dparam(cg_ctx* c, int idx) { return c->dis.w + c->dis.params[idx].offset; }
 static float* dgrad(cg_ctx* c, int idx) { return c->dis.g + c->dis.params[idx].offset; }
 
+// Conv1DTranspose i forward (models/utils.py:79-89): HG[i-1] -> AG[i] (+bias)
+static RsParams convT_fwd_params(cg_ctx* c, int i, int B) {
+  RsParams p;
+  memset(&p, 0, sizeof(p));
+  p.A = c->HG[i - 1]; p.a_bs = (long long)c->gl[i - 1] * c->gcp[i - 1]; p.a_rs = c->gcp[i - 1]; p.a_rows = c->gl[i - 1];
+  p.W = c->Wf_g[i]; p.w_ld = c->K * c->gcp[i - 1];
+  p.out = c->AG[i]; p.o_bs = (long long)c->gl[i] * c->gcp[i]; p.o_rs = 2 * c->gcp[i]; p.o_phase_col = c->gcp[i];
+  p.bias = gparam(c, c->g_b[i]);
+  p.B = B; p.Q = c->gl[i - 1]; p.N = c->gcp[i]; p.n_real = c->gc[i]; p.Kc = c->gcp[i - 1];
+  p.epi = EPI_BIAS;
+  p.seg = seg_transposed(c->K, c->gcp[i - 1]);
+  return p;
+}
+// data gradient of Conv1DTranspose i: dHG[i-1][b,q,ci] = sum_k DAG[i][b, 2q+k-padL, co] * Wt[k][co][ci]
+static RsParams convT_bwd_params(cg_ctx* c, int i, int B) {
+  RsParams p;
+  memset(&p, 0, sizeof(p));
+  p.A = c->DAG[i]; p.a_bs = (long long)c->gl[i] * c->gcp[i]; p.a_rs = 2 * c->gcp[i]; p.a_rows = c->gl[i] / 2;
+  p.W = c->Wb_g[i]; p.w_ld = c->K * c->gcp[i];
+  p.out = c->DHG[i - 1]; p.o_bs = (long long)c->gl[i - 1] * c->gcp[i - 1]; p.o_rs = c->gcp[i - 1];
+  p.B = B; p.Q = c->gl[i - 1]; p.N = c->gcp[i - 1]; p.n_real = c->gc[i - 1]; p.Kc = c->gcp[i]; p.epi = EPI_NONE;
+  p.seg = seg_strided(c->K, c->gcp[i]);
+  return p;
+}
+// dWt[k][co][ci] = sum_{b,q} DAG[i][b, 2q + k - padL, co] * HG[i-1][b, q, ci]
+static WgParams convT_wgrad_params(cg_ctx* c, int i, int B) {
+  WgParams w;
+  memset(&w, 0, sizeof(w));
+  const SegTable st = seg_strided(c->K, c->gcp[i]);
+  w.S = c->DAG[i]; w.s_bs = (long long)c->gl[i] * c->gcp[i]; w.s_rs = 2 * c->gcp[i]; w.s_rows = c->gl[i] / 2;
+  w.P = c->HG[i - 1]; w.p_bs = (long long)c->gl[i - 1] * c->gcp[i - 1]; w.p_rs = c->gcp[i - 1];
+  w.dW = ggrad(c, c->g_k[i]); w.m_real = c->gc[i]; w.n_real = c->gc[i - 1];
+  w.B = B; w.Q = c->gl[i - 1]; w.Mp = c->gcp[i]; w.Np = c->gcp[i - 1]; w.nseg = c->K;
+  for (int k = 0; k < c->K; ++k) { w.shift[k] = st.shift[0][k]; w.scol[k] = st.acol[0][k]; }
+  return w;
+}
+
 // calciumgan.py:22-103. noise (B, nd) fp32 device. Writes FAKE32 (B, L, C).
 static int g_forward(cg_ctx* c, const float* noise, int B) {
   DISPATCH_T(c, dense0_forward_kernel<T><<<grid_for((long long)B * c->w0 * c->gcp[0]), 256, 0, c->stream>>>(
                     noise, gparam(c, 0), gparam(c, 1), (T*)c->HG[0], B, c->nd, c->w0, c->gcp[0]));
   CK(post_launch(c, "dense0_fwd"));
   for (int i = 1; i <= NL; ++i) {
-    RsParams p;
-    memset(&p, 0, sizeof(p));
-    p.A = c->HG[i - 1]; p.a_bs = (long long)c->gl[i - 1] * c->gcp[i - 1]; p.a_rs = c->gcp[i - 1]; p.a_rows = c->gl[i - 1];
-    p.W = c->Wf_g[i]; p.w_ld = c->K * c->gcp[i - 1];
-    p.out = c->AG[i]; p.o_bs = (long long)c->gl[i] * c->gcp[i]; p.o_rs = 2 * c->gcp[i]; p.o_phase_col = c->gcp[i];
-    p.bias = gparam(c, c->g_b[i]);
-    p.B = B; p.Q = c->gl[i - 1]; p.N = c->gcp[i]; p.n_real = c->gc[i]; p.Kc = c->gcp[i - 1];
-    p.epi = EPI_BIAS;
-    p.seg = seg_transposed(c->K, c->gcp[i - 1]);
-    CK(launch_rsgemm(c, p));
+    CK(launch_rsgemm(c, convT_fwd_params(c, i, B)));
     const long long rows = (long long)B * c->gl[i];
     if (c->cfg.layer_norm) {
       DISPATCH_T(c, ln_lrelu_forward_kernel<T><<<grid_for(rows * 32), 256, 0, c->stream>>>(
@@ -552,26 +585,9 @@ static int g_backward(cg_ctx* c, int B) {
                         (const T*)c->DHG[i], (const T*)c->HG[i], (T*)c->DAG[i], rows * c->gcp[i]));
       CK(post_launch(c, "mask_mul"));
     }
-    // dWt[k][co][ci] = sum_{b,q} DAG[b, 2q + k - padL, co] * HG[i-1][b, q, ci]
-    WgParams w;
-    memset(&w, 0, sizeof(w));
-    const SegTable st = seg_strided(c->K, c->gcp[i]);
-    w.S = c->DAG[i]; w.s_bs = (long long)c->gl[i] * c->gcp[i]; w.s_rs = 2 * c->gcp[i]; w.s_rows = c->gl[i] / 2;
-    w.P = c->HG[i - 1]; w.p_bs = (long long)c->gl[i - 1] * c->gcp[i - 1]; w.p_rs = c->gcp[i - 1];
-    w.dW = ggrad(c, c->g_k[i]); w.m_real = c->gc[i]; w.n_real = c->gc[i - 1];
-    w.B = B; w.Q = c->gl[i - 1]; w.Mp = c->gcp[i]; w.Np = c->gcp[i - 1]; w.nseg = c->K;
-    for (int k = 0; k < c->K; ++k) { w.shift[k] = st.shift[0][k]; w.scol[k] = st.acol[0][k]; }
-    CK(launch_wgrad(c, w));
+    CK(launch_wgrad(c, convT_wgrad_params(c, i, B)));
     CK(launch_colsum(c, c->DAG[i], ggrad(c, c->g_b[i]), rows, c->gcp[i], c->gc[i]));
-    // dHG[i-1][b,q,ci] = sum_k DAG[b, 2q+k-padL, co] * Wt[k][co][ci]   (strided-conv form)
-    RsParams p;
-    memset(&p, 0, sizeof(p));
-    p.A = c->DAG[i]; p.a_bs = (long long)c->gl[i] * c->gcp[i]; p.a_rs = 2 * c->gcp[i]; p.a_rows = c->gl[i] / 2;
-    p.W = c->Wb_g[i]; p.w_ld = c->K * c->gcp[i];
-    p.out = c->DHG[i - 1]; p.o_bs = (long long)c->gl[i - 1] * c->gcp[i - 1]; p.o_rs = c->gcp[i - 1];
-    p.B = B; p.Q = c->gl[i - 1]; p.N = c->gcp[i - 1]; p.n_real = c->gc[i - 1]; p.Kc = c->gcp[i]; p.epi = EPI_NONE;
-    p.seg = st;
-    CK(launch_rsgemm(c, p));
+    CK(launch_rsgemm(c, convT_bwd_params(c, i, B)));
   }
   const int tot = (c->nd + 1) * c->w0 * c->nd;
   DISPATCH_T(c, dense0_backward_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
@@ -649,18 +665,23 @@ static int d_backward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh, i
   return 0;
 }
 
+// dW[k][ci][co] = sum_{b,o} X[l-1][b, 2o + k - padL, ci] * DA[l][b, o, co]
+static WgParams conv_wgrad_params(cg_ctx* c, int l, int Bt) {
+  WgParams w;
+  memset(&w, 0, sizeof(w));
+  const SegTable st = seg_strided(c->K, c->dcp[l - 1]);
+  w.S = c->X[l - 1]; w.s_bs = (long long)c->dl[l - 1] * c->dcp[l - 1]; w.s_rs = 2 * c->dcp[l - 1]; w.s_rows = c->dl[l - 1] / 2;
+  w.P = c->DA[l]; w.p_bs = (long long)c->dl[l] * c->dcp[l]; w.p_rs = c->dcp[l];
+  w.dW = dgrad(c, 2 * (l - 1)); w.m_real = c->dc[l - 1]; w.n_real = c->dc[l];
+  w.B = Bt; w.Q = c->dl[l]; w.Mp = c->dcp[l - 1]; w.Np = c->dcp[l]; w.nseg = c->K;
+  for (int k = 0; k < c->K; ++k) { w.shift[k] = st.shift[0][k]; w.scol[k] = st.acol[0][k]; }
+  return w;
+}
+
 // all critic weight gradients from X[l-1] x DA[l] over Bt samples; biases from the first nb_bias samples
 static int d_wgrad(cg_ctx* c, int Bt, int nb_bias) {
   for (int l = 1; l <= NL; ++l) {
-    WgParams w;
-    memset(&w, 0, sizeof(w));
-    const SegTable st = seg_strided(c->K, c->dcp[l - 1]);
-    w.S = c->X[l - 1]; w.s_bs = (long long)c->dl[l - 1] * c->dcp[l - 1]; w.s_rs = 2 * c->dcp[l - 1]; w.s_rows = c->dl[l - 1] / 2;
-    w.P = c->DA[l]; w.p_bs = (long long)c->dl[l] * c->dcp[l]; w.p_rs = c->dcp[l];
-    w.dW = dgrad(c, 2 * (l - 1)); w.m_real = c->dc[l - 1]; w.n_real = c->dc[l];
-    w.B = Bt; w.Q = c->dl[l]; w.Mp = c->dcp[l - 1]; w.Np = c->dcp[l]; w.nseg = c->K;
-    for (int k = 0; k < c->K; ++k) { w.shift[k] = st.shift[0][k]; w.scol[k] = st.acol[0][k]; }
-    CK(launch_wgrad(c, w));
+    CK(launch_wgrad(c, conv_wgrad_params(c, l, Bt)));
     if (nb_bias > 0)
       CK(launch_colsum(c, c->DA[l], dgrad(c, 2 * (l - 1) + 1), (long long)nb_bias * c->dl[l], c->dcp[l], c->dc[l]));
   }
@@ -924,6 +945,60 @@ extern "C" int cg_debug_gp(cg_ctx* c, const float* xhat, int B, const int32_t* s
     DISPATCH_T(c, sumsq_kernel<T><<<B * 8, 256, 0, c->stream>>>((const T*)c->DX[0], c->sumsq, (long long)c->L * c->dcp[0], 8));
     CK(post_launch(c, "sumsq"));
     CU(cudaMemcpyAsync(norms_dev, c->sumsq, (size_t)B * 4, cudaMemcpyDeviceToDevice, c->stream));   // squared norms
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static int pad_in(cg_ctx* c, const float* src, void* dst, int B, int rows, int C, int Cp) {
+  DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for((long long)B * rows * Cp), 256, 0, c->stream>>>(
+                    src, nullptr, nullptr, (T*)dst, B, rows, C, Cp, 1));
+  return post_launch(c, "pad_in");
+}
+static int pad_out(cg_ctx* c, const void* src, float* dst, long long rows, int C, int Cp) {
+  DISPATCH_T(c, unpad_kernel<T><<<grid_for(rows * C), 256, 0, c->stream>>>((const T*)src, dst, rows, C, Cp));
+  return post_launch(c, "pad_out");
+}
+
+extern "C" int cg_debug_layer(cg_ctx* c, int which, int layer, int pass, const float* x, const float* dy, int B,
+                              float* out) {
+  if (layer < 1 || layer > NL || pass < 0 || pass > 2 || !out) return set_err("cg_debug_layer: bad arguments");
+  if ((pass != 1 && !x) || (pass != 0 && !dy)) return set_err("cg_debug_layer: missing input");
+  if (which == CG_DISCRIMINATOR) {
+    const int l = layer;
+    if (B < 1 || B > 3 * c->Bmax || (pass == 1 && l == 1 && B > c->Bmax)) return set_err("cg_debug_layer: batch too large");
+    if (x) CK(pad_in(c, x, c->X[l - 1], B, c->dl[l - 1], c->dc[l - 1], c->dcp[l - 1]));
+    if (dy) CK(pad_in(c, dy, c->DA[l], B, c->dl[l], c->dc[l], c->dcp[l]));
+    if (pass == 0) {
+      CK(launch_rsgemm(c, conv_fwd_params(c, l, c->X[l - 1], c->H[l], B, EPI_BIAS_LRELU, nullptr)));
+      CK(pad_out(c, c->H[l], out, (long long)B * c->dl[l], c->dc[l], c->dcp[l]));
+    } else if (pass == 1) {
+      void* dst = l == 1 ? c->DX[0] : c->DX[l - 1];
+      CK(d_dgrad_layer(c, l, 0, B, dst));
+      CK(pad_out(c, dst, out, (long long)B * c->dl[l - 1], c->dc[l - 1], c->dcp[l - 1]));
+    } else {
+      const ParamInfo& pi = c->dis.params[2 * (l - 1)];
+      CU(cudaMemsetAsync(c->dis.g + pi.offset, 0, pi.size * 4, c->stream));
+      CK(launch_wgrad(c, conv_wgrad_params(c, l, B)));
+      CU(cudaMemcpyAsync(out, c->dis.g + pi.offset, pi.size * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+  } else {
+    const int i = layer;
+    CK(check_batch(c, B));
+    if (x) CK(pad_in(c, x, c->HG[i - 1], B, c->gl[i - 1], c->gc[i - 1], c->gcp[i - 1]));
+    if (dy) CK(pad_in(c, dy, c->DAG[i], B, c->gl[i], c->gc[i], c->gcp[i]));
+    if (pass == 0) {
+      CK(launch_rsgemm(c, convT_fwd_params(c, i, B)));
+      CK(pad_out(c, c->AG[i], out, (long long)B * c->gl[i], c->gc[i], c->gcp[i]));
+    } else if (pass == 1) {
+      CK(launch_rsgemm(c, convT_bwd_params(c, i, B)));
+      CK(pad_out(c, c->DHG[i - 1], out, (long long)B * c->gl[i - 1], c->gc[i - 1], c->gcp[i - 1]));
+    } else {
+      const ParamInfo& pi = c->gen.params[c->g_k[i]];
+      CU(cudaMemsetAsync(c->gen.g + pi.offset, 0, pi.size * 4, c->stream));
+      CK(launch_wgrad(c, convT_wgrad_params(c, i, B)));
+      CU(cudaMemcpyAsync(out, c->gen.g + pi.offset, pi.size * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
   }
   CU(cudaStreamSynchronize(c->stream));
   return 0;

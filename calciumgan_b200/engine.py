@@ -277,6 +277,28 @@ class Engine(object):
     L.check(self.lib.cg_debug_gp(self.ctx, self._ptr(x), B, sh[0], self._ptr(g), self._ptr(n2)))
     return g, n2
 
+  def debug_layer(self, which, layer, pass_, x=None, dy=None):
+    """One conv layer in isolation (cg_debug_layer): fp32 tensors in / out."""
+    self._use_stream()
+    x, dy = self.to_device(x), self.to_device(dy)
+    B = (x if x is not None else dy).shape[0]
+    infos = self.tensor_infos(which)
+    if which == L.DISCRIMINATOR:
+      K, cin, cout = infos[2 * (layer - 1)][0]
+      lin = self.cfg.seq_len >> (layer - 1)
+      lout = lin // 2
+      kshape = (K, cin, cout)
+    else:
+      idx = 2 + (layer - 1) * (4 if self.cfg.layer_norm else 2)
+      K, _, cout, cin = infos[idx][0]
+      lin = (self.cfg.seq_len // 32) << (layer - 1)
+      lout = lin * 2
+      kshape = (K, 1, cout, cin)
+    shape = {0: (B, lout, cout), 1: (B, lin, cin), 2: kshape}[pass_]
+    out = torch.empty(shape, device=self.device, dtype=torch.float32)
+    L.check(self.lib.cg_debug_layer(self.ctx, which, layer, pass_, self._ptr(x), self._ptr(dy), B, self._ptr(out)))
+    return out
+
   def phase_shuffle(self, x, shift):
     self._use_stream()
     x = self.to_device(x)
@@ -302,6 +324,9 @@ class Engine(object):
 
   def launch_count(self):
     return int(self.lib.cg_launch_count(self.ctx))
+
+  def tc_launch_count(self):
+    return int(self.lib.cg_tc_launch_count(self.ctx))
 
   def device_bytes(self):
     return int(self.lib.cg_device_bytes(self.ctx))

@@ -139,6 +139,15 @@ int cg_debug_critic_forward(cg_ctx* ctx, const float* x_dev, int batch, const in
  * norms_dev (batch) fp32 | NULL. shifts_host[4]. */
 int cg_debug_gp(cg_ctx* ctx, const float* xhat_dev, int batch, const int32_t* shifts_host,
                 float* grad_dev, float* norms_dev);
+/* One conv layer in isolation, fp32 in / fp32 out (cast to the compute type inside), for kernel-level
+ * parity: which = CG_DISCRIMINATOR (Conv1D layer 1..5, calciumgan.py:145-185; forward includes bias +
+ * LeakyReLU) or CG_GENERATOR (Conv1DTranspose layer 1..5, models/utils.py:79-89; forward includes bias).
+ *   pass 0 forward : x (batch, Lin, Cin)            -> out (batch, Lout, Cout)
+ *   pass 1 dgrad   : dy (batch, Lout, Cout)         -> out (batch, Lin, Cin)
+ *   pass 2 wgrad   : x and dy                       -> out = kernel gradient in its Keras layout
+ * Critic layers accept batch <= 3*max_batch, generator layers batch <= max_batch. */
+int cg_debug_layer(cg_ctx* ctx, int which, int layer, int pass, const float* x_dev, const float* dy_dev,
+                   int batch, float* out_dev);
 /* PhaseShuffle alone (calciumgan.py:117-138) on a fp32 (batch, w, ch) device tensor, ch % 4 == 0;
  * bit-exact index arithmetic. cg_phase_shuffle_index fills host idx[w] with the source row of each
  * output row (no GPU needed). */
@@ -152,6 +161,8 @@ void* cg_scores_ptr(cg_ctx* ctx);
 void* cg_scalars_ptr(cg_ctx* ctx);
 /* number of kernels this library launched since creation (bench "gpu_launches") */
 int64_t cg_launch_count(cg_ctx* ctx);
+/* how many of those were tcgen05 tensor-core kernels */
+int64_t cg_tc_launch_count(cg_ctx* ctx);
 /* bytes of device memory owned by the context */
 int64_t cg_device_bytes(cg_ctx* ctx);
 /* microbenchmark hook: time `iters` launches of one conv layer kernel with CUDA events on the

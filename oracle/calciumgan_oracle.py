@@ -520,3 +520,120 @@ def synthetic_batch(hp: HParams, batch: int, seed: int = 1234, n_critic: Optiona
   alphas = rng.uniform(0.0, 1.0, size=(n_critic, batch)).astype(np.float32)
   shifts = rng.randint(-hp.m, hp.m + 1, size=(12 * n_critic + 4,)).astype(np.int32)
   return real, noises, alphas, shifts
+
+
+# ----------------------------------------------------------------------------- mixed-precision restatement
+# The reference's --mixed_precision runs Keras' mixed_float16 policy (main.py:22-30): variables stay fp32,
+# every layer computes in and emits the 16-bit compute dtype, the final activations are fp32
+# (calciumgan.py:98-101,190).  The B200 engine's policy is the bf16 analogue: fp32 master weights,
+# bf16 copies of the conv / per-timestep-dense kernels, fp32 accumulation, and every *stored* activation
+# or activation-gradient rounded to bf16 once (the storage points are listed at each R(...) below).
+# Because LeakyReLU's slope is discontinuous at 0, any 16-bit policy flips the slope of pre-activations
+# that round across 0, so its gradients differ from an fp32/fp64 evaluation by O(sqrt(ulp)), not O(ulp)
+# (measured: ~6e-2 for bf16, ~2e-2 for fp16 at random init).  The functions below restate the engine's
+# policy so the CUDA path can be checked at its own rounding points.
+
+def round_bf16(x):
+  return x.to(torch.float32).to(torch.bfloat16).to(x.dtype)
+
+
+class _RoundST(torch.autograd.Function):
+  """Round-to-bf16 on the way forward AND on the gradient coming back (storage rounding of both)."""
+
+  @staticmethod
+  def forward(ctx, x):
+    return round_bf16(x)
+
+  @staticmethod
+  def backward(ctx, g):
+    return _RoundST.apply(g)
+
+
+def _R(x):
+  return _RoundST.apply(x)
+
+
+def generator_forward_mixed(gw, noise, hp: HParams, R=None):
+  """generator_forward with the engine's bf16 storage points (dense0 / LN params / biases stay fp32)."""
+  _R = R if R is not None else _RoundST.apply
+  w, nd = calculate_noise_shape(hp.signal_shape, hp.noise_dim, NUM_LAYERS, hp.strides)
+  x = _R(leaky_relu(noise @ gw[0] + gw[1])).reshape(noise.shape[0], w, nd)
+  i = 2
+  for l in range(NUM_LAYERS):
+    x = _R(conv1d_transpose_same(x, _R(gw[i]), gw[i + 1], hp.strides))   # AG_l
+    i += 2
+    if hp.layer_norm:
+      x = layer_norm(x, gw[i], gw[i + 1])
+      i += 2
+    x = _R(leaky_relu(x))                                                # HG_l
+  x = x @ _R(gw[i]) + gw[i + 1]
+  return torch.sigmoid(x) if hp.normalize else x                        # fp32 output
+
+
+def discriminator_forward_mixed(dw, x, shifts, hp: HParams):
+  x = _R(x)                                                              # X_0
+  for l in range(NUM_LAYERS):
+    x = _R(leaky_relu(conv1d_same(x, _R(dw[2 * l]), dw[2 * l + 1], hp.strides)))   # H_l
+    if l < NUM_LAYERS - 1:
+      x = phase_shuffle(x, int(shifts[l]))
+  return x.reshape(x.shape[0], -1) @ dw[10] + dw[11]                     # fp32 head
+
+
+def generator_step_mixed(gw, dw, real, noise, shifts, hp: HParams, dtype=torch.float64):
+  """generator_step under the bf16 storage policy (autograd with straight-through rounding)."""
+  gw = [_t(a, dtype).clone().requires_grad_(True) for a in gw]
+  dw = [_t(a, dtype) for a in dw]
+  fake = generator_forward_mixed(gw, _t(noise, dtype), hp)
+  fake_out = discriminator_forward_mixed(dw, fake, shifts, hp)
+  loss = -fake_out.mean()
+  grads = torch.autograd.grad(loss, gw)
+  return {'gen_loss': float(loss.detach()), 'fake': fake.detach(), 'fake_out': fake_out.detach(),
+          'grads': [x.detach() for x in grads]}
+
+
+def critic_step_mixed(gw, dw, real, noise, alpha, shifts, hp: HParams, dtype=torch.float64, R=round_bf16):
+  """critic_step under the bf16 storage policy, written in the engine's own pass order
+  (concatenated [real; fake; xhat] batch, 4-pass gradient penalty, one weight-gradient pass)."""
+  gw = [_t(a, dtype) for a in gw]
+  dwm = [_t(a, dtype) for a in dw]
+  dwq = [R(w) if i < 10 and w.ndim > 1 else w for i, w in enumerate(dwm)]
+  real, noise, alpha = _t(real, dtype), _t(noise, dtype), _t(alpha, dtype).reshape(-1, 1, 1)
+  with torch.no_grad():
+    fake = generator_forward_mixed(gw, noise, hp, R)
+  B, K = real.shape[0], hp.kernel_size
+  sh = np.asarray(shifts).reshape(3, 4)
+  X, H = [R(torch.cat([real, fake, alpha * real + (1 - alpha) * fake]))], [None]
+
+  def per_group(fn, x, l):
+    return torch.cat([fn(x[g * B:(g + 1) * B], int(sh[g][l])) for g in range(3)])
+
+  for l in range(NUM_LAYERS):
+    h = R(leaky_relu(conv1d_same(X[l], dwq[2 * l], dwm[2 * l + 1])))
+    H.append(h)
+    X.append(per_group(phase_shuffle, h, l) if l < NUM_LAYERS - 1 else h)
+  scores = X[5].reshape(3 * B, -1) @ dwm[10] + dwm[11]
+  coef = torch.cat([torch.full((B,), -1.0 / B, dtype=dtype), torch.full((B,), 1.0 / B, dtype=dtype),
+                    torch.ones(B, dtype=dtype)]).reshape(-1, 1, 1)
+  slope = lambda h: torch.where(h > 0, torch.ones_like(h), torch.full_like(h, LEAKY_ALPHA))
+  DA = [None] * (NUM_LAYERS + 1)
+  DA[5] = R(slope(H[5]) * coef * dwm[10].reshape(1, H[5].shape[1], H[5].shape[2]))
+  for l in range(NUM_LAYERS, 1, -1):
+    dx = R(conv1d_same_dgrad(DA[l], dwq[2 * (l - 1)], X[l - 1].shape[1]))
+    DA[l - 1] = R(slope(H[l - 1]) * per_group(_ps_transpose, dx, l - 2))
+  g = R(conv1d_same_dgrad(DA[1][2 * B:], dwq[0], real.shape[1]))
+  n = torch.sqrt((g.reshape(B, -1)**2).sum(1))
+  gp = ((n - 1.0)**2).mean()
+  V = [R(hp.gradient_penalty * (2.0 / B) * ((n - 1.0) / n).reshape(B, 1, 1) * g)]
+  for l in range(NUM_LAYERS):
+    c = R(slope(H[l + 1][2 * B:]) * conv1d_same(V[l], dwq[2 * l], None))
+    V.append(phase_shuffle(c, int(sh[2][l])) if l < NUM_LAYERS - 1 else c)
+  grads = []
+  for l in range(NUM_LAYERS):
+    grads.append(conv1d_same_wgrad(torch.cat([X[l][:2 * B], V[l]]), DA[l + 1], K))
+    grads.append(DA[l + 1][:2 * B].sum((0, 1)))
+  grads.append((coef * torch.cat([X[5][:2 * B], V[5]])).sum(0).reshape(-1, 1))
+  grads.append(torch.zeros(1, dtype=dtype))
+  real_loss, fake_loss = -scores[:B].mean(), scores[B:2 * B].mean()
+  return {'dis_loss': float(real_loss + fake_loss + hp.gradient_penalty * gp), 'gradient_penalty': float(gp),
+          'fake': fake, 'real_out': scores[:B], 'fake_out': scores[B:2 * B], 'gp_grad': g, 'gp_norm': n,
+          'grads': grads}
