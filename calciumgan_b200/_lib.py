@@ -66,6 +66,8 @@ SIGNATURES = {
     'cg_launch_count': (_I64, [_P]),
     'cg_tc_launch_count': (_I64, [_P]),
     'cg_device_bytes': (_I64, [_P]),
+    'cg_profile': (_I, [_P, _I]),
+    'cg_profile_report': (_I, [_P, C.POINTER(C.c_double)]),
     'cg_bench_layer': (_I, [_P, _I, _I, _I, _I, _I, _F, C.POINTER(C.c_double)]),
 }
 

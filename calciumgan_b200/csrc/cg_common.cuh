@@ -91,7 +91,7 @@ struct RsParams {
   float* out32; long long o32_bs; int o32_rs;      // optional unpadded fp32 copy (n < n_real)
   const float* bias;                               // fp32, n_real entries
   const void* mask;                                // EPI_MASK: same indexing as out
-  int B, Q, N, n_real, Kc, epi;
+  int B, Q, N, n_real, Kc, k_real, epi;   // k_real: unpadded channels per tap (algorithmic FLOPs only)
   SegTable seg;
 };
 

@@ -88,6 +88,9 @@ struct cg_ctx {
   cudaStream_t stream = 0;
   int64_t launches = 0;
   int64_t tc_launches = 0;
+  bool profiling = false;
+  struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; };
+  std::vector<ProfRec> prof;
   int64_t dev_bytes = 0;
   std::vector<void*> allocs;
 
@@ -185,7 +188,23 @@ static int post_launch(cg_ctx* c, const char* what) {
   return 0;
 }
 
-static int launch_rsgemm(cg_ctx* c, const RsParams& p) {
+static int prof_begin(cg_ctx* c, int cls, double flops) {
+  if (!c->profiling) return 0;
+  cg_ctx::ProfRec r;
+  r.cls = cls; r.flops = flops;
+  CU(cudaEventCreate(&r.e0));
+  CU(cudaEventCreate(&r.e1));
+  CU(cudaEventRecord(r.e0, c->stream));
+  c->prof.push_back(r);
+  return 0;
+}
+static int prof_end(cg_ctx* c) {
+  if (!c->profiling) return 0;
+  CU(cudaEventRecord(c->prof.back().e1, c->stream));
+  return 0;
+}
+
+static int launch_rsgemm_raw(cg_ctx* c, const RsParams& p) {
   if (c->use_tc && tc_rsgemm_supported(p)) {
     CK(tc_rsgemm_launch(&c->tc, p, c->stream));
     c->tc_launches++;
@@ -196,8 +215,21 @@ static int launch_rsgemm(cg_ctx* c, const RsParams& p) {
   DISPATCH_T(c, rsgemm_simt_kernel<T><<<grid, 256, 0, c->stream>>>(p));
   return post_launch(c, "rsgemm_simt");
 }
+static int launch_rsgemm(cg_ctx* c, const RsParams& p) {
+  int nseg = 0;
+  for (int i = 0; i < p.seg.nphase; ++i) nseg += p.seg.nseg[i];
+  CK(prof_begin(c, 0, 2.0 * p.B * p.Q * (double)p.n_real * p.k_real * nseg));
+  CK(launch_rsgemm_raw(c, p));
+  return prof_end(c);
+}
 
-static int launch_wgrad(cg_ctx* c, WgParams p) {
+static int launch_wgrad_raw(cg_ctx* c, WgParams p);
+static int launch_wgrad(cg_ctx* c, const WgParams& p) {
+  CK(prof_begin(c, 1, 2.0 * p.B * p.Q * (double)p.m_real * p.n_real * p.nseg));
+  CK(launch_wgrad_raw(c, p));
+  return prof_end(c);
+}
+static int launch_wgrad_raw(cg_ctx* c, WgParams p) {
   if (c->use_tc && tc_wgrad_supported(p)) {
     CK(tc_wgrad_launch(&c->tc, p, c->stream));
     c->tc_launches++;
@@ -474,7 +506,7 @@ static RsParams convT_fwd_params(cg_ctx* c, int i, int B) {
   p.W = c->Wf_g[i]; p.w_ld = c->K * c->gcp[i - 1];
   p.out = c->AG[i]; p.o_bs = (long long)c->gl[i] * c->gcp[i]; p.o_rs = 2 * c->gcp[i]; p.o_phase_col = c->gcp[i];
   p.bias = gparam(c, c->g_b[i]);
-  p.B = B; p.Q = c->gl[i - 1]; p.N = c->gcp[i]; p.n_real = c->gc[i]; p.Kc = c->gcp[i - 1];
+  p.B = B; p.Q = c->gl[i - 1]; p.N = c->gcp[i]; p.n_real = c->gc[i]; p.Kc = c->gcp[i - 1]; p.k_real = c->gc[i - 1];
   p.epi = EPI_BIAS;
   p.seg = seg_transposed(c->K, c->gcp[i - 1]);
   return p;
@@ -486,7 +518,7 @@ static RsParams convT_bwd_params(cg_ctx* c, int i, int B) {
   p.A = c->DAG[i]; p.a_bs = (long long)c->gl[i] * c->gcp[i]; p.a_rs = 2 * c->gcp[i]; p.a_rows = c->gl[i] / 2;
   p.W = c->Wb_g[i]; p.w_ld = c->K * c->gcp[i];
   p.out = c->DHG[i - 1]; p.o_bs = (long long)c->gl[i - 1] * c->gcp[i - 1]; p.o_rs = c->gcp[i - 1];
-  p.B = B; p.Q = c->gl[i - 1]; p.N = c->gcp[i - 1]; p.n_real = c->gc[i - 1]; p.Kc = c->gcp[i]; p.epi = EPI_NONE;
+  p.B = B; p.Q = c->gl[i - 1]; p.N = c->gcp[i - 1]; p.n_real = c->gc[i - 1]; p.Kc = c->gcp[i]; p.k_real = c->gc[i]; p.epi = EPI_NONE;
   p.seg = seg_strided(c->K, c->gcp[i]);
   return p;
 }
@@ -531,7 +563,7 @@ static int g_forward(cg_ctx* c, const float* noise, int B) {
   p.out32 = c->FAKE32; p.o32_bs = (long long)c->L * c->C; p.o32_rs = c->C;
   p.o_bs = (long long)c->L * Cp; p.o_rs = Cp;
   p.bias = gparam(c, c->g_d1b);
-  p.B = B; p.Q = c->L; p.N = Cp; p.n_real = c->C; p.Kc = Cp;
+  p.B = B; p.Q = c->L; p.N = Cp; p.n_real = c->C; p.Kc = Cp; p.k_real = c->C;
   p.epi = c->cfg.normalize ? EPI_BIAS_SIGMOID : EPI_BIAS;
   p.seg = seg_dense();
   CK(launch_rsgemm(c, p));
@@ -567,7 +599,7 @@ static int g_backward(cg_ctx* c, int B) {
     p.A = c->DO; p.a_bs = (long long)c->L * Cp; p.a_rs = Cp; p.a_rows = c->L;
     p.W = c->Wb_d1; p.w_ld = Cp;
     p.out = c->DHG[NL]; p.o_bs = (long long)c->L * Cp; p.o_rs = Cp;
-    p.B = B; p.Q = c->L; p.N = Cp; p.n_real = c->C; p.Kc = Cp; p.epi = EPI_NONE;
+    p.B = B; p.Q = c->L; p.N = Cp; p.n_real = c->C; p.Kc = Cp; p.k_real = c->C; p.epi = EPI_NONE;
     p.seg = seg_dense();
     CK(launch_rsgemm(c, p));
   }
@@ -614,7 +646,7 @@ static RsParams conv_fwd_params(cg_ctx* c, int l, const void* A, void* out, int 
   p.out = out; p.o_bs = (long long)c->dl[l] * c->dcp[l]; p.o_rs = c->dcp[l];
   p.bias = dparam(c, 2 * (l - 1) + 1);
   p.mask = mask;
-  p.B = Bt; p.Q = c->dl[l]; p.N = c->dcp[l]; p.n_real = c->dc[l]; p.Kc = c->dcp[l - 1]; p.epi = epi;
+  p.B = Bt; p.Q = c->dl[l]; p.N = c->dcp[l]; p.n_real = c->dc[l]; p.Kc = c->dcp[l - 1]; p.k_real = c->dc[l - 1]; p.epi = epi;
   p.seg = seg_strided(c->K, c->dcp[l - 1]);
   return p;
 }
@@ -643,7 +675,7 @@ static int d_dgrad_layer(cg_ctx* c, int l, int b0, int nb, void* out) {
   p.a_bs = (long long)c->dl[l] * c->dcp[l]; p.a_rs = c->dcp[l]; p.a_rows = c->dl[l];
   p.W = c->Wb_d[l]; p.w_ld = c->K * c->dcp[l];
   p.out = out; p.o_bs = (long long)c->dl[l - 1] * c->dcp[l - 1]; p.o_rs = 2 * c->dcp[l - 1]; p.o_phase_col = c->dcp[l - 1];
-  p.B = nb; p.Q = c->dl[l]; p.N = c->dcp[l - 1]; p.n_real = c->dc[l - 1]; p.Kc = c->dcp[l]; p.epi = EPI_NONE;
+  p.B = nb; p.Q = c->dl[l]; p.N = c->dcp[l - 1]; p.n_real = c->dc[l - 1]; p.Kc = c->dcp[l]; p.k_real = c->dc[l]; p.epi = EPI_NONE;
   p.seg = seg_transposed(c->K, c->dcp[l]);
   return launch_rsgemm(c, p);
 }
@@ -1018,6 +1050,26 @@ extern "C" int cg_debug_phase_shuffle(cg_ctx* c, const float* x, int B, int w, i
   ps_gather_kernel<float><<<grid_for((long long)B * w * ch / 4), 256, 0, c->stream>>>(x, out, B, B, w, ch, g);
   CK(post_launch(c, "ps_gather_debug"));
   CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int cg_profile(cg_ctx* c, int enable) {
+  c->profiling = enable != 0;
+  return 0;
+}
+extern "C" int cg_profile_report(cg_ctx* c, double out[8]) {
+  CU(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 8; ++i) out[i] = 0;
+  for (auto& r : c->prof) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    out[r.cls * 3 + 0] += ms;
+    out[r.cls * 3 + 1] += r.flops;
+    out[r.cls * 3 + 2] += 1;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  c->prof.clear();
   return 0;
 }
 

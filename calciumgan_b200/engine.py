@@ -334,6 +334,15 @@ class Engine(object):
   def synchronize(self):
     L.check(self.lib.cg_synchronize(self.ctx))
 
+  def profile(self, enable):
+    L.check(self.lib.cg_profile(self.ctx, int(bool(enable))))
+
+  def profile_report(self):
+    out = (C.c_double * 8)()
+    L.check(self.lib.cg_profile_report(self.ctx, out))
+    return {'gemm': {'ms': out[0], 'flops': out[1], 'launches': int(out[2])},
+            'wgrad': {'ms': out[3], 'flops': out[4], 'launches': int(out[5])}}
+
   def bench_layer(self, which, layer, pass_, batch, iters=10):
     self._use_stream()
     ms, fl = C.c_float(), C.c_double()
