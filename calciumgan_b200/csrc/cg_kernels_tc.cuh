@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <tuple>
@@ -137,6 +138,7 @@ constexpr int kAccStride = 256;             // columns between the two accumulat
 struct RsTcParams {
   RsParams p;
   int BN, n_tiles, m_tiles, rpt, bpt, tiles_per_sample, kchunks, stages;
+  int a_bytes, x_shift, x_baseoff;   // experiment: A box loaded x_shift rows early, descriptor advanced by x_shift rows
 };
 
 // =============================================================================================
@@ -150,7 +152,7 @@ rsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const RsParams& p = P.p;
   const int BN = P.BN;
   const int stages = P.stages;
-  const int stage_bytes = kABytes + BN * 128;
+  const int stage_bytes = P.a_bytes + BN * 128;
   uint8_t* tiles = smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
   uint64_t* empty = full + stages;
@@ -197,8 +199,8 @@ rsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&empty[stage], ph ^ 1);
             uint8_t* sa = tiles + (size_t)stage * stage_bytes;
             mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-            tma_load_3d(sa, &tmA, &full[stage], acol + kc * 64, row, b0);
-            tma_load_2d(sa + kABytes, &tmW, &full[stage], wk + kc * 64, nt * BN);
+            tma_load_3d(sa, &tmA, &full[stage], acol + kc * 64, row - P.x_shift, b0);
+            tma_load_2d(sa + P.a_bytes, &tmW, &full[stage], wk + kc * 64, nt * BN);
             if (++stage == stages) { stage = 0; ph ^= 1; }
           }
         }
@@ -221,8 +223,10 @@ rsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&full[stage], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(tiles + (size_t)stage * stage_bytes);
-          const uint64_t adesc = make_desc(sa, 16, 1024);
-          const uint64_t bdesc = make_desc(sa + kABytes, 16, 1024);
+          const uint32_t sa_shift = sa + P.x_shift * 128;
+          uint64_t adesc = make_desc(sa_shift, 16, 1024);
+          if (P.x_baseoff) adesc |= (uint64_t)((sa_shift >> 7) & 7) << 49;
+          const uint64_t bdesc = make_desc(sa + P.a_bytes, 16, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k)   // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle row
             umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (ki | k) != 0);
@@ -559,14 +563,20 @@ static inline int tc_rsgemm_launch(TcState* s, const RsParams& p, cudaStream_t s
   if (p.Q >= 128) { P.rpt = 128; P.bpt = 1; P.tiles_per_sample = p.Q / 128; P.m_tiles = p.B * P.tiles_per_sample; }
   else { P.rpt = p.Q; P.bpt = 128 / p.Q; P.tiles_per_sample = 0; P.m_tiles = (p.B + P.bpt - 1) / P.bpt; }
   P.kchunks = p.Kc / 64;
-  const int stage_bytes = tc::kABytes + P.BN * 128;
+  P.x_shift = 0; P.x_baseoff = 0;
+  if (const char* e = getenv("CG_TC_XSHIFT")) P.x_shift = atoi(e);
+  if (const char* e = getenv("CG_TC_XBASEOFF")) P.x_baseoff = atoi(e);
+  if (P.rpt != 128) P.x_shift = 0;
+  const int a_rows_box = P.x_shift ? 128 + ((P.x_shift + 7) / 8) * 8 : P.rpt;
+  P.a_bytes = P.x_shift ? a_rows_box * 128 : tc::kABytes;
+  const int stage_bytes = P.a_bytes + P.BN * 128;
   int stages = (s->max_smem - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return cg_tc_set_err("rsgemm_tc: not enough shared memory for 2 stages");
   P.stages = stages;
   CUtensorMap tmA, tmW;
   // A viewed as (B, a_rows, a_rs): column extent = a_rs (the strided view covers both parities)
-  if (tc_get_map3(s, p.A, p.a_rs, p.a_rows, p.B, p.a_rs, p.a_bs, P.rpt, P.bpt, &tmA)) return 1;
+  if (tc_get_map3(s, p.A, p.a_rs, p.a_rows, p.B, p.a_rs, p.a_bs, a_rows_box, P.bpt, &tmA)) return 1;
   if (tc_get_map2(s, p.W, p.w_ld, p.N, p.w_ld, P.BN, &tmW)) return 1;
   const int total = p.seg.nphase * P.n_tiles * P.m_tiles;
   const int grid = total < s->sm_count ? total : s->sm_count;
