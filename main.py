@@ -1,0 +1,151 @@
+"""Training driver with the reference's command line (main.py:227-267 of bryanlimy/CalciumGAN).
+
+Same flags and defaults; the epoch loop calls `gan.train(signal)` exactly like main.py:33-75 and
+checkpoints with the reference's pickle layout. The input pipeline / TensorBoard / spike analysis of
+the reference are out of scope: signals come from `<input_dir>/signals.npy`
+(float32 (N, seq, neurons), already normalised to [0, 1]) or, with --synthetic, from a seeded
+uniform generator of shape (N, 2048, 102).
+"""
+import argparse
+import os
+import sys
+from shutil import rmtree
+from time import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+
+def get_dataset(hparams):
+  """Sets the hparams fields the models read (dataset_helper.py:84-91,120-136,186)."""
+  path = os.path.join(hparams.input_dir, 'signals.npy')
+  if hparams.synthetic or not os.path.exists(path):
+    rng = np.random.RandomState(1234)
+    signals = rng.uniform(0, 1, size=(hparams.synthetic_size, 2048, 102)).astype(np.float32)
+  else:
+    signals = np.load(path).astype(np.float32)
+  n_train = int(len(signals) * 0.9) if len(signals) >= 10 else len(signals)
+  train, val = signals[:n_train], signals[n_train:] if n_train < len(signals) else signals[:1]
+  hparams.train_size, hparams.validation_size = len(train), len(val)
+  hparams.signal_shape = tuple(train.shape[1:])
+  hparams.sequence_length, hparams.num_neurons = train.shape[1], train.shape[-1]
+  hparams.num_channels = train.shape[-1]
+  hparams.normalize, hparams.fft, hparams.conv2d = True, False, False
+  hparams.signals_min, hparams.signals_max = 0.0, 1.0
+  hparams.noise_shape = (hparams.noise_dim,)
+  hparams.train_steps = int(np.ceil(len(train) / hparams.batch_size))
+  hparams.validation_steps = int(np.ceil(len(val) / hparams.batch_size))
+
+  def batches(x, shuffle):
+    idx = np.random.permutation(len(x)) if shuffle else np.arange(len(x))
+    for i in range(0, len(x), hparams.batch_size):    # no drop_remainder (dataset_helper.py:173)
+      yield x[idx[i:i + hparams.batch_size]], None
+
+  return (lambda: batches(train, True)), (lambda: batches(val, False))
+
+
+def train(hparams, train_ds, gan, epoch):
+  gen_losses, dis_losses, gradient_penalties = [], [], []
+  start = time()
+  for signal, _ in train_ds():
+    gen_loss, dis_loss, gradient_penalty, metrics = gan.train(signal)
+    gen_losses.append(gen_loss)
+    dis_losses.append(dis_loss)
+    if gradient_penalty is not None:
+      gradient_penalties.append(gradient_penalty)
+    hparams.global_step += 1
+  end = time()
+  gen_loss, dis_loss = np.mean(gen_losses), np.mean(dis_losses)
+  if hparams.verbose:
+    print('Train epoch {:03d}: generator {:.4f} discriminator {:.4f} gradient_penalty {:.4f} elapse {:.2f}s'.format(
+        epoch, gen_loss, dis_loss, np.mean(gradient_penalties), end - start))
+  return gen_loss, dis_loss
+
+
+def validate(hparams, validation_ds, gan, epoch):
+  gen_losses, dis_losses, gradient_penalties, results = [], [], [], {}
+  for signal, _ in validation_ds():
+    fake, gen_loss, dis_loss, gradient_penalty, metrics = gan.validate(signal)
+    gen_losses.append(gen_loss)
+    dis_losses.append(dis_loss)
+    gradient_penalties.append(gradient_penalty)
+    for k, v in metrics.items():
+      results.setdefault(k, []).append(v)
+  if hparams.verbose:
+    print('Validation epoch {:03d}: generator {:.4f} discriminator {:.4f} gradient_penalty {:.4f} '.format(
+        epoch, np.mean(gen_losses), np.mean(dis_losses), np.mean(gradient_penalties)) +
+          ' '.join('{} {:.5f}'.format(k.split('/')[-1], np.mean(v)) for k, v in results.items()))
+  return {key: np.mean(item) for key, item in results.items()}
+
+
+def main(hparams, return_metrics=False):
+  from calciumgan_b200.algorithms.registry import get_algorithm
+  from calciumgan_b200.models.registry import get_models
+  from calciumgan_b200.utils import utils
+
+  if hparams.clear_output_dir and os.path.exists(hparams.output_dir):
+    rmtree(hparams.output_dir)
+  os.makedirs(hparams.output_dir, exist_ok=True)
+  np.random.seed(1234)
+
+  train_ds, validation_ds = get_dataset(hparams)
+  generator, discriminator = get_models(hparams, None)
+  gan = get_algorithm(hparams, generator, discriminator, None)
+  utils.load_models(hparams, gan)
+
+  start = time()
+  results = {}
+  for epoch in range(hparams.start_epoch, hparams.epochs):
+    train(hparams, train_ds, gan, epoch)
+    results = validate(hparams, validation_ds, gan, epoch)
+    if not hparams.skip_checkpoints and (epoch % 10 == 0 or epoch == hparams.epochs - 1):
+      utils.save_models(hparams, gan, epoch)
+  if hparams.verbose:
+    print('elapse/total {:.2f}s'.format(time() - start))
+  if return_metrics:
+    return results
+
+
+def build_parser():
+  parser = argparse.ArgumentParser()
+  parser.add_argument('--input_dir', default='dataset/tfrecords')
+  parser.add_argument('--output_dir', default='runs')
+  parser.add_argument('--batch_size', default=64, type=int)
+  parser.add_argument('--num_units', default=32, type=int)
+  parser.add_argument('--kernel_size', default=24, type=int)
+  parser.add_argument('--strides', default=2, type=int)
+  parser.add_argument('--m', default=2, type=int, help='phase shuffle m')
+  parser.add_argument('--n', default=2, type=int, help='phase shuffle n')
+  parser.add_argument('--epochs', default=20, type=int)
+  parser.add_argument('--dropout', default=0.2, type=float)
+  parser.add_argument('--learning_rate', default=0.0001, type=float)
+  parser.add_argument('--noise_dim', default=32, type=int)
+  parser.add_argument('--gradient_penalty', default=10.0, type=float)
+  parser.add_argument('--model', default='wavegan', type=str)
+  parser.add_argument('--activation', default='leakyrelu', type=str)
+  parser.add_argument('--batch_norm', action='store_true')
+  parser.add_argument('--layer_norm', action='store_true')
+  parser.add_argument('--algorithm', default='wgan-gp', type=str)
+  parser.add_argument('--n_critic', default=5, type=int, help='number of steps between each generator update')
+  parser.add_argument('--clear_output_dir', action='store_true')
+  parser.add_argument('--save_generated', default="", choices=["", "last", "all"], type=str)
+  parser.add_argument('--plot_weights', action='store_true')
+  parser.add_argument('--skip_checkpoints', action='store_true')
+  parser.add_argument('--mixed_precision', action='store_true')
+  parser.add_argument('--profile', action='store_true', help='enable profiling (use ncu; see profiles/)')
+  parser.add_argument('--dpi', default=120, type=int)
+  parser.add_argument('--verbose', default=1, type=int)
+  # additions (not in the reference): data source when no TFRecord pipeline is available
+  parser.add_argument('--synthetic', action='store_true', help='uniform [0,1) signals of shape (N, 2048, 102)')
+  parser.add_argument('--synthetic_size', default=512, type=int)
+  return parser
+
+
+if __name__ == '__main__':
+  params = build_parser().parse_args()
+  params.global_step = 0
+  params.surrogate_ds = True if 'surrogate' in params.input_dir else False
+  main(params)
