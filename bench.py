@@ -228,12 +228,13 @@ def main():
   # ---- live roofline of the dominant kernel (tcgen05 implicit-GEMM conv), CUDA events on its stream
   peaks, peak_kind = measured_peaks()
   roof, kernels = None, None
+  eng.profile(True)          # every rank runs these steps (they contain the DP all-reduces)
+  for _ in range(2):
+    step_resident()
+  rep = eng.profile_report()
+  eng.profile(False)
+  barrier()
   if rank == 0:
-    eng.profile(True)
-    for _ in range(2):
-      step_resident()
-    rep = eng.profile_report()
-    eng.profile(False)
     g, w = rep['gemm'], rep['wgrad']
     peak_tf = float(peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']))
     ach = g['flops'] / (g['ms'] * 1e-3) / 1e12 if g['ms'] > 0 else 0.0

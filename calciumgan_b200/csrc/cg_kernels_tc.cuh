@@ -10,7 +10,9 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <string>
 #include <tuple>
@@ -89,6 +91,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// descriptor passed as 32-bit halves (lo = start address | LBO field, hi = SBO | version | swizzle): the issue
+// loop only ever adds to `lo`, which keeps the per-MMA instruction count minimal
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                               uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n .reg .pred p;\n .reg .b64 da, db;\n setp.ne.b32 p, %5, 0;\n mov.b64 da, {%1, %3};\n mov.b64 db, {%2, %3};\n"
+      " tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// one elected lane of a fully converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);   // version 1 (bit 46), SWIZZLE_128B (bits 61-63)
+}
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -135,15 +159,140 @@ constexpr int kABytes = 128 * 128;          // 128 rows x 64 bf16
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;             // columns between the two accumulator buffers
 
+// ---- epilogue -----------------------------------------------------------------------------------------
+constexpr int kStgBytes = 4096;   // per-warp staging: 32 rows x 64 bf16, 16-byte chunks XOR-swizzled by (row & 7)
+constexpr int kEpiSmem = 4 * kStgBytes + 1024;   // + bias tile (256 floats)
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // 4 epilogue warps
+
+// Per tile, each lane precomputes the element offsets of the 8 rows it stores in the coalesced phase
+// (row rr = 4*i + lane/8 of this warp's 32 rows); negative = masked. rpt < 128 is a power of two.
+struct EpiRows { long long off[8]; long long my_off; long long my_o32; bool my_ok; };
+__device__ __forceinline__ void epi_rows(const RsParams& p, int b0, int q0, int rpt_log2, int phase, int lq, int lane,
+                                         EpiRows& R) {
+  const int crow = lane >> 3;
+#pragma unroll
+  for (int i = 0; i <= 8; ++i) {
+    const int r = lq * 32 + (i < 8 ? i * 4 + crow : lane);
+    int b, q;
+    if (rpt_log2 >= 7) { b = b0; q = q0 + r; } else { b = b0 + (r >> rpt_log2); q = r & ((1 << rpt_log2) - 1); }
+    const long long o = b < p.B ? (long long)b * p.o_bs + (long long)q * p.o_rs + phase * p.o_phase_col : -1;
+    if (i < 8) R.off[i] = o;
+    else { R.my_off = o; R.my_ok = b < p.B; R.my_o32 = (long long)b * p.o32_bs + (long long)q * p.o32_rs; }
+  }
+}
+
+// One 128-row x BN-column accumulator block: TMEM -> registers (thread = row) -> bias / LeakyReLU / sigmoid /
+// slope mask in fp32 -> bf16 -> swizzled smem transpose -> global stores where every warp instruction writes
+// four full 128-byte row segments. EPI is a compile-time mode: the first version of this epilogue spent ~10k clk
+// per 128x64 block on per-element mode checks, integer divisions and 64-bit address math (profiles/).
+// Padded columns come out as exact zeros because padded weight rows and the staged bias are zero.
+template <int EPI>
+__device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_cols, int BN, int n_base,
+                                               const EpiRows& R, const float* bias_s, uint8_t* stg, int lq, int lane) {
+  bf16* out = reinterpret_cast<bf16*>(p.out);
+  const bf16* mask = reinterpret_cast<const bf16*>(p.mask);
+  const int cj = lane & 7;
+  for (int c0 = 0; c0 < BN; c0 += 64) {
+    const int ncols = BN - c0 < 64 ? BN - c0 : 64;   // 64 or 32 (BN % 32 == 0)
+    uint32_t v[64];
+    {
+      uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+      uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+      tmem_ld32(tmem_cols + ((uint32_t)(lq * 32) << 16) + c0, v0);
+      if (ncols > 32) tmem_ld32(tmem_cols + ((uint32_t)(lq * 32) << 16) + c0 + 32, v1);
+      tmem_ld_wait();
+    }
+    const int n0 = n_base + c0;
+    const bool col_ok = cj * 8 < ncols;
+    if (EPI == EPI_MASK) {   // coalesced read of the slope source (same indexing as out), transposed through smem
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3);
+        uint4 mv = make_uint4(0, 0, 0, 0);
+        if (R.off[i] >= 0 && col_ok) mv = *reinterpret_cast<const uint4*>(mask + R.off[i] + n0 + cj * 8);
+        *reinterpret_cast<uint4*>(stg + rr * 128 + ((cj ^ (rr & 7)) << 4)) = mv;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 mv = *reinterpret_cast<const uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4));
+        const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+        for (int w2 = 0; w2 < 4; ++w2) {
+          const __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(&mw[w2]);
+          v[j * 8 + w2 * 2] = __float_as_uint(__uint_as_float(v[j * 8 + w2 * 2]) * lrelu_slope(__low2float(hv)));
+          v[j * 8 + w2 * 2 + 1] = __float_as_uint(__uint_as_float(v[j * 8 + w2 * 2 + 1]) * lrelu_slope(__high2float(hv)));
+        }
+      }
+      __syncwarp();
+    }
+    if (EPI == EPI_BIAS || EPI == EPI_BIAS_LRELU || EPI == EPI_BIAS_SIGMOID) {
+#pragma unroll
+      for (int j4 = 0; j4 < 16; ++j4) {
+        const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + j4 * 4);   // smem broadcast
+        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float x = __uint_as_float(v[j4 * 4 + e]) + bv[e];
+          if (EPI == EPI_BIAS_LRELU) x = lrelu(x);
+          if (EPI == EPI_BIAS_SIGMOID) x = __fdividef(1.f, 1.f + __expf(-x));
+          v[j4 * 4 + e] = __float_as_uint(x);
+        }
+      }
+    }
+    if (p.out32 && R.my_ok) {   // unpadded fp32 copy (generator head only)
+      float* o32 = p.out32 + R.my_o32;
+#pragma unroll
+      for (int j = 0; j < 64; ++j)
+        if (j < ncols && n0 + j < p.n_real) o32[n0 + j] = __uint_as_float(v[j]);
+    }
+    if (out) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
+        o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
+        o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
+        o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
+        *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3);
+        const uint4 o = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((cj ^ (rr & 7)) << 4));
+        if (R.off[i] >= 0 && col_ok) *reinterpret_cast<uint4*>(out + R.off[i] + n0 + cj * 8) = o;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// stage bias[n_base .. n_base+BN) (zero beyond n_real) into smem for the 4 epilogue warps
+template <int EPI>
+__device__ __forceinline__ void epi_load_bias(const RsParams& p, float* bias_s, int n_base, int BN, int tid128) {
+  if (EPI == EPI_BIAS || EPI == EPI_BIAS_LRELU || EPI == EPI_BIAS_SIGMOID) {
+    epi_bar();   // previous tile's readers are done
+    for (int i = tid128; i < 256; i += 128) {
+      const int n = n_base + i;
+      bias_s[i] = (i < BN && n < p.n_real) ? __ldg(&p.bias[n]) : 0.f;
+    }
+    epi_bar();
+  }
+}
+
 struct RsTcParams {
   RsParams p;
   int BN, n_tiles, m_tiles, rpt, bpt, tiles_per_sample, kchunks, stages;
-  int a_bytes, x_shift, x_baseoff;   // experiment: A box loaded x_shift rows early, descriptor advanced by x_shift rows
+  int a_bytes, x_shift, x_baseoff;   // x_baseoff: timing-experiment bits (1 no stores, 2 no W loads, 4 no A loads)
+  long long* dbg;                    // optional per-role cycle counters of CTA 0 (CG_TC_TIMING=1)
 };
 
 // =============================================================================================
 // rsgemm_tc
 // =============================================================================================
+template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 rsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ RsTcParams P) {
@@ -159,6 +308,8 @@ rsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull = empty + stages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* stage_buf = smem + (size_t)stages * stage_bytes + 512;   // 4 x kStgBytes epilogue staging + bias tile
+  float* bias_s = reinterpret_cast<float*>(stage_buf + 4 * kStgBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -179,134 +330,285 @@ rsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int total_tiles = p.seg.nphase * P.n_tiles * P.m_tiles;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int mt = t % P.m_tiles;
-        const int rest = t / P.m_tiles;
-        const int nt = rest % P.n_tiles;
-        const int phase = rest / P.n_tiles;
-        int b0, q0;
-        if (P.tiles_per_sample > 0) { b0 = mt / P.tiles_per_sample; q0 = (mt % P.tiles_per_sample) * 128; }
-        else { b0 = mt * P.bpt; q0 = 0; }
-        const int nseg = p.seg.nseg[phase];
-        for (int s = 0; s < nseg; ++s) {
-          const int row = q0 + p.seg.shift[phase][s];
-          const int acol = p.seg.acol[phase][s];
-          const int wk = p.seg.wk[phase][s];
-          for (int kc = 0; kc < P.kchunks; ++kc) {
-            mbar_wait(&empty[stage], ph ^ 1);
+    int stage = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int mt = t % P.m_tiles;
+      const int rest = t / P.m_tiles;
+      const int nt = rest % P.n_tiles;
+      const int phase = rest / P.n_tiles;
+      int b0, q0;
+      if (P.tiles_per_sample > 0) { b0 = mt / P.tiles_per_sample; q0 = (mt % P.tiles_per_sample) * 128; }
+      else { b0 = mt * P.bpt; q0 = 0; }
+      const int nseg = p.seg.nseg[phase];
+      for (int s = 0; s < nseg; ++s) {
+        const int row = q0 + p.seg.shift[phase][s];
+        const int acol = p.seg.acol[phase][s];
+        const int wk = p.seg.wk[phase][s];
+        for (int kc = 0; kc < P.kchunks; ++kc) {
+          const long long tw0 = clock64();
+          mbar_wait(&empty[stage], ph ^ 1);
+          if (P.dbg && blockIdx.x == 0 && lane == 0) { atomicAdd((unsigned long long*)&P.dbg[0], (unsigned long long)(clock64() - tw0)); atomicAdd((unsigned long long*)&P.dbg[1], 1ull); }
+          if (elect_one()) {
             uint8_t* sa = tiles + (size_t)stage * stage_bytes;
-            mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-            tma_load_3d(sa, &tmA, &full[stage], acol + kc * 64, row - P.x_shift, b0);
-            tma_load_2d(sa + P.a_bytes, &tmW, &full[stage], wk + kc * 64, nt * BN);
-            if (++stage == stages) { stage = 0; ph ^= 1; }
+            const uint32_t tx = ((P.x_baseoff & 4) ? 0u : (uint32_t)P.a_bytes) + ((P.x_baseoff & 2) ? 0u : (uint32_t)(BN * 128));
+            if (tx) mbar_expect_tx(&full[stage], tx); else mbar_arrive(&full[stage]);
+            if (!(P.x_baseoff & 4)) tma_load_3d(sa, &tmA, &full[stage], acol + kc * 64, row, b0);
+            if (!(P.x_baseoff & 2)) tma_load_2d(sa + P.a_bytes, &tmW, &full[stage], wk + kc * 64, nt * BN);
           }
+          if (++stage == stages) { stage = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, BN, 0, 0);
-      int stage = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        const int phase = (t / P.m_tiles) / P.n_tiles;
-        const int acc = it & 1;
-        mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1) ^ 1);
+    const uint32_t idesc = make_idesc(128, BN, 0, 0);
+    const uint32_t hi = desc_hi(1024);
+    const uint32_t lo0 = desc_lo(smem_u32(tiles), 16);
+    const uint32_t stage_step = (uint32_t)stage_bytes >> 4, b_off = (uint32_t)P.a_bytes >> 4;
+    int stage = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int phase = (t / P.m_tiles) / P.n_tiles;
+      const int acc = it & 1;
+      long long tw0 = clock64();
+      mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1) ^ 1);
+      if (P.dbg && blockIdx.x == 0 && lane == 0) { atomicAdd((unsigned long long*)&P.dbg[2], (unsigned long long)(clock64() - tw0)); atomicAdd((unsigned long long*)&P.dbg[3], 1ull); }
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kAccStride;
+      const int kiters = p.seg.nseg[phase] * P.kchunks;
+      for (int ki = 0; ki < kiters; ++ki) {
+        tw0 = clock64();
+        mbar_wait(&full[stage], ph);
+        if (P.dbg && blockIdx.x == 0 && lane == 0) { atomicAdd((unsigned long long*)&P.dbg[4], (unsigned long long)(clock64() - tw0)); atomicAdd((unsigned long long*)&P.dbg[5], 1ull); }
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kAccStride;
-        const int kiters = p.seg.nseg[phase] * P.kchunks;
-        for (int ki = 0; ki < kiters; ++ki) {
-          mbar_wait(&full[stage], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(tiles + (size_t)stage * stage_bytes);
-          const uint32_t sa_shift = sa + P.x_shift * 128;
-          uint64_t adesc = make_desc(sa_shift, 16, 1024);
-          if (P.x_baseoff) adesc |= (uint64_t)((sa_shift >> 7) & 7) << 49;
-          const uint64_t bdesc = make_desc(sa + P.a_bytes, 16, 1024);
+        const uint32_t a_lo = lo0 + stage * stage_step;
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)   // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzle row
-            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (ki | k) != 0);
+            umma_bf16_lohi(d_tmem, a_lo + 2 * k, a_lo + b_off + 2 * k, hi, idesc, (uint32_t)(ki | k));
           umma_commit(&empty[stage]);
           if (ki == kiters - 1) umma_commit(&tfull[acc]);
-          if (++stage == stages) { stage = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; ph ^= 1; }
       }
     }
   } else {
     // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  == tile rows
     const int lq = warp & 3;
-    const int r = lq * 32 + lane;
-    bf16* out = reinterpret_cast<bf16*>(p.out);
-    const bf16* mask = reinterpret_cast<const bf16*>(p.mask);
-    int it = 0;
+    uint8_t* stg = stage_buf + (warp - 2) * kStgBytes;
+    int rpt_log2 = 7;
+    if (P.tiles_per_sample == 0) { rpt_log2 = 0; while ((1 << rpt_log2) < P.rpt) ++rpt_log2; }
+    int it = 0, last_nt = -1;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int mt = t % P.m_tiles;
       const int rest = t / P.m_tiles;
       const int nt = rest % P.n_tiles;
       const int phase = rest / P.n_tiles;
-      int b, q;
-      if (P.tiles_per_sample > 0) { b = mt / P.tiles_per_sample; q = (mt % P.tiles_per_sample) * 128 + r; }
-      else { b = mt * P.bpt + r / P.rpt; q = r % P.rpt; }
-      const bool row_ok = b < p.B;
+      int b0, q0;
+      if (P.tiles_per_sample > 0) { b0 = mt / P.tiles_per_sample; q0 = (mt % P.tiles_per_sample) * 128; }
+      else { b0 = mt * P.bpt; q0 = 0; }
+      EpiRows R;
+      epi_rows(p, b0, q0, rpt_log2, phase, lq, lane, R);
+      if (nt != last_nt) { epi_load_bias<EPI>(p, bias_s, nt * BN, BN, threadIdx.x - 64); last_nt = nt; }
       const int acc = it & 1;
+      const long long te0 = clock64();
       mbar_wait(&tfull[acc], ((uint32_t)it >> 1) & 1);
+      const long long te1 = clock64();
       tc_fence_after();
-      const long long obase = (long long)b * p.o_bs + (long long)q * p.o_rs + phase * p.o_phase_col;
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + acc * kAccStride + c0, v);
-        tmem_ld_wait();
-        if (row_ok) {
-          const int n0 = nt * BN + c0;
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + j;
-            float x = __uint_as_float(v[j]);
-            const bool real = n < p.n_real;
-            if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_LRELU || p.epi == EPI_BIAS_SIGMOID) x += real ? __ldg(&p.bias[n]) : 0.f;
-            if (p.epi == EPI_BIAS_LRELU) x = lrelu(x);
-            if (p.epi == EPI_BIAS_SIGMOID) x = 1.f / (1.f + __expf(-x));
-            f[j] = real ? x : 0.f;
-          }
-          if (p.epi == EPI_MASK) {
-            const uint4* mp = reinterpret_cast<const uint4*>(mask + obase + n0);
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const uint4 mv = mp[j4];
-              const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-              for (int w2 = 0; w2 < 4; ++w2) {
-                const __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(&mw[w2]);
-                f[j4 * 8 + w2 * 2] *= lrelu_slope(__low2float(hv));
-                f[j4 * 8 + w2 * 2 + 1] *= lrelu_slope(__high2float(hv));
-              }
+      epilogue_block<EPI>(p, tmem_base + acc * kAccStride, BN, nt * BN, R, bias_s, stg, lq, lane);
+      if (P.dbg && blockIdx.x == 0 && threadIdx.x == 64) {
+        atomicAdd((unsigned long long*)&P.dbg[6], (unsigned long long)(te1 - te0));
+        atomicAdd((unsigned long long*)&P.dbg[7], (unsigned long long)(clock64() - te1));
+        atomicAdd((unsigned long long*)&P.dbg[8], 1ull);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// =============================================================================================
+// rsgemm2_tc: slab-reuse variant (time rows per sample >= 128).
+//  * per (64-channel chunk, tap group) ONE activation slab = MB boxes of (128 + span) rows is loaded; every
+//    tap of the group reads its 128-row window through a UMMA descriptor that starts `shift` rows into the
+//    slab (SWIZZLE_128B is a function of the absolute smem address, so any 128-byte row start is legal with
+//    base_offset = 0 - verified on B200). Activation traffic from L2 drops by the number of taps per group.
+//  * MB (1|2) accumulators of 128 rows share each weight tile, halving weight bytes per MAC.
+// =============================================================================================
+struct SlabGroup {
+  int acol, min_shift, nseg;
+  unsigned char shift_rel[32];
+  int wk[32];
+};
+struct RsTc2Params {
+  RsParams p;
+  int BN, n_tiles, m_tiles, MB, blocks_per_sample, total_blocks, kchunks;
+  int box_rows, box_bytes, slab_bytes, slab_stages, b_stages, double_acc;
+  int ngroups[2];
+  SlabGroup grp[2][2];
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+rsgemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ RsTc2Params P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const RsParams& p = P.p;
+  const int BN = P.BN, MB = P.MB;
+  const int SS = P.slab_stages, BS = P.b_stages;
+  const int b_bytes = BN * 128;
+  uint8_t* slabs = smem;
+  uint8_t* btiles = smem + (size_t)SS * P.slab_bytes;
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(btiles + (size_t)BS * b_bytes);
+  uint64_t* s_empty = s_full + SS;
+  uint64_t* b_full = s_empty + SS;
+  uint64_t* b_empty = b_full + BS;
+  uint64_t* tfull = b_empty + BS;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* stage_buf = btiles + (size_t)BS * b_bytes + 512;   // 4 x kStgBytes epilogue staging + bias tile
+  float* bias_s = reinterpret_cast<float*>(stage_buf + 4 * kStgBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+    for (int i = 0; i < SS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+    for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.seg.nphase * P.n_tiles * P.m_tiles;
+  const int acc_stride = MB * BN;
+
+  if (warp == 0) {
+    int ss = 0, bs = 0;
+    uint32_t sph = 0, bph = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int mt = t % P.m_tiles;
+      const int rest = t / P.m_tiles;
+      const int nt = rest % P.n_tiles;
+      const int phase = rest / P.n_tiles;
+      for (int kc = 0; kc < P.kchunks; ++kc) {
+        for (int g = 0; g < P.ngroups[phase]; ++g) {
+          const SlabGroup& G = P.grp[phase][g];
+          mbar_wait(&s_empty[ss], sph ^ 1);
+          if (elect_one()) {
+            uint8_t* sl = slabs + (size_t)ss * P.slab_bytes;
+            mbar_expect_tx(&s_full[ss], (uint32_t)P.slab_bytes);
+            for (int mb = 0; mb < MB; ++mb) {
+              const int blk = mt * MB + mb;
+              const int b = blk / P.blocks_per_sample;
+              const int q0 = (blk % P.blocks_per_sample) * 128;
+              tma_load_3d(sl + (size_t)mb * P.box_bytes, &tmA, &s_full[ss], G.acol + kc * 64, q0 + G.min_shift, b);
             }
           }
-          if (out) {
-            uint4* op = reinterpret_cast<uint4*>(out + obase + n0);
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              uint4 o;
-              o.x = pack_bf16x2(f[j4 * 8 + 0], f[j4 * 8 + 1]);
-              o.y = pack_bf16x2(f[j4 * 8 + 2], f[j4 * 8 + 3]);
-              o.z = pack_bf16x2(f[j4 * 8 + 4], f[j4 * 8 + 5]);
-              o.w = pack_bf16x2(f[j4 * 8 + 6], f[j4 * 8 + 7]);
-              op[j4] = o;
+          if (++ss == SS) { ss = 0; sph ^= 1; }
+          for (int s = 0; s < G.nseg; ++s) {
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&b_full[bs], (uint32_t)b_bytes);
+              tma_load_2d(btiles + (size_t)bs * b_bytes, &tmW, &b_full[bs], G.wk[s] + kc * 64, nt * BN);
             }
-          }
-          if (p.out32) {
-            float* o32 = p.out32 + (long long)b * p.o32_bs + (long long)q * p.o32_rs;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.n_real) o32[n0 + j] = f[j];
+            if (++bs == BS) { bs = 0; bph ^= 1; }
           }
         }
       }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(128, BN, 0, 0);
+    const uint32_t hi = desc_hi(1024);
+    const uint32_t slab_lo0 = desc_lo(smem_u32(slabs), 16), b_lo0 = desc_lo(smem_u32(btiles), 16);
+    const uint32_t slab_step = (uint32_t)P.slab_bytes >> 4, b_step = (uint32_t)b_bytes >> 4;
+    const uint32_t box_step = (uint32_t)P.box_bytes >> 4;
+    int ss = 0, bs = 0;
+    uint32_t sph = 0, bph = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int phase = (t / P.m_tiles) / P.n_tiles;
+      const int acc = P.double_acc ? (it & 1) : 0;
+      const uint32_t use = P.double_acc ? ((uint32_t)it >> 1) : (uint32_t)it;
+      mbar_wait(&tempty[acc], (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * acc_stride;
+      uint32_t accum = 0;
+      for (int kc = 0; kc < P.kchunks; ++kc) {
+        for (int g = 0; g < P.ngroups[phase]; ++g) {
+          const SlabGroup& G = P.grp[phase][g];
+          mbar_wait(&s_full[ss], sph);
+          tc_fence_after();
+          const uint32_t sl_lo = slab_lo0 + ss * slab_step;
+          for (int s = 0; s < G.nseg; ++s) {
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            const uint32_t b_lo = b_lo0 + bs * b_step;
+            const uint32_t a_lo = sl_lo + (uint32_t)G.shift_rel[s] * 8;   // one row = 128 B = 8 x 16 B
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, accum | (uint32_t)k);
+              if (MB == 2) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_lohi(d_tmem + BN, a_lo + box_step + 2 * k, b_lo + 2 * k, hi, idesc, accum | (uint32_t)k);
+              }
+              umma_commit(&b_empty[bs]);
+            }
+            __syncwarp();
+            accum = 1;
+            if (++bs == BS) { bs = 0; bph ^= 1; }
+          }
+          if (elect_one()) umma_commit(&s_empty[ss]);
+          __syncwarp();
+          if (++ss == SS) { ss = 0; sph ^= 1; }
+        }
+      }
+      if (elect_one()) umma_commit(&tfull[acc]);
+      __syncwarp();
+    }
+  } else {
+    const int lq = warp & 3;
+    uint8_t* stg = stage_buf + (warp - 2) * kStgBytes;
+    int it = 0, last_nt = -1;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int mt = t % P.m_tiles;
+      const int rest = t / P.m_tiles;
+      const int nt = rest % P.n_tiles;
+      const int phase = rest / P.n_tiles;
+      EpiRows R[2];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        if (mb < MB) {
+          const int blk = mt * MB + mb;   // blocks past the end map to samples >= B and are masked
+          epi_rows(p, blk / P.blocks_per_sample, (blk % P.blocks_per_sample) * 128, 7, phase, lq, lane, R[mb]);
+        }
+      }
+      if (nt != last_nt) { epi_load_bias<EPI>(p, bias_s, nt * BN, BN, threadIdx.x - 64); last_nt = nt; }
+      const int acc = P.double_acc ? (it & 1) : 0;
+      const uint32_t use = P.double_acc ? ((uint32_t)it >> 1) : (uint32_t)it;
+      mbar_wait(&tfull[acc], use & 1);
+      tc_fence_after();
+      epilogue_block<EPI>(p, tmem_base + acc * acc_stride, BN, nt * BN, R[0], bias_s, stg, lq, lane);
+      if (MB == 2) epilogue_block<EPI>(p, tmem_base + acc * acc_stride + BN, BN, nt * BN, R[1], bias_s, stg, lq, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -378,48 +680,50 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t ph = 0;
-      int shift[2], scol[2];
-      for (int u = 0; u < 2; ++u) {
-        const int seg = unit[u] / P.mblocks, mb = unit[u] % P.mblocks;
-        shift[u] = p.shift[seg];
-        scol[u] = p.scol[seg] + mb * 64;
-      }
-      for (int ch = ch_begin; ch < ch_end; ++ch) {
-        int b0, q0;
-        if (P.chunks_per_sample > 0) { b0 = ch / P.chunks_per_sample; q0 = (ch % P.chunks_per_sample) * 64; }
-        else { b0 = ch * P.bpt; q0 = 0; }
-        mbar_wait(&empty[stage], ph ^ 1);
+    int stage = 0;
+    uint32_t ph = 0;
+    int shift[2], scol[2];
+    for (int u = 0; u < 2; ++u) {
+      const int seg = unit[u] / P.mblocks, mb = unit[u] % P.mblocks;
+      shift[u] = p.shift[seg];
+      scol[u] = p.scol[seg] + mb * 64;
+    }
+    for (int ch = ch_begin; ch < ch_end; ++ch) {
+      int b0, q0;
+      if (P.chunks_per_sample > 0) { b0 = ch / P.chunks_per_sample; q0 = (ch % P.chunks_per_sample) * 64; }
+      else { b0 = ch * P.bpt; q0 = 0; }
+      mbar_wait(&empty[stage], ph ^ 1);
+      if (elect_one()) {
         uint8_t* sa = tiles + (size_t)stage * stage_bytes;
         mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
         tma_load_3d(sa, &tmS, &full[stage], scol[0], q0 + shift[0], b0);
         tma_load_3d(sa + 8192, &tmS, &full[stage], scol[1], q0 + shift[1], b0);
         for (int j = 0; j < BN / 64; ++j)
           tma_load_3d(sa + kABytes + j * 8192, &tmP, &full[stage], n_begin + j * 64, q0, b0);
-        if (++stage == stages) { stage = 0; ph ^= 1; }
       }
+      if (++stage == stages) { stage = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, BN, 1, 1);
-      int stage = 0;
-      uint32_t ph = 0;
-      for (int ci = 0; ci < nchunks; ++ci) {
-        mbar_wait(&full[stage], ph);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(tiles + (size_t)stage * stage_bytes);
-        // MN-major, SWIZZLE_128B: LBO = stride between 64-channel blocks (8192 B), SBO = stride between 8-row groups
-        const uint64_t adesc = make_desc(sa, 8192, 1024);
-        const uint64_t bdesc = make_desc(sa + kABytes, 8192, 1024);
+    const uint32_t idesc = make_idesc(128, BN, 1, 1);
+    // MN-major, SWIZZLE_128B: LBO = stride between 64-channel blocks (8192 B), SBO = stride between 8-row groups
+    const uint32_t hi = desc_hi(1024);
+    const uint32_t lo0 = desc_lo(smem_u32(tiles), 8192);
+    const uint32_t stage_step = (uint32_t)stage_bytes >> 4;
+    int stage = 0;
+    uint32_t ph = 0;
+    for (int ci = 0; ci < nchunks; ++ci) {
+      mbar_wait(&full[stage], ph);
+      tc_fence_after();
+      const uint32_t a_lo = lo0 + stage * stage_step;
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // K = 16 rows = 2 groups of 8 rows = 2048 bytes per step
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (ci | k) != 0);
+          umma_bf16_lohi(tmem_base, a_lo + 128 * k, a_lo + (kABytes >> 4) + 128 * k, hi, idesc, (uint32_t)(ci | k));
         umma_commit(&empty[stage]);
         if (ci == nchunks - 1) umma_commit(&tfull[0]);
-        if (++stage == stages) { stage = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++stage == stages) { stage = 0; ph ^= 1; }
     }
   } else {
     const int lq = warp & 3;
@@ -464,6 +768,7 @@ struct TcState {
   std::map<std::tuple<const void*, long long, long long, long long, long long, int, int, int>, CUtensorMap> cache;
   int sm_count = 148;
   int max_smem = 0;
+  bool force_v1 = false;   // CG_TC_V1=1: per-tap boxes everywhere (A/B comparison)
   std::string err;
 };
 
@@ -483,7 +788,14 @@ static inline int tc_init(TcState* s) {
   if (prop.major != 10) return cg_tc_set_err("the bf16 tensor-core path needs an sm_100 device (tcgen05/TMEM)");
   s->sm_count = prop.multiProcessorCount;
   s->max_smem = (int)prop.sharedMemPerBlockOptin;
-  if (cudaFuncSetAttribute(tc::rsgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) != cudaSuccess ||
+  if (const char* e = getenv("CG_TC_V1")) s->force_v1 = atoi(e) != 0;
+  bool ok = true;
+#define CG_SET_SMEM(E)                                                                                                         \
+  ok = ok && cudaFuncSetAttribute(tc::rsgemm_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess && \
+       cudaFuncSetAttribute(tc::rsgemm2_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess;
+  CG_SET_SMEM(EPI_NONE) CG_SET_SMEM(EPI_BIAS) CG_SET_SMEM(EPI_BIAS_LRELU) CG_SET_SMEM(EPI_MASK) CG_SET_SMEM(EPI_BIAS_SIGMOID)
+#undef CG_SET_SMEM
+  if (!ok ||
       cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) != cudaSuccess)
     return cg_tc_set_err("cudaFuncSetAttribute(max dynamic smem) failed");
   return 0;
@@ -550,12 +862,107 @@ static inline bool tc_rsgemm_supported(const RsParams& p) {
 }
 
 static inline int tc_pick_bn(int N) {
-  for (int bn = 256; bn >= 64; bn -= 16)
+  for (int bn = 256; bn >= 64; bn -= 32)
     if (N % bn == 0) return bn;
   return 64;
 }
 
+// ---- v2 (slab reuse) -------------------------------------------------------------------------------
+static inline bool tc_rsgemm2_supported(const RsParams& p) {
+  if (p.Q < 128 || p.Q % 128) return false;
+  for (int ph = 0; ph < p.seg.nphase; ++ph) {
+    int acols[2], na = 0, cnt[2] = {0, 0};
+    for (int s = 0; s < p.seg.nseg[ph]; ++s) {
+      int g = -1;
+      for (int i = 0; i < na; ++i) if (acols[i] == p.seg.acol[ph][s]) g = i;
+      if (g < 0) { if (na == 2) return false; acols[na] = p.seg.acol[ph][s]; g = na++; }
+      if (++cnt[g] > 32) return false;
+    }
+  }
+  return true;
+}
+
+static inline int tc_rsgemm2_launch(TcState* s, const RsParams& p, cudaStream_t stream) {
+  tc::RsTc2Params P;
+  memset(&P, 0, sizeof(P));
+  P.p = p;
+  int span = 0;
+  for (int ph = 0; ph < p.seg.nphase; ++ph) {
+    int na = 0;
+    for (int sg = 0; sg < p.seg.nseg[ph]; ++sg) {
+      int g = -1;
+      for (int i = 0; i < na; ++i) if (P.grp[ph][i].acol == p.seg.acol[ph][sg]) g = i;
+      if (g < 0) { g = na++; P.grp[ph][g].acol = p.seg.acol[ph][sg]; P.grp[ph][g].min_shift = 1 << 20; P.grp[ph][g].nseg = 0; }
+      if (p.seg.shift[ph][sg] < P.grp[ph][g].min_shift) P.grp[ph][g].min_shift = p.seg.shift[ph][sg];
+    }
+    P.ngroups[ph] = na;
+    for (int sg = 0; sg < p.seg.nseg[ph]; ++sg) {
+      int g = 0;
+      for (int i = 0; i < na; ++i) if (P.grp[ph][i].acol == p.seg.acol[ph][sg]) g = i;
+      tc::SlabGroup& G = P.grp[ph][g];
+      const int rel = p.seg.shift[ph][sg] - G.min_shift;
+      G.shift_rel[G.nseg] = (unsigned char)rel;
+      G.wk[G.nseg] = p.seg.wk[ph][sg];
+      G.nseg++;
+      if (rel > span) span = rel;
+    }
+  }
+  P.box_rows = (128 + span + 7) / 8 * 8;
+  if (P.box_rows > 256) return cg_tc_set_err("rsgemm2_tc: tap span too large for one TMA box");
+  P.box_bytes = P.box_rows * 128;
+  P.blocks_per_sample = p.Q / 128;
+  P.total_blocks = p.B * P.blocks_per_sample;
+  P.kchunks = p.Kc / 64;
+  int kiters = 0;
+  for (int ph = 0; ph < p.seg.nphase; ++ph) if (p.seg.nseg[ph] > kiters) kiters = p.seg.nseg[ph];
+  // tile shape: minimise (waves x per-tile time) under the L2 -> SMEM model (42 B/clk/SM, 4096 MAC/clk/SM)
+  double best = 1e30;
+  int bestMB = 1, bestBN = 64;
+  for (int MB = 1; MB <= 2; ++MB) {
+    for (int BN = 256; BN >= 64; BN -= 32) {
+      if (p.N % BN) continue;
+      const long long tiles = (long long)p.seg.nphase * (p.N / BN) * ((P.total_blocks + MB - 1) / MB);
+      const double waves = (double)((tiles + s->sm_count - 1) / s->sm_count);
+      const double mma_clk = MB * 128.0 * BN * 64 / 4096.0;                                   // per tap per chunk
+      const double bytes = BN * 128.0 + MB * P.box_bytes / (double)(kiters > 0 ? kiters : 1); // weights + amortised slab
+      const double l2_clk = bytes / 42.0;
+      const double smem_clk = mma_clk * (BN < 128 ? 1.5 : 1.0);                               // N=64: A re-read bound
+      double per = mma_clk > l2_clk ? mma_clk : l2_clk;
+      if (smem_clk > per) per = smem_clk;
+      const double epi = MB * BN * 6.0 * ((2 * MB * BN <= 512) ? 0.25 : 1.0) / (double)(P.kchunks * kiters);
+      const double cost = waves * (per + epi);
+      if (cost < best) { best = cost; bestMB = MB; bestBN = BN; }
+    }
+  }
+  P.MB = bestMB; P.BN = bestBN;
+  P.n_tiles = p.N / P.BN;
+  P.m_tiles = (P.total_blocks + P.MB - 1) / P.MB;
+  P.double_acc = (2 * P.MB * P.BN <= 512) ? 1 : 0;
+  P.slab_bytes = P.MB * P.box_bytes;
+  P.slab_stages = 2;
+  const int b_bytes = P.BN * 128;
+  int bst = (s->max_smem - 1024 - 512 - tc::kEpiSmem - P.slab_stages * P.slab_bytes) / b_bytes;
+  if (bst > 8) bst = 8;
+  if (bst < 2) return cg_tc_set_err("rsgemm2_tc: not enough shared memory");
+  P.b_stages = bst;
+  CUtensorMap tmA, tmW;
+  if (tc_get_map3(s, p.A, p.a_rs, p.a_rows, p.B, p.a_rs, p.a_bs, P.box_rows, 1, &tmA)) return 1;
+  if (tc_get_map2(s, p.W, p.w_ld, p.N, p.w_ld, P.BN, &tmW)) return 1;
+  const int total = p.seg.nphase * P.n_tiles * P.m_tiles;
+  const int grid = total < s->sm_count ? total : s->sm_count;
+  const size_t smem = (size_t)P.slab_stages * P.slab_bytes + (size_t)bst * b_bytes + 1024 + 512 + tc::kEpiSmem;
+  switch (p.epi) {
+    case EPI_NONE: tc::rsgemm2_tc_kernel<EPI_NONE><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+    case EPI_BIAS: tc::rsgemm2_tc_kernel<EPI_BIAS><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+    case EPI_BIAS_LRELU: tc::rsgemm2_tc_kernel<EPI_BIAS_LRELU><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+    case EPI_MASK: tc::rsgemm2_tc_kernel<EPI_MASK><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+    default: tc::rsgemm2_tc_kernel<EPI_BIAS_SIGMOID><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+  }
+  return 0;
+}
+
 static inline int tc_rsgemm_launch(TcState* s, const RsParams& p, cudaStream_t stream) {
+  if (!s->force_v1 && tc_rsgemm2_supported(p)) return tc_rsgemm2_launch(s, p, stream);
   tc::RsTcParams P;
   P.p = p;
   P.BN = tc_pick_bn(p.N);
@@ -564,13 +971,11 @@ static inline int tc_rsgemm_launch(TcState* s, const RsParams& p, cudaStream_t s
   else { P.rpt = p.Q; P.bpt = 128 / p.Q; P.tiles_per_sample = 0; P.m_tiles = (p.B + P.bpt - 1) / P.bpt; }
   P.kchunks = p.Kc / 64;
   P.x_shift = 0; P.x_baseoff = 0;
-  if (const char* e = getenv("CG_TC_XSHIFT")) P.x_shift = atoi(e);
-  if (const char* e = getenv("CG_TC_XBASEOFF")) P.x_baseoff = atoi(e);
-  if (P.rpt != 128) P.x_shift = 0;
-  const int a_rows_box = P.x_shift ? 128 + ((P.x_shift + 7) / 8) * 8 : P.rpt;
-  P.a_bytes = P.x_shift ? a_rows_box * 128 : tc::kABytes;
+  if (const char* e = getenv("CG_TC_DBG")) P.x_baseoff = atoi(e);   // timing experiments: 1 no stores, 2 no W loads, 4 no A loads
+  const int a_rows_box = P.rpt;
+  P.a_bytes = tc::kABytes;
   const int stage_bytes = P.a_bytes + P.BN * 128;
-  int stages = (s->max_smem - 2048) / stage_bytes;
+  int stages = (s->max_smem - 1024 - 512 - tc::kEpiSmem) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return cg_tc_set_err("rsgemm_tc: not enough shared memory for 2 stages");
   P.stages = stages;
@@ -580,8 +985,30 @@ static inline int tc_rsgemm_launch(TcState* s, const RsParams& p, cudaStream_t s
   if (tc_get_map2(s, p.W, p.w_ld, p.N, p.w_ld, P.BN, &tmW)) return 1;
   const int total = p.seg.nphase * P.n_tiles * P.m_tiles;
   const int grid = total < s->sm_count ? total : s->sm_count;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-  tc::rsgemm_tc_kernel<<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P);
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 512 + tc::kEpiSmem;
+  static long long* dbg_buf = nullptr;
+  P.dbg = nullptr;
+  if (getenv("CG_TC_TIMING")) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), stream);
+    P.dbg = dbg_buf;
+  }
+  const long long t_host0 = 0;
+  (void)t_host0;
+  switch (p.epi) {
+    case EPI_NONE: tc::rsgemm_tc_kernel<EPI_NONE><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+    case EPI_BIAS: tc::rsgemm_tc_kernel<EPI_BIAS><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+    case EPI_BIAS_LRELU: tc::rsgemm_tc_kernel<EPI_BIAS_LRELU><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+    case EPI_MASK: tc::rsgemm_tc_kernel<EPI_MASK><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+    default: tc::rsgemm_tc_kernel<EPI_BIAS_SIGMOID><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+  }
+  if (P.dbg) {
+    long long h[16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tc timing] N=%d BN=%d Q=%d tiles=%d grid=%d stages=%d | producer wait-empty %lld clk/%lld | mma wait-tempty %lld/%lld, wait-full %lld/%lld | epi wait-tfull %lld, work %lld over %lld tiles\n",
+            p.N, P.BN, p.Q, total, grid, stages, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8]);
+  }
   return 0;
 }
 
