@@ -250,37 +250,40 @@ static int launch_wgrad_raw(cg_ctx* c, WgParams p) {
   return post_launch(c, "wgrad_simt");
 }
 
-static int launch_pack(cg_ctx* c, const float* src, void* dst, int N, int n_real, int nseg, int Cp, int c_real,
-                       long long sk, long long sn, long long sc) {
-  const long long total = (long long)N * nseg * Cp;
-  DISPATCH_T(c, pack_weight_kernel<T><<<grid_for(total), 256, 0, c->stream>>>(src, (T*)dst, N, n_real, nseg, Cp,
-                                                                              c_real, sk, sn, sc));
-  return post_launch(c, "pack");
+static void add_pack(PackOps& ops, const float* src, void* dst, int N, int n_real, int nseg, int Cp, int c_real,
+                     long long sk, long long sn, long long sc) {
+  PackOp& o = ops.op[ops.n++];
+  o.src = src; o.dst = dst; o.N = N; o.n_real = n_real; o.nseg = nseg; o.Cp = Cp; o.c_real = c_real;
+  o.sk = sk; o.sn = sn; o.sc = sc;
 }
 
-// refresh packed T copies of one model's GEMM weights from the fp32 master
+// refresh packed T copies of one model's GEMM weights from the fp32 master (one launch)
 static int repack(cg_ctx* c, int which) {
   const int K = c->K;
+  PackOps ops;
+  ops.n = 0;
   if (which == CG_DISCRIMINATOR) {
     for (int l = 1; l <= NL; ++l) {
       const float* w = c->dis.w + c->dis.params[2 * (l - 1)].offset;   // (K, Cin, Cout)
       const int ci = c->dc[l - 1], co = c->dc[l], cip = c->dcp[l - 1], cop = c->dcp[l];
-      CK(launch_pack(c, w, c->Wf_d[l], cop, co, K, cip, ci, (long long)ci * co, 1, co));
-      CK(launch_pack(c, w, c->Wb_d[l], cip, ci, K, cop, co, (long long)ci * co, co, 1));
+      add_pack(ops, w, c->Wf_d[l], cop, co, K, cip, ci, (long long)ci * co, 1, co);
+      add_pack(ops, w, c->Wb_d[l], cip, ci, K, cop, co, (long long)ci * co, co, 1);
     }
   } else {
     for (int i = 1; i <= NL; ++i) {
       const float* w = c->gen.w + c->gen.params[c->g_k[i]].offset;     // (K, 1, Cout, Cin)
       const int ci = c->gc[i - 1], co = c->gc[i], cip = c->gcp[i - 1], cop = c->gcp[i];
-      CK(launch_pack(c, w, c->Wf_g[i], cop, co, K, cip, ci, (long long)ci * co, ci, 1));
-      CK(launch_pack(c, w, c->Wb_g[i], cip, ci, K, cop, co, (long long)ci * co, 1, ci));
+      add_pack(ops, w, c->Wf_g[i], cop, co, K, cip, ci, (long long)ci * co, ci, 1);
+      add_pack(ops, w, c->Wb_g[i], cip, ci, K, cop, co, (long long)ci * co, 1, ci);
     }
     const float* w1 = c->gen.w + c->gen.params[c->g_d1k].offset;       // (C_in, C_out)
     const int C = c->C, Cp = c->gcp[NL];
-    CK(launch_pack(c, w1, c->Wf_d1, Cp, C, 1, Cp, C, 0, 1, C));        // [n=out][c=in]
-    CK(launch_pack(c, w1, c->Wb_d1, Cp, C, 1, Cp, C, 0, C, 1));        // [n=in][c=out]
+    add_pack(ops, w1, c->Wf_d1, Cp, C, 1, Cp, C, 0, 1, C);             // [n=out][c=in]
+    add_pack(ops, w1, c->Wb_d1, Cp, C, 1, Cp, C, 0, C, 1);             // [n=in][c=out]
   }
-  return 0;
+  dim3 grid(148, ops.n);
+  DISPATCH_T(c, pack_weights_kernel<T><<<grid, 256, 0, c->stream>>>(ops));
+  return post_launch(c, "pack_weights");
 }
 
 // ------------------------------------------------------------------------------------------ create
@@ -327,6 +330,12 @@ extern "C" int cg_create(const cg_config* cfg, cg_ctx** out) {
     c->gc[i] = gcs[i]; c->gcp[i] = round_up(gcs[i], CG_CPAD); c->gl[i] = c->w0 << i;
     c->dc[i] = dcs[i]; c->dcp[i] = round_up(dcs[i], CG_CPAD); c->dl[i] = c->L >> i;
   }
+  for (int i = 0; i <= NL; ++i)
+    if (c->gcp[i] > 32 * 4 * (16 / c->esz)) {
+      const int bad = c->gcp[i];
+      delete c;
+      return set_err("cg_create: %d generator channels exceed the layer-norm kernel's row width", bad);
+    }
   // ---- parameter tables in Keras get_weights() order
   Model& G = c->gen;
   Model& D = c->dis;
@@ -687,7 +696,7 @@ static int d_backward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh, i
   CK(post_launch(c, "head_bwd"));
   for (int l = NL; l >= 2; --l) {
     CK(d_dgrad_layer(c, l, 0, Bt, c->DX[l - 1]));
-    const long long tot = (long long)Bt * c->dl[l - 1] * c->dcp[l - 1];
+    const long long tot = (long long)Bt * c->dl[l - 1] * c->dcp[l - 1] / (16 / c->esz);
     DISPATCH_T(c, ps_scatter_mask_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
                       (const T*)c->DX[l - 1], (const T*)c->H[l - 1], (T*)c->DA[l - 1], Bt, B, c->dl[l - 1],
                       c->dcp[l - 1], group_shifts(sh, groups, l - 1)));
@@ -718,7 +727,8 @@ static int d_wgrad(cg_ctx* c, int Bt, int nb_bias) {
       CK(launch_colsum(c, c->DA[l], dgrad(c, 2 * (l - 1) + 1), (long long)nb_bias * c->dl[l], c->dcp[l], c->dc[l]));
   }
   const int tot = c->dl[NL] * c->dc[NL];
-  DISPATCH_T(c, head_wgrad_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
+  dim3 hgrid(grid_for(tot), Bt >= 64 ? 16 : 1);
+  DISPATCH_T(c, head_wgrad_kernel<T><<<hgrid, 256, 0, c->stream>>>(
                     (const T*)c->X[NL], c->coef, dgrad(c, 10), dgrad(c, 11), Bt, nb_bias, c->dl[NL], c->dc[NL], c->dcp[NL]));
   return post_launch(c, "head_wgrad");
 }
@@ -768,7 +778,7 @@ static int fetch_scalars(cg_ctx* c, int slot, int flags, float* scalars_host) {
 static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
                              const int32_t* sh, int slot) {
   CK(g_forward(c, noise, B));
-  const long long tot = (long long)B * c->L * c->dcp[0];
+  const long long tot = (long long)B * c->L * c->dcp[0] / 4;
   DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(real, c->FAKE32, alpha, (T*)c->X[0], B,
                                                                            c->L, c->C, c->dcp[0], 0));
   CK(post_launch(c, "assemble_x0"));
@@ -791,7 +801,7 @@ static int critic_step_impl(cg_ctx* c, const float* real, int B, const float* no
   CK(critic_forward_gp(c, real, B, noise, alpha, sh, slot));
   // GP second-order term without the second-order graph: v0 = u = d(lambda*GP)/dg
   const long long per = (long long)c->L * c->dcp[0];
-  DISPATCH_T(c, scale_rows_kernel<T><<<grid_for(per * B), 256, 0, c->stream>>>(
+  DISPATCH_T(c, scale_rows_kernel<T><<<grid_for(per * B / (16 / c->esz)), 256, 0, c->stream>>>(
                     (const T*)c->DX[0], c->ucoef, (T*)off(c, c->X[0], 2 * B * per), per, per * B));
   CK(post_launch(c, "scale_rows"));
   const int32_t* sh2 = sh + 8;
@@ -847,7 +857,7 @@ static int generator_step_impl(cg_ctx* c, const float* real, int B, const float*
                                int slot) {
   CU(cudaMemcpyAsync(c->Z, noise, (size_t)B * c->nd * 4, cudaMemcpyDeviceToDevice, c->stream));
   CK(g_forward(c, c->Z, B));
-  const long long tot = (long long)B * c->L * c->dcp[0];
+  const long long tot = (long long)B * c->L * c->dcp[0] / 4;
   DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(c->FAKE32, nullptr, nullptr, (T*)c->X[0],
                                                                            B, c->L, c->C, c->dcp[0], 1));
   CK(post_launch(c, "assemble_x0_fake"));
@@ -946,7 +956,7 @@ extern "C" int cg_generate(cg_ctx* c, const float* noise, int B, int denorm, flo
 extern "C" int cg_debug_critic_forward(cg_ctx* c, const float* x, int B, const int32_t* sh, float* scores_dev) {
   CK(check_batch(c, B));
   if (!x || !sh || !scores_dev) return set_err("cg_debug_critic_forward: null pointer");
-  const long long tot = (long long)B * c->L * c->dcp[0];
+  const long long tot = (long long)B * c->L * c->dcp[0] / 4;
   DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(x, nullptr, nullptr, (T*)c->X[0], B, c->L,
                                                                            c->C, c->dcp[0], 1));
   CK(post_launch(c, "assemble_x0"));
@@ -959,7 +969,7 @@ extern "C" int cg_debug_critic_forward(cg_ctx* c, const float* x, int B, const i
 extern "C" int cg_debug_gp(cg_ctx* c, const float* xhat, int B, const int32_t* sh, float* grad_dev, float* norms_dev) {
   CK(check_batch(c, B));
   if (!xhat || !sh) return set_err("cg_debug_gp: null pointer");
-  const long long tot = (long long)B * c->L * c->dcp[0];
+  const long long tot = (long long)B * c->L * c->dcp[0] / 4;
   DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(xhat, nullptr, nullptr, (T*)c->X[0], B,
                                                                            c->L, c->C, c->dcp[0], 1));
   CK(post_launch(c, "assemble_x0"));
@@ -983,7 +993,7 @@ extern "C" int cg_debug_gp(cg_ctx* c, const float* xhat, int B, const int32_t* s
 }
 
 static int pad_in(cg_ctx* c, const float* src, void* dst, int B, int rows, int C, int Cp) {
-  DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for((long long)B * rows * Cp), 256, 0, c->stream>>>(
+  DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for((long long)B * rows * Cp / 4), 256, 0, c->stream>>>(
                     src, nullptr, nullptr, (T*)dst, B, rows, C, Cp, 1));
   return post_launch(c, "pad_in");
 }

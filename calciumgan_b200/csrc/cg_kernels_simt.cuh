@@ -4,6 +4,38 @@
 #pragma once
 #include "cg_common.cuh"
 
+// ---- 16-byte vector helpers: V = 16/sizeof(T) elements (4 fp32 or 8 bf16) ---------------------------------
+template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
+template <typename T> __device__ __forceinline__ void vload(const T* p, float (&v)[Vec16<T>::N]);
+template <> __device__ __forceinline__ void vload<float>(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void vload<bf16>(const bf16* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    v[2 * i] = __low2float(h); v[2 * i + 1] = __high2float(h);
+  }
+}
+template <typename T> __device__ __forceinline__ void vstore(T* p, const float (&v)[Vec16<T>::N]);
+template <> __device__ __forceinline__ void vstore<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void vstore<bf16>(bf16* p, const float (&v)[8]) {
+  uint4 t;
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  t.x = w[0]; t.y = w[1]; t.z = w[2]; t.w = w[3];
+  *reinterpret_cast<uint4*>(p) = t;
+}
+
 // =============================================================================================
 // Row-shift implicit GEMM on CUDA cores (fp32 accumulate). 64x64 tile, 256 threads, 4x4/thread.
 // Used for: strided Conv1D fwd (reference calciumgan.py:145-185), Conv1DTranspose fwd
@@ -185,6 +217,25 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict_
   }
 }
 
+// all packed copies of one model in ONE launch: blockIdx.y selects the op
+struct PackOp { const float* src; void* dst; int N, n_real, nseg, Cp, c_real; long long sk, sn, sc; };
+struct PackOps { int n; PackOp op[24]; };
+template <typename T>
+__global__ void pack_weights_kernel(const __grid_constant__ PackOps ops) {
+  const PackOp& o = ops.op[blockIdx.y];
+  T* dst = reinterpret_cast<T*>(o.dst);
+  const long long total = (long long)o.N * o.nseg * o.Cp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % o.Cp);
+    const int k = (int)((i / o.Cp) % o.nseg);
+    const int n = (int)(i / ((long long)o.Cp * o.nseg));
+    float v = 0.f;
+    if (n < o.n_real && c < o.c_real) v = o.src[k * o.sk + n * o.sn + c * o.sc];
+    dst[i] = Elem<T>::from_f(v);
+  }
+}
+
 // =============================================================================================
 // PhaseShuffle gather (calciumgan.py:117-138): X[b,t,:] = H[b, ps_index(t, shift[group(b)]), :].
 // 16-byte vectors; shifts are per call-group (one scalar per layer per critic call).
@@ -213,25 +264,43 @@ __global__ void ps_gather_kernel(const T* __restrict__ H, T* __restrict__ X, int
 template <typename T>
 __global__ void ps_scatter_mask_kernel(const T* __restrict__ DX, const T* __restrict__ H, T* __restrict__ DA,
                                        int Bt, int group_b, int w, int Cp, GroupShifts sh) {
-  const long long total = (long long)Bt * w * Cp;
+  constexpr int V = Vec16<T>::N;
+  const int cv = Cp / V;
+  const long long total = (long long)Bt * w * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % Cp);
-    const int j = (int)((i / Cp) % w);
-    const int b = (int)(i / ((long long)Cp * w));
+    const int c = (int)(i % cv) * V;
+    const int j = (int)((i / cv) % w);
+    const int b = (int)(i / ((long long)cv * w));
     const int s = sh.s[b / group_b];
     const T* dx = DX + (long long)b * w * Cp + c;
-    float acc = 0.f;
+    float acc[V], t[V], h[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
     const int t0 = j - s;                 // direct: t + s = j
-    if (t0 >= 0 && t0 < w) acc += Elem<T>::to_f(dx[(long long)t0 * Cp]);
-    if (s > 0) {                          // reflected at the end: t + s > w-1, j = 2(w-1) - (t+s)
-      const int t1 = 2 * (w - 1) - j - s;
-      if (t1 >= 0 && t1 < w && t1 + s > w - 1) acc += Elem<T>::to_f(dx[(long long)t1 * Cp]);
-    } else if (s < 0) {                   // reflected at the front: t + s < 0, j = -(t+s)
-      const int t1 = -j - s;
-      if (t1 >= 0 && t1 < w && t1 + s < 0) acc += Elem<T>::to_f(dx[(long long)t1 * Cp]);
+    if (t0 >= 0 && t0 < w) {
+      vload<T>(dx + (long long)t0 * Cp, t);
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] += t[e];
     }
-    DA[i] = Elem<T>::from_f(acc * lrelu_slope(Elem<T>::to_f(H[i])));
+    int t1 = -1;
+    if (s > 0) {                          // reflected at the end: t + s > w-1, j = 2(w-1) - (t+s)
+      t1 = 2 * (w - 1) - j - s;
+      if (!(t1 >= 0 && t1 < w && t1 + s > w - 1)) t1 = -1;
+    } else if (s < 0) {                   // reflected at the front: t + s < 0, j = -(t+s)
+      t1 = -j - s;
+      if (!(t1 >= 0 && t1 < w && t1 + s < 0)) t1 = -1;
+    }
+    if (t1 >= 0) {
+      vload<T>(dx + (long long)t1 * Cp, t);
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] += t[e];
+    }
+    const long long o = ((long long)b * w + j) * Cp + c;
+    vload<T>(H + o, h);
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] *= lrelu_slope(h[e]);
+    vstore<T>(DA + o, acc);
   }
 }
 
@@ -260,27 +329,36 @@ template <typename T>
 __global__ void assemble_x0_kernel(const float* __restrict__ real, const float* __restrict__ fake,
                                    const float* __restrict__ alpha, T* __restrict__ X0, int B, int L, int C,
                                    int Cp, int mode) {
+  const int c4 = Cp / 4;
   const long long per = (long long)L * Cp;
-  const long long total = (long long)B * per;
+  const long long total = (long long)B * L * c4;
+  const long long gtot = (long long)B * per;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % Cp);
-    const long long bt = i / Cp;
+    const int c = (int)(i % c4) * 4;
+    const long long bt = i / c4;
     const int b = (int)(bt / L);
-    if (mode == 1) {
-      X0[i] = Elem<T>::from_f(c < C ? real[bt * C + c] : 0.f);
-      continue;
+    float r[4] = {0.f, 0.f, 0.f, 0.f}, f[4] = {0.f, 0.f, 0.f, 0.f}, x[4] = {0.f, 0.f, 0.f, 0.f};
+    const float a = mode == 0 ? alpha[b] : 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (c + e < C) {
+        r[e] = real[bt * C + c + e];
+        if (mode == 0) {
+          f[e] = fake[bt * C + c + e];
+          x[e] = a * r[e] + (1.f - a) * f[e];
+        }
+      }
     }
-    float r = 0.f, f = 0.f, x = 0.f;
-    if (c < C) {
-      r = real[bt * C + c];
-      f = fake[bt * C + c];
-      const float a = alpha[b];
-      x = a * r + (1.f - a) * f;
+    const long long o = bt * Cp + c;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      X0[o + e] = Elem<T>::from_f(r[e]);
+      if (mode == 0) {
+        X0[gtot + o + e] = Elem<T>::from_f(f[e]);
+        X0[2 * gtot + o + e] = Elem<T>::from_f(x[e]);
+      }
     }
-    X0[i] = Elem<T>::from_f(r);
-    X0[total + i] = Elem<T>::from_f(f);
-    X0[2 * total + i] = Elem<T>::from_f(x);
   }
 }
 
@@ -338,18 +416,21 @@ __global__ void head_backward_kernel(const T* __restrict__ H5, const float* __re
   }
 }
 
-// dwd[t*c5+c] += sum_b coef[b] * X5[b,t,c];  dbd += sum_{b<nb_bias} coef[b]
+// dwd[t*c5+c] += sum_b coef[b] * X5[b,t,c];  dbd += sum_{b<nb_bias} coef[b].  grid.y splits the batch.
 template <typename T>
 __global__ void head_wgrad_kernel(const T* __restrict__ X5, const float* __restrict__ coef, float* __restrict__ dwd,
                                   float* __restrict__ dbd, int Bt, int nb_bias, int w5, int c5, int Cp) {
   const int total = w5 * c5;
+  const int per = (Bt + gridDim.y - 1) / gridDim.y;
+  const int b_lo = blockIdx.y * per;
+  const int b_hi = b_lo + per < Bt ? b_lo + per : Bt;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = i % c5, t = i / c5;
     float acc = 0.f;
-    for (int b = 0; b < Bt; ++b) acc += coef[b] * Elem<T>::to_f(X5[((long long)b * w5 + t) * Cp + c]);
-    dwd[i] += acc;
+    for (int b = b_lo; b < b_hi; ++b) acc += coef[b] * Elem<T>::to_f(X5[((long long)b * w5 + t) * Cp + c]);
+    atomicAdd(&dwd[i], acc);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     float s = 0.f;
     for (int b = 0; b < nb_bias; ++b) s += coef[b];
     dbd[0] += s;
@@ -385,25 +466,50 @@ __global__ void __launch_bounds__(256) ln_lrelu_forward_kernel(const T* __restri
                                                                const float* __restrict__ beta, T* __restrict__ H,
                                                                float* __restrict__ mu_out, float* __restrict__ rstd_out,
                                                                long long rows, int C, int Cp) {
+  constexpr int V = Vec16<T>::N;
+  constexpr int MAXV = 4;               // vectors per lane: Cp <= 32 * 4 * V (1024 bf16 / 512 fp32 channels)
   const int lane = threadIdx.x & 31;
+  const int nv = Cp / V;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long r = warp; r < rows; r += nwarps) {
     const T* a = A + r * Cp;
+    float x[MAXV][V];
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += Elem<T>::to_f(a[c]);
-    const float mu = warp_sum(s) / C;
-    float v = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float d = Elem<T>::to_f(a[c]) - mu;
-      v += d * d;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + 32 * k;
+      if (vi < nv) {
+        vload<T>(a + vi * V, x[k]);
+#pragma unroll
+        for (int e = 0; e < V; ++e) s += x[k][e];   // pad channels hold exact zeros
+      }
     }
-    const float rstd = rsqrtf(warp_sum(v) / C + CG_LN_EPS);
+    const float mu = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + 32 * k;
+      if (vi < nv) {
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+          if (vi * V + e < C) { const float d = x[k][e] - mu; q += d * d; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + CG_LN_EPS);
     T* h = H + r * Cp;
-    for (int c = lane; c < Cp; c += 32) {
-      float o = 0.f;
-      if (c < C) o = lrelu((Elem<T>::to_f(a[c]) - mu) * rstd * gamma[c] + beta[c]);
-      h[c] = Elem<T>::from_f(o);
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + 32 * k;
+      if (vi < nv) {
+        float o[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const int c = vi * V + e;
+          o[e] = c < C ? lrelu((x[k][e] - mu) * rstd * gamma[c] + beta[c]) : 0.f;
+        }
+        vstore<T>(h + vi * V, o);
+      }
     }
     if (lane == 0) {
       mu_out[r] = mu;
@@ -610,13 +716,20 @@ __global__ void fill_coef_kernel(float* coef, int B, int groups, float single) {
   else coef[i] = i < B ? -1.f / B : (i < 2 * B ? 1.f / B : 1.f);
 }
 
-// V0[b] = ucoef[b] * G[b]
+// V0[b] = ucoef[b] * G[b]   (16-byte vectors; per_sample % (16/sizeof(T)) == 0)
 template <typename T>
 __global__ void scale_rows_kernel(const T* __restrict__ G, const float* __restrict__ ucoef, T* __restrict__ V,
                                   long long per_sample, long long total) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x)
-    V[i] = Elem<T>::from_f(Elem<T>::to_f(G[i]) * ucoef[i / per_sample]);
+  constexpr int W = Vec16<T>::N;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * W; i < total;
+       i += (long long)gridDim.x * blockDim.x * W) {
+    float v[W];
+    vload<T>(G + i, v);
+    const float u = ucoef[i / per_sample];
+#pragma unroll
+    for (int e = 0; e < W; ++e) v[e] *= u;
+    vstore<T>(V + i, v);
+  }
 }
 
 // =============================================================================================

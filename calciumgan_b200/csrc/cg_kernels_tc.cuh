@@ -756,6 +756,170 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__
   }
 }
 
+// =============================================================================================
+// wgrad2_tc: slab-reuse weight gradient (time rows per sample >= 64).
+//   work item = (tap group g, 64-channel block mb, tap subset, n-tile, row split). Per 64-row chunk ONE slab
+//   S[b, q0+min_shift .. q0+64+max_shift, acol_g + 64*mb .. +64] is loaded; accumulator a holds taps (ta, tb):
+//   its M = 128 operand is the slab read at row offsets shift(ta) and shift(tb) -- the second 64-channel MN block
+//   is reached through the descriptor's LBO = (shift(tb) - shift(ta)) rows. All accumulators share the P tile.
+// =============================================================================================
+struct Wg2Params {
+  WgParams p;
+  int BN, n_origin, n_tiles;
+  int mblocks, ngroups, nsub[2], taps_per_cta;       // nsub[g] = tap subsets of group g
+  int items_per_split, splits;                        // items = sum_g mblocks * nsub[g] * n_tiles
+  int chunks_per_sample, total_chunks, chunks_per_split;
+  int box_rows, slab_bytes, stages;
+  int g_acol[2], g_min_shift[2], g_nseg[2];
+  unsigned char g_rel[2][32];                         // shift - min_shift of tap s of group g
+  unsigned char g_seg[2][32];                         // original tap index (output slice)
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmP,
+                 const __grid_constant__ Wg2Params P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const WgParams& p = P.p;
+  const int BN = P.BN;
+  const int stages = P.stages;
+  const int stage_bytes = P.slab_bytes + BN * 128;
+  uint8_t* tiles = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* empty = full + stages;
+  uint64_t* tfull = empty + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- decode the work item
+  int w = blockIdx.x;
+  const int split = w / P.items_per_split;
+  w -= split * P.items_per_split;
+  const int nt = w % P.n_tiles; w /= P.n_tiles;
+  int g = 0;
+  if (w >= P.mblocks * P.nsub[0]) { g = 1; w -= P.mblocks * P.nsub[0]; }
+  const int sub = w % P.nsub[g];
+  const int mb = w / P.nsub[g];
+  const int tap0 = sub * P.taps_per_cta;
+  int ntaps = P.g_nseg[g] - tap0;
+  if (ntaps > P.taps_per_cta) ntaps = P.taps_per_cta;
+  const int nacc = (ntaps + 1) / 2;
+  const int ch_begin = split * P.chunks_per_split;
+  int ch_end = ch_begin + P.chunks_per_split;
+  if (ch_end > P.total_chunks) ch_end = P.total_chunks;
+  const int nchunks = ch_end - ch_begin;
+  const int n_begin = P.n_origin + nt * BN;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmS);
+    prefetch_tmap(&tmP);
+    for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&tfull[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t ph = 0;
+    const int scol = P.g_acol[g] + mb * 64;
+    for (int ch = ch_begin; ch < ch_end; ++ch) {
+      const int b0 = ch / P.chunks_per_sample, q0 = (ch % P.chunks_per_sample) * 64;
+      mbar_wait(&empty[stage], ph ^ 1);
+      if (elect_one()) {
+        uint8_t* sa = tiles + (size_t)stage * stage_bytes;
+        mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+        tma_load_3d(sa, &tmS, &full[stage], scol, q0 + P.g_min_shift[g], b0);
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_3d(sa + P.slab_bytes + j * 8192, &tmP, &full[stage], n_begin + j * 64, q0, b0);
+      }
+      if (++stage == stages) { stage = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(128, BN, 1, 1);
+    const uint32_t hi = desc_hi(1024);
+    const uint32_t lo0 = (smem_u32(tiles) >> 4) & 0x3FFF;
+    const uint32_t stage_step = (uint32_t)stage_bytes >> 4;
+    const uint32_t b_off = ((uint32_t)P.slab_bytes >> 4) | (512u << 16);   // P tile: LBO = 8192 B between 64-channel blocks
+    // per accumulator: row offset of the first tap (16-byte units) | LBO = distance to the second tap
+    uint32_t a_off[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int ta = tap0 + 2 * a, tb = (2 * a + 1 < ntaps) ? ta + 1 : ta;
+      const uint32_t ra = a < nacc ? P.g_rel[g][ta] : 0, rb = a < nacc ? P.g_rel[g][tb] : 0;
+      a_off[a] = ra * 8 + (((rb - ra) * 8) << 16);
+    }
+    int stage = 0;
+    uint32_t ph = 0;
+    for (int ci = 0; ci < nchunks; ++ci) {
+      mbar_wait(&full[stage], ph);
+      tc_fence_after();
+      const uint32_t s_lo = lo0 + stage * stage_step;
+      if (elect_one()) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          if (a < nacc) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // K = 16 rows = 2048 bytes per step
+              umma_bf16_lohi(tmem_base + a * BN, s_lo + a_off[a] + 128 * k, s_lo + b_off + 128 * k, hi, idesc,
+                             (uint32_t)(ci | k));
+          }
+        }
+        umma_commit(&empty[stage]);
+        if (ci == nchunks - 1) umma_commit(&tfull[0]);
+      }
+      __syncwarp();
+      if (++stage == stages) { stage = 0; ph ^= 1; }
+    }
+  } else {
+    const int lq = warp & 3;
+    const int r = lq * 32 + lane;       // accumulator row: tap (r / 64) of the pair, channel r % 64
+    const int m = mb * 64 + (r & 63);
+    const bool vec_ok = (p.n_real & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.dW) & 15) == 0);
+    mbar_wait(&tfull[0], 0);
+    tc_fence_after();
+    for (int a = 0; a < nacc; ++a) {
+      const int ti = tap0 + 2 * a + (r >> 6);
+      const bool row_ok = ti < tap0 + ntaps && m < p.m_real;
+      const int seg = P.g_seg[g][ti < 32 ? ti : 0];
+      float* dst = p.dW + ((long long)seg * p.m_real + m) * p.n_real;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + a * BN + c0, v);
+        tmem_ld_wait();
+        if (row_ok) {
+          const int n0 = n_begin + c0;
+          if (vec_ok && n0 + 32 <= p.n_real) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              red_add_v4(dst + n0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                         __uint_as_float(v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.n_real) atomicAdd(dst + n0 + j, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------- host side
@@ -796,7 +960,8 @@ static inline int tc_init(TcState* s) {
   CG_SET_SMEM(EPI_NONE) CG_SET_SMEM(EPI_BIAS) CG_SET_SMEM(EPI_BIAS_LRELU) CG_SET_SMEM(EPI_MASK) CG_SET_SMEM(EPI_BIAS_SIGMOID)
 #undef CG_SET_SMEM
   if (!ok ||
-      cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) != cudaSuccess)
+      cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(tc::wgrad2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) != cudaSuccess)
     return cg_tc_set_err("cudaFuncSetAttribute(max dynamic smem) failed");
   return 0;
 }
@@ -1019,7 +1184,85 @@ static inline bool tc_wgrad_supported(const WgParams& p) {
   return true;
 }
 
+// ---- wgrad v2 (slab reuse) -----------------------------------------------------------------------------
+static inline bool tc_wgrad2_supported(const WgParams& p) {
+  if (p.Q < 64 || p.Q % 64 || p.s_rows != p.Q) return false;
+  int cols[2], nc = 0, cnt[2] = {0, 0};
+  for (int s = 0; s < p.nseg; ++s) {
+    int g = -1;
+    for (int i = 0; i < nc; ++i) if (cols[i] == p.scol[s]) g = i;
+    if (g < 0) { if (nc == 2) return false; cols[nc] = p.scol[s]; g = nc++; }
+    if (++cnt[g] > 32) return false;
+  }
+  return true;
+}
+
+static inline int tc_wgrad2_launch(TcState* s, const WgParams& p, cudaStream_t stream) {
+  tc::Wg2Params P;
+  memset(&P, 0, sizeof(P));
+  P.p = p;
+  P.mblocks = p.Mp / 64;
+  // tap groups (same column offset = same parity), taps sorted by shift so LBO >= 0
+  for (int sg = 0; sg < p.nseg; ++sg) {
+    int g = -1;
+    for (int i = 0; i < P.ngroups; ++i) if (P.g_acol[i] == p.scol[sg]) g = i;
+    if (g < 0) { g = P.ngroups++; P.g_acol[g] = p.scol[sg]; P.g_min_shift[g] = 1 << 20; }
+    if (p.shift[sg] < P.g_min_shift[g]) P.g_min_shift[g] = p.shift[sg];
+  }
+  int span = 0;
+  for (int g = 0; g < P.ngroups; ++g) {
+    int idx[32], n = 0;
+    for (int sg = 0; sg < p.nseg; ++sg) if (p.scol[sg] == P.g_acol[g]) idx[n++] = sg;
+    for (int i = 0; i < n; ++i)
+      for (int j = i + 1; j < n; ++j)
+        if (p.shift[idx[j]] < p.shift[idx[i]]) { int t = idx[i]; idx[i] = idx[j]; idx[j] = t; }
+    P.g_nseg[g] = n;
+    for (int i = 0; i < n; ++i) {
+      P.g_rel[g][i] = (unsigned char)(p.shift[idx[i]] - P.g_min_shift[g]);
+      P.g_seg[g][i] = (unsigned char)idx[i];
+      if (P.g_rel[g][i] > span) span = P.g_rel[g][i];
+    }
+  }
+  P.box_rows = (64 + span + 7) / 8 * 8;
+  if (P.box_rows > 256) return cg_tc_set_err("wgrad2_tc: tap span too large for one TMA box");
+  P.slab_bytes = P.box_rows * 128;
+  P.chunks_per_sample = p.Q / 64;
+  P.total_chunks = p.B * P.chunks_per_sample;
+  CUtensorMap tmS, tmP;
+  if (tc_get_map3(s, p.S, p.s_rs, p.s_rows, p.B, p.s_rs, p.s_bs, P.box_rows, 1, &tmS)) return 1;
+  if (tc_get_map3(s, p.P, p.p_rs, p.Q, p.B, p.p_rs, p.p_bs, 64, 1, &tmP)) return 1;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int full_tiles = p.Np / 256, rem = p.Np % 256;
+    if (pass == 0) { if (!full_tiles) continue; P.BN = 256; P.n_origin = 0; P.n_tiles = full_tiles; }
+    else { if (!rem) continue; P.BN = rem; P.n_origin = full_tiles * 256; P.n_tiles = 1; }
+    int max_acc = 512 / P.BN;
+    if (max_acc > 8) max_acc = 8;
+    P.taps_per_cta = 2 * max_acc;
+    int items = 0;
+    for (int g = 0; g < 2; ++g) {
+      P.nsub[g] = g < P.ngroups ? (P.g_nseg[g] + P.taps_per_cta - 1) / P.taps_per_cta : 0;
+      items += P.mblocks * P.nsub[g] * P.n_tiles;
+    }
+    if (P.nsub[0] == 0) return cg_tc_set_err("wgrad2_tc: empty tap group");
+    P.items_per_split = items;
+    int splits = (2 * s->sm_count + items - 1) / items;
+    if (splits > P.total_chunks) splits = P.total_chunks;
+    if (splits < 1) splits = 1;
+    P.chunks_per_split = (P.total_chunks + splits - 1) / splits;
+    P.splits = (P.total_chunks + P.chunks_per_split - 1) / P.chunks_per_split;
+    const int stage_bytes = P.slab_bytes + P.BN * 128;
+    int stages = (s->max_smem - 2048) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) return cg_tc_set_err("wgrad2_tc: not enough shared memory");
+    P.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    tc::wgrad2_tc_kernel<<<items * P.splits, tc::kThreads, smem, stream>>>(tmS, tmP, P);
+  }
+  return 0;
+}
+
 static inline int tc_wgrad_launch(TcState* s, const WgParams& p, cudaStream_t stream) {
+  if (!s->force_v1 && tc_wgrad2_supported(p)) return tc_wgrad2_launch(s, p, stream);
   tc::WgTcParams P;
   P.p = p;
   P.mblocks = p.Mp / 64;
