@@ -41,7 +41,7 @@ def measured_peaks():
 
 class ClockSampler(object):
   """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-  Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+  Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
        'clocks_event_reasons.sw_power_cap')
 
@@ -51,7 +51,7 @@ class ClockSampler(object):
   def start(self):
     try:
       self.proc = subprocess.Popen(
-          ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+          ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '20'],
           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
@@ -62,7 +62,9 @@ class ClockSampler(object):
     for line in self.proc.stdout:
       self.rows.append([x.strip() for x in line.split(',')])
 
-  def stop(self):
+  def stop(self, t0=None, t1=None):
+    """Summarise the samples whose timestamp lies in the timed window [t0, t1] (host epoch seconds)."""
+    import datetime
     if self.proc is None:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
     time.sleep(0.15)
@@ -75,9 +77,12 @@ class ClockSampler(object):
     names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
     for r in self.rows:
       try:
-        sm.append(float(r[0]))
-        mx.append(float(r[1]))
-        for n, v in zip(names, r[3:7]):
+        ts = datetime.datetime.strptime(r[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+        if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.05):
+          continue
+        sm.append(float(r[1]))
+        mx.append(float(r[2]))
+        for n, v in zip(names, r[4:8]):
           if v.lower().startswith('active'):
             reasons.add(n)
       except Exception:
@@ -202,15 +207,17 @@ def main():
   def step_resident():
     return gan.train(real_dev)
 
-  for _ in range(warmup):
-    out = step_resident()
   clocks = ClockSampler(local_rank)
   if rank == 0:
-    clocks.start()
+    clocks.start()     # started before the warm-up so the sampler is streaming when the timed region begins
+  for _ in range(warmup):
+    out = step_resident()
   l0 = eng.launch_count()
+  t_wall0 = time.time()
   ms = timed(step_resident, args.steps)
+  t_wall1 = time.time()
   launches = eng.launch_count() - l0
-  clk = clocks.stop() if rank == 0 else None
+  clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
   ms_per_step = ms / args.steps
   value = world * B * args.steps / (ms * 1e-3)
 
