@@ -545,7 +545,7 @@ static WgParams convT_wgrad_params(cg_ctx* c, int i, int B) {
 }
 
 // calciumgan.py:22-103. noise (B, nd) fp32 device. Writes FAKE32 (B, L, C).
-static int g_forward(cg_ctx* c, const float* noise, int B) {
+static int g_forward(cg_ctx* c, const float* noise, int B, void* fake_slot = nullptr) {
   DISPATCH_T(c, dense0_forward_kernel<T><<<grid_for((long long)B * c->w0 * c->gcp[0]), 256, 0, c->stream>>>(
                     noise, gparam(c, 0), gparam(c, 1), (T*)c->HG[0], B, c->nd, c->w0, c->gcp[0]));
   CK(post_launch(c, "dense0_fwd"));
@@ -553,9 +553,14 @@ static int g_forward(cg_ctx* c, const float* noise, int B) {
     CK(launch_rsgemm(c, convT_fwd_params(c, i, B)));
     const long long rows = (long long)B * c->gl[i];
     if (c->cfg.layer_norm) {
-      DISPATCH_T(c, ln_lrelu_forward_kernel<T><<<grid_for(rows * 32), 256, 0, c->stream>>>(
-                        (const T*)c->AG[i], gparam(c, c->g_gam[i]), gparam(c, c->g_bet[i]), (T*)c->HG[i], c->MU[i],
-                        c->RSTD[i], rows, c->gc[i], c->gcp[i]));
+      const int nvec = c->gcp[i] / (16 / c->esz);
+      const int lpr = nvec > 16 ? 32 : (nvec > 8 ? 16 : 8);
+#define CG_LN(LPRV)                                                                                              \
+  DISPATCH_T(c, ln_lrelu_forward_kernel<T, LPRV><<<grid_for(rows * LPRV), 256, 0, c->stream>>>(                    \
+                    (const T*)c->AG[i], gparam(c, c->g_gam[i]), gparam(c, c->g_bet[i]), (T*)c->HG[i], c->MU[i], \
+                    c->RSTD[i], rows, c->gc[i], c->gcp[i]))
+      if (lpr == 32) CG_LN(32); else if (lpr == 16) CG_LN(16); else CG_LN(8);
+#undef CG_LN
       CK(post_launch(c, "ln_fwd"));
     } else {
       DISPATCH_T(c, lrelu_kernel<T><<<grid_for(rows * c->gcp[i]), 256, 0, c->stream>>>((const T*)c->AG[i],
@@ -568,7 +573,7 @@ static int g_forward(cg_ctx* c, const float* noise, int B) {
   const int Cp = c->gcp[NL];
   p.A = c->HG[NL]; p.a_bs = (long long)c->L * Cp; p.a_rs = Cp; p.a_rows = c->L;
   p.W = c->Wf_d1; p.w_ld = Cp;
-  p.out = nullptr;
+  p.out = fake_slot;     // optional compute-type copy (critic input slot; Cp == dcp[0])
   p.out32 = c->FAKE32; p.o32_bs = (long long)c->L * c->C; p.o32_rs = c->C;
   p.o_bs = (long long)c->L * Cp; p.o_rs = Cp;
   p.bias = gparam(c, c->g_d1b);
@@ -776,20 +781,28 @@ static int fetch_scalars(cg_ctx* c, int slot, int flags, float* scalars_host) {
 // ------------------------------------------------------------------------------------------ critic step
 // forward part shared by cg_critic_step and cg_validate: fake, D on [real; fake; xhat], dgrad chain, GP scalars
 static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
-                             const int32_t* sh, int slot) {
-  CK(g_forward(c, noise, B));
-  const long long tot = (long long)B * c->L * c->dcp[0] / 4;
-  DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(real, c->FAKE32, alpha, (T*)c->X[0], B,
-                                                                           c->L, c->C, c->dcp[0], 0));
-  CK(post_launch(c, "assemble_x0"));
+                             const int32_t* sh, int slot, bool real_ready = false) {
+  const long long per = (long long)B * c->L * c->dcp[0];
+  // generator head writes fp32 FAKE32 and the compute-type copy straight into the critic's "fake" slot
+  CK(g_forward(c, noise, B, off(c, c->X[0], per)));
+  const long long tot = per / 4;
+  if (!real_ready) {   // the 5 critic sub-steps of one train step share the real batch (wgan_gp.py:85-86)
+    DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(real, nullptr, nullptr, (T*)c->X[0], B,
+                                                                             c->L, c->C, c->dcp[0], 1));
+    CK(post_launch(c, "real_to_x0"));
+  }
+  DISPATCH_T(c, interp_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(real, c->FAKE32, alpha,
+                                                                      (T*)off(c, c->X[0], 2 * per), B, c->L, c->C,
+                                                                      c->dcp[0]));
+  CK(post_launch(c, "interp"));
   CK(d_forward(c, 3 * B, B, 3, sh));
   fill_coef_kernel<<<(3 * B + 255) / 256, 256, 0, c->stream>>>(c->coef, B, 3, 0.f);
   CK(post_launch(c, "fill_coef"));
   CK(d_backward(c, 3 * B, B, 3, sh, 2 * B, B));
   CU(cudaMemsetAsync(c->sumsq, 0, (size_t)B * 4, c->stream));
-  const long long per = (long long)c->L * c->dcp[0];
+  const long long per_sample = (long long)c->L * c->dcp[0];
   const int chunks = 8;
-  DISPATCH_T(c, sumsq_kernel<T><<<B * chunks, 256, 0, c->stream>>>((const T*)c->DX[0], c->sumsq, per, chunks));
+  DISPATCH_T(c, sumsq_kernel<T><<<B * chunks, 256, 0, c->stream>>>((const T*)c->DX[0], c->sumsq, per_sample, chunks));
   CK(post_launch(c, "sumsq"));
   critic_scalars_kernel<<<1, 256, 0, c->stream>>>(c->scores, c->sumsq, c->ucoef, c->norms,
                                                   c->d_scal + (size_t)slot * CG_NUM_SCALARS, B, c->cfg.gp_lambda);
@@ -797,8 +810,8 @@ static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* n
 }
 
 static int critic_step_impl(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
-                            const int32_t* sh, int flags, int slot) {
-  CK(critic_forward_gp(c, real, B, noise, alpha, sh, slot));
+                            const int32_t* sh, int flags, int slot, bool real_ready = false) {
+  CK(critic_forward_gp(c, real, B, noise, alpha, sh, slot, real_ready));
   // GP second-order term without the second-order graph: v0 = u = d(lambda*GP)/dg
   const long long per = (long long)c->L * c->dcp[0];
   DISPATCH_T(c, scale_rows_kernel<T><<<grid_for(per * B / (16 / c->esz)), 256, 0, c->stream>>>(
@@ -856,11 +869,7 @@ extern "C" int cg_critic_step(cg_ctx* c, const float* real, int B, const float* 
 static int generator_step_impl(cg_ctx* c, const float* real, int B, const float* noise, const int32_t* sh, int flags,
                                int slot) {
   CU(cudaMemcpyAsync(c->Z, noise, (size_t)B * c->nd * 4, cudaMemcpyDeviceToDevice, c->stream));
-  CK(g_forward(c, c->Z, B));
-  const long long tot = (long long)B * c->L * c->dcp[0] / 4;
-  DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(c->FAKE32, nullptr, nullptr, (T*)c->X[0],
-                                                                           B, c->L, c->C, c->dcp[0], 1));
-  CK(post_launch(c, "assemble_x0_fake"));
+  CK(g_forward(c, c->Z, B, c->X[0]));
   CK(d_forward(c, B, B, 1, sh));
   float* scal = c->d_scal + (size_t)slot * CG_NUM_SCALARS;
   gen_loss_kernel<<<1, 256, 0, c->stream>>>(c->scores, scal, B);
@@ -902,7 +911,7 @@ extern "C" int cg_train_step(cg_ctx* c, const float* real, int B, const float* n
   for (int i = 0; i < 12 * nc + 4; ++i)
     if (sh[i] < -c->cfg.phase_m || sh[i] > c->cfg.phase_m) return set_err("phase-shuffle shift out of range");
   for (int i = 0; i < nc; ++i)
-    CK(critic_step_impl(c, real, B, noise + (size_t)i * B * c->nd, alpha + (size_t)i * B, sh + 12 * i, 0, i));
+    CK(critic_step_impl(c, real, B, noise + (size_t)i * B * c->nd, alpha + (size_t)i * B, sh + 12 * i, 0, i, i > 0));
   CK(generator_step_impl(c, real, B, noise + (size_t)nc * B * c->nd, sh + 12 * nc, 0, nc));
   CU(cudaMemcpyAsync(c->h_scal, c->d_scal, (size_t)(nc + 1) * CG_NUM_SCALARS * 4, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));

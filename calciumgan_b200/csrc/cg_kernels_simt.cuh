@@ -362,6 +362,26 @@ __global__ void assemble_x0_kernel(const float* __restrict__ real, const float* 
   }
 }
 
+// xhat = alpha*real + (1-alpha)*fake (wgan_gp.py:38-41), fp32 in, T (B,L,Cp) out, 4 channels per thread
+template <typename T>
+__global__ void interp_kernel(const float* __restrict__ real, const float* __restrict__ fake,
+                              const float* __restrict__ alpha, T* __restrict__ Xh, int B, int L, int C, int Cp) {
+  const int c4 = Cp / 4;
+  const long long total = (long long)B * L * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) * 4;
+    const long long bt = i / c4;
+    const float a = alpha[(int)(bt / L)];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float x = 0.f;
+      if (c + e < C) x = a * real[bt * C + c + e] + (1.f - a) * fake[bt * C + c + e];
+      Xh[bt * Cp + c + e] = Elem<T>::from_f(x);
+    }
+  }
+}
+
 // unpad + cast: T (B,L,Cp) -> fp32 (B,L,C)
 template <typename T>
 __global__ void unpad_kernel(const T* __restrict__ src, float* __restrict__ dst, long long rows, int C, int Cp) {
@@ -461,59 +481,69 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, fl
 // =============================================================================================
 // Generator layer-norm + LeakyReLU (calciumgan.py:45-46): one warp per (b,t) row, channels C of Cp.
 // =============================================================================================
-template <typename T>
+template <typename T, int LPR>   // LPR lanes per row (8 | 16 | 32): short rows share a warp
 __global__ void __launch_bounds__(256) ln_lrelu_forward_kernel(const T* __restrict__ A, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, T* __restrict__ H,
                                                                float* __restrict__ mu_out, float* __restrict__ rstd_out,
                                                                long long rows, int C, int Cp) {
   constexpr int V = Vec16<T>::N;
-  constexpr int MAXV = 4;               // vectors per lane: Cp <= 32 * 4 * V (1024 bf16 / 512 fp32 channels)
+  constexpr int MAXV = 4;               // vectors per lane: Cp <= LPR * 4 * V
+  constexpr int RPW = 32 / LPR;         // rows per warp
   const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
   const int nv = Cp / V;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long r = warp; r < rows; r += nwarps) {
-    const T* a = A + r * Cp;
+  for (long long r0 = warp * RPW; r0 < rows; r0 += nwarps * RPW) {
+    const long long r = r0 + sub;
+    const bool ok = r < rows;
+    const T* a = A + (ok ? r : 0) * Cp;
     float x[MAXV][V];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
-      const int vi = lane + 32 * k;
+      const int vi = sl + LPR * k;
       if (vi < nv) {
         vload<T>(a + vi * V, x[k]);
 #pragma unroll
         for (int e = 0; e < V; ++e) s += x[k][e];   // pad channels hold exact zeros
       }
     }
-    const float mu = warp_sum(s) / C;
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mu = s / C;
     float q = 0.f;
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
-      const int vi = lane + 32 * k;
+      const int vi = sl + LPR * k;
       if (vi < nv) {
 #pragma unroll
         for (int e = 0; e < V; ++e)
           if (vi * V + e < C) { const float d = x[k][e] - mu; q += d * d; }
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) / C + CG_LN_EPS);
-    T* h = H + r * Cp;
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      const int vi = lane + 32 * k;
-      if (vi < nv) {
-        float o[V];
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / C + CG_LN_EPS);
+    if (ok) {
+      T* h = H + r * Cp;
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-          const int c = vi * V + e;
-          o[e] = c < C ? lrelu((x[k][e] - mu) * rstd * gamma[c] + beta[c]) : 0.f;
+      for (int k = 0; k < MAXV; ++k) {
+        const int vi = sl + LPR * k;
+        if (vi < nv) {
+          float o[V];
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            const int c = vi * V + e;
+            o[e] = c < C ? lrelu((x[k][e] - mu) * rstd * gamma[c] + beta[c]) : 0.f;
+          }
+          vstore<T>(h + vi * V, o);
         }
-        vstore<T>(h + vi * V, o);
       }
-    }
-    if (lane == 0) {
-      mu_out[r] = mu;
-      rstd_out[r] = rstd;
+      if (sl == 0) {
+        mu_out[r] = mu;
+        rstd_out[r] = rstd;
+      }
     }
   }
 }

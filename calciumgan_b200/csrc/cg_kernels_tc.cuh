@@ -236,7 +236,7 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
         for (int e = 0; e < 4; ++e) {
           float x = __uint_as_float(v[j4 * 4 + e]) + bv[e];
           if (EPI == EPI_BIAS_LRELU) x = lrelu(x);
-          if (EPI == EPI_BIAS_SIGMOID) x = __fdividef(1.f, 1.f + __expf(-x));
+          if (EPI == EPI_BIAS_SIGMOID) x = (n0 + j4 * 4 + e < p.n_real) ? __fdividef(1.f, 1.f + __expf(-x)) : 0.f;
           v[j4 * 4 + e] = __float_as_uint(x);
         }
       }
