@@ -89,7 +89,7 @@ struct cg_ctx {
   int64_t launches = 0;
   int64_t tc_launches = 0;
   bool profiling = false;
-  struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; };
+  struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; char desc[96]; };
   std::vector<ProfRec> prof;
   int64_t dev_bytes = 0;
   std::vector<void*> allocs;
@@ -188,10 +188,11 @@ static int post_launch(cg_ctx* c, const char* what) {
   return 0;
 }
 
-static int prof_begin(cg_ctx* c, int cls, double flops) {
+static int prof_begin(cg_ctx* c, int cls, double flops, const char* desc = "") {
   if (!c->profiling) return 0;
   cg_ctx::ProfRec r;
   r.cls = cls; r.flops = flops;
+  snprintf(r.desc, sizeof(r.desc), "%s", desc);
   CU(cudaEventCreate(&r.e0));
   CU(cudaEventCreate(&r.e1));
   CU(cudaEventRecord(r.e0, c->stream));
@@ -218,14 +219,18 @@ static int launch_rsgemm_raw(cg_ctx* c, const RsParams& p) {
 static int launch_rsgemm(cg_ctx* c, const RsParams& p) {
   int nseg = 0;
   for (int i = 0; i < p.seg.nphase; ++i) nseg += p.seg.nseg[i];
-  CK(prof_begin(c, 0, 2.0 * p.B * p.Q * (double)p.n_real * p.k_real * nseg));
+  char d[96];
+  snprintf(d, sizeof(d), "gemm  B=%d Q=%d N=%d Kc=%d taps=%d ph=%d epi=%d", p.B, p.Q, p.N, p.Kc, nseg, p.seg.nphase, p.epi);
+  CK(prof_begin(c, 0, 2.0 * p.B * p.Q * (double)p.n_real * p.k_real * nseg, d));
   CK(launch_rsgemm_raw(c, p));
   return prof_end(c);
 }
 
 static int launch_wgrad_raw(cg_ctx* c, WgParams p);
 static int launch_wgrad(cg_ctx* c, const WgParams& p) {
-  CK(prof_begin(c, 1, 2.0 * p.B * p.Q * (double)p.m_real * p.n_real * p.nseg));
+  char d[96];
+  snprintf(d, sizeof(d), "wgrad B=%d Q=%d M=%d N=%d taps=%d", p.B, p.Q, p.Mp, p.Np, p.nseg);
+  CK(prof_begin(c, 1, 2.0 * p.B * p.Q * (double)p.m_real * p.n_real * p.nseg, d));
   CK(launch_wgrad_raw(c, p));
   return prof_end(c);
 }
@@ -1082,6 +1087,7 @@ extern "C" int cg_profile_report(cg_ctx* c, double out[8]) {
   for (auto& r : c->prof) {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    if (getenv("CG_PROF_DUMP")) fprintf(stderr, "[prof] %-60s %8.1f us %7.1f TF/s\n", r.desc, ms * 1e3, r.flops / ms / 1e9);
     out[r.cls * 3 + 0] += ms;
     out[r.cls * 3 + 1] += r.flops;
     out[r.cls * 3 + 2] += 1;

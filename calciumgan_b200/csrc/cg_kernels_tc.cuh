@@ -241,11 +241,25 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
         }
       }
     }
-    if (p.out32 && R.my_ok) {   // unpadded fp32 copy (generator head only)
-      float* o32 = p.out32 + R.my_o32;
+    if (p.out32) {   // unpadded fp32 copy (generator head only): 32x32 fp32 transpose through the staging buffer so
+                     // every warp store writes 32 consecutive floats of one output row
+      float* stf = reinterpret_cast<float*>(stg);
 #pragma unroll
-      for (int j = 0; j < 64; ++j)
-        if (j < ncols && n0 + j < p.n_real) o32[n0 + j] = __uint_as_float(v[j]);
+      for (int h = 0; h < 2; ++h) {
+        if (h * 32 < ncols) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stf[lane * 32 + (j ^ lane)] = __uint_as_float(v[h * 32 + j]);
+          __syncwarp();
+          const int n = n0 + h * 32 + lane;
+          for (int rr = 0; rr < 32; ++rr) {
+            const float val = stf[rr * 32 + (lane ^ rr)];
+            const long long o = __shfl_sync(0xffffffffu, R.my_o32, rr);
+            const int ok = __shfl_sync(0xffffffffu, (int)R.my_ok, rr);
+            if (ok && n < p.n_real) p.out32[o + n] = val;
+          }
+          __syncwarp();
+        }
+      }
     }
     if (out) {
 #pragma unroll
