@@ -113,6 +113,58 @@ __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) 
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) {
   return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);   // version 1 (bit 46), SWIZZLE_128B (bits 61-63)
 }
+// ---- CTA-pair (cta_group::2) helpers --------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local smem address` in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data lands in the executing CTA's smem, bytes are counted on the barrier at `mbar_cluster`
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* map, uint32_t mbar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(mbar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, uint32_t mbar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(mbar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// M = 256 MMA over the CTA pair (issued by the leader CTA only)
+__device__ __forceinline__ void umma2_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                                uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n .reg .pred p;\n .reg .b64 da, db;\n setp.ne.b32 p, %5, 0;\n mov.b64 da, {%1, %3};\n mov.b64 db, {%2, %3};\n"
+      " tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// completion of all prior MMAs of this thread -> arrive on the barrier at the same smem offset in both CTAs
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((unsigned short)3)
+               : "memory");
+}
+
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -459,6 +511,7 @@ rsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //    base_offset = 0 - verified on B200). Activation traffic from L2 drops by the number of taps per group.
 //  * MB (1|2) accumulators of 128 rows share each weight tile, halving weight bytes per MAC.
 // =============================================================================================
+#define CG_DBG_ADD(i, t0) do { if (P.dbg && blockIdx.x == 0 && lane == 0) { atomicAdd((unsigned long long*)&P.dbg[i], (unsigned long long)(clock64() - (t0))); atomicAdd((unsigned long long*)&P.dbg[(i) + 8], 1ull); } } while (0)
 struct SlabGroup {
   int acol, min_shift, nseg;
   unsigned char shift_rel[32];
@@ -468,8 +521,10 @@ struct RsTc2Params {
   RsParams p;
   int BN, n_tiles, m_tiles, MB, blocks_per_sample, total_blocks, kchunks;
   int box_rows, box_bytes, slab_bytes, slab_stages, b_stages, double_acc;
+  int tps;              // taps per weight stage (pair kernel): more MMAs per barrier round-trip for narrow N
   int ngroups[2];
   SlabGroup grp[2][2];
+  long long* dbg;   // optional role cycle counters of CTA 0 (CG_TC_TIMING=1)
 };
 
 template <int EPI>
@@ -525,7 +580,9 @@ rsgemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int kc = 0; kc < P.kchunks; ++kc) {
         for (int g = 0; g < P.ngroups[phase]; ++g) {
           const SlabGroup& G = P.grp[phase][g];
+          long long tq = clock64();
           mbar_wait(&s_empty[ss], sph ^ 1);
+          CG_DBG_ADD(0, tq);
           if (elect_one()) {
             uint8_t* sl = slabs + (size_t)ss * P.slab_bytes;
             mbar_expect_tx(&s_full[ss], (uint32_t)P.slab_bytes);
@@ -538,7 +595,9 @@ rsgemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           if (++ss == SS) { ss = 0; sph ^= 1; }
           for (int s = 0; s < G.nseg; ++s) {
+            tq = clock64();
             mbar_wait(&b_empty[bs], bph ^ 1);
+            CG_DBG_ADD(1, tq);
             if (elect_one()) {
               mbar_expect_tx(&b_full[bs], (uint32_t)b_bytes);
               tma_load_2d(btiles + (size_t)bs * b_bytes, &tmW, &b_full[bs], G.wk[s] + kc * 64, nt * BN);
@@ -561,18 +620,24 @@ rsgemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int phase = (t / P.m_tiles) / P.n_tiles;
       const int acc = P.double_acc ? (it & 1) : 0;
       const uint32_t use = P.double_acc ? ((uint32_t)it >> 1) : (uint32_t)it;
+      long long tq = clock64();
       mbar_wait(&tempty[acc], (use & 1) ^ 1);
+      CG_DBG_ADD(2, tq);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * acc_stride;
       uint32_t accum = 0;
       for (int kc = 0; kc < P.kchunks; ++kc) {
         for (int g = 0; g < P.ngroups[phase]; ++g) {
           const SlabGroup& G = P.grp[phase][g];
+          tq = clock64();
           mbar_wait(&s_full[ss], sph);
+          CG_DBG_ADD(3, tq);
           tc_fence_after();
           const uint32_t sl_lo = slab_lo0 + ss * slab_step;
           for (int s = 0; s < G.nseg; ++s) {
+            tq = clock64();
             mbar_wait(&b_full[bs], bph);
+            CG_DBG_ADD(4, tq);
             tc_fence_after();
             const uint32_t b_lo = b_lo0 + bs * b_step;
             const uint32_t a_lo = sl_lo + (uint32_t)G.shift_rel[s] * 8;   // one row = 128 B = 8 x 16 B
@@ -619,10 +684,14 @@ rsgemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (nt != last_nt) { epi_load_bias<EPI>(p, bias_s, nt * BN, BN, threadIdx.x - 64); last_nt = nt; }
       const int acc = P.double_acc ? (it & 1) : 0;
       const uint32_t use = P.double_acc ? ((uint32_t)it >> 1) : (uint32_t)it;
+      long long tq = clock64();
       mbar_wait(&tfull[acc], use & 1);
+      if (warp == 2) CG_DBG_ADD(5, tq);
+      tq = clock64();
       tc_fence_after();
       epilogue_block<EPI>(p, tmem_base + acc * acc_stride, BN, nt * BN, R[0], bias_s, stg, lq, lane);
       if (MB == 2) epilogue_block<EPI>(p, tmem_base + acc * acc_stride + BN, BN, nt * BN, R[1], bias_s, stg, lq, lane);
+      if (warp == 2) CG_DBG_ADD(6, tq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -634,6 +703,179 @@ rsgemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// =============================================================================================
+// rsgemm3_tc: CTA-pair (cta_group::2) version of rsgemm2. A cluster of two CTAs computes a 256-row x BN tile:
+// each CTA owns one 128-row block (its own slab, its own TMEM accumulator and epilogue) and HALF of every weight
+// tile; the leader issues tcgen05.mma.cta_group::2 (M = 256), so each SM reads only BN/2 weight rows per MMA and
+// receives half the weight bytes from TMA -- the measured limiter of the single-CTA kernel is shared-memory
+// bandwidth: (A 4 KB + B N*32 B + TMA fill share) / 128 B/clk per MMA.
+// Barrier protocol: full barriers live in the leader (both CTAs' TMA loads complete_tx there); empty / accumulator
+// -full barriers are multicast-committed to both CTAs; accumulator-empty is counted on the leader (8 warps).
+// =============================================================================================
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ RsTc2Params P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const RsParams& p = P.p;
+  const int BN = P.BN;
+  const int SS = P.slab_stages, BS = P.b_stages;
+  const int tap_bytes = BN * 64;               // this CTA's half of one tap's weight tile: BN/2 rows x 128 B
+  const int TPS = P.tps;
+  const int b_bytes = TPS * tap_bytes;         // one weight stage carries TPS taps
+  uint8_t* slabs = smem;
+  uint8_t* btiles = smem + (size_t)SS * P.slab_bytes;
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(btiles + (size_t)BS * b_bytes);
+  uint64_t* s_empty = s_full + SS;
+  uint64_t* b_full = s_empty + SS;
+  uint64_t* b_empty = b_full + BS;
+  uint64_t* tfull = b_empty + BS;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* stage_buf = btiles + (size_t)BS * b_bytes + 512;
+  float* bias_s = reinterpret_cast<float*>(stage_buf + 4 * kStgBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+    for (int i = 0; i < SS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+    for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();          // barriers of both CTAs initialised before any remote arrive / TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.seg.nphase * P.n_tiles * P.m_tiles;   // m_tiles = ceil(total_blocks / 2)
+
+  if (warp == 0) {
+    int ss = 0, bs = 0;
+    uint32_t sph = 0, bph = 0;
+    for (int t = pair; t < total_tiles; t += npairs) {
+      const int mt = t % P.m_tiles;
+      const int rest = t / P.m_tiles;
+      const int nt = rest % P.n_tiles;
+      const int phase = rest / P.n_tiles;
+      const int blk = mt * 2 + (int)rank;
+      const int b = blk / P.blocks_per_sample;
+      const int q0 = (blk % P.blocks_per_sample) * 128;
+      for (int kc = 0; kc < P.kchunks; ++kc) {
+        for (int g = 0; g < P.ngroups[phase]; ++g) {
+          const SlabGroup& G = P.grp[phase][g];
+          mbar_wait(&s_empty[ss], sph ^ 1);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(&s_full[ss], (uint32_t)(2 * P.slab_bytes));
+            tma2_load_3d(slabs + (size_t)ss * P.slab_bytes, &tmA, mapa_u32(smem_u32(&s_full[ss]), 0), G.acol + kc * 64,
+                         q0 + G.min_shift, b);
+          }
+          if (++ss == SS) { ss = 0; sph ^= 1; }
+          for (int s = 0; s < G.nseg; s += TPS) {
+            const int cnt = G.nseg - s < TPS ? G.nseg - s : TPS;
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            if (elect_one()) {
+              if (rank == 0) mbar_expect_tx(&b_full[bs], (uint32_t)(2 * cnt * tap_bytes));
+              const uint32_t bar = mapa_u32(smem_u32(&b_full[bs]), 0);
+              for (int j = 0; j < cnt; ++j)
+                tma2_load_2d(btiles + (size_t)bs * b_bytes + (size_t)j * tap_bytes, &tmW, bar, G.wk[s + j] + kc * 64,
+                             nt * BN + (int)rank * (BN / 2));
+            }
+            if (++bs == BS) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc(256, BN, 0, 0);
+      const uint32_t hi = desc_hi(1024);
+      const uint32_t slab_lo0 = desc_lo(smem_u32(slabs), 16), b_lo0 = desc_lo(smem_u32(btiles), 16);
+      const uint32_t slab_step = (uint32_t)P.slab_bytes >> 4, b_step = (uint32_t)b_bytes >> 4;
+      const uint32_t tap_step = (uint32_t)tap_bytes >> 4;
+      int ss = 0, bs = 0;
+      uint32_t sph = 0, bph = 0;
+      int it = 0;
+      for (int t = pair; t < total_tiles; t += npairs, ++it) {
+        const int phase = (t / P.m_tiles) / P.n_tiles;
+        const int acc = it & 1;
+        mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t accum = 0;
+        for (int kc = 0; kc < P.kchunks; ++kc) {
+          for (int g = 0; g < P.ngroups[phase]; ++g) {
+            const SlabGroup& G = P.grp[phase][g];
+            mbar_wait(&s_full[ss], sph);
+            tc_fence_after();
+            const uint32_t sl_lo = slab_lo0 + ss * slab_step;
+            for (int s = 0; s < G.nseg; s += TPS) {
+              const int cnt = G.nseg - s < TPS ? G.nseg - s : TPS;
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              const uint32_t b_lo = b_lo0 + bs * b_step;
+              if (elect_one()) {
+                for (int j = 0; j < cnt; ++j) {
+                  const uint32_t a_lo = sl_lo + (uint32_t)G.shift_rel[s + j] * 8;
+                  const uint32_t bj = b_lo + j * tap_step;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma2_bf16_lohi(d_tmem, a_lo + 2 * k, bj + 2 * k, hi, idesc, accum | (uint32_t)(j | k));
+                }
+                umma2_commit_mc(&b_empty[bs]);
+              }
+              __syncwarp();
+              accum = 1;
+              if (++bs == BS) { bs = 0; bph ^= 1; }
+            }
+            if (elect_one()) umma2_commit_mc(&s_empty[ss]);
+            __syncwarp();
+            if (++ss == SS) { ss = 0; sph ^= 1; }
+          }
+        }
+        if (elect_one()) umma2_commit_mc(&tfull[acc]);
+        __syncwarp();
+      }
+    }
+  } else {
+    const int lq = warp & 3;
+    uint8_t* stg = stage_buf + (warp - 2) * kStgBytes;
+    const uint32_t tempty_leader[2] = {mapa_u32(smem_u32(&tempty[0]), 0), mapa_u32(smem_u32(&tempty[1]), 0)};
+    int it = 0, last_nt = -1;
+    for (int t = pair; t < total_tiles; t += npairs, ++it) {
+      const int mt = t % P.m_tiles;
+      const int rest = t / P.m_tiles;
+      const int nt = rest % P.n_tiles;
+      const int phase = rest / P.n_tiles;
+      const int blk = mt * 2 + (int)rank;   // blocks past the end map to samples >= B and are masked
+      EpiRows R;
+      epi_rows(p, blk / P.blocks_per_sample, (blk % P.blocks_per_sample) * 128, 7, phase, lq, lane, R);
+      if (nt != last_nt) { epi_load_bias<EPI>(p, bias_s, nt * BN, BN, threadIdx.x - 64); last_nt = nt; }
+      const int acc = it & 1;
+      mbar_wait(&tfull[acc], ((uint32_t)it >> 1) & 1);
+      tc_fence_after();
+      epilogue_block<EPI>(p, tmem_base + acc * BN, BN, nt * BN, R, bias_s, stg, lq, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();          // nobody may exit (or free TMEM) while the peer can still signal / read
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, kTmemCols);
   }
 }
 
@@ -947,6 +1189,7 @@ struct TcState {
   int sm_count = 148;
   int max_smem = 0;
   bool force_v1 = false;   // CG_TC_V1=1: per-tap boxes everywhere (A/B comparison)
+  bool use_pair = true;    // CG_TC_PAIR=0: single-CTA slab kernel instead of the cta_group::2 kernel
   std::string err;
 };
 
@@ -967,10 +1210,12 @@ static inline int tc_init(TcState* s) {
   s->sm_count = prop.multiProcessorCount;
   s->max_smem = (int)prop.sharedMemPerBlockOptin;
   if (const char* e = getenv("CG_TC_V1")) s->force_v1 = atoi(e) != 0;
+  if (const char* e = getenv("CG_TC_PAIR")) s->use_pair = atoi(e) != 0;
   bool ok = true;
 #define CG_SET_SMEM(E)                                                                                                         \
   ok = ok && cudaFuncSetAttribute(tc::rsgemm_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess && \
-       cudaFuncSetAttribute(tc::rsgemm2_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess;
+       cudaFuncSetAttribute(tc::rsgemm2_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess && \
+       cudaFuncSetAttribute(tc::rsgemm3_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess;
   CG_SET_SMEM(EPI_NONE) CG_SET_SMEM(EPI_BIAS) CG_SET_SMEM(EPI_BIAS_LRELU) CG_SET_SMEM(EPI_MASK) CG_SET_SMEM(EPI_BIAS_SIGMOID)
 #undef CG_SET_SMEM
   if (!ok ||
@@ -1130,6 +1375,13 @@ static inline int tc_rsgemm2_launch(TcState* s, const RsParams& p, cudaStream_t 
   const int total = p.seg.nphase * P.n_tiles * P.m_tiles;
   const int grid = total < s->sm_count ? total : s->sm_count;
   const size_t smem = (size_t)P.slab_stages * P.slab_bytes + (size_t)bst * b_bytes + 1024 + 512 + tc::kEpiSmem;
+  static long long* dbg_buf2 = nullptr;
+  P.dbg = nullptr;
+  if (getenv("CG_TC_TIMING")) {
+    if (!dbg_buf2) cudaMalloc(&dbg_buf2, 16 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf2, 0, 16 * sizeof(long long), stream);
+    P.dbg = dbg_buf2;
+  }
   switch (p.epi) {
     case EPI_NONE: tc::rsgemm2_tc_kernel<EPI_NONE><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
     case EPI_BIAS: tc::rsgemm2_tc_kernel<EPI_BIAS><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
@@ -1137,10 +1389,101 @@ static inline int tc_rsgemm2_launch(TcState* s, const RsParams& p, cudaStream_t 
     case EPI_MASK: tc::rsgemm2_tc_kernel<EPI_MASK><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
     default: tc::rsgemm2_tc_kernel<EPI_BIAS_SIGMOID><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
   }
+  if (P.dbg) {
+    long long h[16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dbg_buf2, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tc2 timing] B=%d Q=%d N=%d Kc=%d epi=%d | MB=%d BN=%d tiles=%d grid=%d bst=%d dacc=%d | prod wait s_empty %lld/%lld b_empty %lld/%lld | mma wait tempty %lld/%lld s_full %lld/%lld b_full %lld/%lld | epi wait %lld/%lld work %lld/%lld\n",
+            p.B, p.Q, p.N, p.Kc, p.epi, P.MB, P.BN, total, grid, bst, P.double_acc, h[0], h[8], h[1], h[9], h[2], h[10], h[3], h[11], h[4], h[12], h[5], h[13], h[6], h[14]);
+  }
+  return 0;
+}
+
+// ---- v3: CTA-pair kernel -----------------------------------------------------------------------------
+static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t stream) {
+  tc::RsTc2Params P;
+  memset(&P, 0, sizeof(P));
+  P.p = p;
+  int span = 0;
+  for (int ph = 0; ph < p.seg.nphase; ++ph) {
+    int na = 0;
+    for (int sg = 0; sg < p.seg.nseg[ph]; ++sg) {
+      int g = -1;
+      for (int i = 0; i < na; ++i) if (P.grp[ph][i].acol == p.seg.acol[ph][sg]) g = i;
+      if (g < 0) { g = na++; P.grp[ph][g].acol = p.seg.acol[ph][sg]; P.grp[ph][g].min_shift = 1 << 20; P.grp[ph][g].nseg = 0; }
+      if (p.seg.shift[ph][sg] < P.grp[ph][g].min_shift) P.grp[ph][g].min_shift = p.seg.shift[ph][sg];
+    }
+    P.ngroups[ph] = na;
+    for (int sg = 0; sg < p.seg.nseg[ph]; ++sg) {
+      int g = 0;
+      for (int i = 0; i < na; ++i) if (P.grp[ph][i].acol == p.seg.acol[ph][sg]) g = i;
+      tc::SlabGroup& G = P.grp[ph][g];
+      const int rel = p.seg.shift[ph][sg] - G.min_shift;
+      G.shift_rel[G.nseg] = (unsigned char)rel;
+      G.wk[G.nseg] = p.seg.wk[ph][sg];
+      G.nseg++;
+      if (rel > span) span = rel;
+    }
+  }
+  P.box_rows = (128 + span + 7) / 8 * 8;
+  if (P.box_rows > 256) return cg_tc_set_err("rsgemm3_tc: tap span too large for one TMA box");
+  P.box_bytes = P.box_rows * 128;
+  P.blocks_per_sample = p.Q / 128;
+  P.total_blocks = p.B * P.blocks_per_sample;
+  P.kchunks = p.Kc / 64;
+  P.MB = 1;
+  P.m_tiles = (P.total_blocks + 1) / 2;
+  const int npairs_max = s->sm_count / 2;
+  // widest BN (<= 256, multiple of 32) that divides N, unless a narrower one gives fewer waves over the CTA pairs
+  double best = 1e30;
+  int bestBN = 64;
+  for (int BN = 256; BN >= 64; BN -= 32) {
+    if (p.N % BN) continue;
+    const long long tiles = (long long)p.seg.nphase * (p.N / BN) * P.m_tiles;
+    const double waves = (double)((tiles + npairs_max - 1) / npairs_max);
+    const double math = BN * 2.0;                                            // 4 MMAs x BN/2 clk per SM
+    const double smem_clk = (4.0 * (4096 + BN * 16) + BN * 64 + P.box_bytes / 12.0) / 128.0;
+    const double per = math > smem_clk ? math : smem_clk;
+    const double cost = waves * per;
+    if (cost < best) { best = cost; bestBN = BN; }
+  }
+  P.BN = bestBN;
+  P.n_tiles = p.N / P.BN;
+  P.double_acc = 1;
+  P.slab_bytes = P.box_bytes;
+  P.slab_stages = 2;
+  // taps per weight stage: enough MMA time per stage (4 MMAs x BN/2 clk per tap) to cover a cross-CTA barrier round-trip
+  int stage_clk = 1000;
+  if (const char* e = getenv("CG_TC_STAGE_CLK")) stage_clk = atoi(e);
+  P.tps = (stage_clk + 2 * P.BN - 1) / (2 * P.BN);
+  if (P.tps < 1) P.tps = 1;
+  if (P.tps > 6) P.tps = 6;
+  if (const char* e = getenv("CG_TC_TPS")) P.tps = atoi(e);
+  const int b_bytes = P.tps * P.BN * 64;
+  int bst = (s->max_smem - 1024 - 512 - tc::kEpiSmem - P.slab_stages * P.slab_bytes) / b_bytes;
+  if (bst > 10) bst = 10;
+  if (bst < 2) return cg_tc_set_err("rsgemm3_tc: not enough shared memory");
+  P.b_stages = bst;
+  P.dbg = nullptr;
+  CUtensorMap tmA, tmW;
+  if (tc_get_map3(s, p.A, p.a_rs, p.a_rows, p.B, p.a_rs, p.a_bs, P.box_rows, 1, &tmA)) return 1;
+  if (tc_get_map2(s, p.W, p.w_ld, p.N, p.w_ld, P.BN / 2, &tmW)) return 1;
+  const int total = p.seg.nphase * P.n_tiles * P.m_tiles;
+  const int npairs = total < npairs_max ? total : npairs_max;
+  const int grid = 2 * npairs;
+  const size_t smem = (size_t)P.slab_stages * P.slab_bytes + (size_t)bst * b_bytes + 1024 + 512 + tc::kEpiSmem;
+  switch (p.epi) {
+    case EPI_NONE: tc::rsgemm3_tc_kernel<EPI_NONE><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+    case EPI_BIAS: tc::rsgemm3_tc_kernel<EPI_BIAS><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+    case EPI_BIAS_LRELU: tc::rsgemm3_tc_kernel<EPI_BIAS_LRELU><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+    case EPI_MASK: tc::rsgemm3_tc_kernel<EPI_MASK><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+    default: tc::rsgemm3_tc_kernel<EPI_BIAS_SIGMOID><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+  }
   return 0;
 }
 
 static inline int tc_rsgemm_launch(TcState* s, const RsParams& p, cudaStream_t stream) {
+  if (!s->force_v1 && s->use_pair && tc_rsgemm2_supported(p)) return tc_rsgemm3_launch(s, p, stream);
   if (!s->force_v1 && tc_rsgemm2_supported(p)) return tc_rsgemm2_launch(s, p, stream);
   tc::RsTcParams P;
   P.p = p;
