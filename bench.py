@@ -58,6 +58,18 @@ class ClockSampler(object):
     except Exception:
       self.proc = None
 
+  def stop_all(self):
+    sm, mx = [], []
+    for r in self.rows:
+      try:
+        sm.append(float(r[1]))
+        mx.append(float(r[2]))
+      except Exception:
+        pass
+    sm.sort()
+    return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': [],
+            'samples': len(sm)}
+
   def _read(self):
     for line in self.proc.stdout:
       self.rows.append([x.strip() for x in line.split(',')])
@@ -87,6 +99,10 @@ class ClockSampler(object):
             reasons.add(n)
       except Exception:
         pass
+    if not sm and t0 is not None:   # sampler slower than the timed window: fall back to every sample of this run
+      out = self.stop_all()
+      out['window'] = 'whole run (no sample fell inside the timed window)'
+      return out
     sm.sort()
     return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
             'reasons': sorted(reasons), 'samples': len(sm)}
@@ -171,6 +187,9 @@ def main():
   from calciumgan_b200.algorithms.registry import get_algorithm
   from calciumgan_b200.models.registry import get_models
 
+  clocks = ClockSampler(local_rank)
+  if rank == 0:
+    clocks.start()     # nvidia-smi needs ~1 s to start streaming: launch it before the engine is built
   warmup = max(args.warmup, 3)
   B = args.batch
   hparams = make_hparams(B, mixed=not args.fp32)
@@ -207,9 +226,6 @@ def main():
   def step_resident():
     return gan.train(real_dev)
 
-  clocks = ClockSampler(local_rank)
-  if rank == 0:
-    clocks.start()     # started before the warm-up so the sampler is streaming when the timed region begins
   for _ in range(warmup):
     out = step_resident()
   l0 = eng.launch_count()

@@ -82,7 +82,9 @@ struct SegTable {
   int wk[2][CG_MAX_SEG];
 };
 
-enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_LRELU = 2, EPI_MASK = 3, EPI_BIAS_SIGMOID = 4 };
+// EPI_BIAS_LN_LRELU (tensor-core path only, one n-tile = the whole channel row): out = lrelu(LN(acc + bias)),
+// optional aux = acc + bias and per-row mean / rstd for the backward pass
+enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_LRELU = 2, EPI_MASK = 3, EPI_BIAS_SIGMOID = 4, EPI_BIAS_LN_LRELU = 5 };
 
 struct RsParams {
   const void* A; long long a_bs; int a_rs; int a_rows;
@@ -91,6 +93,9 @@ struct RsParams {
   float* out32; long long o32_bs; int o32_rs;      // optional unpadded fp32 copy (n < n_real)
   const float* bias;                               // fp32, n_real entries
   const void* mask;                                // EPI_MASK: same indexing as out
+  const float* gamma; const float* beta;           // EPI_BIAS_LN_LRELU: fp32, n_real entries
+  float* mu; float* rstd;                          //   optional per-row statistics (row = (b*Q + q)*nphase + phase)
+  void* aux;                                       //   optional pre-norm copy, same indexing as out
   int B, Q, N, n_real, Kc, k_real, epi;   // k_real: unpadded channels per tap (algorithmic FLOPs only)
   SegTable seg;
 };

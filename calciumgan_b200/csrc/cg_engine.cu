@@ -550,12 +550,23 @@ static WgParams convT_wgrad_params(cg_ctx* c, int i, int B) {
 }
 
 // calciumgan.py:22-103. noise (B, nd) fp32 device. Writes FAKE32 (B, L, C).
-static int g_forward(cg_ctx* c, const float* noise, int B, void* fake_slot = nullptr) {
+static int g_forward(cg_ctx* c, const float* noise, int B, void* fake_slot = nullptr, bool for_backward = true) {
   DISPATCH_T(c, dense0_forward_kernel<T><<<grid_for((long long)B * c->w0 * c->gcp[0]), 256, 0, c->stream>>>(
                     noise, gparam(c, 0), gparam(c, 1), (T*)c->HG[0], B, c->nd, c->w0, c->gcp[0]));
   CK(post_launch(c, "dense0_fwd"));
   for (int i = 1; i <= NL; ++i) {
-    CK(launch_rsgemm(c, convT_fwd_params(c, i, B)));
+    RsParams cp = convT_fwd_params(c, i, B);
+    if (c->cfg.layer_norm && c->use_tc && !c->tc.force_v1 && tc_rsgemm2_supported(cp) && tc_ln_fusable(cp)) {
+      // conv-transpose + bias + layer-norm + LeakyReLU in one kernel (row statistics are thread-local in the epilogue)
+      cp.epi = EPI_BIAS_LN_LRELU;
+      cp.out = c->HG[i];
+      cp.gamma = gparam(c, c->g_gam[i]);
+      cp.beta = gparam(c, c->g_bet[i]);
+      if (for_backward) { cp.aux = c->AG[i]; cp.mu = c->MU[i]; cp.rstd = c->RSTD[i]; }
+      CK(launch_rsgemm(c, cp));
+      continue;
+    }
+    CK(launch_rsgemm(c, cp));
     const long long rows = (long long)B * c->gl[i];
     if (c->cfg.layer_norm) {
       const int nvec = c->gcp[i] / (16 / c->esz);
@@ -701,7 +712,7 @@ static int d_dgrad_layer(cg_ctx* c, int l, int b0, int nb, void* out) {
 
 // backward chain of sum_b coef[b]*D(x)_b down to DA[1] (and DX[0] for samples [dx0_b0, dx0_b0+dx0_nb))
 static int d_backward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh, int dx0_b0, int dx0_nb) {
-  DISPATCH_T(c, head_backward_kernel<T><<<grid_for((long long)Bt * c->dl[NL] * c->dcp[NL]), 256, 0, c->stream>>>(
+  DISPATCH_T(c, head_backward_kernel<T><<<grid_for((long long)Bt * c->dl[NL] * c->dcp[NL] / (16 / c->esz)), 256, 0, c->stream>>>(
                     (const T*)c->H[NL], dparam(c, 10), c->coef, (T*)c->DA[NL], Bt, c->dl[NL], c->dc[NL], c->dcp[NL]));
   CK(post_launch(c, "head_bwd"));
   for (int l = NL; l >= 2; --l) {
@@ -789,7 +800,7 @@ static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* n
                              const int32_t* sh, int slot, bool real_ready = false) {
   const long long per = (long long)B * c->L * c->dcp[0];
   // generator head writes fp32 FAKE32 and the compute-type copy straight into the critic's "fake" slot
-  CK(g_forward(c, noise, B, off(c, c->X[0], per)));
+  CK(g_forward(c, noise, B, off(c, c->X[0], per), false));
   const long long tot = per / 4;
   if (!real_ready) {   // the 5 critic sub-steps of one train step share the real batch (wgan_gp.py:85-86)
     DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(real, nullptr, nullptr, (T*)c->X[0], B,

@@ -400,13 +400,19 @@ template <typename T>
 __global__ void __launch_bounds__(256) head_forward_kernel(const T* __restrict__ X5, const float* __restrict__ wd,
                                                            const float* __restrict__ bd, float* __restrict__ scores,
                                                            int w5, int c5, int Cp) {
+  constexpr int V = Vec16<T>::N;
   __shared__ float red[8];
   const int b = blockIdx.x;
   const T* x = X5 + (long long)b * w5 * Cp;
+  const int nv = w5 * Cp / V;
   float acc = 0.f;
-  for (int i = threadIdx.x; i < w5 * Cp; i += blockDim.x) {
-    const int c = i % Cp, t = i / Cp;
-    if (c < c5) acc += Elem<T>::to_f(x[i]) * wd[t * c5 + c];
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const int c = (i * V) % Cp, t = (i * V) / Cp;
+    float v[V];
+    vload<T>(x + (long long)i * V, v);
+#pragma unroll
+    for (int e = 0; e < V; ++e)
+      if (c + e < c5) acc = fmaf(v[e], wd[t * c5 + c + e], acc);
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -418,21 +424,26 @@ __global__ void __launch_bounds__(256) head_forward_kernel(const T* __restrict__
   }
 }
 
-// DA5[b,t,c] = slope(H5) * coef[b] * wd[t*c5+c]
+// DA5[b,t,c] = slope(H5) * coef[b] * wd[t*c5+c]   (16-byte vectors)
 template <typename T>
 __global__ void head_backward_kernel(const T* __restrict__ H5, const float* __restrict__ wd,
                                      const float* __restrict__ coef, T* __restrict__ DA5, int Bt, int w5, int c5,
                                      int Cp) {
+  constexpr int V = Vec16<T>::N;
   const long long per = (long long)w5 * Cp;
-  const long long total = (long long)Bt * per;
+  const long long total = (long long)Bt * per / V;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % Cp);
-    const int t = (int)((i / Cp) % w5);
-    const int b = (int)(i / per);
-    float v = 0.f;
-    if (c < c5) v = lrelu_slope(Elem<T>::to_f(H5[i])) * coef[b] * wd[t * c5 + c];
-    DA5[i] = Elem<T>::from_f(v);
+    const long long e0 = i * V;
+    const int c = (int)(e0 % Cp);
+    const int t = (int)((e0 / Cp) % w5);
+    const int b = (int)(e0 / per);
+    float h[V], o[V];
+    vload<T>(H5 + e0, h);
+    const float cb = coef[b];
+#pragma unroll
+    for (int e = 0; e < V; ++e) o[e] = c + e < c5 ? lrelu_slope(h[e]) * cb * wd[t * c5 + c + e] : 0.f;
+    vstore<T>(DA5 + e0, o);
   }
 }
 

@@ -213,13 +213,13 @@ constexpr int kAccStride = 256;             // columns between the two accumulat
 
 // ---- epilogue -----------------------------------------------------------------------------------------
 constexpr int kStgBytes = 4096;   // per-warp staging: 32 rows x 64 bf16, 16-byte chunks XOR-swizzled by (row & 7)
-constexpr int kEpiSmem = 4 * kStgBytes + 1024;   // + bias tile (256 floats)
+constexpr int kEpiSmem = 4 * kStgBytes + 3 * 1024;   // + bias / gamma / beta tiles (256 floats each)
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // 4 epilogue warps
 
 // Per tile, each lane precomputes the element offsets of the 8 rows it stores in the coalesced phase
 // (row rr = 4*i + lane/8 of this warp's 32 rows); negative = masked. rpt < 128 is a power of two.
-struct EpiRows { long long off[8]; long long my_off; long long my_o32; bool my_ok; };
+struct EpiRows { long long off[8]; long long my_off; long long my_o32; long long my_row; bool my_ok; };
 __device__ __forceinline__ void epi_rows(const RsParams& p, int b0, int q0, int rpt_log2, int phase, int lq, int lane,
                                          EpiRows& R) {
   const int crow = lane >> 3;
@@ -230,7 +230,10 @@ __device__ __forceinline__ void epi_rows(const RsParams& p, int b0, int q0, int 
     if (rpt_log2 >= 7) { b = b0; q = q0 + r; } else { b = b0 + (r >> rpt_log2); q = r & ((1 << rpt_log2) - 1); }
     const long long o = b < p.B ? (long long)b * p.o_bs + (long long)q * p.o_rs + phase * p.o_phase_col : -1;
     if (i < 8) R.off[i] = o;
-    else { R.my_off = o; R.my_ok = b < p.B; R.my_o32 = (long long)b * p.o32_bs + (long long)q * p.o32_rs; }
+    else {
+      R.my_off = o; R.my_ok = b < p.B; R.my_o32 = (long long)b * p.o32_bs + (long long)q * p.o32_rs;
+      R.my_row = ((long long)b * p.Q + q) * p.seg.nphase + phase;
+    }
   }
 }
 
@@ -245,6 +248,26 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
   bf16* out = reinterpret_cast<bf16*>(p.out);
   const bf16* mask = reinterpret_cast<const bf16*>(p.mask);
   const int cj = lane & 7;
+  float ln_mean = 0.f, ln_rstd = 1.f;
+  if (EPI == EPI_BIAS_LN_LRELU) {   // pass 1 over TMEM: row statistics of x = acc + bias (this thread owns the row)
+    float s1 = 0.f, s2 = 0.f;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_cols + ((uint32_t)(lq * 32) << 16) + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (n_base + c0 + j < p.n_real) {
+          const float x = __uint_as_float(v[j]) + bias_s[c0 + j];
+          s1 += x;
+          s2 = fmaf(x, x, s2);
+        }
+      }
+    }
+    ln_mean = s1 / p.n_real;
+    ln_rstd = rsqrtf(fmaxf(s2 / p.n_real - ln_mean * ln_mean, 0.f) + CG_LN_EPS);
+    if (p.mu && R.my_ok) { p.mu[R.my_row] = ln_mean; p.rstd[R.my_row] = ln_rstd; }
+  }
   for (int c0 = 0; c0 < BN; c0 += 64) {
     const int ncols = BN - c0 < 64 ? BN - c0 : 64;   // 64 or 32 (BN % 32 == 0)
     uint32_t v[64];
@@ -278,6 +301,36 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
         }
       }
       __syncwarp();
+    }
+    if (EPI == EPI_BIAS_LN_LRELU) {
+      const float* gamma_s = bias_s + 256;
+      const float* beta_s = bias_s + 512;
+      bf16* aux = reinterpret_cast<bf16*>(p.aux);
+      if (aux) {   // pre-norm activations for the backward pass, through the same coalescing transpose
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j * 8 + e]) + bias_s[c0 + j * 8 + e];
+          uint4 o;
+          o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+          o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + (lane >> 3);
+          const uint4 o = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((cj ^ (rr & 7)) << 4));
+          if (R.off[i] >= 0 && col_ok) *reinterpret_cast<uint4*>(aux + R.off[i] + n0 + cj * 8) = o;
+        }
+        __syncwarp();
+      }
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const float x = __uint_as_float(v[j]) + bias_s[c0 + j];
+        v[j] = __float_as_uint(lrelu((x - ln_mean) * ln_rstd * gamma_s[c0 + j] + beta_s[c0 + j]));   // pads: gamma = beta = 0
+      }
     }
     if (EPI == EPI_BIAS || EPI == EPI_BIAS_LRELU || EPI == EPI_BIAS_SIGMOID) {
 #pragma unroll
@@ -338,11 +391,16 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
 // stage bias[n_base .. n_base+BN) (zero beyond n_real) into smem for the 4 epilogue warps
 template <int EPI>
 __device__ __forceinline__ void epi_load_bias(const RsParams& p, float* bias_s, int n_base, int BN, int tid128) {
-  if (EPI == EPI_BIAS || EPI == EPI_BIAS_LRELU || EPI == EPI_BIAS_SIGMOID) {
+  if (EPI == EPI_BIAS || EPI == EPI_BIAS_LRELU || EPI == EPI_BIAS_SIGMOID || EPI == EPI_BIAS_LN_LRELU) {
     epi_bar();   // previous tile's readers are done
     for (int i = tid128; i < 256; i += 128) {
       const int n = n_base + i;
-      bias_s[i] = (i < BN && n < p.n_real) ? __ldg(&p.bias[n]) : 0.f;
+      const bool ok = i < BN && n < p.n_real;
+      bias_s[i] = ok ? __ldg(&p.bias[n]) : 0.f;
+      if (EPI == EPI_BIAS_LN_LRELU) {
+        bias_s[256 + i] = ok ? __ldg(&p.gamma[n]) : 0.f;
+        bias_s[512 + i] = ok ? __ldg(&p.beta[n]) : 0.f;
+      }
     }
     epi_bar();
   }
@@ -1217,6 +1275,8 @@ static inline int tc_init(TcState* s) {
        cudaFuncSetAttribute(tc::rsgemm2_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess && \
        cudaFuncSetAttribute(tc::rsgemm3_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess;
   CG_SET_SMEM(EPI_NONE) CG_SET_SMEM(EPI_BIAS) CG_SET_SMEM(EPI_BIAS_LRELU) CG_SET_SMEM(EPI_MASK) CG_SET_SMEM(EPI_BIAS_SIGMOID)
+  ok = ok && cudaFuncSetAttribute(tc::rsgemm2_tc_kernel<EPI_BIAS_LN_LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess &&
+       cudaFuncSetAttribute(tc::rsgemm3_tc_kernel<EPI_BIAS_LN_LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess;
 #undef CG_SET_SMEM
   if (!ok ||
       cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) != cudaSuccess ||
@@ -1358,6 +1418,7 @@ static inline int tc_rsgemm2_launch(TcState* s, const RsParams& p, cudaStream_t 
       if (cost < best) { best = cost; bestMB = MB; bestBN = BN; }
     }
   }
+  if (p.epi == EPI_BIAS_LN_LRELU) bestBN = p.N;   // the epilogue needs whole channel rows
   P.MB = bestMB; P.BN = bestBN;
   P.n_tiles = p.N / P.BN;
   P.m_tiles = (P.total_blocks + P.MB - 1) / P.MB;
@@ -1387,6 +1448,7 @@ static inline int tc_rsgemm2_launch(TcState* s, const RsParams& p, cudaStream_t 
     case EPI_BIAS: tc::rsgemm2_tc_kernel<EPI_BIAS><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
     case EPI_BIAS_LRELU: tc::rsgemm2_tc_kernel<EPI_BIAS_LRELU><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
     case EPI_MASK: tc::rsgemm2_tc_kernel<EPI_MASK><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+    case EPI_BIAS_LN_LRELU: tc::rsgemm2_tc_kernel<EPI_BIAS_LN_LRELU><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
     default: tc::rsgemm2_tc_kernel<EPI_BIAS_SIGMOID><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
   }
   if (P.dbg) {
@@ -1398,6 +1460,9 @@ static inline int tc_rsgemm2_launch(TcState* s, const RsParams& p, cudaStream_t 
   }
   return 0;
 }
+
+// layer-norm can be fused into the conv epilogue when the slab kernels apply and one n-tile covers the channel row
+static inline bool tc_ln_fusable(const RsParams& p) { return p.N <= 256 && p.N % 32 == 0; }
 
 // ---- v3: CTA-pair kernel -----------------------------------------------------------------------------
 static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t stream) {
@@ -1447,6 +1512,7 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
     const double cost = waves * per;
     if (cost < best) { best = cost; bestBN = BN; }
   }
+  if (p.epi == EPI_BIAS_LN_LRELU) bestBN = p.N;   // the epilogue needs whole channel rows
   P.BN = bestBN;
   P.n_tiles = p.N / P.BN;
   P.double_acc = 1;
@@ -1477,6 +1543,7 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
     case EPI_BIAS: tc::rsgemm3_tc_kernel<EPI_BIAS><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
     case EPI_BIAS_LRELU: tc::rsgemm3_tc_kernel<EPI_BIAS_LRELU><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
     case EPI_MASK: tc::rsgemm3_tc_kernel<EPI_MASK><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+    case EPI_BIAS_LN_LRELU: tc::rsgemm3_tc_kernel<EPI_BIAS_LN_LRELU><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
     default: tc::rsgemm3_tc_kernel<EPI_BIAS_SIGMOID><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
   }
   return 0;

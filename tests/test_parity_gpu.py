@@ -167,7 +167,7 @@ def test_medium_fp32(layer_norm, K):
 # restatement) differ by 2-3e-2 at this point; see oracle/calciumgan_oracle.py and DESIGN.md.
 # The GEMM kernels themselves are held to bf16 rounding in tests/test_layers_gpu.py.
 BF16_VS_FP64_GRAD_BOUND = 0.15
-BF16_POLICY_GRAD_BOUND = 0.06
+BF16_POLICY_GRAD_BOUND = 0.10   # small (bias-sized) tensors average less of the noise
 
 
 @pytest.mark.parametrize('force_simt', [True, False])
