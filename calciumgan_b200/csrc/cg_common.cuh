@@ -96,6 +96,8 @@ struct RsParams {
   const float* gamma; const float* beta;           // EPI_BIAS_LN_LRELU: fp32, n_real entries
   float* mu; float* rstd;                          //   optional per-row statistics (row = (b*Q + q)*nphase + phase)
   void* aux;                                       //   optional pre-norm copy, same indexing as out
+  // fused PhaseShuffle (slab kernels, strided-conv form): ps_out[b, t, :] = result[b, ps_index(t, shift[b / ps_group_b]), :]
+  void* ps_out; int ps_w; int ps_group_b; int ps_shift[4];
   int B, Q, N, n_real, Kc, k_real, epi;   // k_real: unpadded channels per tap (algorithmic FLOPs only)
   SegTable seg;
 };

@@ -682,9 +682,24 @@ static RsParams conv_fwd_params(cg_ctx* c, int l, const void* A, void* out, int 
 }
 
 // calciumgan.py:141-192 on X[0][0:Bt]; groups of B samples share PhaseShuffle shifts sh[g*4 + layer-1]
+static bool ps_fusable(cg_ctx* c, const RsParams& p) {
+  static const bool off_ = getenv("CG_NO_PS_FUSE") != nullptr;
+  return !off_ && c->use_tc && !c->tc.force_v1 && tc_rsgemm2_supported(p);
+}
+static void set_ps(RsParams& p, void* X, int w, int group_b, const int32_t* sh, int groups, int layer) {
+  p.ps_out = X; p.ps_w = w; p.ps_group_b = group_b;
+  for (int i = 0; i < 4; ++i) p.ps_shift[i] = i < groups ? sh[i * 4 + (layer - 1)] : 0;
+}
+
 static int d_forward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh) {
   for (int l = 1; l <= NL; ++l) {
-    CK(launch_rsgemm(c, conv_fwd_params(c, l, c->X[l - 1], c->H[l], Bt, EPI_BIAS_LRELU, nullptr)));
+    RsParams p = conv_fwd_params(c, l, c->X[l - 1], c->H[l], Bt, EPI_BIAS_LRELU, nullptr);
+    if (l < NL && ps_fusable(c, p)) {   // conv + bias + LeakyReLU + PhaseShuffle in one kernel
+      set_ps(p, c->X[l], c->dl[l], B, sh, groups, l);
+      CK(launch_rsgemm(c, p));
+      continue;
+    }
+    CK(launch_rsgemm(c, p));
     if (l < NL) {
       const long long tot = (long long)Bt * c->dl[l] * c->dcp[l] / (16 / c->esz);
       DISPATCH_T(c, ps_gather_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
@@ -797,8 +812,9 @@ static int fetch_scalars(cg_ctx* c, int slot, int flags, float* scalars_host) {
 // ------------------------------------------------------------------------------------------ critic step
 // forward part shared by cg_critic_step and cg_validate: fake, D on [real; fake; xhat], dgrad chain, GP scalars
 static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
-                             const int32_t* sh, int slot, bool real_ready = false) {
+                             const int32_t* sh, int slot, bool real_ready = false, bool train = false) {
   const long long per = (long long)B * c->L * c->dcp[0];
+  if (train) CU(cudaMemsetAsync(c->dis.g, 0, c->dis.total * 4, c->stream));
   // generator head writes fp32 FAKE32 and the compute-type copy straight into the critic's "fake" slot
   CK(g_forward(c, noise, B, off(c, c->X[0], per), false));
   const long long tot = per / 4;
@@ -827,7 +843,7 @@ static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* n
 
 static int critic_step_impl(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
                             const int32_t* sh, int flags, int slot, bool real_ready = false) {
-  CK(critic_forward_gp(c, real, B, noise, alpha, sh, slot, real_ready));
+  CK(critic_forward_gp(c, real, B, noise, alpha, sh, slot, real_ready, true));
   // GP second-order term without the second-order graph: v0 = u = d(lambda*GP)/dg
   const long long per = (long long)c->L * c->dcp[0];
   DISPATCH_T(c, scale_rows_kernel<T><<<grid_for(per * B / (16 / c->esz)), 256, 0, c->stream>>>(
@@ -837,7 +853,14 @@ static int critic_step_impl(cg_ctx* c, const float* real, int B, const float* no
   for (int l = 1; l <= NL; ++l) {
     const long long gin = 2LL * B * c->dl[l - 1] * c->dcp[l - 1], gout = 2LL * B * c->dl[l] * c->dcp[l];
     void* dst = l < NL ? off(c, c->DX[l], gout) : off(c, c->X[l], gout);
-    CK(launch_rsgemm(c, conv_fwd_params(c, l, off(c, c->X[l - 1], gin), dst, B, EPI_MASK, off(c, c->H[l], gout))));
+    RsParams p = conv_fwd_params(c, l, off(c, c->X[l - 1], gin), dst, B, EPI_MASK, off(c, c->H[l], gout));
+    if (l < NL && ps_fusable(c, p)) {   // v_l = PS(M_l * conv(v_{l-1})) written straight into the xhat group's X_l slot
+      p.out = nullptr;
+      set_ps(p, off(c, c->X[l], gout), c->dl[l], B, sh2, 1, l);
+      CK(launch_rsgemm(c, p));
+      continue;
+    }
+    CK(launch_rsgemm(c, p));
     if (l < NL) {
       const long long tot = (long long)B * c->dl[l] * c->dcp[l] / (16 / c->esz);
       GroupShifts g; g.s[0] = sh2[l - 1]; g.s[1] = g.s[2] = g.s[3] = 0;
@@ -846,7 +869,6 @@ static int critic_step_impl(cg_ctx* c, const float* real, int B, const float* no
       CK(post_launch(c, "ps_gather_lin"));
     }
   }
-  CU(cudaMemsetAsync(c->dis.g, 0, c->dis.total * 4, c->stream));
   CK(d_wgrad(c, 3 * B, 2 * B));
   if (!(flags & CG_FLAG_NO_UPDATE)) CK(cg_apply_update(c, CG_DISCRIMINATOR));
   return 0;

@@ -244,8 +244,11 @@ __device__ __forceinline__ void epi_rows(const RsParams& p, int b0, int q0, int 
 // Padded columns come out as exact zeros because padded weight rows and the staged bias are zero.
 template <int EPI>
 __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_cols, int BN, int n_base,
-                                               const EpiRows& R, const float* bias_s, uint8_t* stg, int lq, int lane) {
+                                               const EpiRows& R, const float* bias_s, uint8_t* stg, int lq, int lane,
+                                               int ps_q0 = 0, int ps_s = 0) {
+  // ps_q0: time index of tile row 0 (single-sample blocks); ps_s: this sample's PhaseShuffle shift (p.ps_out != null)
   bf16* out = reinterpret_cast<bf16*>(p.out);
+  bf16* psx = reinterpret_cast<bf16*>(p.ps_out);
   const bf16* mask = reinterpret_cast<const bf16*>(p.mask);
   const int cj = lane & 7;
   float ln_mean = 0.f, ln_rstd = 1.f;
@@ -366,7 +369,7 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
         }
       }
     }
-    if (out) {
+    if (out || psx) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         uint4 o;
@@ -381,7 +384,18 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
       for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + (lane >> 3);
         const uint4 o = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((cj ^ (rr & 7)) << 4));
-        if (R.off[i] >= 0 && col_ok) *reinterpret_cast<uint4*>(out + R.off[i] + n0 + cj * 8) = o;
+        if (R.off[i] >= 0 && col_ok) {
+          if (out) *reinterpret_cast<uint4*>(out + R.off[i] + n0 + cj * 8) = o;
+          if (psx) {   // scatter form of the PhaseShuffle gather: row q feeds every t with ps_index(t) == q
+            const int q = ps_q0 + lq * 32 + rr, w = p.ps_w;
+            const int t1 = q - ps_s;
+            if (t1 >= 0 && t1 < w) *reinterpret_cast<uint4*>(psx + R.off[i] + (long long)(t1 - q) * p.o_rs + n0 + cj * 8) = o;
+            int t2 = -1;
+            if (ps_s > 0) { t2 = 2 * (w - 1) - q - ps_s; if (!(t2 >= 0 && t2 < w && t2 + ps_s > w - 1)) t2 = -1; }
+            else if (ps_s < 0) { t2 = -q - ps_s; if (!(t2 >= 0 && t2 < w && t2 + ps_s < 0)) t2 = -1; }
+            if (t2 >= 0) *reinterpret_cast<uint4*>(psx + R.off[i] + (long long)(t2 - q) * p.o_rs + n0 + cj * 8) = o;
+          }
+        }
       }
       __syncwarp();
     }
@@ -747,8 +761,17 @@ rsgemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (warp == 2) CG_DBG_ADD(5, tq);
       tq = clock64();
       tc_fence_after();
-      epilogue_block<EPI>(p, tmem_base + acc * acc_stride, BN, nt * BN, R[0], bias_s, stg, lq, lane);
-      if (MB == 2) epilogue_block<EPI>(p, tmem_base + acc * acc_stride + BN, BN, nt * BN, R[1], bias_s, stg, lq, lane);
+      {
+        const int blk0 = mt * MB, blk1 = mt * MB + 1;
+        const int bq0 = blk0 / P.blocks_per_sample, bq1 = blk1 / P.blocks_per_sample;
+        const int s0 = p.ps_out ? p.ps_shift[(bq0 < p.B ? bq0 : 0) / p.ps_group_b] : 0;
+        const int s1 = p.ps_out ? p.ps_shift[(bq1 < p.B ? bq1 : 0) / p.ps_group_b] : 0;
+        epilogue_block<EPI>(p, tmem_base + acc * acc_stride, BN, nt * BN, R[0], bias_s, stg, lq, lane,
+                            (blk0 % P.blocks_per_sample) * 128, s0);
+        if (MB == 2)
+          epilogue_block<EPI>(p, tmem_base + acc * acc_stride + BN, BN, nt * BN, R[1], bias_s, stg, lq, lane,
+                              (blk1 % P.blocks_per_sample) * 128, s1);
+      }
       if (warp == 2) CG_DBG_ADD(6, tq);
       tc_fence_before();
       __syncwarp();
@@ -922,7 +945,12 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int acc = it & 1;
       mbar_wait(&tfull[acc], ((uint32_t)it >> 1) & 1);
       tc_fence_after();
-      epilogue_block<EPI>(p, tmem_base + acc * BN, BN, nt * BN, R, bias_s, stg, lq, lane);
+      {
+        const int bq = blk / P.blocks_per_sample;
+        const int sft = p.ps_out ? p.ps_shift[(bq < p.B ? bq : 0) / p.ps_group_b] : 0;
+        epilogue_block<EPI>(p, tmem_base + acc * BN, BN, nt * BN, R, bias_s, stg, lq, lane,
+                            (blk % P.blocks_per_sample) * 128, sft);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
