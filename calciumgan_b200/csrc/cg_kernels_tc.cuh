@@ -1697,7 +1697,10 @@ static inline int tc_wgrad2_launch(TcState* s, const WgParams& p, cudaStream_t s
     }
     if (P.nsub[0] == 0) return cg_tc_set_err("wgrad2_tc: empty tap group");
     P.items_per_split = items;
-    int splits = (2 * s->sm_count + items - 1) / items;
+    // whole waves only: items x splits <= waves x SMs (a ceil here used to leave a third, nearly empty wave)
+    int waves = 1;
+    if (const char* e = getenv("CG_WG_WAVES")) waves = atoi(e);
+    int splits = (waves * s->sm_count) / items;
     if (splits > P.total_chunks) splits = P.total_chunks;
     if (splits < 1) splits = 1;
     P.chunks_per_split = (P.total_chunks + splits - 1) / splits;
