@@ -211,6 +211,24 @@ constexpr int kABytes = 128 * 128;          // 128 rows x 64 bf16
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;             // columns between the two accumulator buffers
 
+// explicit shared-space accesses for the epilogue staging buffer: with generic pointers the compiler must assume
+// the staging stores alias the global loads/stores around them and serialises every global round-trip
+__device__ __forceinline__ void sts_v4(uint32_t sa, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t sa) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t sa, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa), "f"(v)); }
+__device__ __forceinline__ float lds_f32(uint32_t sa) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sa)); return v; }
+// 16-byte global -> shared copy without registers; src_bytes = 0 writes zeros
+__device__ __forceinline__ void cp_async16(uint32_t sa, const void* g, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(g), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- epilogue -----------------------------------------------------------------------------------------
 constexpr int kStgBytes = 4096;   // per-warp staging: 32 rows x 64 bf16, 16-byte chunks XOR-swizzled by (row & 7)
 constexpr int kEpiSmem = 4 * kStgBytes + 3 * 1024;   // + bias / gamma / beta tiles (256 floats each)
@@ -249,6 +267,7 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
   // ps_q0: time index of tile row 0 (single-sample blocks); ps_s: this sample's PhaseShuffle shift (p.ps_out != null)
   bf16* out = reinterpret_cast<bf16*>(p.out);
   bf16* psx = reinterpret_cast<bf16*>(p.ps_out);
+  const uint32_t stg_s = smem_u32(stg);
   const bf16* mask = reinterpret_cast<const bf16*>(p.mask);
   const int cj = lane & 7;
   float ln_mean = 0.f, ln_rstd = 1.f;
@@ -273,6 +292,14 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
   }
   for (int c0 = 0; c0 < BN; c0 += 64) {
     const int ncols = BN - c0 < 64 ? BN - c0 : 64;   // 64 or 32 (BN % 32 == 0)
+    if (EPI == EPI_MASK) {   // coalesced, register-free read of the slope source (same indexing as out) into the staging tile
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3);
+        const bool ok = R.off[i] >= 0 && cj * 8 < ncols;
+        cp_async16(stg_s + rr * 128 + ((cj ^ (rr & 7)) << 4), mask + (ok ? R.off[i] + n_base + c0 + cj * 8 : 0), ok ? 16u : 0u);
+      }
+    }
     uint32_t v[64];
     {
       uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
@@ -283,18 +310,12 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
     }
     const int n0 = n_base + c0;
     const bool col_ok = cj * 8 < ncols;
-    if (EPI == EPI_MASK) {   // coalesced read of the slope source (same indexing as out), transposed through smem
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = i * 4 + (lane >> 3);
-        uint4 mv = make_uint4(0, 0, 0, 0);
-        if (R.off[i] >= 0 && col_ok) mv = *reinterpret_cast<const uint4*>(mask + R.off[i] + n0 + cj * 8);
-        *reinterpret_cast<uint4*>(stg + rr * 128 + ((cj ^ (rr & 7)) << 4)) = mv;
-      }
+    if (EPI == EPI_MASK) {
+      cp_async_wait_all();
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const uint4 mv = *reinterpret_cast<const uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4));
+        const uint4 mv = lds_v4(stg_s + lane * 128 + ((j ^ (lane & 7)) << 4));
         const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
         for (int w2 = 0; w2 < 4; ++w2) {
@@ -318,13 +339,13 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
           uint4 o;
           o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
           o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+          sts_v4(stg_s + lane * 128 + ((j ^ (lane & 7)) << 4), o);
         }
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + (lane >> 3);
-          const uint4 o = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((cj ^ (rr & 7)) << 4));
+          const uint4 o = lds_v4(stg_s + rr * 128 + ((cj ^ (rr & 7)) << 4));
           if (R.off[i] >= 0 && col_ok) *reinterpret_cast<uint4*>(aux + R.off[i] + n0 + cj * 8) = o;
         }
         __syncwarp();
@@ -351,19 +372,20 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
     }
     if (p.out32) {   // unpadded fp32 copy (generator head only): 32x32 fp32 transpose through the staging buffer so
                      // every warp store writes 32 consecutive floats of one output row
-      float* stf = reinterpret_cast<float*>(stg);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (h * 32 < ncols) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stf[lane * 32 + (j ^ lane)] = __uint_as_float(v[h * 32 + j]);
+          for (int j = 0; j < 32; ++j) sts_f32(stg_s + (lane * 32 + (j ^ lane)) * 4, __uint_as_float(v[h * 32 + j]));
           __syncwarp();
           const int n = n0 + h * 32 + lane;
+          const bool n_ok = n < p.n_real;
+#pragma unroll 8
           for (int rr = 0; rr < 32; ++rr) {
-            const float val = stf[rr * 32 + (lane ^ rr)];
+            const float val = lds_f32(stg_s + (rr * 32 + (lane ^ rr)) * 4);
             const long long o = __shfl_sync(0xffffffffu, R.my_o32, rr);
             const int ok = __shfl_sync(0xffffffffu, (int)R.my_ok, rr);
-            if (ok && n < p.n_real) p.out32[o + n] = val;
+            if (ok && n_ok) p.out32[o + n] = val;
           }
           __syncwarp();
         }
@@ -377,13 +399,13 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
         o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
         o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
         o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
-        *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+        sts_v4(stg_s + lane * 128 + ((j ^ (lane & 7)) << 4), o);
       }
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + (lane >> 3);
-        const uint4 o = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((cj ^ (rr & 7)) << 4));
+        const uint4 o = lds_v4(stg_s + rr * 128 + ((cj ^ (rr & 7)) << 4));
         if (R.off[i] >= 0 && col_ok) {
           if (out) *reinterpret_cast<uint4*>(out + R.off[i] + n0 + cj * 8) = o;
           if (psx) {   // scatter form of the PhaseShuffle gather: row q feeds every t with ps_index(t) == q
