@@ -595,6 +595,7 @@ static int g_forward(cg_ctx* c, const float* noise, int B, void* fake_slot = nul
   p.bias = gparam(c, c->g_d1b);
   p.B = B; p.Q = c->L; p.N = Cp; p.n_real = c->C; p.Kc = Cp; p.k_real = c->C;
   p.epi = c->cfg.normalize ? EPI_BIAS_SIGMOID : EPI_BIAS;
+  if (const char* e = getenv("CG_HEAD_DBG")) p.dbg = atoi(e);
   p.seg = seg_dense();
   CK(launch_rsgemm(c, p));
   return 0;

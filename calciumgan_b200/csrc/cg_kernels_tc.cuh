@@ -229,6 +229,14 @@ __device__ __forceinline__ void cp_async16(uint32_t sa, const void* g, uint32_t 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5 with the hardware tanh approximation: ONE MUFU op per element instead of
+// EX2 + RCP (abs error ~1e-4, far inside the bf16 path's 2e-2; the fp32 path uses expf)
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
+
 // ---- epilogue -----------------------------------------------------------------------------------------
 constexpr int kStgBytes = 4096;   // per-warp staging: 32 rows x 64 bf16, 16-byte chunks XOR-swizzled by (row & 7)
 constexpr int kEpiSmem = 4 * kStgBytes + 3 * 1024;   // + bias / gamma / beta tiles (256 floats each)
@@ -237,7 +245,10 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: 
 
 // Per tile, each lane precomputes the element offsets of the 8 rows it stores in the coalesced phase
 // (row rr = 4*i + lane/8 of this warp's 32 rows); negative = masked. rpt < 128 is a power of two.
-struct EpiRows { long long off[8]; long long my_off; long long my_o32; long long my_row; bool my_ok; };
+struct EpiRows {
+  long long off[8]; long long my_off; long long my_o32; long long my_row; bool my_ok;
+  long long o32_base; bool uniform;   // single-sample blocks: fp32 row rr of this warp is at o32_base + rr * o32_rs
+};
 __device__ __forceinline__ void epi_rows(const RsParams& p, int b0, int q0, int rpt_log2, int phase, int lq, int lane,
                                          EpiRows& R) {
   const int crow = lane >> 3;
@@ -252,6 +263,10 @@ __device__ __forceinline__ void epi_rows(const RsParams& p, int b0, int q0, int 
       R.my_off = o; R.my_ok = b < p.B; R.my_o32 = (long long)b * p.o32_bs + (long long)q * p.o32_rs;
       R.my_row = ((long long)b * p.Q + q) * p.seg.nphase + phase;
     }
+  }
+  {
+    R.uniform = rpt_log2 >= 7;
+    R.o32_base = (long long)b0 * p.o32_bs + (long long)(q0 + lq * 32) * p.o32_rs;
   }
 }
 
@@ -365,7 +380,7 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
         for (int e = 0; e < 4; ++e) {
           float x = __uint_as_float(v[j4 * 4 + e]) + bv[e];
           if (EPI == EPI_BIAS_LRELU) x = lrelu(x);
-          if (EPI == EPI_BIAS_SIGMOID) x = (n0 + j4 * 4 + e < p.n_real) ? __fdividef(1.f, 1.f + __expf(-x)) : 0.f;
+          if (EPI == EPI_BIAS_SIGMOID) x = (n0 + j4 * 4 + e < p.n_real) ? sigmoid_fast(x) : 0.f;
           v[j4 * 4 + e] = __float_as_uint(x);
         }
       }
@@ -383,9 +398,13 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
 #pragma unroll 8
           for (int rr = 0; rr < 32; ++rr) {
             const float val = lds_f32(stg_s + (rr * 32 + (lane ^ rr)) * 4);
-            const long long o = __shfl_sync(0xffffffffu, R.my_o32, rr);
-            const int ok = __shfl_sync(0xffffffffu, (int)R.my_ok, rr);
-            if (ok && n_ok) p.out32[o + n] = val;
+            if (R.uniform) {   // all 32 rows belong to one sample: plain address arithmetic (3 SHFL per row made this shuffle-bound)
+              if (R.my_ok && n_ok) p.out32[R.o32_base + (long long)rr * p.o32_rs + n] = val;
+            } else {
+              const long long o = __shfl_sync(0xffffffffu, R.my_o32, rr);
+              const int ok = __shfl_sync(0xffffffffu, (int)R.my_ok, rr);
+              if (ok && n_ok) p.out32[o + n] = val;
+            }
           }
           __syncwarp();
         }
@@ -1567,7 +1586,10 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   P.n_tiles = p.N / P.BN;
   P.double_acc = 1;
   P.slab_bytes = P.box_bytes;
-  P.slab_stages = 2;
+  int groups_per_tile = 0;
+  for (int ph = 0; ph < p.seg.nphase; ++ph) if (P.ngroups[ph] > groups_per_tile) groups_per_tile = P.ngroups[ph];
+  groups_per_tile *= P.kchunks;
+  P.slab_stages = groups_per_tile <= 2 ? 4 : (groups_per_tile <= 4 ? 3 : 2);   // short K loops: prefetch the next tile's slabs
   // taps per weight stage: enough MMA time per stage (4 MMAs x BN/2 clk per tap) to cover a cross-CTA barrier round-trip
   int stage_clk = 1000;
   if (const char* e = getenv("CG_TC_STAGE_CLK")) stage_clk = atoi(e);
