@@ -261,12 +261,17 @@ def main():
     g, w = rep['gemm'], rep['wgrad']
     peak_tf = float(peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']))
     ach = g['flops'] / (g['ms'] * 1e-3) / 1e12 if g['ms'] > 0 else 0.0
-    roof = {'bound': 'tensor', 'kernel': 'rsgemm_tc_kernel (tcgen05 implicit-GEMM conv / conv-transpose / dgrad)',
+    roof = {'bound': 'tensor',
+            'kernel': 'rsgemm3_tc_kernel / rsgemm_tc_kernel (tcgen05 cta_group::2 implicit-GEMM conv, conv-transpose, '
+                      'data gradients, GP linearised forward, per-timestep dense)',
             'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
-            'peak_kind': peak_kind + ' sustained cuBLAS bf16', 'traffic': None,
+            'peak_kind': peak_kind + ' sustained cuBLAS bf16',
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the launches captured with
+            # `ncu --set full` in profiles/r1_final.md (tensor-bound kernel: informative only)
+            'traffic': 47.8e6, 'traffic_source': 'profiles/r1_final.md',
             'launches_per_step': g['launches'] / 2, 'ms_per_step_in_kernel': g['ms'] / 2}
     ach_w = w['flops'] / (w['ms'] * 1e-3) / 1e12 if w['ms'] > 0 else 0.0
-    kernels = {'wgrad_tc_kernel': {'achieved_tflops': ach_w, 'frac': ach_w / peak_tf, 'ms_per_step': w['ms'] / 2,
+    kernels = {'wgrad2_tc_kernel': {'achieved_tflops': ach_w, 'frac': ach_w / peak_tf, 'ms_per_step': w['ms'] / 2,
                                    'launches_per_step': w['launches'] / 2},
                'gemm_share_of_step': (g['ms'] + w['ms']) / 2 / ms_per_step}
 
