@@ -286,7 +286,7 @@ static int repack(cg_ctx* c, int which) {
     add_pack(ops, w1, c->Wf_d1, Cp, C, 1, Cp, C, 0, 1, C);             // [n=out][c=in]
     add_pack(ops, w1, c->Wb_d1, Cp, C, 1, Cp, C, 0, C, 1);             // [n=in][c=out]
   }
-  dim3 grid(148, ops.n);
+  dim3 grid(16, c->K, ops.n);
   DISPATCH_T(c, pack_weights_kernel<T><<<grid, 256, 0, c->stream>>>(ops));
   return post_launch(c, "pack_weights");
 }
@@ -637,11 +637,16 @@ static int g_backward(cg_ctx* c, int B) {
   for (int i = NL; i >= 1; --i) {
     const long long rows = (long long)B * c->gl[i];
     if (c->cfg.layer_norm) {
-      int blocks = grid_for(rows * 32, 256, 148 * 4);
-      DISPATCH_T(c, ln_lrelu_backward_kernel<T><<<blocks, 256, 2 * c->gc[i] * sizeof(float), c->stream>>>(
-                        (const T*)c->DHG[i], (const T*)c->AG[i], (const T*)c->HG[i], c->MU[i], c->RSTD[i],
-                        gparam(c, c->g_gam[i]), (T*)c->DAG[i], ggrad(c, c->g_gam[i]), ggrad(c, c->g_bet[i]), rows,
-                        c->gc[i], c->gcp[i]));
+      const int nvec_b = c->gcp[i] / (16 / c->esz);
+      const int lpr_b = nvec_b > 16 ? 32 : (nvec_b > 8 ? 16 : 8);
+      const int blocks = grid_for(rows * lpr_b, 256, 148 * 2);
+#define CG_LNB(LPRV)                                                                                                 \
+  DISPATCH_T(c, ln_lrelu_backward_kernel<T, LPRV><<<blocks, 256, 2 * c->gcp[i] * sizeof(float), c->stream>>>(          \
+                    (const T*)c->DHG[i], (const T*)c->AG[i], (const T*)c->HG[i], c->MU[i], c->RSTD[i],               \
+                    gparam(c, c->g_gam[i]), (T*)c->DAG[i], ggrad(c, c->g_gam[i]), ggrad(c, c->g_bet[i]), rows,       \
+                    c->gc[i], c->gcp[i]))
+      if (lpr_b == 32) CG_LNB(32); else if (lpr_b == 16) CG_LNB(16); else CG_LNB(8);
+#undef CG_LNB
       CK(post_launch(c, "ln_bwd"));
     } else {
       DISPATCH_T(c, mask_mul_kernel<T><<<grid_for(rows * c->gcp[i]), 256, 0, c->stream>>>(

@@ -220,19 +220,36 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict_
 // all packed copies of one model in ONE launch: blockIdx.y selects the op
 struct PackOp { const float* src; void* dst; int N, n_real, nseg, Cp, c_real; long long sk, sn, sc; };
 struct PackOps { int n; PackOp op[24]; };
+// grid (x = 32x32 tiles of the (n, c) plane, y = tap, z = op): reads follow the source's fastest axis, writes follow
+// the destination's (c), transposing through shared memory when they differ.
 template <typename T>
-__global__ void pack_weights_kernel(const __grid_constant__ PackOps ops) {
-  const PackOp& o = ops.op[blockIdx.y];
+__global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackOps ops) {
+  __shared__ float tile[32][33];
+  const PackOp& o = ops.op[blockIdx.z];
+  const int k = blockIdx.y;
+  if (k >= o.nseg) return;
+  const int ct = (o.Cp + 31) / 32, ntl = (o.N + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
   T* dst = reinterpret_cast<T*>(o.dst);
-  const long long total = (long long)o.N * o.nseg * o.Cp;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % o.Cp);
-    const int k = (int)((i / o.Cp) % o.nseg);
-    const int n = (int)(i / ((long long)o.Cp * o.nseg));
-    float v = 0.f;
-    if (n < o.n_real && c < o.c_real) v = o.src[k * o.sk + n * o.sn + c * o.sc];
-    dst[i] = Elem<T>::from_f(v);
+  for (int tIdx = blockIdx.x; tIdx < ct * ntl; tIdx += gridDim.x) {
+    const int n0 = (tIdx / ct) * 32, c0 = (tIdx % ct) * 32;
+    const bool n_fast = o.sn == 1;          // source contiguous along n (else along c or strided: read c-fastest)
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int a = ty + 8 * j;             // slow index of this read
+      const int n = n_fast ? n0 + tx : n0 + a;
+      const int c = n_fast ? c0 + a : c0 + tx;
+      float v = 0.f;
+      if (n < o.n_real && c < o.c_real) v = o.src[k * o.sk + n * o.sn + c * o.sc];
+      tile[n - n0][c - c0] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + ty + 8 * j, c = c0 + tx;
+      if (n < o.N && c < o.Cp) dst[((long long)n * o.nseg + k) * o.Cp + c] = Elem<T>::from_f(tile[n - n0][c - c0]);
+    }
   }
 }
 
@@ -559,52 +576,98 @@ __global__ void __launch_bounds__(256) ln_lrelu_forward_kernel(const T* __restri
   }
 }
 
-// backward of LN + LeakyReLU: DA, dgamma, dbeta. Shared-memory partials then global atomics.
-template <typename T>
+// backward of LN + LeakyReLU: DA, dgamma, dbeta. Same sub-warp row layout as the forward kernel; every lane owns fixed
+// channel vectors, so dgamma / dbeta accumulate in registers over all rows of the thread and are reduced once per
+// block through shared memory (the first version did two shared atomics per element).
+template <typename T, int LPR>
 __global__ void __launch_bounds__(256) ln_lrelu_backward_kernel(
     const T* __restrict__ DH, const T* __restrict__ A, const T* __restrict__ H, const float* __restrict__ mu_in,
     const float* __restrict__ rstd_in, const float* __restrict__ gamma, T* __restrict__ DA,
     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C, int Cp) {
-  extern __shared__ float sm[];   // [2*C]
-  float* sg = sm;
-  float* sb = sm + C;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  constexpr int V = Vec16<T>::N;
+  constexpr int MAXV = 4;
+  constexpr int RPW = 32 / LPR;
+  extern __shared__ float sm[];   // [2 * Cp]
+  for (int i = threadIdx.x; i < 2 * Cp; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const int nv = Cp / V;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long r = warp; r < rows; r += nwarps) {
-    const T* a = A + r * Cp;
-    const T* dh = DH + r * Cp;
-    const T* h = H + r * Cp;
-    const float mu = mu_in[r], rstd = rstd_in[r];
-    float s1 = 0.f, s2 = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float xh = (Elem<T>::to_f(a[c]) - mu) * rstd;
-      const float dn = Elem<T>::to_f(dh[c]) * lrelu_slope(Elem<T>::to_f(h[c]));
-      const float gd = gamma[c] * dn;
-      s1 += gd;
-      s2 += gd * xh;
-      atomicAdd(&sg[c], dn * xh);
-      atomicAdd(&sb[c], dn);
+  float gacc[MAXV][V], bacc[MAXV][V], gam[MAXV][V];
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k)
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      gacc[k][e] = 0.f; bacc[k][e] = 0.f;
+      const int c = (sl + LPR * k) * V + e;
+      gam[k][e] = c < C ? gamma[c] : 0.f;
     }
-    s1 = warp_sum(s1) / C;
-    s2 = warp_sum(s2) / C;
-    T* da = DA + r * Cp;
-    for (int c = lane; c < Cp; c += 32) {
-      float o = 0.f;
-      if (c < C) {
-        const float xh = (Elem<T>::to_f(a[c]) - mu) * rstd;
-        const float dn = Elem<T>::to_f(dh[c]) * lrelu_slope(Elem<T>::to_f(h[c]));
-        o = rstd * (gamma[c] * dn - s1 - xh * s2);
+  for (long long r0 = warp * RPW; r0 < rows; r0 += nwarps * RPW) {
+    const long long r = r0 + sub;
+    const bool ok = r < rows;
+    const long long rr = ok ? r : 0;
+    const float mu = mu_in[rr], rstd = rstd_in[rr];
+    float xh[MAXV][V], dn[MAXV][V];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = sl + LPR * k;
+      if (vi < nv) {
+        float a[V], dh[V], h[V];
+        vload<T>(A + rr * Cp + vi * V, a);
+        vload<T>(DH + rr * Cp + vi * V, dh);
+        vload<T>(H + rr * Cp + vi * V, h);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const bool real = vi * V + e < C && ok;
+          xh[k][e] = real ? (a[e] - mu) * rstd : 0.f;
+          dn[k][e] = real ? dh[e] * lrelu_slope(h[e]) : 0.f;
+          const float gd = gam[k][e] * dn[k][e];
+          s1 += gd;
+          s2 += gd * xh[k][e];
+          gacc[k][e] += dn[k][e] * xh[k][e];
+          bacc[k][e] += dn[k][e];
+        }
       }
-      da[c] = Elem<T>::from_f(o);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 /= C;
+    s2 /= C;
+    if (ok) {
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        const int vi = sl + LPR * k;
+        if (vi < nv) {
+          float o[V];
+#pragma unroll
+          for (int e = 0; e < V; ++e)
+            o[e] = vi * V + e < C ? rstd * (gam[k][e] * dn[k][e] - s1 - xh[k][e] * s2) : 0.f;
+          vstore<T>(DA + r * Cp + vi * V, o);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int vi = sl + LPR * k;
+    if (vi < nv) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        atomicAdd(&sm[vi * V + e], gacc[k][e]);
+        atomicAdd(&sm[Cp + vi * V + e], bacc[k][e]);
+      }
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(&dgamma[i], sg[i]);
-    atomicAdd(&dbeta[i], sb[i]);
+    atomicAdd(&dgamma[i], sm[i]);
+    atomicAdd(&dbeta[i], sm[Cp + i]);
   }
 }
 
