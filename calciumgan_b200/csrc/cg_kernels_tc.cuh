@@ -635,6 +635,8 @@ struct RsTc2Params {
   int BN, n_tiles, m_tiles, MB, blocks_per_sample, total_blocks, kchunks;
   int box_rows, box_bytes, slab_bytes, slab_stages, b_stages, double_acc;
   int tps;              // taps per weight stage (pair kernel): more MMAs per barrier round-trip for narrow N
+  int per_tap;          // 1: rows per sample < 128 -> no slab reuse: a slab stage holds one 128-row box PER TAP (tps boxes)
+  int rpt, bpt, rpt_log2;
   int ngroups[2];
   SlabGroup grp[2][2];
   long long* dbg;   // optional role cycle counters of CTA 0 (CG_TC_TIMING=1)
@@ -881,6 +883,9 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_tiles = p.seg.nphase * P.n_tiles * P.m_tiles;   // m_tiles = ceil(total_blocks / 2)
+  const bool PT = P.per_tap != 0;
+  // stage structure: slab mode  -> groups = tap-parity groups, each split into weight stages of TPS taps sharing one slab;
+  //                  per-tap mode -> groups = ceil(nseg / TPS) bundles of TPS taps, each tap with its own 16 KB box
 
   if (warp == 0) {
     int ss = 0, bs = 0;
@@ -891,9 +896,34 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int nt = rest % P.n_tiles;
       const int phase = rest / P.n_tiles;
       const int blk = mt * 2 + (int)rank;
-      const int b = blk / P.blocks_per_sample;
-      const int q0 = (blk % P.blocks_per_sample) * 128;
+      const int b = PT ? blk * P.bpt : blk / P.blocks_per_sample;
+      const int q0 = PT ? 0 : (blk % P.blocks_per_sample) * 128;
       for (int kc = 0; kc < P.kchunks; ++kc) {
+        if (PT) {
+          const int nseg = p.seg.nseg[phase];
+          for (int s = 0; s < nseg; s += TPS) {
+            const int cnt = nseg - s < TPS ? nseg - s : TPS;
+            mbar_wait(&s_empty[ss], sph ^ 1);
+            if (elect_one()) {
+              if (rank == 0) mbar_expect_tx(&s_full[ss], (uint32_t)(2 * cnt * kABytes));
+              const uint32_t bar = mapa_u32(smem_u32(&s_full[ss]), 0);
+              for (int j = 0; j < cnt; ++j)
+                tma2_load_3d(slabs + (size_t)ss * P.slab_bytes + (size_t)j * kABytes, &tmA, bar,
+                             p.seg.acol[phase][s + j] + kc * 64, q0 + p.seg.shift[phase][s + j], b);
+            }
+            if (++ss == SS) { ss = 0; sph ^= 1; }
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            if (elect_one()) {
+              if (rank == 0) mbar_expect_tx(&b_full[bs], (uint32_t)(2 * cnt * tap_bytes));
+              const uint32_t bar = mapa_u32(smem_u32(&b_full[bs]), 0);
+              for (int j = 0; j < cnt; ++j)
+                tma2_load_2d(btiles + (size_t)bs * b_bytes + (size_t)j * tap_bytes, &tmW, bar,
+                             p.seg.wk[phase][s + j] + kc * 64, nt * BN + (int)rank * (BN / 2));
+            }
+            if (++bs == BS) { bs = 0; bph ^= 1; }
+          }
+          continue;
+        }
         for (int g = 0; g < P.ngroups[phase]; ++g) {
           const SlabGroup& G = P.grp[phase][g];
           mbar_wait(&s_empty[ss], sph ^ 1);
@@ -936,6 +966,33 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t d_tmem = tmem_base + acc * BN;
         uint32_t accum = 0;
         for (int kc = 0; kc < P.kchunks; ++kc) {
+          if (PT) {
+            const int nseg = p.seg.nseg[phase];
+            for (int s = 0; s < nseg; s += TPS) {
+              const int cnt = nseg - s < TPS ? nseg - s : TPS;
+              mbar_wait(&s_full[ss], sph);
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              const uint32_t sl_lo = slab_lo0 + ss * slab_step;
+              const uint32_t b_lo = b_lo0 + bs * b_step;
+              if (elect_one()) {
+                for (int j = 0; j < cnt; ++j) {
+                  const uint32_t a_lo = sl_lo + j * (kABytes >> 4);
+                  const uint32_t bj = b_lo + j * tap_step;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma2_bf16_lohi(d_tmem, a_lo + 2 * k, bj + 2 * k, hi, idesc, accum | (uint32_t)(j | k));
+                }
+                umma2_commit_mc(&b_empty[bs]);
+                umma2_commit_mc(&s_empty[ss]);
+              }
+              __syncwarp();
+              accum = 1;
+              if (++bs == BS) { bs = 0; bph ^= 1; }
+              if (++ss == SS) { ss = 0; sph ^= 1; }
+            }
+            continue;
+          }
           for (int g = 0; g < P.ngroups[phase]; ++g) {
             const SlabGroup& G = P.grp[phase][g];
             mbar_wait(&s_full[ss], sph);
@@ -981,7 +1038,8 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int phase = rest / P.n_tiles;
       const int blk = mt * 2 + (int)rank;   // blocks past the end map to samples >= B and are masked
       EpiRows R;
-      epi_rows(p, blk / P.blocks_per_sample, (blk % P.blocks_per_sample) * 128, 7, phase, lq, lane, R);
+      if (PT) epi_rows(p, blk * P.bpt, 0, P.rpt_log2, phase, lq, lane, R);
+      else epi_rows(p, blk / P.blocks_per_sample, (blk % P.blocks_per_sample) * 128, 7, phase, lq, lane, R);
       if (nt != last_nt) { epi_load_bias<EPI>(p, bias_s, nt * BN, BN, threadIdx.x - 64); last_nt = nt; }
       const int acc = it & 1;
       mbar_wait(&tfull[acc], ((uint32_t)it >> 1) & 1);
@@ -1317,6 +1375,7 @@ struct TcState {
   int max_smem = 0;
   bool force_v1 = false;   // CG_TC_V1=1: per-tap boxes everywhere (A/B comparison)
   bool use_pair = true;    // CG_TC_PAIR=0: single-CTA slab kernel instead of the cta_group::2 kernel
+  bool pair_short = true;  // CG_TC_PAIR_SHORT=0: per-tap single-CTA kernel for layers with < 128 time rows
   std::string err;
 };
 
@@ -1338,6 +1397,7 @@ static inline int tc_init(TcState* s) {
   s->max_smem = (int)prop.sharedMemPerBlockOptin;
   if (const char* e = getenv("CG_TC_V1")) s->force_v1 = atoi(e) != 0;
   if (const char* e = getenv("CG_TC_PAIR")) s->use_pair = atoi(e) != 0;
+  if (const char* e = getenv("CG_TC_PAIR_SHORT")) s->pair_short = atoi(e) != 0;
   bool ok = true;
 #define CG_SET_SMEM(E)                                                                                                         \
   ok = ok && cudaFuncSetAttribute(tc::rsgemm_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess && \
@@ -1538,6 +1598,7 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   tc::RsTc2Params P;
   memset(&P, 0, sizeof(P));
   P.p = p;
+  P.per_tap = p.Q < 128 ? 1 : 0;
   int span = 0;
   for (int ph = 0; ph < p.seg.nphase; ++ph) {
     int na = 0;
@@ -1564,6 +1625,14 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   P.box_bytes = P.box_rows * 128;
   P.blocks_per_sample = p.Q / 128;
   P.total_blocks = p.B * P.blocks_per_sample;
+  if (P.per_tap) {   // whole samples per 128-row block
+    P.rpt = p.Q; P.bpt = 128 / p.Q;
+    P.rpt_log2 = 0;
+    while ((1 << P.rpt_log2) < P.rpt) ++P.rpt_log2;
+    P.blocks_per_sample = 1;
+    P.total_blocks = (p.B + P.bpt - 1) / P.bpt;
+    P.box_bytes = tc::kABytes;
+  }
   P.kchunks = p.Kc / 64;
   P.MB = 1;
   P.m_tiles = (P.total_blocks + 1) / 2;
@@ -1596,7 +1665,9 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   P.tps = (stage_clk + 2 * P.BN - 1) / (2 * P.BN);
   if (P.tps < 1) P.tps = 1;
   if (P.tps > 6) P.tps = 6;
+  if (P.per_tap && P.tps > 3) P.tps = 3;
   if (const char* e = getenv("CG_TC_TPS")) P.tps = atoi(e);
+  if (P.per_tap) { P.slab_bytes = P.tps * tc::kABytes; P.slab_stages = 3; }
   const int b_bytes = P.tps * P.BN * 64;
   int bst = (s->max_smem - 1024 - 512 - tc::kEpiSmem - P.slab_stages * P.slab_bytes) / b_bytes;
   if (bst > 10) bst = 10;
@@ -1604,7 +1675,8 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   P.b_stages = bst;
   P.dbg = nullptr;
   CUtensorMap tmA, tmW;
-  if (tc_get_map3(s, p.A, p.a_rs, p.a_rows, p.B, p.a_rs, p.a_bs, P.box_rows, 1, &tmA)) return 1;
+  if (P.per_tap) { if (tc_get_map3(s, p.A, p.a_rs, p.a_rows, p.B, p.a_rs, p.a_bs, P.rpt, P.bpt, &tmA)) return 1; }
+  else if (tc_get_map3(s, p.A, p.a_rs, p.a_rows, p.B, p.a_rs, p.a_bs, P.box_rows, 1, &tmA)) return 1;
   if (tc_get_map2(s, p.W, p.w_ld, p.N, p.w_ld, P.BN / 2, &tmW)) return 1;
   const int total = p.seg.nphase * P.n_tiles * P.m_tiles;
   const int npairs = total < npairs_max ? total : npairs_max;
@@ -1622,7 +1694,9 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
 }
 
 static inline int tc_rsgemm_launch(TcState* s, const RsParams& p, cudaStream_t stream) {
-  if (!s->force_v1 && s->use_pair && tc_rsgemm2_supported(p)) return tc_rsgemm3_launch(s, p, stream);
+  if (!s->force_v1 && s->use_pair && (tc_rsgemm2_supported(p) || (s->pair_short && p.Q < 128 && p.B * p.Q >= 256 &&
+                                                                (double)p.B * p.Q * p.N * p.Kc * (p.seg.nseg[0] + p.seg.nseg[1]) >= 8e9)))
+    return tc_rsgemm3_launch(s, p, stream);
   if (!s->force_v1 && tc_rsgemm2_supported(p)) return tc_rsgemm2_launch(s, p, stream);
   tc::RsTcParams P;
   P.p = p;
