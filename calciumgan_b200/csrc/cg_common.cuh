@@ -99,6 +99,7 @@ struct RsParams {
   // fused PhaseShuffle (slab kernels, strided-conv form): ps_out[b, t, :] = result[b, ps_index(t, shift[b / ps_group_b]), :]
   void* ps_out; int ps_w; int ps_group_b; int ps_shift[4];
   int dbg;                                         // timing experiments only
+  float* sumsq;                                    // optional: sumsq[b] += sum of squares of the fp32 results of sample b
   int B, Q, N, n_real, Kc, k_real, epi;   // k_real: unpadded channels per tap (algorithmic FLOPs only)
   SegTable seg;
 };

@@ -719,7 +719,7 @@ static int d_forward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh) {
 }
 
 // data-gradient of conv layer l: DA[l] (rows dl[l]) -> out (rows dl[l-1]) for samples [b0, b0+nb)
-static int d_dgrad_layer(cg_ctx* c, int l, int b0, int nb, void* out) {
+static int d_dgrad_layer(cg_ctx* c, int l, int b0, int nb, void* out, float* sumsq = nullptr) {
   RsParams p;
   memset(&p, 0, sizeof(p));
   p.A = off(c, c->DA[l], (long long)b0 * c->dl[l] * c->dcp[l]);
@@ -728,11 +728,13 @@ static int d_dgrad_layer(cg_ctx* c, int l, int b0, int nb, void* out) {
   p.out = out; p.o_bs = (long long)c->dl[l - 1] * c->dcp[l - 1]; p.o_rs = 2 * c->dcp[l - 1]; p.o_phase_col = c->dcp[l - 1];
   p.B = nb; p.Q = c->dl[l]; p.N = c->dcp[l - 1]; p.n_real = c->dc[l - 1]; p.Kc = c->dcp[l]; p.k_real = c->dc[l]; p.epi = EPI_NONE;
   p.seg = seg_transposed(c->K, c->dcp[l]);
+  p.sumsq = sumsq;
   return launch_rsgemm(c, p);
 }
 
 // backward chain of sum_b coef[b]*D(x)_b down to DA[1] (and DX[0] for samples [dx0_b0, dx0_b0+dx0_nb))
-static int d_backward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh, int dx0_b0, int dx0_nb) {
+static int d_backward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh, int dx0_b0, int dx0_nb,
+                      float* sumsq = nullptr) {   // sumsq: per-sample squared norm of dX0, fused into the last GEMM
   DISPATCH_T(c, head_backward_kernel<T><<<grid_for((long long)Bt * c->dl[NL] * c->dcp[NL] / (16 / c->esz)), 256, 0, c->stream>>>(
                     (const T*)c->H[NL], dparam(c, 10), c->coef, (T*)c->DA[NL], Bt, c->dl[NL], c->dc[NL], c->dcp[NL]));
   CK(post_launch(c, "head_bwd"));
@@ -744,7 +746,7 @@ static int d_backward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh, i
                       c->dcp[l - 1], group_shifts(sh, groups, l - 1)));
     CK(post_launch(c, "ps_scatter_mask"));
   }
-  if (dx0_nb > 0) CK(d_dgrad_layer(c, 1, dx0_b0, dx0_nb, c->DX[0]));
+  if (dx0_nb > 0) CK(d_dgrad_layer(c, 1, dx0_b0, dx0_nb, c->DX[0], sumsq));
   return 0;
 }
 
@@ -763,10 +765,19 @@ static WgParams conv_wgrad_params(cg_ctx* c, int l, int Bt) {
 
 // all critic weight gradients from X[l-1] x DA[l] over Bt samples; biases from the first nb_bias samples
 static int d_wgrad(cg_ctx* c, int Bt, int nb_bias) {
-  for (int l = 1; l <= NL; ++l) {
-    CK(launch_wgrad(c, conv_wgrad_params(c, l, Bt)));
-    if (nb_bias > 0)
-      CK(launch_colsum(c, c->DA[l], dgrad(c, 2 * (l - 1) + 1), (long long)nb_bias * c->dl[l], c->dcp[l], c->dc[l]));
+  for (int l = 1; l <= NL; ++l) CK(launch_wgrad(c, conv_wgrad_params(c, l, Bt)));
+  if (nb_bias > 0) {   // all five bias gradients in one launch
+    ColsumOps ops;
+    ops.n = NL;
+    int maxc = 0;
+    for (int l = 1; l <= NL; ++l) {
+      ops.op[l - 1].X = c->DA[l]; ops.op[l - 1].out = dgrad(c, 2 * (l - 1) + 1);
+      ops.op[l - 1].rows = (long long)nb_bias * c->dl[l]; ops.op[l - 1].Cp = c->dcp[l]; ops.op[l - 1].c_real = c->dc[l];
+      if (c->dc[l] > maxc) maxc = c->dc[l];
+    }
+    dim3 grid(148, (maxc + 63) / 64, NL), block(64, 4);
+    DISPATCH_T(c, colsum_multi_kernel<T><<<grid, block, 0, c->stream>>>(ops));
+    CK(post_launch(c, "colsum_multi"));
   }
   const int tot = c->dl[NL] * c->dc[NL];
   dim3 hgrid(grid_for(tot), Bt >= 64 ? 16 : 1);
@@ -836,12 +847,16 @@ static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* n
   CK(d_forward(c, 3 * B, B, 3, sh));
   fill_coef_kernel<<<(3 * B + 255) / 256, 256, 0, c->stream>>>(c->coef, B, 3, 0.f);
   CK(post_launch(c, "fill_coef"));
-  CK(d_backward(c, 3 * B, B, 3, sh, 2 * B, B));
   CU(cudaMemsetAsync(c->sumsq, 0, (size_t)B * 4, c->stream));
-  const long long per_sample = (long long)c->L * c->dcp[0];
-  const int chunks = 8;
-  DISPATCH_T(c, sumsq_kernel<T><<<B * chunks, 256, 0, c->stream>>>((const T*)c->DX[0], c->sumsq, per_sample, chunks));
-  CK(post_launch(c, "sumsq"));
+  // tensor-core path: ||g_b||^2 accumulates in the epilogue of the last data-gradient GEMM (fp32 accumulators)
+  const bool fuse_norm = c->use_tc && c->dl[1] >= 128 && !c->tc.force_v1;
+  CK(d_backward(c, 3 * B, B, 3, sh, 2 * B, B, fuse_norm ? c->sumsq : nullptr));
+  if (!fuse_norm) {
+    const long long per_sample = (long long)c->L * c->dcp[0];
+    const int chunks = 8;
+    DISPATCH_T(c, sumsq_kernel<T><<<B * chunks, 256, 0, c->stream>>>((const T*)c->DX[0], c->sumsq, per_sample, chunks));
+    CK(post_launch(c, "sumsq"));
+  }
   critic_scalars_kernel<<<1, 256, 0, c->stream>>>(c->scores, c->sumsq, c->ucoef, c->norms,
                                                   c->d_scal + (size_t)slot * CG_NUM_SCALARS, B, c->cfg.gp_lambda);
   return post_launch(c, "critic_scalars");

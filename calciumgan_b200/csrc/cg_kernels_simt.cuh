@@ -506,6 +506,27 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, fl
   }
 }
 
+// several column sums in one launch (blockIdx.z selects the tensor): bias gradients of all conv layers of a sub-step
+struct ColsumOps { int n; struct { const void* X; float* out; long long rows; int Cp, c_real; } op[8]; };
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_multi_kernel(const __grid_constant__ ColsumOps ops) {
+  const auto& o = ops.op[blockIdx.z];
+  const int c = blockIdx.y * 64 + threadIdx.x;
+  if (blockIdx.y * 64 >= o.c_real) return;
+  const T* X = reinterpret_cast<const T*>(o.X);
+  float acc = 0.f;
+  if (c < o.c_real)
+    for (long long r = (long long)blockIdx.x * 4 + threadIdx.y; r < o.rows; r += (long long)gridDim.x * 4)
+      acc += Elem<T>::to_f(X[r * o.Cp + c]);
+  __shared__ float red[4][64];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < o.c_real) {
+    const float s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    atomicAdd(&o.out[c], s);
+  }
+}
+
 // =============================================================================================
 // Generator layer-norm + LeakyReLU (calciumgan.py:45-46): one warp per (b,t) row, channels C of Cp.
 // =============================================================================================

@@ -285,6 +285,7 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
   const uint32_t stg_s = smem_u32(stg);
   const bf16* mask = reinterpret_cast<const bf16*>(p.mask);
   const int cj = lane & 7;
+  float ssq = 0.f;   // p.sumsq: gradient-penalty norm fused into the last data-gradient GEMM (fp32 accumulators)
   float ln_mean = 0.f, ln_rstd = 1.f;
   if (EPI == EPI_BIAS_LN_LRELU) {   // pass 1 over TMEM: row statistics of x = acc + bias (this thread owns the row)
     float s1 = 0.f, s2 = 0.f;
@@ -385,6 +386,11 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
         }
       }
     }
+    if (EPI == EPI_NONE && p.sumsq) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j)
+        if (j < ncols) ssq = fmaf(__uint_as_float(v[j]), __uint_as_float(v[j]), ssq);
+    }
     if (p.out32) {   // unpadded fp32 copy (generator head only): 32x32 fp32 transpose through the staging buffer so
                      // every warp store writes 32 consecutive floats of one output row
 #pragma unroll
@@ -439,6 +445,14 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
         }
       }
       __syncwarp();
+    }
+  }
+  if (EPI == EPI_NONE && p.sumsq) {
+    if (R.uniform) {   // all 32 rows of the warp belong to one sample
+      ssq = warp_sum(R.my_ok ? ssq : 0.f);
+      if (lane == 0 && R.my_ok) atomicAdd(&p.sumsq[R.my_row / ((long long)p.Q * p.seg.nphase)], ssq);
+    } else if (R.my_ok) {
+      atomicAdd(&p.sumsq[R.my_row / ((long long)p.Q * p.seg.nphase)], ssq);
     }
   }
 }
