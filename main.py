@@ -50,7 +50,8 @@ def get_dataset(hparams):
 def train(hparams, train_ds, gan, epoch):
   gen_losses, dis_losses, gradient_penalties = [], [], []
   start = time()
-  for signal, _ in train_ds():
+  from calciumgan_b200.utils.prefetch import prefetch_to_device
+  for signal, _ in prefetch_to_device(train_ds()):     # H2D copy of batch i+1 overlaps step i
     gen_loss, dis_loss, gradient_penalty, metrics = gan.train(signal)
     gen_losses.append(gen_loss)
     dis_losses.append(dis_loss)

@@ -280,3 +280,18 @@ def test_checkpoint_roundtrip(tmp_path):
   for a, b in zip(dw, gan2.discriminator.get_weights()):
     np.testing.assert_array_equal(a, b)
   assert gan2.gen_optimizer.iterations == 1 and gan2.dis_optimizer.iterations == 1
+
+
+def test_prefetch_to_device_ragged():
+  from calciumgan_b200.utils.prefetch import prefetch_to_device
+  rng = np.random.RandomState(0)
+  batches = [(rng.rand(b, 16, 5).astype(np.float32), i) for i, b in enumerate([4, 4, 4, 3])]
+  pinned = [(torch.from_numpy(x).pin_memory(), i) for x, i in batches]
+  for src in (batches, pinned):
+    seen = []
+    for signal, extra in prefetch_to_device(iter(src)):
+      assert signal.is_cuda and signal.dtype == torch.float32
+      seen.append((signal.cpu().numpy().copy(), extra))
+    assert [e for _, e in seen] == [0, 1, 2, 3]
+    for (got, _), (ref, _) in zip(seen, batches):
+      np.testing.assert_array_equal(got, ref)
