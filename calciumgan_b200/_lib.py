@@ -13,7 +13,7 @@ FP32, BF16 = 0, 1
 NUM_SCALARS = 16
 S_DIS_LOSS, S_GP, S_REAL_LOSS, S_FAKE_LOSS, S_GEN_LOSS = 0, 1, 2, 3, 4
 S_MET_MIN, S_MET_MAX, S_MET_MEAN, S_MET_STD = 5, 6, 7, 8
-FLAG_NO_UPDATE, FLAG_NO_SYNC = 1, 2
+FLAG_NO_UPDATE, FLAG_NO_SYNC, FLAG_SAME_REAL = 1, 2, 4
 
 
 class CgConfig(C.Structure):
@@ -46,6 +46,9 @@ SIGNATURES = {
     'cg_init_weights': (_I, [_P, C.c_uint64]),
     'cg_get_grads': (_I, [_P, _I, _P]),
     'cg_grad_ptr': (_P, [_P, _I]),
+    'cg_num_buckets': (_I, [_P, _I]),
+    'cg_bucket_info': (_I, [_P, _I, _I, C.POINTER(_I64), C.POINTER(_I64)]),
+    'cg_stream_wait_bucket': (_I, [_P, _I, _I, _P]),
     'cg_get_opt_state': (_I, [_P, _I, _P, _P, C.POINTER(_I64)]),
     'cg_set_opt_state': (_I, [_P, _I, _P, _P, _I64]),
     'cg_seed': (_I, [_P, C.c_uint64]),

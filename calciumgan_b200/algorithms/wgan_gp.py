@@ -62,13 +62,33 @@ class WGAN_GP(GAN):
     return loss, gradient_penalty
 
   # ------------------------------------------------------------------ steps (wgan_gp.py:22-36,64-95)
+  def _allreduce_buckets(self, dist, which):
+    """Bucketed gradient all-reduce overlapped with the backward pass: bucket b is reduced on a side stream as soon as
+    the library's event for its last writer has fired; the remaining wgrad kernels keep running on the main stream."""
+    eng = self.engine
+    if eng.device.type != 'cuda':        # host-logic tests drive this class over a CPU stub engine (gloo)
+      for view, _ in eng.grad_buckets(which):
+        dist.all_reduce(view)
+      return
+    if not hasattr(self, '_comm_stream'):
+      self._comm_stream = torch.cuda.Stream(device=eng.device)
+    main = torch.cuda.current_stream()
+    works = []
+    with torch.cuda.stream(self._comm_stream):
+      for view, b in eng.grad_buckets(which):
+        eng.stream_wait_bucket(which, b, self._comm_stream)
+        works.append(dist.all_reduce(view, async_op=True))
+      for w in works:
+        w.wait()
+    main.wait_stream(self._comm_stream)
+
   def _train_discriminator(self, inputs, noise=None, alpha=None, shifts=None):
     dist = _dist()
     if dist is None:
       s = self.engine.critic_step(inputs, noise, alpha, shifts, update=True)
     else:
       s = self.engine.critic_step(inputs, noise, alpha, shifts, update=False)
-      dist.all_reduce(self.engine.grad_tensor(L.DISCRIMINATOR))
+      self._allreduce_buckets(dist, L.DISCRIMINATOR)
       self.dis_optimizer.update()
     return float(s[L.S_DIS_LOSS]), float(s[L.S_GP])
 
@@ -78,7 +98,7 @@ class WGAN_GP(GAN):
       s = self.engine.generator_step(inputs, noise, shifts, update=True)
     else:
       s = self.engine.generator_step(inputs, noise, shifts, update=False)
-      dist.all_reduce(self.engine.grad_tensor(L.GENERATOR))
+      self._allreduce_buckets(dist, L.GENERATOR)
       self.gen_optimizer.update()
     return float(s[L.S_GEN_LOSS]), metrics_from_scalars(s)
 
@@ -96,17 +116,16 @@ class WGAN_GP(GAN):
     shifts = None if shifts is None else np.asarray(shifts, np.int32).reshape(-1)
     hist = torch.zeros((nc + 1, L.NUM_SCALARS), device=eng.device)
     scal = eng.scalars_tensor()
-    gd, gg = eng.grad_tensor(L.DISCRIMINATOR), eng.grad_tensor(L.GENERATOR)
     for i in range(nc):
       eng.critic_step(real, None if noise is None else noise[i], None if alpha is None else alpha[i],
-                      None if shifts is None else shifts[12 * i:12 * i + 12], update=False, sync=False)
+                      None if shifts is None else shifts[12 * i:12 * i + 12], update=False, sync=False, same_real=i > 0)
       hist[i].copy_(scal)
-      dist.all_reduce(gd)
+      self._allreduce_buckets(dist, L.DISCRIMINATOR)
       eng.apply_update(L.DISCRIMINATOR)
     eng.generator_step(real, None if noise is None else noise[nc],
                        None if shifts is None else shifts[12 * nc:12 * nc + 4], update=False, sync=False)
     hist[nc].copy_(scal)
-    dist.all_reduce(gg)
+    self._allreduce_buckets(dist, L.GENERATOR)
     eng.apply_update(L.GENERATOR)
     out = torch.zeros(L.NUM_SCALARS, device=eng.device)
     out[L.S_DIS_LOSS] = hist[:nc, L.S_DIS_LOSS].mean()

@@ -115,6 +115,9 @@ struct cg_ctx {
   float* d_scal;        // [n_critic+1][CG_NUM_SCALARS]
   float* h_scal;        // pinned
   uint64_t seed = 1234, rng_counter = 0;
+  static const int NB = 3;                 // gradient buckets per model (ready order: last layers first)
+  cudaEvent_t bucket_evt[2][NB] = {};
+  int64_t bucket_off[2][NB + 1] = {};
   TcState tc;
 };
 
@@ -300,6 +303,9 @@ extern "C" void cg_destroy(cg_ctx* c) {
   cudaDeviceSynchronize();
   tc_destroy(&c->tc);
   for (void* p : c->allocs) cudaFree(p);
+  for (int w = 0; w < 2; ++w)
+    for (int b = 0; b < cg_ctx::NB; ++b)
+      if (c->bucket_evt[w][b]) cudaEventDestroy(c->bucket_evt[w][b]);
   if (c->h_scal) cudaFreeHost(c->h_scal);
   delete c;
 }
@@ -358,6 +364,17 @@ extern "C" int cg_create(const cg_config* cfg, cg_ctx** out) {
   for (int l = 1; l <= NL; ++l) { D.add({c->K, c->dc[l - 1], c->dc[l]}); D.add({c->dc[l]}); }
   D.add({(int64_t)c->dl[NL] * c->dc[NL], 1}); D.add({1});
 
+ // bucket ranges: generator {[convT5 .. end), [convT3 .. convT5), [0 .. convT3)}; critic {[conv5 .. end), [conv4 .. conv5), [0 .. conv4)}
+  c->bucket_off[CG_GENERATOR][0] = G.params[c->g_k[5]].offset; c->bucket_off[CG_GENERATOR][1] = G.params[c->g_k[3]].offset;
+  c->bucket_off[CG_GENERATOR][2] = 0; c->bucket_off[CG_GENERATOR][3] = G.total;
+  c->bucket_off[CG_DISCRIMINATOR][0] = D.params[8].offset; c->bucket_off[CG_DISCRIMINATOR][1] = D.params[6].offset;
+  c->bucket_off[CG_DISCRIMINATOR][2] = 0; c->bucket_off[CG_DISCRIMINATOR][3] = D.total;
+  for (int w = 0; w < 2; ++w)
+    for (int b = 0; b < cg_ctx::NB; ++b)
+      if (cudaEventCreateWithFlags(&c->bucket_evt[w][b], cudaEventDisableTiming) != cudaSuccess) {
+        delete c;
+        return set_err("cudaEventCreate failed");
+      }
 #define DA_(ptr, bytes)                                          \
   do {                                                           \
     if (dalloc(c, (void**)&(ptr), (size_t)(bytes))) { cg_destroy(c); return 1; } \
@@ -449,6 +466,21 @@ extern "C" int cg_get_grads(cg_ctx* c, int which, float* host) {
   return 0;
 }
 extern "C" void* cg_grad_ptr(cg_ctx* c, int which) { return model_of(c, which)->g; }
+extern "C" int cg_num_buckets(cg_ctx*, int) { return cg_ctx::NB; }
+extern "C" int cg_bucket_info(cg_ctx* c, int which, int bucket, int64_t* offset, int64_t* count) {
+  if (which < 0 || which > 1 || bucket < 0 || bucket >= cg_ctx::NB) return set_err("cg_bucket_info: bad arguments");
+  // bucket b spans [off[b], end_b) where end_0 = total and end_b = off[b-1]
+  const int64_t lo = c->bucket_off[which][bucket];
+  const int64_t hi = bucket == 0 ? c->bucket_off[which][cg_ctx::NB] : c->bucket_off[which][bucket - 1];
+  *offset = lo;
+  *count = hi - lo;
+  return 0;
+}
+extern "C" int cg_stream_wait_bucket(cg_ctx* c, int which, int bucket, void* stream) {
+  if (which < 0 || which > 1 || bucket < 0 || bucket >= cg_ctx::NB) return set_err("cg_stream_wait_bucket: bad arguments");
+  CU(cudaStreamWaitEvent((cudaStream_t)stream, c->bucket_evt[which][bucket], 0));
+  return 0;
+}
 extern "C" int cg_get_opt_state(cg_ctx* c, int which, float* hm, float* hv, int64_t* step) {
   Model* m = model_of(c, which);
   if (hm) CU(cudaMemcpyAsync(hm, m->m, m->total * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -655,6 +687,8 @@ static int g_backward(cg_ctx* c, int B) {
     }
     CK(launch_wgrad(c, convT_wgrad_params(c, i, B)));
     CK(launch_colsum(c, c->DAG[i], ggrad(c, c->g_b[i]), rows, c->gcp[i], c->gc[i]));
+    if (i == NL) CU(cudaEventRecord(c->bucket_evt[CG_GENERATOR][0], c->stream));       // output dense + convT5 done
+    if (i == NL - 2) CU(cudaEventRecord(c->bucket_evt[CG_GENERATOR][1], c->stream));   // convT4, convT3 done
     CK(launch_rsgemm(c, convT_bwd_params(c, i, B)));
   }
   const int tot = (c->nd + 1) * c->w0 * c->nd;
@@ -662,6 +696,7 @@ static int g_backward(cg_ctx* c, int B) {
                     c->Z, (const T*)c->DHG[0], (const T*)c->HG[0], ggrad(c, 0), ggrad(c, 1), B, c->nd, c->w0,
                     c->gcp[0]));
   CK(post_launch(c, "dense0_bwd"));
+  CU(cudaEventRecord(c->bucket_evt[CG_GENERATOR][2], c->stream));
   return 0;
 }
 
@@ -765,7 +800,6 @@ static WgParams conv_wgrad_params(cg_ctx* c, int l, int Bt) {
 
 // all critic weight gradients from X[l-1] x DA[l] over Bt samples; biases from the first nb_bias samples
 static int d_wgrad(cg_ctx* c, int Bt, int nb_bias) {
-  for (int l = 1; l <= NL; ++l) CK(launch_wgrad(c, conv_wgrad_params(c, l, Bt)));
   if (nb_bias > 0) {   // all five bias gradients in one launch
     ColsumOps ops;
     ops.n = NL;
@@ -783,7 +817,15 @@ static int d_wgrad(cg_ctx* c, int Bt, int nb_bias) {
   dim3 hgrid(grid_for(tot), Bt >= 64 ? 16 : 1);
   DISPATCH_T(c, head_wgrad_kernel<T><<<hgrid, 256, 0, c->stream>>>(
                     (const T*)c->X[NL], c->coef, dgrad(c, 10), dgrad(c, 11), Bt, nb_bias, c->dl[NL], c->dc[NL], c->dcp[NL]));
-  return post_launch(c, "head_wgrad");
+  CK(post_launch(c, "head_wgrad"));
+  // reverse layer order: the data-parallel host all-reduces bucket b as soon as its last writer has finished
+  for (int l = NL; l >= 1; --l) {
+    CK(launch_wgrad(c, conv_wgrad_params(c, l, Bt)));
+    if (l == NL) CU(cudaEventRecord(c->bucket_evt[CG_DISCRIMINATOR][0], c->stream));
+    if (l == NL - 1) CU(cudaEventRecord(c->bucket_evt[CG_DISCRIMINATOR][1], c->stream));
+  }
+  CU(cudaEventRecord(c->bucket_evt[CG_DISCRIMINATOR][2], c->stream));
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------ rng
@@ -920,7 +962,7 @@ extern "C" int cg_critic_step(cg_ctx* c, const float* real, int B, const float* 
   CK(check_batch(c, B));
   int32_t shbuf[12];
   CK(prep_random(c, B, noise, &alpha, sh, shbuf, 12));
-  CK(critic_step_impl(c, real, B, noise, alpha, sh, flags, 0));
+  CK(critic_step_impl(c, real, B, noise, alpha, sh, flags, 0, (flags & CG_FLAG_SAME_REAL) != 0));
   return fetch_scalars(c, 0, flags, scalars_host);
 }
 

@@ -171,6 +171,20 @@ class Engine(object):
       self._grad_views[which] = torch.as_tensor(_DevArray(ptr, self.num_params(which)), device=self.device)
     return self._grad_views[which]
 
+  def grad_buckets(self, which):
+    """[(flat slice of the gradient tensor, bucket index)] in the order the backward pass completes them."""
+    if ('b', which) not in self._grad_views:
+      g, out = self.grad_tensor(which), []
+      for b in range(self.lib.cg_num_buckets(self.ctx, which)):
+        off, cnt = C.c_int64(), C.c_int64()
+        L.check(self.lib.cg_bucket_info(self.ctx, which, b, C.byref(off), C.byref(cnt)))
+        out.append((g[off.value:off.value + cnt.value], b))
+      self._grad_views[('b', which)] = out
+    return self._grad_views[('b', which)]
+
+  def stream_wait_bucket(self, which, bucket, stream):
+    L.check(self.lib.cg_stream_wait_bucket(self.ctx, which, bucket, C.c_void_p(stream.cuda_stream)))
+
   def init_weights(self, seed):
     self._use_stream()
     L.check(self.lib.cg_init_weights(self.ctx, C.c_uint64(int(seed))))
@@ -199,14 +213,14 @@ class Engine(object):
     self.set_opt_state(which, None, None, step)
 
   # ---------------------------------------------------------------- hot path
-  def critic_step(self, real, noise=None, alpha=None, shifts=None, update=True, sync=True):
+  def critic_step(self, real, noise=None, alpha=None, shifts=None, update=True, sync=True, same_real=False):
     self._use_stream()
     real = self.to_device(real)
     B = real.shape[0]
     noise = self.to_device(noise, (B, self.cfg.noise_dim)) if noise is not None else None
     alpha = self.to_device(alpha).reshape(-1) if alpha is not None else None
     sh = self._shifts(shifts, 12)
-    flags = (0 if update else L.FLAG_NO_UPDATE) | (0 if sync else L.FLAG_NO_SYNC)
+    flags = (0 if update else L.FLAG_NO_UPDATE) | (0 if sync else L.FLAG_NO_SYNC) | (L.FLAG_SAME_REAL if same_real else 0)
     L.check(self.lib.cg_critic_step(self.ctx, self._ptr(real), B, self._ptr(noise), self._ptr(alpha),
                                     sh[0] if sh else None, flags, self._scal))
     return np.array(self._scal[:], np.float32) if sync else None

@@ -69,7 +69,9 @@ enum {
 /* flags for the step functions */
 enum {
   CG_FLAG_NO_UPDATE = 1,   /* leave gradients in the flat buffer, do not run Adam (DP host allreduces first) */
-  CG_FLAG_NO_SYNC = 2      /* do not copy scalars back / synchronise (scalars_host may be NULL) */
+  CG_FLAG_NO_SYNC = 2,     /* do not copy scalars back / synchronise (scalars_host may be NULL) */
+  CG_FLAG_SAME_REAL = 4    /* real_dev holds the same batch as in the previous cg_critic_step (wgan_gp.py:85-86):
+                              skip its conversion to the compute type */
 };
 
 int cg_version(void);
@@ -92,6 +94,13 @@ int cg_init_weights(cg_ctx* ctx, uint64_t seed);            /* glorot-uniform / 
 int cg_get_grads(cg_ctx* ctx, int which, float* host_flat);
 /* device pointer of the flat fp32 gradient buffer (the DP host all-reduces it in place) */
 void* cg_grad_ptr(cg_ctx* ctx, int which);
+/* Gradient buckets for the overlapped data-parallel all-reduce (no reference counterpart). The flat
+ * gradient buffer of each model is cut into cg_num_buckets contiguous ranges in the order the backward pass
+ * completes them (last layers first). After a step with CG_FLAG_NO_UPDATE, cg_stream_wait_bucket makes `cuda_stream`
+ * wait for the last kernel that writes bucket `bucket`, so its all-reduce can overlap the remaining wgrad kernels. */
+int cg_num_buckets(cg_ctx* ctx, int which);
+int cg_bucket_info(cg_ctx* ctx, int which, int bucket, int64_t* offset, int64_t* count);
+int cg_stream_wait_bucket(cg_ctx* ctx, int which, int bucket, void* cuda_stream);
 /* Adam moments + iteration counter (optimizer.py:15-21; extra checkpoint keys) */
 int cg_get_opt_state(cg_ctx* ctx, int which, float* host_m, float* host_v, int64_t* step);
 int cg_set_opt_state(cg_ctx* ctx, int which, const float* host_m, const float* host_v, int64_t step);

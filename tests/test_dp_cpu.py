@@ -32,10 +32,14 @@ class StubEngine(object):
   def grad_tensor(self, which):
     return self.g[which]
 
+  def grad_buckets(self, which):
+    g = self.g[which]
+    return [(g[4:], 0), (g[2:4], 1), (g[:2], 2)]     # last layers first, contiguous views of the flat buffer
+
   def scalars_tensor(self):
     return self.scal
 
-  def critic_step(self, real, noise, alpha, shifts, update=True, sync=True):
+  def critic_step(self, real, noise, alpha, shifts, update=True, sync=True, same_real=False):
     assert not update and not sync
     self.seen_shifts.append(None if shifts is None else np.asarray(shifts).copy())
     self.g[1][:] = float(real.sum()) * torch.arange(1, 7)       # rank-dependent "gradient"
