@@ -1,0 +1,40 @@
+"""Scalar logging with the reference's TensorBoard tags (gan/utils/summary_helper.py:27-119,559-588).
+
+Only the scalar part of the reference's `Summary` is reproduced (train / validation writers under output_dir,
+`scalar`, `log`); plotting, histograms and the TF profiler hooks are out of scope."""
+import os
+
+
+class Summary(object):
+
+  def __init__(self, hparams, policy=None):
+    from torch.utils.tensorboard import SummaryWriter
+    self._hparams = hparams
+    self.train_writer = SummaryWriter(hparams.output_dir)
+    self.val_writer = SummaryWriter(os.path.join(hparams.output_dir, 'validation'))
+    self.metrics_writer = SummaryWriter(os.path.join(hparams.output_dir, 'metrics'))
+    self._policy = policy
+
+  def _writer(self, training):
+    return self.train_writer if training else self.val_writer
+
+  def scalar(self, tag, value, step=0, training=True):
+    self._writer(training).add_scalar(tag, float(value), global_step=step)
+
+  def log(self, gen_loss, dis_loss, gradient_penalty, metrics=None, elapse=None, gan=None, step=0, training=True):
+    """summary_helper.py:559-588."""
+    self.scalar('loss/generator', gen_loss, step=step, training=training)
+    self.scalar('loss/discriminator', dis_loss, step=step, training=training)
+    if gradient_penalty is not None:
+      self.scalar('loss/gradient_penalty', gradient_penalty, step=step, training=training)
+    if metrics is not None:
+      for tag, value in metrics.items():
+        self.scalar(tag, value, step=step, training=training)
+    if elapse is not None:
+      self.scalar('elapse', elapse, step=step, training=training)
+    if not training and gan is not None and getattr(self._hparams, 'mixed_precision', False):
+      self.scalar('model/loss_scale', gan.gen_optimizer.loss_scale, step=step, training=training)
+
+  def flush(self):
+    for w in (self.train_writer, self.val_writer, self.metrics_writer):
+      w.flush()

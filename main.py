@@ -1,10 +1,10 @@
 """Training driver with the reference's command line (main.py:227-267 of bryanlimy/CalciumGAN).
 
-Same flags and defaults; the epoch loop calls `gan.train(signal)` exactly like main.py:33-75 and
-checkpoints with the reference's pickle layout. The input pipeline / TensorBoard / spike analysis of
-the reference are out of scope: signals come from `<input_dir>/signals.npy`
-(float32 (N, seq, neurons), already normalised to [0, 1]) or, with --synthetic, from a seeded
-uniform generator of shape (N, 2048, 102).
+Same flags and defaults; the epoch loop calls `gan.train(signal)` exactly like main.py:33-75, logs the reference's
+TensorBoard scalar tags and checkpoints with the reference's pickle layout. Signals come from, in this order:
+the reference's TFRecord layout (`<input_dir>/info.pkl` + `train-*.record` / `validation-*.record`, read without
+TensorFlow), `<input_dir>/signals.npy` (float32 (N, seq, neurons), already in [0, 1]), or with --synthetic a seeded
+uniform generator of shape (N, 2048, 102). Spike analysis / plotting of the reference are out of scope.
 """
 import argparse
 import os
@@ -21,6 +21,10 @@ if ROOT not in sys.path:
 
 def get_dataset(hparams):
   """Sets the hparams fields the models read (dataset_helper.py:84-91,120-136,186)."""
+  if not hparams.synthetic and os.path.exists(os.path.join(hparams.input_dir, 'info.pkl')):
+    from calciumgan_b200.utils import dataset_helper
+    train_ds, validation_ds = dataset_helper.get_dataset(hparams)
+    return (lambda: iter(train_ds)), (lambda: iter(validation_ds))
   path = os.path.join(hparams.input_dir, 'signals.npy')
   if hparams.synthetic or not os.path.exists(path):
     rng = np.random.RandomState(1234)
@@ -47,7 +51,7 @@ def get_dataset(hparams):
   return (lambda: batches(train, True)), (lambda: batches(val, False))
 
 
-def train(hparams, train_ds, gan, epoch):
+def train(hparams, train_ds, gan, summary, epoch):
   gen_losses, dis_losses, gradient_penalties = [], [], []
   start = time()
   from calciumgan_b200.utils.prefetch import prefetch_to_device
@@ -60,13 +64,16 @@ def train(hparams, train_ds, gan, epoch):
     hparams.global_step += 1
   end = time()
   gen_loss, dis_loss = np.mean(gen_losses), np.mean(dis_losses)
+  summary.log(gen_loss, dis_loss, np.mean(gradient_penalties) if gradient_penalties else None, elapse=end - start,
+              gan=gan, step=epoch, training=True)
   if hparams.verbose:
     print('Train epoch {:03d}: generator {:.4f} discriminator {:.4f} gradient_penalty {:.4f} elapse {:.2f}s'.format(
         epoch, gen_loss, dis_loss, np.mean(gradient_penalties), end - start))
   return gen_loss, dis_loss
 
 
-def validate(hparams, validation_ds, gan, epoch):
+def validate(hparams, validation_ds, gan, summary, epoch):
+  start = time()
   gen_losses, dis_losses, gradient_penalties, results = [], [], [], {}
   for signal, _ in validation_ds():
     fake, gen_loss, dis_loss, gradient_penalty, metrics = gan.validate(signal)
@@ -75,11 +82,14 @@ def validate(hparams, validation_ds, gan, epoch):
     gradient_penalties.append(gradient_penalty)
     for k, v in metrics.items():
       results.setdefault(k, []).append(v)
+  results = {key: np.mean(item) for key, item in results.items()}
+  summary.log(np.mean(gen_losses), np.mean(dis_losses), np.mean(gradient_penalties), metrics=results,
+              elapse=time() - start, gan=gan, step=epoch, training=False)
   if hparams.verbose:
     print('Validation epoch {:03d}: generator {:.4f} discriminator {:.4f} gradient_penalty {:.4f} '.format(
         epoch, np.mean(gen_losses), np.mean(dis_losses), np.mean(gradient_penalties)) +
-          ' '.join('{} {:.5f}'.format(k.split('/')[-1], np.mean(v)) for k, v in results.items()))
-  return {key: np.mean(item) for key, item in results.items()}
+          ' '.join('{} {:.5f}'.format(k.split('/')[-1], v) for k, v in results.items()))
+  return results
 
 
 def main(hparams, return_metrics=False):
@@ -92,18 +102,22 @@ def main(hparams, return_metrics=False):
   os.makedirs(hparams.output_dir, exist_ok=True)
   np.random.seed(1234)
 
+  from calciumgan_b200.utils.summary_helper import Summary
+  summary = Summary(hparams)
   train_ds, validation_ds = get_dataset(hparams)
-  generator, discriminator = get_models(hparams, None)
-  gan = get_algorithm(hparams, generator, discriminator, None)
+  generator, discriminator = get_models(hparams, summary)
+  gan = get_algorithm(hparams, generator, discriminator, summary)
   utils.load_models(hparams, gan)
 
   start = time()
   results = {}
   for epoch in range(hparams.start_epoch, hparams.epochs):
-    train(hparams, train_ds, gan, epoch)
-    results = validate(hparams, validation_ds, gan, epoch)
+    train(hparams, train_ds, gan, summary, epoch)
+    results = validate(hparams, validation_ds, gan, summary, epoch)
     if not hparams.skip_checkpoints and (epoch % 10 == 0 or epoch == hparams.epochs - 1):
       utils.save_models(hparams, gan, epoch)
+  summary.scalar('elapse/total', time() - start)
+  summary.flush()
   if hparams.verbose:
     print('elapse/total {:.2f}s'.format(time() - start))
   if return_metrics:

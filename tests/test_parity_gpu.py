@@ -295,3 +295,28 @@ def test_prefetch_to_device_ragged():
     assert [e for _, e in seen] == [0, 1, 2, 3]
     for (got, _), (ref, _) in zip(seen, batches):
       np.testing.assert_array_equal(got, ref)
+
+
+def test_main_end_to_end_on_tfrecords(tmp_path):
+  """main.py with the reference's flags on the reference's TFRecord layout: trains, validates, logs, checkpoints, resumes."""
+  import glob
+  import main as driver
+  from calciumgan_b200.utils import dataset_helper
+  rng = np.random.RandomState(0)
+  data_dir, out_dir = str(tmp_path / 'tfrecords'), str(tmp_path / 'runs')
+  signals = rng.rand(10, 256, 20).astype(np.float32)
+  dataset_helper.write_dataset(data_dir, signals, np.zeros_like(signals), train_size=7, num_per_shard=4)
+  argv = ['--input_dir', data_dir, '--output_dir', out_dir, '--batch_size', '4', '--num_units', '16', '--kernel_size', '24',
+          '--m', '3', '--epochs', '2', '--noise_dim', '8', '--model', 'calciumgan', '--layer_norm', '--n_critic', '2',
+          '--mixed_precision', '--verbose', '0']
+  hp = driver.build_parser().parse_args(argv)
+  hp.global_step, hp.surrogate_ds = 0, False
+  res = driver.main(hp, return_metrics=True)
+  assert set(res) == {'signals_metrics/min', 'signals_metrics/max', 'signals_metrics/mean', 'signals_metrics/std'}
+  assert hp.global_step == 4                                  # 2 epochs x ceil(7 / 4) batches
+  assert os.path.exists(os.path.join(out_dir, 'checkpoints', 'epoch-001.pkl'))
+  assert glob.glob(os.path.join(out_dir, 'events.out.tfevents.*'))
+  hp2 = driver.build_parser().parse_args(argv[:-4] + ['--mixed_precision', '--verbose', '0', '--epochs', '3'])
+  hp2.global_step, hp2.surrogate_ds = 0, False
+  driver.main(hp2)
+  assert hp2.start_epoch == 2 and hp2.global_step == 2        # resumed from epoch-001, one more epoch
