@@ -316,7 +316,9 @@ def test_main_end_to_end_on_tfrecords(tmp_path):
   assert hp.global_step == 4                                  # 2 epochs x ceil(7 / 4) batches
   assert os.path.exists(os.path.join(out_dir, 'checkpoints', 'epoch-001.pkl'))
   assert glob.glob(os.path.join(out_dir, 'events.out.tfevents.*'))
-  hp2 = driver.build_parser().parse_args(argv[:-4] + ['--mixed_precision', '--verbose', '0', '--epochs', '3'])
+  argv2 = list(argv)
+  argv2[argv2.index('--epochs') + 1] = '3'
+  hp2 = driver.build_parser().parse_args(argv2)
   hp2.global_step, hp2.surrogate_ds = 0, False
   driver.main(hp2)
   assert hp2.start_epoch == 2 and hp2.global_step == 2        # resumed from epoch-001, one more epoch
