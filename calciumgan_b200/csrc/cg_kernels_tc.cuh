@@ -901,6 +901,7 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // stage structure: slab mode  -> groups = tap-parity groups, each split into weight stages of TPS taps sharing one slab;
   //                  per-tap mode -> groups = ceil(nseg / TPS) bundles of TPS taps, each tap with its own 16 KB box
 
+  const long long t_kernel0 = clock64();
   if (warp == 0) {
     int ss = 0, bs = 0;
     uint32_t sph = 0, bph = 0;
@@ -975,7 +976,9 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int t = pair; t < total_tiles; t += npairs, ++it) {
         const int phase = (t / P.m_tiles) / P.n_tiles;
         const int acc = it & 1;
+        long long tq = clock64();
         mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1) ^ 1);
+        CG_DBG_ADD(2, tq);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         uint32_t accum = 0;
@@ -1009,12 +1012,16 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           for (int g = 0; g < P.ngroups[phase]; ++g) {
             const SlabGroup& G = P.grp[phase][g];
+            tq = clock64();
             mbar_wait(&s_full[ss], sph);
+            CG_DBG_ADD(3, tq);
             tc_fence_after();
             const uint32_t sl_lo = slab_lo0 + ss * slab_step;
             for (int s = 0; s < G.nseg; s += TPS) {
               const int cnt = G.nseg - s < TPS ? G.nseg - s : TPS;
+              tq = clock64();
               mbar_wait(&b_full[bs], bph);
+              CG_DBG_ADD(4, tq);
               tc_fence_after();
               const uint32_t b_lo = b_lo0 + bs * b_step;
               if (elect_one()) {
@@ -1056,7 +1063,10 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       else epi_rows(p, blk / P.blocks_per_sample, (blk % P.blocks_per_sample) * 128, 7, phase, lq, lane, R);
       if (nt != last_nt) { epi_load_bias<EPI>(p, bias_s, nt * BN, BN, threadIdx.x - 64); last_nt = nt; }
       const int acc = it & 1;
+      long long tq = clock64();
       mbar_wait(&tfull[acc], ((uint32_t)it >> 1) & 1);
+      if (warp == 2) CG_DBG_ADD(5, tq);
+      tq = clock64();
       tc_fence_after();
       {
         const int bq = blk / P.blocks_per_sample;
@@ -1064,12 +1074,14 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         epilogue_block<EPI>(p, tmem_base + acc * BN, BN, nt * BN, R, bias_s, stg, lq, lane,
                             (blk % P.blocks_per_sample) * 128, sft);
       }
+      if (warp == 2) CG_DBG_ADD(6, tq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader[acc]);
     }
   }
 
+  if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[7] = clock64() - t_kernel0;
   tc_fence_before();
   cluster_sync_all();          // nobody may exit (or free TMEM) while the peer can still signal / read
   if (warp == 1) {
@@ -1687,7 +1699,13 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   if (bst > 10) bst = 10;
   if (bst < 2) return cg_tc_set_err("rsgemm3_tc: not enough shared memory");
   P.b_stages = bst;
+  static long long* dbg_buf3 = nullptr;
   P.dbg = nullptr;
+  if (getenv("CG_TC_TIMING")) {
+    if (!dbg_buf3) cudaMalloc(&dbg_buf3, 16 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf3, 0, 16 * sizeof(long long), stream);
+    P.dbg = dbg_buf3;
+  }
   CUtensorMap tmA, tmW;
   if (P.per_tap) { if (tc_get_map3(s, p.A, p.a_rs, p.a_rows, p.B, p.a_rs, p.a_bs, P.rpt, P.bpt, &tmA)) return 1; }
   else if (tc_get_map3(s, p.A, p.a_rs, p.a_rows, p.B, p.a_rs, p.a_bs, P.box_rows, 1, &tmA)) return 1;
@@ -1703,6 +1721,13 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
     case EPI_MASK: tc::rsgemm3_tc_kernel<EPI_MASK><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
     case EPI_BIAS_LN_LRELU: tc::rsgemm3_tc_kernel<EPI_BIAS_LN_LRELU><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
     default: tc::rsgemm3_tc_kernel<EPI_BIAS_SIGMOID><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+  }
+  if (P.dbg) {
+    long long h[16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dbg_buf3, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tc3 timing] B=%d Q=%d N=%d Kc=%d epi=%d | BN=%d tps=%d tiles=%d pairs=%d sst=%d bst=%d pt=%d | total %lld clk | mma wait tempty %lld/%lld s_full %lld/%lld b_full %lld/%lld | epi wait %lld/%lld work %lld/%lld\n",
+            p.B, p.Q, p.N, p.Kc, p.epi, P.BN, P.tps, total, npairs, P.slab_stages, bst, P.per_tap, h[7], h[2], h[10], h[3], h[11], h[4], h[12], h[5], h[13], h[6], h[14]);
   }
   return 0;
 }
