@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libcalciumgan_b200.so')
+LIB_PATH = os.environ.get('CG_LIB') or os.path.join(_HERE, 'libcalciumgan_b200.so')   # CG_LIB: A/B builds in tools/
 
 GENERATOR, DISCRIMINATOR = 0, 1
 FP32, BF16 = 0, 1

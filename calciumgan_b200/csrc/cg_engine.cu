@@ -22,6 +22,7 @@
 #include "../../include/calciumgan_b200.h"
 #include "cg_kernels_simt.cuh"
 #include "cg_kernels_tc.cuh"
+#include "cg_kernels_head.cuh"
 
 // ------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -582,7 +583,11 @@ static WgParams convT_wgrad_params(cg_ctx* c, int i, int B) {
 }
 
 // calciumgan.py:22-103. noise (B, nd) fp32 device. Writes FAKE32 (B, L, C).
-static int g_forward(cg_ctx* c, const float* noise, int B, void* fake_slot = nullptr, bool for_backward = true) {
+// Optional fusion on the tensor-core path: xhat_slot != null also writes x_hat = alpha * real + (1 - alpha) * fake
+// (wgan_gp.py:38-41) from the same epilogue; want32 = false skips the fp32 copy (critic sub-steps of a train step).
+static int g_forward(cg_ctx* c, const float* noise, int B, void* fake_slot = nullptr, bool for_backward = true,
+                     void* xhat_slot = nullptr, const float* real = nullptr, const float* alpha = nullptr,
+                     bool want32 = true, bool* xhat_done = nullptr) {
   DISPATCH_T(c, dense0_forward_kernel<T><<<grid_for((long long)B * c->w0 * c->gcp[0]), 256, 0, c->stream>>>(
                     noise, gparam(c, 0), gparam(c, 1), (T*)c->HG[0], B, c->nd, c->w0, c->gcp[0]));
   CK(post_launch(c, "dense0_fwd"));
@@ -616,9 +621,30 @@ static int g_forward(cg_ctx* c, const float* noise, int B, void* fake_slot = nul
       CK(post_launch(c, "lrelu"));
     }
   }
+  const int Cp = c->gcp[NL];
+  if (xhat_done) *xhat_done = false;
+  if (c->use_tc && !c->tc.force_v1 && !getenv("CG_NO_GHEAD")) {   // dedicated HBM-bound head kernel (cg_kernels_head.cuh)
+    GHeadArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = c->HG[NL]; a.W = c->Wf_d1; a.bias = gparam(c, c->g_d1b);
+    a.fake16 = fake_slot; a.xhat16 = xhat_slot; a.real = real; a.alpha = alpha;
+    a.out32 = (want32 || !fake_slot) ? c->FAKE32 : nullptr;
+    a.B = B; a.L = c->L; a.C = c->C; a.Cp = Cp; a.sigmoid = c->cfg.normalize ? 1 : 0;
+    if (Cp == c->dcp[0] && tc_ghead_supported(a)) {
+      char d[96];
+      snprintf(d, sizeof(d), "ghead B=%d L=%d C=%d f=%d x=%d o32=%d", B, c->L, c->C, a.fake16 != nullptr, a.xhat16 != nullptr,
+               a.out32 != nullptr);
+      CK(prof_begin(c, 2, 2.0 * B * c->L * (double)c->C * c->C, d));
+      CK(tc_ghead_launch(&c->tc, a, c->stream));
+      c->tc_launches++;
+      CK(post_launch(c, "ghead_tc"));
+      CK(prof_end(c));
+      if (xhat_done) *xhat_done = xhat_slot != nullptr;
+      return 0;
+    }
+  }
   RsParams p;
   memset(&p, 0, sizeof(p));
-  const int Cp = c->gcp[NL];
   p.A = c->HG[NL]; p.a_bs = (long long)c->L * Cp; p.a_rs = Cp; p.a_rows = c->L;
   p.W = c->Wf_d1; p.w_ld = Cp;
   p.out = fake_slot;     // optional compute-type copy (critic input slot; Cp == dcp[0])
@@ -871,21 +897,25 @@ static int fetch_scalars(cg_ctx* c, int slot, int flags, float* scalars_host) {
 // ------------------------------------------------------------------------------------------ critic step
 // forward part shared by cg_critic_step and cg_validate: fake, D on [real; fake; xhat], dgrad chain, GP scalars
 static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
-                             const int32_t* sh, int slot, bool real_ready = false, bool train = false) {
+                             const int32_t* sh, int slot, bool real_ready = false, bool train = false,
+                             bool want_fake32 = true) {
   const long long per = (long long)B * c->L * c->dcp[0];
   if (train) CU(cudaMemsetAsync(c->dis.g, 0, c->dis.total * 4, c->stream));
   // generator head writes fp32 FAKE32 and the compute-type copy straight into the critic's "fake" slot
-  CK(g_forward(c, noise, B, off(c, c->X[0], per), false));
+  bool xhat_done = false;
+  CK(g_forward(c, noise, B, off(c, c->X[0], per), false, off(c, c->X[0], 2 * per), real, alpha, want_fake32, &xhat_done));
   const long long tot = per / 4;
   if (!real_ready) {   // the 5 critic sub-steps of one train step share the real batch (wgan_gp.py:85-86)
     DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(real, nullptr, nullptr, (T*)c->X[0], B,
                                                                              c->L, c->C, c->dcp[0], 1));
     CK(post_launch(c, "real_to_x0"));
   }
-  DISPATCH_T(c, interp_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(real, c->FAKE32, alpha,
-                                                                      (T*)off(c, c->X[0], 2 * per), B, c->L, c->C,
-                                                                      c->dcp[0]));
-  CK(post_launch(c, "interp"));
+  if (!xhat_done) {
+    DISPATCH_T(c, interp_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(real, c->FAKE32, alpha,
+                                                                        (T*)off(c, c->X[0], 2 * per), B, c->L, c->C,
+                                                                        c->dcp[0]));
+    CK(post_launch(c, "interp"));
+  }
   CK(d_forward(c, 3 * B, B, 3, sh));
   fill_coef_kernel<<<(3 * B + 255) / 256, 256, 0, c->stream>>>(c->coef, B, 3, 0.f);
   CK(post_launch(c, "fill_coef"));
@@ -905,8 +935,8 @@ static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* n
 }
 
 static int critic_step_impl(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
-                            const int32_t* sh, int flags, int slot, bool real_ready = false) {
-  CK(critic_forward_gp(c, real, B, noise, alpha, sh, slot, real_ready, true));
+                            const int32_t* sh, int flags, int slot, bool real_ready = false, bool want_fake32 = true) {
+  CK(critic_forward_gp(c, real, B, noise, alpha, sh, slot, real_ready, true, want_fake32));
   // GP second-order term without the second-order graph: v0 = u = d(lambda*GP)/dg
   const long long per = (long long)c->L * c->dcp[0];
   DISPATCH_T(c, scale_rows_kernel<T><<<grid_for(per * B / (16 / c->esz)), 256, 0, c->stream>>>(
@@ -1012,7 +1042,8 @@ extern "C" int cg_train_step(cg_ctx* c, const float* real, int B, const float* n
   for (int i = 0; i < 12 * nc + 4; ++i)
     if (sh[i] < -c->cfg.phase_m || sh[i] > c->cfg.phase_m) return set_err("phase-shuffle shift out of range");
   for (int i = 0; i < nc; ++i)
-    CK(critic_step_impl(c, real, B, noise + (size_t)i * B * c->nd, alpha + (size_t)i * B, sh + 12 * i, 0, i, i > 0));
+    CK(critic_step_impl(c, real, B, noise + (size_t)i * B * c->nd, alpha + (size_t)i * B, sh + 12 * i, 0, i, i > 0,
+                        /*want_fake32=*/false));   // the generator step rewrites FAKE32 before anything reads it
   CK(generator_step_impl(c, real, B, noise + (size_t)nc * B * c->nd, sh + 12 * nc, 0, nc));
   CU(cudaMemcpyAsync(c->h_scal, c->d_scal, (size_t)(nc + 1) * CG_NUM_SCALARS * 4, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -1177,9 +1208,9 @@ extern "C" int cg_profile(cg_ctx* c, int enable) {
   c->profiling = enable != 0;
   return 0;
 }
-extern "C" int cg_profile_report(cg_ctx* c, double out[8]) {
+extern "C" int cg_profile_report(cg_ctx* c, double out[12]) {
   CU(cudaStreamSynchronize(c->stream));
-  for (int i = 0; i < 8; ++i) out[i] = 0;
+  for (int i = 0; i < 12; ++i) out[i] = 0;
   for (auto& r : c->prof) {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, r.e0, r.e1));

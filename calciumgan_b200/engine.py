@@ -352,10 +352,11 @@ class Engine(object):
     L.check(self.lib.cg_profile(self.ctx, int(bool(enable))))
 
   def profile_report(self):
-    out = (C.c_double * 8)()
+    out = (C.c_double * 12)()
     L.check(self.lib.cg_profile_report(self.ctx, out))
     return {'gemm': {'ms': out[0], 'flops': out[1], 'launches': int(out[2])},
-            'wgrad': {'ms': out[3], 'flops': out[4], 'launches': int(out[5])}}
+            'wgrad': {'ms': out[3], 'flops': out[4], 'launches': int(out[5])},
+            'head': {'ms': out[6], 'flops': out[7], 'launches': int(out[8])}}
 
   def bench_layer(self, which, layer, pass_, batch, iters=10):
     self._use_stream()

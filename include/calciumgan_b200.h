@@ -175,11 +175,12 @@ int64_t cg_tc_launch_count(cg_ctx* ctx);
 /* bytes of device memory owned by the context */
 int64_t cg_device_bytes(cg_ctx* ctx);
 /* Live kernel timing: while enabled, every implicit-GEMM launch is bracketed by CUDA events on the
- * context stream. cg_profile_report synchronises and fills out[8] =
- * {conv/dgrad GEMM ms, its algorithmic FLOPs, its launches, wgrad GEMM ms, FLOPs, launches, 0, 0}
+ * context stream. cg_profile_report synchronises and fills out[12] =
+ * {conv/dgrad GEMM ms, its algorithmic FLOPs, its launches, wgrad GEMM ms, FLOPs, launches,
+ *  generator-head kernel ms, FLOPs, launches, 0, 0, 0}
  * accumulated since cg_profile(ctx, 1), then clears the accumulators. */
 int cg_profile(cg_ctx* ctx, int enable);
-int cg_profile_report(cg_ctx* ctx, double out[8]);
+int cg_profile_report(cg_ctx* ctx, double out[12]);
 /* microbenchmark hook: time `iters` launches of one conv layer kernel with CUDA events on the
  * context stream. which/layer: CG_DISCRIMINATOR conv 1..5 or CG_GENERATOR convT 1..5; pass: 0 fwd,
  * 1 dgrad, 2 wgrad. Writes avg milliseconds and the algorithmic FLOPs of one launch. */

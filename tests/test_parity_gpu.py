@@ -322,3 +322,46 @@ def test_main_end_to_end_on_tfrecords(tmp_path):
   hp2.global_step, hp2.surrogate_ds = 0, False
   driver.main(hp2)
   assert hp2.start_epoch == 2 and hp2.global_step == 2        # resumed from epoch-001, one more epoch
+
+
+def test_generator_head_kernel_modes_bf16(monkeypatch):
+  """The dedicated generator-head kernel (dense + sigmoid + fused WGAN-GP interpolation, cg_kernels_head.cuh)
+  against the generic implicit-GEMM path + interp_kernel (CG_NO_GHEAD=1) in its four output modes:
+  train step (fake16 + x_hat16), public critic step / validate (+ fp32 copy, in place over the real tile),
+  generator step (fake16 + fp32) and generate (fp32 only). Same fp32 arithmetic on both paths => tight bounds."""
+  hp = _medium_hp(signal_shape=(512, 102), num_units=32, n_critic=2)
+  B = 5   # 20 row tiles of 128: several tiles per sample, odd batch
+  gw, dw = O.init_weights(hp, seed=21)
+  gw, dw = O.randomize_weights(gw, 22), O.randomize_weights(dw, 23)
+  real, noises, alphas, shifts = O.synthetic_batch(hp, B, seed=24, n_critic=2)
+  res = {}
+  for mode in ('generic', 'fused'):
+    if mode == 'generic':
+      monkeypatch.setenv('CG_NO_GHEAD', '1')
+    else:
+      monkeypatch.delenv('CG_NO_GHEAD', raising=False)
+    ns, gan = build(hp, B, mixed=True)
+    gan.generator.set_weights(gw)
+    gan.discriminator.set_weights(dw)
+    r = {}
+    f, gl, dl, gp, met = gan.validate(real, noise=noises[0], alpha=alphas[0], shifts=shifts[:12])
+    r['val_fake'], r['val'] = f.cpu().numpy(), np.array([gl, dl, gp] + [met[k] for k in sorted(met)])
+    r['gen'] = gan.generate(noises[1]).cpu().numpy()
+    s = gan.engine.critic_step(real, noises[0], alphas[0], shifts[:12], update=False)
+    r['c_scal'], r['c_fake'] = np.array(s[:5]), gan.engine.fake(B).cpu().numpy()
+    r['c_scores'], r['c_grads'] = gan.engine.scores(3 * B).cpu().numpy(), gan.engine.get_grads(1)
+    out = gan.train(real, noise=noises, alpha=alphas, shifts=shifts)
+    r['train'] = np.array(out[:3])
+    r['gw'], r['dw'] = gan.generator.get_weights(), gan.discriminator.get_weights()
+    res[mode] = r
+    if mode == 'fused':
+      assert gan.engine.tc_launch_count() > 0
+  a, b = res['fused'], res['generic']
+  for k in ('val_fake', 'gen', 'c_fake'):
+    assert rel_err(a[k], b[k]) <= 1e-6, k          # same MMA, same fp32 epilogue arithmetic
+  for k in ('val', 'c_scal', 'c_scores', 'train'):
+    assert rel_err(a[k], b[k]) <= 2e-3, (k, a[k], b[k])
+  check_list(a['c_grads'], b['c_grads'], 2e-2, 'critic grads fused vs generic head')
+  # Adam's first two steps are sign-like (lr * g / |g|): compare the weights, not the update
+  check_list(a['gw'], b['gw'], 1e-3, 'generator weights after a train step')
+  check_list(a['dw'], b['dw'], 1e-3, 'critic weights after a train step')
