@@ -84,7 +84,9 @@ struct SegTable {
 
 // EPI_BIAS_LN_LRELU (tensor-core path only, one n-tile = the whole channel row): out = lrelu(LN(acc + bias)),
 // optional aux = acc + bias and per-row mean / rstd for the backward pass
-enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_LRELU = 2, EPI_MASK = 3, EPI_BIAS_SIGMOID = 4, EPI_BIAS_LN_LRELU = 5 };
+// EPI_PS_MASK (CTA-pair tensor-core kernel only): adjoint of the PhaseShuffle gather fused with the LeakyReLU slope of
+// the layer below: out[b, j, :] = slope(mask[b, j, :]) * sum_{t : ps_index(t) = j} acc[b, t, :]   (ps_w / ps_shift fields)
+enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_LRELU = 2, EPI_MASK = 3, EPI_BIAS_SIGMOID = 4, EPI_BIAS_LN_LRELU = 5, EPI_PS_MASK = 6 };
 
 struct RsParams {
   const void* A; long long a_bs; int a_rs; int a_rows;

@@ -780,7 +780,24 @@ static int d_forward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh) {
 }
 
 // data-gradient of conv layer l: DA[l] (rows dl[l]) -> out (rows dl[l-1]) for samples [b0, b0+nb)
-static int d_dgrad_layer(cg_ctx* c, int l, int b0, int nb, void* out, float* sumsq = nullptr) {
+static RsParams d_dgrad_params(cg_ctx* c, int l, int b0, int nb, void* out);
+static bool d_dgrad_ps_fusable(cg_ctx* c, int l, int Bt) {
+  if (getenv("CG_NO_PS_BWD_FUSE") || !c->use_tc || c->tc.force_v1 || !c->tc.use_pair || c->cfg.phase_m > 10) return false;
+  const RsParams p = d_dgrad_params(c, l, 0, Bt, nullptr);
+  return tc_rsgemm_supported(p) && tc_rsgemm2_supported(p) && p.seg.nphase == 2;
+}
+static int d_dgrad_layer(cg_ctx* c, int l, int b0, int nb, void* out, float* sumsq = nullptr, const void* ps_mask = nullptr,
+                         int group_b = 0, const int32_t* sh = nullptr, int groups = 0) {
+  RsParams p = d_dgrad_params(c, l, b0, nb, out);
+  p.sumsq = sumsq;
+  if (ps_mask) {
+    p.epi = EPI_PS_MASK; p.mask = ps_mask;
+    p.ps_w = c->dl[l - 1]; p.ps_group_b = group_b;
+    for (int i = 0; i < 4; ++i) p.ps_shift[i] = i < groups ? sh[i * 4 + (l - 2)] : 0;
+  }
+  return launch_rsgemm(c, p);
+}
+static RsParams d_dgrad_params(cg_ctx* c, int l, int b0, int nb, void* out) {
   RsParams p;
   memset(&p, 0, sizeof(p));
   p.A = off(c, c->DA[l], (long long)b0 * c->dl[l] * c->dcp[l]);
@@ -789,8 +806,7 @@ static int d_dgrad_layer(cg_ctx* c, int l, int b0, int nb, void* out, float* sum
   p.out = out; p.o_bs = (long long)c->dl[l - 1] * c->dcp[l - 1]; p.o_rs = 2 * c->dcp[l - 1]; p.o_phase_col = c->dcp[l - 1];
   p.B = nb; p.Q = c->dl[l]; p.N = c->dcp[l - 1]; p.n_real = c->dc[l - 1]; p.Kc = c->dcp[l]; p.k_real = c->dc[l]; p.epi = EPI_NONE;
   p.seg = seg_transposed(c->K, c->dcp[l]);
-  p.sumsq = sumsq;
-  return launch_rsgemm(c, p);
+  return p;
 }
 
 // backward chain of sum_b coef[b]*D(x)_b down to DA[1] (and DX[0] for samples [dx0_b0, dx0_b0+dx0_nb))
@@ -800,6 +816,10 @@ static int d_backward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh, i
                     (const T*)c->H[NL], dparam(c, 10), c->coef, (T*)c->DA[NL], Bt, c->dl[NL], c->dc[NL], c->dcp[NL]));
   CK(post_launch(c, "head_bwd"));
   for (int l = NL; l >= 2; --l) {
+    if (d_dgrad_ps_fusable(c, l, Bt)) {   // data gradient + PhaseShuffle adjoint + LeakyReLU slope in one kernel
+      CK(d_dgrad_layer(c, l, 0, Bt, c->DA[l - 1], nullptr, c->H[l - 1], B, sh, groups));
+      continue;
+    }
     CK(d_dgrad_layer(c, l, 0, Bt, c->DX[l - 1]));
     const long long tot = (long long)Bt * c->dl[l - 1] * c->dcp[l - 1] / (16 / c->esz);
     DISPATCH_T(c, ps_scatter_mask_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(

@@ -246,21 +246,27 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: 
 // Per tile, each lane precomputes the element offsets of the 8 rows it stores in the coalesced phase
 // (row rr = 4*i + lane/8 of this warp's 32 rows); negative = masked. rpt < 128 is a power of two.
 struct EpiRows {
-  long long off[8]; long long my_off; long long my_o32; long long my_row; bool my_ok;
+  long long base;                     // element offset of sample b0; off[] / my_off are 32-bit offsets relative to it
+  int off[8]; int my_off; long long my_o32; long long my_row; bool my_ok;
   long long o32_base; bool uniform;   // single-sample blocks: fp32 row rr of this warp is at o32_base + rr * o32_rs
+  int x_src, x_par; bool x_zero;      // EPI_PS_MASK: exchange slot this row fills / adds (-1 = none), row without a source
 };
 __device__ __forceinline__ void epi_rows(const RsParams& p, int b0, int q0, int rpt_log2, int phase, int lq, int lane,
                                          EpiRows& R) {
   const int crow = lane >> 3;
+  const int ph_off = phase * p.o_phase_col;
+  R.base = (long long)b0 * p.o_bs;
 #pragma unroll
   for (int i = 0; i <= 8; ++i) {
     const int r = lq * 32 + (i < 8 ? i * 4 + crow : lane);
-    int b, q;
-    if (rpt_log2 >= 7) { b = b0; q = q0 + r; } else { b = b0 + (r >> rpt_log2); q = r & ((1 << rpt_log2) - 1); }
-    const long long o = b < p.B ? (long long)b * p.o_bs + (long long)q * p.o_rs + phase * p.o_phase_col : -1;
+    int db, q;
+    if (rpt_log2 >= 7) { db = 0; q = q0 + r; } else { db = r >> rpt_log2; q = r & ((1 << rpt_log2) - 1); }
+    const bool ok = b0 + db < p.B;
+    const int o = ok ? db * (int)p.o_bs + q * p.o_rs + ph_off : -1;   // per-sample extents are far below 2^31 elements
     if (i < 8) R.off[i] = o;
     else {
-      R.my_off = o; R.my_ok = b < p.B; R.my_o32 = (long long)b * p.o32_bs + (long long)q * p.o32_rs;
+      const int b = b0 + db;
+      R.my_off = o; R.my_ok = ok; R.my_o32 = (long long)b * p.o32_bs + (long long)q * p.o32_rs;
       R.my_row = ((long long)b * p.Q + q) * p.seg.nphase + phase;
     }
   }
@@ -268,6 +274,39 @@ __device__ __forceinline__ void epi_rows(const RsParams& p, int b0, int q0, int 
     R.uniform = rpt_log2 >= 7;
     R.o32_base = (long long)b0 * p.o32_bs + (long long)(q0 + lq * 32) * p.o32_rs;
   }
+}
+
+// EPI_PS_MASK rows (single-sample 128-row blocks of one output phase): accumulator row t = (q0 + r) * nphase + phase goes
+// to time j = t + s when that is inside [0, w); rows pushed over an edge are reflected (calciumgan.py:126-133) onto a
+// row of the SAME block and phase (t + t' is even and both lie within 2|s| <= 20 steps of the edge), so the sum is formed
+// in registers through a small shared-memory exchange: the reflected row fills slot x_src, its partner adds slot x_par.
+// Rows nobody maps to (x_zero) are written as zeros by the thread that owns the same index.
+__device__ __forceinline__ void epi_rows_ps(const RsParams& p, int b, int q0, int phase, int s, int lq, int lane, EpiRows& R) {
+  const int w = p.Q * 2;   // two output phases (host-checked): time t = 2 q + phase
+  const int crow = lane >> 3;
+  const bool bok = b < p.B;
+  R.base = (long long)b * p.o_bs;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = (q0 + lq * 32 + i * 4 + crow) * 2 + phase + s;
+    R.off[i] = (bok && j >= 0 && j < w) ? (j >> 1) * p.o_rs + (j & 1) * p.o_phase_col : -1;
+  }
+  const int q = q0 + lq * 32 + lane;
+  const int t = q * 2 + phase;
+  R.my_ok = bok;
+  R.my_off = q * p.o_rs + phase * p.o_phase_col;
+  R.my_o32 = 0; R.my_row = 0; R.o32_base = 0; R.uniform = true;
+  R.x_src = -1; R.x_par = -1;
+  if (s > 0) {
+    if (t + s > w - 1) R.x_src = (w - 1 - t) >> 1;
+    const int tp = 2 * (w - 1) - t - 2 * s;
+    if (tp <= w - 1 && tp + s > w - 1) R.x_par = (w - 1 - tp) >> 1;
+  } else if (s < 0) {
+    if (t + s < 0) R.x_src = t >> 1;
+    const int tp = -t - 2 * s;
+    if (tp >= 0 && tp + s < 0) R.x_par = tp >> 1;
+  }
+  R.x_zero = t - s < 0 || t - s > w - 1;
 }
 
 // One 128-row x BN-column accumulator block: TMEM -> registers (thread = row) -> bias / LeakyReLU / sigmoid /
@@ -278,7 +317,7 @@ __device__ __forceinline__ void epi_rows(const RsParams& p, int b0, int q0, int 
 template <int EPI>
 __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_cols, int BN, int n_base,
                                                const EpiRows& R, const float* bias_s, uint8_t* stg, int lq, int lane,
-                                               int ps_q0 = 0, int ps_s = 0) {
+                                               int ps_q0 = 0, int ps_s = 0, bool need_x = false) {
   // ps_q0: time index of tile row 0 (single-sample blocks); ps_s: this sample's PhaseShuffle shift (p.ps_out != null)
   bf16* out = reinterpret_cast<bf16*>(p.out);
   bf16* psx = reinterpret_cast<bf16*>(p.ps_out);
@@ -308,12 +347,12 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
   }
   for (int c0 = 0; c0 < BN; c0 += 64) {
     const int ncols = BN - c0 < 64 ? BN - c0 : 64;   // 64 or 32 (BN % 32 == 0)
-    if (EPI == EPI_MASK) {   // coalesced, register-free read of the slope source (same indexing as out) into the staging tile
+    if (EPI == EPI_MASK || EPI == EPI_PS_MASK) {   // coalesced, register-free read of the slope source (same indexing as out) into the staging tile
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + (lane >> 3);
         const bool ok = R.off[i] >= 0 && cj * 8 < ncols;
-        cp_async16(stg_s + rr * 128 + ((cj ^ (rr & 7)) << 4), mask + (ok ? R.off[i] + n_base + c0 + cj * 8 : 0), ok ? 16u : 0u);
+        cp_async16(stg_s + rr * 128 + ((cj ^ (rr & 7)) << 4), mask + (ok ? R.base + R.off[i] + n_base + c0 + cj * 8 : 0), ok ? 16u : 0u);
       }
     }
     uint32_t v[64];
@@ -326,7 +365,25 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
     }
     const int n0 = n_base + c0;
     const bool col_ok = cj * 8 < ncols;
-    if (EPI == EPI_MASK) {
+    if (EPI == EPI_PS_MASK && need_x) {   // reflected rows meet their partners (bias tile area: 2 x 5 slots x 64 floats)
+      const uint32_t xb = smem_u32(bias_s) + ((c0 >> 6) & 1) * 1280;
+      if (R.x_src >= 0) {
+#pragma unroll
+        for (int j4 = 0; j4 < 16; ++j4) sts_v4(xb + R.x_src * 256 + j4 * 16, make_uint4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]));
+      }
+      epi_bar();
+      if (R.x_par >= 0) {
+#pragma unroll
+        for (int j4 = 0; j4 < 16; ++j4) {
+          const uint4 o = lds_v4(xb + R.x_par * 256 + j4 * 16);
+          v[j4 * 4] = __float_as_uint(__uint_as_float(v[j4 * 4]) + __uint_as_float(o.x));
+          v[j4 * 4 + 1] = __float_as_uint(__uint_as_float(v[j4 * 4 + 1]) + __uint_as_float(o.y));
+          v[j4 * 4 + 2] = __float_as_uint(__uint_as_float(v[j4 * 4 + 2]) + __uint_as_float(o.z));
+          v[j4 * 4 + 3] = __float_as_uint(__uint_as_float(v[j4 * 4 + 3]) + __uint_as_float(o.w));
+        }
+      }
+    }
+    if (EPI == EPI_MASK || EPI == EPI_PS_MASK) {
       cp_async_wait_all();
       __syncwarp();
 #pragma unroll
@@ -362,7 +419,7 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + (lane >> 3);
           const uint4 o = lds_v4(stg_s + rr * 128 + ((cj ^ (rr & 7)) << 4));
-          if (R.off[i] >= 0 && col_ok) *reinterpret_cast<uint4*>(aux + R.off[i] + n0 + cj * 8) = o;
+          if (R.off[i] >= 0 && col_ok) *reinterpret_cast<uint4*>(aux + R.base + R.off[i] + n0 + cj * 8) = o;
         }
         __syncwarp();
       }
@@ -432,20 +489,23 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
         const int rr = i * 4 + (lane >> 3);
         const uint4 o = lds_v4(stg_s + rr * 128 + ((cj ^ (rr & 7)) << 4));
         if (R.off[i] >= 0 && col_ok) {
-          if (out) *reinterpret_cast<uint4*>(out + R.off[i] + n0 + cj * 8) = o;
+          if (out) *reinterpret_cast<uint4*>(out + R.base + R.off[i] + n0 + cj * 8) = o;
           if (psx) {   // scatter form of the PhaseShuffle gather: row q feeds every t with ps_index(t) == q
             const int q = ps_q0 + lq * 32 + rr, w = p.ps_w;
             const int t1 = q - ps_s;
-            if (t1 >= 0 && t1 < w) *reinterpret_cast<uint4*>(psx + R.off[i] + (long long)(t1 - q) * p.o_rs + n0 + cj * 8) = o;
+            if (t1 >= 0 && t1 < w) *reinterpret_cast<uint4*>(psx + R.base + (R.off[i] + (t1 - q) * p.o_rs + n0 + cj * 8)) = o;
             int t2 = -1;
             if (ps_s > 0) { t2 = 2 * (w - 1) - q - ps_s; if (!(t2 >= 0 && t2 < w && t2 + ps_s > w - 1)) t2 = -1; }
             else if (ps_s < 0) { t2 = -q - ps_s; if (!(t2 >= 0 && t2 < w && t2 + ps_s < 0)) t2 = -1; }
-            if (t2 >= 0) *reinterpret_cast<uint4*>(psx + R.off[i] + (long long)(t2 - q) * p.o_rs + n0 + cj * 8) = o;
+            if (t2 >= 0) *reinterpret_cast<uint4*>(psx + R.base + (R.off[i] + (t2 - q) * p.o_rs + n0 + cj * 8)) = o;
           }
         }
       }
       __syncwarp();
     }
+  }
+  if (EPI == EPI_PS_MASK && R.x_zero && R.my_ok) {   // times no t maps to
+    for (int c = 0; c < BN; c += 8) *reinterpret_cast<uint4*>(out + R.base + R.my_off + n_base + c) = make_uint4(0u, 0u, 0u, 0u);
   }
   if (EPI == EPI_NONE && p.sumsq) {
     if (R.uniform) {   // all 32 rows of the warp belong to one sample
@@ -1059,8 +1119,15 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int phase = rest / P.n_tiles;
       const int blk = mt * 2 + (int)rank;   // blocks past the end map to samples >= B and are masked
       EpiRows R;
-      if (PT) epi_rows(p, blk * P.bpt, 0, P.rpt_log2, phase, lq, lane, R);
-      else epi_rows(p, blk / P.blocks_per_sample, (blk % P.blocks_per_sample) * 128, 7, phase, lq, lane, R);
+      const int bq = blk / P.blocks_per_sample;
+      const int sft = (p.ps_out || EPI == EPI_PS_MASK) ? p.ps_shift[(bq < p.B ? bq : 0) / p.ps_group_b] : 0;
+      bool need_x = false;
+      if (EPI == EPI_PS_MASK) {   // host guarantees single-sample blocks (Q % 128 == 0)
+        const int bi = blk % P.blocks_per_sample;
+        epi_rows_ps(p, bq, bi * 128, phase, sft, lq, lane, R);
+        need_x = (sft > 0 && bi == P.blocks_per_sample - 1) || (sft < 0 && bi == 0);
+      } else if (PT) epi_rows(p, blk * P.bpt, 0, P.rpt_log2, phase, lq, lane, R);
+      else epi_rows(p, bq, (blk % P.blocks_per_sample) * 128, 7, phase, lq, lane, R);
       if (nt != last_nt) { epi_load_bias<EPI>(p, bias_s, nt * BN, BN, threadIdx.x - 64); last_nt = nt; }
       const int acc = it & 1;
       long long tq = clock64();
@@ -1068,12 +1135,8 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (warp == 2) CG_DBG_ADD(5, tq);
       tq = clock64();
       tc_fence_after();
-      {
-        const int bq = blk / P.blocks_per_sample;
-        const int sft = p.ps_out ? p.ps_shift[(bq < p.B ? bq : 0) / p.ps_group_b] : 0;
-        epilogue_block<EPI>(p, tmem_base + acc * BN, BN, nt * BN, R, bias_s, stg, lq, lane,
-                            (blk % P.blocks_per_sample) * 128, sft);
-      }
+      epilogue_block<EPI>(p, tmem_base + acc * BN, BN, nt * BN, R, bias_s, stg, lq, lane,
+                          (blk % P.blocks_per_sample) * 128, sft, need_x);
       if (warp == 2) CG_DBG_ADD(6, tq);
       tc_fence_before();
       __syncwarp();
@@ -1431,7 +1494,8 @@ static inline int tc_init(TcState* s) {
        cudaFuncSetAttribute(tc::rsgemm3_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess;
   CG_SET_SMEM(EPI_NONE) CG_SET_SMEM(EPI_BIAS) CG_SET_SMEM(EPI_BIAS_LRELU) CG_SET_SMEM(EPI_MASK) CG_SET_SMEM(EPI_BIAS_SIGMOID)
   ok = ok && cudaFuncSetAttribute(tc::rsgemm2_tc_kernel<EPI_BIAS_LN_LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess &&
-       cudaFuncSetAttribute(tc::rsgemm3_tc_kernel<EPI_BIAS_LN_LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess;
+       cudaFuncSetAttribute(tc::rsgemm3_tc_kernel<EPI_BIAS_LN_LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess &&
+       cudaFuncSetAttribute(tc::rsgemm3_tc_kernel<EPI_PS_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess;
 #undef CG_SET_SMEM
   if (!ok ||
       cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) != cudaSuccess ||
@@ -1625,6 +1689,8 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   memset(&P, 0, sizeof(P));
   P.p = p;
   P.per_tap = p.Q < 128 ? 1 : 0;
+  if (p.epi == EPI_PS_MASK && (P.per_tap || p.seg.nphase != 2 || !p.mask || p.ps_w != 2 * p.Q))
+    return cg_tc_set_err("rsgemm3_tc: EPI_PS_MASK needs single-sample blocks (Q % 128 == 0) and the two-phase data-gradient form");
   int span = 0;
   for (int ph = 0; ph < p.seg.nphase; ++ph) {
     int na = 0;
@@ -1720,6 +1786,7 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
     case EPI_BIAS_LRELU: tc::rsgemm3_tc_kernel<EPI_BIAS_LRELU><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
     case EPI_MASK: tc::rsgemm3_tc_kernel<EPI_MASK><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
     case EPI_BIAS_LN_LRELU: tc::rsgemm3_tc_kernel<EPI_BIAS_LN_LRELU><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+    case EPI_PS_MASK: tc::rsgemm3_tc_kernel<EPI_PS_MASK><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
     default: tc::rsgemm3_tc_kernel<EPI_BIAS_SIGMOID><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
   }
   if (P.dbg) {

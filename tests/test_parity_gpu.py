@@ -365,3 +365,38 @@ def test_generator_head_kernel_modes_bf16(monkeypatch):
   # Adam's first two steps are sign-like (lr * g / |g|): compare the weights, not the update
   check_list(a['gw'], b['gw'], 1e-3, 'generator weights after a train step')
   check_list(a['dw'], b['dw'], 1e-3, 'critic weights after a train step')
+
+
+@pytest.mark.parametrize('shifts4', [(10, -10, 7, -1), (-10, 10, 0, 3), (1, -9, -10, 10)])
+def test_phase_shuffle_adjoint_fused_into_dgrad_bf16(monkeypatch, shifts4):
+  """Data-gradient GEMM with the PhaseShuffle adjoint (edge reflection summed in registers) and the LeakyReLU slope
+  fused into its epilogue (EPI_PS_MASK) against the unfused dgrad + ps_scatter_mask_kernel path, at the full
+  sequence length (three layers with >= 128 rows per sample) and the extreme shifts of m = 10. The fused path sums
+  the two contributors of a reflected row in fp32 instead of after bf16 rounding => bf16-ulp agreement."""
+  hp = _medium_hp(signal_shape=(2048, 20), num_units=16, m=10)
+  B = 3
+  gw, dw = O.init_weights(hp, seed=31)
+  gw, dw = O.randomize_weights(gw, 32), O.randomize_weights(dw, 33)
+  real, noises, alphas, _ = O.synthetic_batch(hp, B, seed=34, n_critic=1)
+  shifts = np.array(list(shifts4) + list(shifts4[::-1]) + [shifts4[1], shifts4[0], shifts4[3], shifts4[2]], np.int32)
+  res = {}
+  for mode in ('unfused', 'fused'):
+    if mode == 'unfused':
+      monkeypatch.setenv('CG_NO_PS_BWD_FUSE', '1')
+    else:
+      monkeypatch.delenv('CG_NO_PS_BWD_FUSE', raising=False)
+    ns, gan = build(hp, B, mixed=True)
+    gan.generator.set_weights(gw)
+    gan.discriminator.set_weights(dw)
+    n0 = gan.engine.launch_count()
+    s = gan.engine.critic_step(real, noises[0], alphas[0], shifts, update=False)
+    res[mode] = dict(scal=np.array(s[:5]), grads=gan.engine.get_grads(1), launches=gan.engine.launch_count() - n0)
+    s = gan.engine.generator_step(real, noises[1], shifts[:4], update=False)
+    res[mode]['ggrads'] = gan.engine.get_grads(0)
+  assert res['fused']['launches'] == res['unfused']['launches'] - 3     # three ps_scatter_mask launches gone
+  assert rel_err(res['fused']['scal'], res['unfused']['scal']) <= 1e-3
+  check_list(res['fused']['grads'], res['unfused']['grads'], 1e-2, 'critic grads, fused vs unfused PS adjoint')
+  check_list(res['fused']['ggrads'], res['unfused']['ggrads'], 1e-2, 'generator grads, fused vs unfused PS adjoint')
+  ref = O.critic_step_mixed(gw, dw, real, noises[0], alphas[0], shifts, hp)
+  # batch 3: bias-sized tensors sit right at the 16-bit noise floor (see BF16_* bounds above)
+  check_list(res['fused']['grads'], ref['grads'], BF16_VS_FP64_GRAD_BOUND, 'critic grads vs bf16-policy oracle')
