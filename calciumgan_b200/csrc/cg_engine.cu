@@ -659,19 +659,32 @@ static int g_forward(cg_ctx* c, const float* noise, int B, void* fake_slot = nul
   return 0;
 }
 
-static int launch_colsum(cg_ctx* c, const void* X, float* out, long long rows, int Cp, int c_real) {
-  int gx = (int)((rows + 3) / 4);
-  if (gx > 148 * 4) gx = 148 * 4;
-  dim3 grid(gx, (c_real + 63) / 64), block(64, 4);
-  DISPATCH_T(c, colsum_kernel<T><<<grid, block, 0, c->stream>>>((const T*)X, out, rows, Cp, c_real));
+static int launch_colsum_ops(cg_ctx* c, const ColsumOps& ops) {
+  for (int i = 0; i < ops.n; ++i)
+    if (ops.op[i].Cp / (16 / c->esz) > 256) return set_err("colsum: more than 256 16-byte vectors per row");
+  dim3 grid(148 * 2, ops.n);
+  DISPATCH_T(c, colsum_multi_kernel<T><<<grid, 256, 0, c->stream>>>(ops));
   return post_launch(c, "colsum");
+}
+static int launch_colsum(cg_ctx* c, const void* X, float* out, long long rows, int Cp, int c_real) {
+  if (Cp / (16 / c->esz) > 256) {
+    int gx = (int)((rows + 3) / 4);
+    if (gx > 148 * 4) gx = 148 * 4;
+    dim3 grid(gx, (c_real + 63) / 64), block(64, 4);
+    DISPATCH_T(c, colsum_kernel<T><<<grid, block, 0, c->stream>>>((const T*)X, out, rows, Cp, c_real));
+    return post_launch(c, "colsum");
+  }
+  ColsumOps ops;
+  ops.n = 1;
+  ops.op[0].X = X; ops.op[0].out = out; ops.op[0].rows = rows; ops.op[0].Cp = Cp; ops.op[0].c_real = c_real;
+  return launch_colsum_ops(c, ops);
 }
 
 // backward of the generator given DX[0] = dLoss/dfake (B, L, dcp0); accumulates into gen.g
 static int g_backward(cg_ctx* c, int B) {
   const int Cp = c->gcp[NL];
   const long long rowsL = (long long)B * c->L;
-  DISPATCH_T(c, sigmoid_backward_kernel<T><<<grid_for(rowsL * Cp), 256, 0, c->stream>>>(
+  DISPATCH_T(c, sigmoid_backward_kernel<T><<<grid_for(rowsL * Cp / (16 / c->esz)), 256, 0, c->stream>>>(
                     (const T*)c->DX[0], c->FAKE32, (T*)c->DO, rowsL, c->C, Cp, c->cfg.normalize));
   CK(post_launch(c, "sigmoid_bwd"));
   {  // output dense: dW1[c_in][c_out] = sum_rows HG5[row,c_in] * DO[row,c_out]
@@ -697,7 +710,8 @@ static int g_backward(cg_ctx* c, int B) {
     if (c->cfg.layer_norm) {
       const int nvec_b = c->gcp[i] / (16 / c->esz);
       const int lpr_b = nvec_b > 16 ? 32 : (nvec_b > 8 ? 16 : 8);
-      const int blocks = grid_for(rows * lpr_b, 256, 148 * 2);
+      static const int lnb_cap = getenv("CG_LNB_CAP") ? atoi(getenv("CG_LNB_CAP")) : 148 * 2;
+      const int blocks = grid_for(rows * lpr_b, 256, lnb_cap);
 #define CG_LNB(LPRV)                                                                                                 \
   DISPATCH_T(c, ln_lrelu_backward_kernel<T, LPRV><<<blocks, 256, 2 * c->gcp[i] * sizeof(float), c->stream>>>(          \
                     (const T*)c->DHG[i], (const T*)c->AG[i], (const T*)c->HG[i], c->MU[i], c->RSTD[i],               \
@@ -849,15 +863,16 @@ static int d_wgrad(cg_ctx* c, int Bt, int nb_bias) {
   if (nb_bias > 0) {   // all five bias gradients in one launch
     ColsumOps ops;
     ops.n = NL;
-    int maxc = 0;
+    bool vec_ok = true;
     for (int l = 1; l <= NL; ++l) {
       ops.op[l - 1].X = c->DA[l]; ops.op[l - 1].out = dgrad(c, 2 * (l - 1) + 1);
       ops.op[l - 1].rows = (long long)nb_bias * c->dl[l]; ops.op[l - 1].Cp = c->dcp[l]; ops.op[l - 1].c_real = c->dc[l];
-      if (c->dc[l] > maxc) maxc = c->dc[l];
+      if (c->dcp[l] / (16 / c->esz) > 256) vec_ok = false;
     }
-    dim3 grid(148, (maxc + 63) / 64, NL), block(64, 4);
-    DISPATCH_T(c, colsum_multi_kernel<T><<<grid, block, 0, c->stream>>>(ops));
-    CK(post_launch(c, "colsum_multi"));
+    if (vec_ok) CK(launch_colsum_ops(c, ops));
+    else
+      for (int l = 1; l <= NL; ++l)
+        CK(launch_colsum(c, ops.op[l - 1].X, ops.op[l - 1].out, ops.op[l - 1].rows, ops.op[l - 1].Cp, ops.op[l - 1].c_real));
   }
   const int tot = c->dl[NL] * c->dc[NL];
   dim3 hgrid(grid_for(tot), Bt >= 64 ? 16 : 1);
@@ -912,6 +927,17 @@ static int fetch_scalars(cg_ctx* c, int slot, int flags, float* scalars_host) {
   CU(cudaStreamSynchronize(c->stream));
   if (scalars_host) memcpy(scalars_host, c->h_scal, CG_NUM_SCALARS * 4);
   return 0;
+}
+
+// gan.py:32-41 / signals_metrics.py:9-28 on (real, FAKE32); acc[0..3] must be zeroed by the caller
+static int launch_metrics(cg_ctx* c, const float* real, float* acc, long long rows) {
+  if (c->C % 2 == 0 && c->C <= 128 && (reinterpret_cast<uintptr_t>(real) & 7) == 0)
+    metrics8_kernel<<<grid_for(rows * 8, 256, 148 * 8), 256, 0, c->stream>>>(real, c->FAKE32, acc, rows, c->C, c->cfg.signals_min,
+                                                                            c->cfg.signals_max, c->cfg.normalize);
+  else
+    metrics_kernel<<<grid_for(rows * 32, 256, 148 * 4), 256, 0, c->stream>>>(real, c->FAKE32, acc, rows, c->C, c->cfg.signals_min,
+                                                                            c->cfg.signals_max, c->cfg.normalize);
+  return post_launch(c, "metrics");
 }
 
 // ------------------------------------------------------------------------------------------ critic step
@@ -1033,9 +1059,7 @@ static int generator_step_impl(cg_ctx* c, const float* real, int B, const float*
   if (real) {
     CU(cudaMemsetAsync(scal + CG_S_MET_MIN, 0, 4 * 4, c->stream));
     const long long rows = (long long)B * c->L;
-    metrics_kernel<<<grid_for(rows * 32, 256, 148 * 4), 256, 0, c->stream>>>(
-        real, c->FAKE32, scal + CG_S_MET_MIN, rows, c->C, c->cfg.signals_min, c->cfg.signals_max, c->cfg.normalize);
-    CK(post_launch(c, "metrics"));
+    CK(launch_metrics(c, real, scal + CG_S_MET_MIN, rows));
   }
   if (!(flags & CG_FLAG_NO_UPDATE)) CK(cg_apply_update(c, CG_GENERATOR));
   return 0;
@@ -1091,9 +1115,7 @@ extern "C" int cg_validate(cg_ctx* c, const float* real, int B, const float* noi
   CK(post_launch(c, "gen_loss"));
   CU(cudaMemsetAsync(scal + CG_S_MET_MIN, 0, 4 * 4, c->stream));
   const long long rows = (long long)B * c->L;
-  metrics_kernel<<<grid_for(rows * 32, 256, 148 * 4), 256, 0, c->stream>>>(
-      real, c->FAKE32, scal + CG_S_MET_MIN, rows, c->C, c->cfg.signals_min, c->cfg.signals_max, c->cfg.normalize);
-  CK(post_launch(c, "metrics"));
+  CK(launch_metrics(c, real, scal + CG_S_MET_MIN, rows));
   if (fake_out) CU(cudaMemcpyAsync(fake_out, c->FAKE32, (size_t)rows * c->C * 4, cudaMemcpyDeviceToDevice, c->stream));
   return fetch_scalars(c, 0, 0, scalars_host);
 }

@@ -506,24 +506,48 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, fl
   }
 }
 
-// several column sums in one launch (blockIdx.z selects the tensor): bias gradients of all conv layers of a sub-step
+// several column sums in one launch (blockIdx.y selects the tensor): bias gradients of all conv layers of a sub-step.
+// 16-byte loads: thread = (row within the pass, 16-byte column vector), rows grid-strided; partial sums meet in shared
+// memory, one atomicAdd per channel and block.
 struct ColsumOps { int n; struct { const void* X; float* out; long long rows; int Cp, c_real; } op[8]; };
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_multi_kernel(const __grid_constant__ ColsumOps ops) {
-  const auto& o = ops.op[blockIdx.z];
-  const int c = blockIdx.y * 64 + threadIdx.x;
-  if (blockIdx.y * 64 >= o.c_real) return;
+  constexpr int V = Vec16<T>::N;
+  const auto& o = ops.op[blockIdx.y];
+  const int cv = o.Cp / V;                 // host: cv <= 256
+  const int rpp = 256 / cv;                // rows per pass of this block
+  const int tr = threadIdx.x / cv, tc = threadIdx.x - tr * cv;
   const T* X = reinterpret_cast<const T*>(o.X);
-  float acc = 0.f;
-  if (c < o.c_real)
-    for (long long r = (long long)blockIdx.x * 4 + threadIdx.y; r < o.rows; r += (long long)gridDim.x * 4)
-      acc += Elem<T>::to_f(X[r * o.Cp + c]);
-  __shared__ float red[4][64];
-  red[threadIdx.y][threadIdx.x] = acc;
+  float acc[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) acc[e] = 0.f;
+  if (tr < rpp) {
+    const long long step = (long long)gridDim.x * rpp;
+    long long r = (long long)blockIdx.x * rpp + tr;
+    for (; r + 3 * step < o.rows; r += 4 * step) {   // four independent 16-byte loads in flight per thread
+      float t0[V], t1[V], t2[V], t3[V];
+      vload<T>(X + r * o.Cp + tc * V, t0);
+      vload<T>(X + (r + step) * o.Cp + tc * V, t1);
+      vload<T>(X + (r + 2 * step) * o.Cp + tc * V, t2);
+      vload<T>(X + (r + 3 * step) * o.Cp + tc * V, t3);
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] += (t0[e] + t1[e]) + (t2[e] + t3[e]);
+    }
+    for (; r < o.rows; r += step) {
+      float t0[V];
+      vload<T>(X + r * o.Cp + tc * V, t0);
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] += t0[e];
+    }
+  }
+  __shared__ float red[256 * V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) red[threadIdx.x * V + e] = acc[e];
   __syncthreads();
-  if (threadIdx.y == 0 && c < o.c_real) {
-    const float s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
-    atomicAdd(&o.out[c], s);
+  for (int c = threadIdx.x; c < o.c_real; c += 256) {
+    float sum = 0.f;
+    for (int k = 0; k < rpp; ++k) sum += red[(k * cv + c / V) * V + c % V];
+    atomicAdd(&o.out[c], sum);
   }
 }
 
@@ -738,23 +762,40 @@ __global__ void dense0_backward_kernel(const float* __restrict__ z, const T* __r
   }
 }
 
-// DO[b,t,c] = DX0[b,t,c] * f(1-f) with f = fake32[b,t,c] (sigmoid head backward); pad -> 0
+// DO[b,t,c] = DX0[b,t,c] * f(1-f) with f = fake32[b,t,c] (sigmoid head backward); pad -> 0.
+// One 16-byte vector of DX0 / DO per thread; the unpadded fp32 rows are read as float2 (C even) or scalars.
 template <typename T>
 __global__ void sigmoid_backward_kernel(const T* __restrict__ DX0, const float* __restrict__ fake, T* __restrict__ DO,
                                         long long rows, int C, int Cp, int normalize) {
-  const long long total = rows * Cp;
+  constexpr int V = Vec16<T>::N;
+  const int cv = Cp / V;
+  const long long total = rows * cv;
+  const bool pairs = (C & 1) == 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % Cp);
-    float v = 0.f;
+    const long long row = i / cv;
+    const int c = (int)(i - row * cv) * V;
+    float v[V];
     if (c < C) {
-      v = Elem<T>::to_f(DX0[i]);
-      if (normalize) {
-        const float f = fake[(i / Cp) * C + c];
-        v *= f * (1.f - f);
+      vload<T>(DX0 + row * Cp + c, v);
+      const float* f = fake + row * C + c;
+#pragma unroll
+      for (int e = 0; e < V; e += 2) {
+        float f0 = 0.f, f1 = 0.f;
+        if (normalize) {
+          if (pairs) { if (c + e < C) { const float2 t = *reinterpret_cast<const float2*>(f + e); f0 = t.x; f1 = t.y; } }
+          else { if (c + e < C) f0 = f[e]; if (c + e + 1 < C) f1 = f[e + 1]; }
+          v[e] *= f0 * (1.f - f0);
+          v[e + 1] *= f1 * (1.f - f1);
+        }
+        if (c + e >= C) v[e] = 0.f;
+        if (c + e + 1 >= C) v[e + 1] = 0.f;
       }
+    } else {
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] = 0.f;
     }
-    DO[i] = Elem<T>::from_f(v);
+    vstore<T>(DO + row * Cp + c, v);
   }
 }
 
@@ -894,6 +935,74 @@ __global__ void __launch_bounds__(256) metrics_kernel(const float* __restrict__ 
     a3 += (st[0][3] - st[1][3]) * (st[0][3] - st[1][3]);
   }
   if (lane == 0) {
+    const float inv = 1.f / (float)rows;
+    atomicAdd(&acc[0], a0 * inv); atomicAdd(&acc[1], a1 * inv);
+    atomicAdd(&acc[2], a2 * inv); atomicAdd(&acc[3], a3 * inv);
+  }
+}
+
+// Same statistics with 8 lanes per (b,t) row (four rows per warp) for even C <= 128: each lane keeps its <= 16
+// elements of the real and of the fake row in registers (float2 loads, all issued up front), so the exact two-pass
+// variance costs no second read and every reduction is 3 shuffles instead of 5 per row.
+__global__ void __launch_bounds__(256) metrics8_kernel(const float* __restrict__ real, const float* __restrict__ fake,
+                                                       float* __restrict__ acc, long long rows, int C, float smin,
+                                                       float smax, int normalize) {
+  const int sub = threadIdx.x & 7;
+  const long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const long long ngrp = ((long long)gridDim.x * blockDim.x) >> 3;
+  const float sc = normalize ? (smax - smin) : 1.f, of = normalize ? smin : 0.f;
+  const int half = C >> 1;   // float2 per row
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (long long r0 = 0; r0 < rows; r0 += ngrp) {   // every lane runs the same number of iterations (full-mask shuffles)
+    const long long r = r0 + grp;
+    const bool rok = r < rows;
+    float2 v[2][8];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const float2* x = reinterpret_cast<const float2*>((w == 0 ? real : fake) + (rok ? r : 0) * C);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[w][k] = (rok && sub + 8 * k < half) ? x[sub + 8 * k] : make_float2(0.f, 0.f);
+    }
+    float st[2][4];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      float mn = INFINITY, mx = -INFINITY, s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (sub + 8 * k < half) {
+          v[w][k].x = v[w][k].x * sc + of; v[w][k].y = v[w][k].y * sc + of;
+          mn = fminf(mn, fminf(v[w][k].x, v[w][k].y)); mx = fmaxf(mx, fmaxf(v[w][k].x, v[w][k].y));
+          s += v[w][k].x + v[w][k].y;
+        }
+      }
+#pragma unroll
+      for (int o = 4; o >= 1; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+      }
+      const float mean = s / C;
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (sub + 8 * k < half) {
+          const float d0 = v[w][k].x - mean, d1 = v[w][k].y - mean;
+          q += d0 * d0 + d1 * d1;
+        }
+      }
+#pragma unroll
+      for (int o = 4; o >= 1; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      st[w][0] = mn; st[w][1] = mx; st[w][2] = mean; st[w][3] = sqrtf(q / C);
+    }
+    if (rok && sub == 0) {
+      a0 += (st[0][0] - st[1][0]) * (st[0][0] - st[1][0]);
+      a1 += (st[0][1] - st[1][1]) * (st[0][1] - st[1][1]);
+      a2 += (st[0][2] - st[1][2]) * (st[0][2] - st[1][2]);
+      a3 += (st[0][3] - st[1][3]) * (st[0][3] - st[1][3]);
+    }
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+  if ((threadIdx.x & 31) == 0) {
     const float inv = 1.f / (float)rows;
     atomicAdd(&acc[0], a0 * inv); atomicAdd(&acc[1], a1 * inv);
     atomicAdd(&acc[2], a2 * inv); atomicAdd(&acc[3], a3 * inv);
