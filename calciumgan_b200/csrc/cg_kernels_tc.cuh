@@ -206,7 +206,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;               // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int kEpiWarps = 8;
+constexpr int kWgThreads = 192;             // weight-gradient kernels: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int kABytes = 128 * 128;          // 128 rows x 64 bf16
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;             // columns between the two accumulator buffers
@@ -238,42 +240,50 @@ __device__ __forceinline__ float sigmoid_fast(float x) {
 }
 
 // ---- epilogue -----------------------------------------------------------------------------------------
-constexpr int kStgBytes = 4096;   // per-warp staging: 32 rows x 64 bf16, 16-byte chunks XOR-swizzled by (row & 7)
-constexpr int kEpiSmem = 4 * kStgBytes + 3 * 1024;   // + bias / gamma / beta tiles (256 floats each)
+// Eight epilogue warps: warp w reads TMEM lanes 32 * (w % 4) .. +31 (hardware rule), and the two warps of a lane
+// quarter take alternate 32-column chunks (half = 0 / 1). One warp per scheduler left every TMEM / shared / global
+// latency of the epilogue exposed (measured 2.4k - 4.9k clk per 128 x 64 block against 3k - 6k clk of MMA work).
+constexpr int kStgBytes = 2048;   // per-warp staging: 32 rows x 32 bf16 (64-byte rows), 16-byte chunks XOR-swizzled by (row >> 1) & 3
+constexpr int kEpiSmem = kEpiWarps * kStgBytes + 3 * 1024;   // + bias / gamma / beta tiles (256 floats each)
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // 4 epilogue warps
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // all 8 epilogue warps
+__device__ __forceinline__ void epi_bar_half(int half) {                                       // the 4 warps of one column half
+  asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+}
+__device__ __forceinline__ uint32_t stg_addr(uint32_t stg_s, int row, int chunk) {
+  return stg_s + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+}
 
-// Per tile, each lane precomputes the element offsets of the 8 rows it stores in the coalesced phase
-// (row rr = 4*i + lane/8 of this warp's 32 rows); negative = masked. rpt < 128 is a power of two.
+// Per tile, each lane precomputes the element offsets of the 4 rows it stores in the coalesced phase
+// (row rr = 8*i + lane/4 of this warp's 32 rows); negative = masked. rpt < 128 is a power of two.
 struct EpiRows {
   long long base;                     // element offset of sample b0; off[] / my_off are 32-bit offsets relative to it
-  int off[8]; int my_off; long long my_o32; long long my_row; bool my_ok;
+  int off[4]; int my_off; long long my_o32; long long my_row; bool my_ok;
   long long o32_base; bool uniform;   // single-sample blocks: fp32 row rr of this warp is at o32_base + rr * o32_rs
   int x_src, x_par; bool x_zero;      // EPI_PS_MASK: exchange slot this row fills / adds (-1 = none), row without a source
 };
 __device__ __forceinline__ void epi_rows(const RsParams& p, int b0, int q0, int rpt_log2, int phase, int lq, int lane,
                                          EpiRows& R) {
-  const int crow = lane >> 3;
+  const int crow = lane >> 2;
   const int ph_off = phase * p.o_phase_col;
   R.base = (long long)b0 * p.o_bs;
 #pragma unroll
-  for (int i = 0; i <= 8; ++i) {
-    const int r = lq * 32 + (i < 8 ? i * 4 + crow : lane);
+  for (int i = 0; i <= 4; ++i) {
+    const int r = lq * 32 + (i < 4 ? i * 8 + crow : lane);
     int db, q;
     if (rpt_log2 >= 7) { db = 0; q = q0 + r; } else { db = r >> rpt_log2; q = r & ((1 << rpt_log2) - 1); }
     const bool ok = b0 + db < p.B;
     const int o = ok ? db * (int)p.o_bs + q * p.o_rs + ph_off : -1;   // per-sample extents are far below 2^31 elements
-    if (i < 8) R.off[i] = o;
+    if (i < 4) R.off[i] = o;
     else {
       const int b = b0 + db;
       R.my_off = o; R.my_ok = ok; R.my_o32 = (long long)b * p.o32_bs + (long long)q * p.o32_rs;
       R.my_row = ((long long)b * p.Q + q) * p.seg.nphase + phase;
     }
   }
-  {
-    R.uniform = rpt_log2 >= 7;
-    R.o32_base = (long long)b0 * p.o32_bs + (long long)(q0 + lq * 32) * p.o32_rs;
-  }
+  R.uniform = rpt_log2 >= 7;
+  R.o32_base = (long long)b0 * p.o32_bs + (long long)(q0 + lq * 32) * p.o32_rs;
+  R.x_src = -1; R.x_par = -1; R.x_zero = false;
 }
 
 // EPI_PS_MASK rows (single-sample 128-row blocks of one output phase): accumulator row t = (q0 + r) * nphase + phase goes
@@ -283,12 +293,12 @@ __device__ __forceinline__ void epi_rows(const RsParams& p, int b0, int q0, int 
 // Rows nobody maps to (x_zero) are written as zeros by the thread that owns the same index.
 __device__ __forceinline__ void epi_rows_ps(const RsParams& p, int b, int q0, int phase, int s, int lq, int lane, EpiRows& R) {
   const int w = p.Q * 2;   // two output phases (host-checked): time t = 2 q + phase
-  const int crow = lane >> 3;
+  const int crow = lane >> 2;
   const bool bok = b < p.B;
   R.base = (long long)b * p.o_bs;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int j = (q0 + lq * 32 + i * 4 + crow) * 2 + phase + s;
+  for (int i = 0; i < 4; ++i) {
+    const int j = (q0 + lq * 32 + i * 8 + crow) * 2 + phase + s;
     R.off[i] = (bok && j >= 0 && j < w) ? (j >> 1) * p.o_rs + (j & 1) * p.o_phase_col : -1;
   }
   const int q = q0 + lq * 32 + lane;
@@ -309,28 +319,32 @@ __device__ __forceinline__ void epi_rows_ps(const RsParams& p, int b, int q0, in
   R.x_zero = t - s < 0 || t - s > w - 1;
 }
 
-// One 128-row x BN-column accumulator block: TMEM -> registers (thread = row) -> bias / LeakyReLU / sigmoid /
-// slope mask in fp32 -> bf16 -> swizzled smem transpose -> global stores where every warp instruction writes
-// four full 128-byte row segments. EPI is a compile-time mode: the first version of this epilogue spent ~10k clk
-// per 128x64 block on per-element mode checks, integer divisions and 64-bit address math (profiles/).
-// Padded columns come out as exact zeros because padded weight rows and the staged bias are zero.
+// The 32-column chunks c0 = 32 * half, 32 * half + 64, ... of one 128-row x BN-column accumulator block:
+// TMEM -> registers (thread = row) -> bias / LeakyReLU / sigmoid / layer-norm / slope mask in fp32 -> bf16 -> swizzled
+// smem transpose -> global stores where every warp instruction writes eight 64-byte row segments. EPI is a
+// compile-time mode: the first version of this epilogue spent ~10k clk per 128x64 block on per-element mode checks,
+// integer divisions and 64-bit address math (profiles/). Padded columns come out as exact zeros because padded
+// weight rows and the staged bias are zero.
 template <int EPI>
 __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_cols, int BN, int n_base,
-                                               const EpiRows& R, const float* bias_s, uint8_t* stg, int lq, int lane,
-                                               int ps_q0 = 0, int ps_s = 0, bool need_x = false) {
-  // ps_q0: time index of tile row 0 (single-sample blocks); ps_s: this sample's PhaseShuffle shift (p.ps_out != null)
+                                               const EpiRows& R, const float* bias_s, uint8_t* stg, uint8_t* stg_partner,
+                                               int lq, int lane, int half, int ps_q0 = 0, int ps_s = 0, bool need_x = false) {
+  // ps_q0: time index of tile row 0 (single-sample blocks); ps_s: this sample's PhaseShuffle shift
   bf16* out = reinterpret_cast<bf16*>(p.out);
   bf16* psx = reinterpret_cast<bf16*>(p.ps_out);
   const uint32_t stg_s = smem_u32(stg);
   const bf16* mask = reinterpret_cast<const bf16*>(p.mask);
-  const int cj = lane & 7;
+  const int cj = lane & 3, crow = lane >> 2;
+  const uint32_t my_st = stg_s + lane * 64;
+  const int msw = (lane >> 1) & 3;
+  const uint32_t taddr = tmem_cols + ((uint32_t)(lq * 32) << 16);
   float ssq = 0.f;   // p.sumsq: gradient-penalty norm fused into the last data-gradient GEMM (fp32 accumulators)
   float ln_mean = 0.f, ln_rstd = 1.f;
-  if (EPI == EPI_BIAS_LN_LRELU) {   // pass 1 over TMEM: row statistics of x = acc + bias (this thread owns the row)
+  if (EPI == EPI_BIAS_LN_LRELU) {   // pass 1 over TMEM: row statistics of x = acc + bias; this thread sees half of its row
     float s1 = 0.f, s2 = 0.f;
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = half * 32; c0 < BN; c0 += 64) {
       uint32_t v[32];
-      tmem_ld32(tmem_cols + ((uint32_t)(lq * 32) << 16) + c0, v);
+      tmem_ld32(taddr + c0, v);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -341,41 +355,41 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
         }
       }
     }
+    // the other half of the row lives in the partner warp (same lane quarter): swap partial sums through the staging buffers
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(stg_s + lane * 8), "f"(s1), "f"(s2) : "memory");
+    epi_bar();
+    float o1, o2;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(o1), "=f"(o2) : "r"(smem_u32(stg_partner) + lane * 8) : "memory");
+    epi_bar();   // everybody has read before the staging buffers are reused
+    s1 += o1; s2 += o2;
     ln_mean = s1 / p.n_real;
     ln_rstd = rsqrtf(fmaxf(s2 / p.n_real - ln_mean * ln_mean, 0.f) + CG_LN_EPS);
-    if (p.mu && R.my_ok) { p.mu[R.my_row] = ln_mean; p.rstd[R.my_row] = ln_rstd; }
+    if (half == 0 && p.mu && R.my_ok) { p.mu[R.my_row] = ln_mean; p.rstd[R.my_row] = ln_rstd; }
   }
-  for (int c0 = 0; c0 < BN; c0 += 64) {
-    const int ncols = BN - c0 < 64 ? BN - c0 : 64;   // 64 or 32 (BN % 32 == 0)
+  for (int c0 = half * 32; c0 < BN; c0 += 64) {
+    const int n0 = n_base + c0;
     if (EPI == EPI_MASK || EPI == EPI_PS_MASK) {   // coalesced, register-free read of the slope source (same indexing as out) into the staging tile
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = i * 4 + (lane >> 3);
-        const bool ok = R.off[i] >= 0 && cj * 8 < ncols;
-        cp_async16(stg_s + rr * 128 + ((cj ^ (rr & 7)) << 4), mask + (ok ? R.base + R.off[i] + n_base + c0 + cj * 8 : 0), ok ? 16u : 0u);
+      for (int i = 0; i < 4; ++i) {
+        const int rr = i * 8 + crow;
+        const bool ok = R.off[i] >= 0;
+        cp_async16(stg_addr(stg_s, rr, cj), mask + (ok ? R.base + R.off[i] + n0 + cj * 8 : 0), ok ? 16u : 0u);
       }
     }
-    uint32_t v[64];
-    {
-      uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-      uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-      tmem_ld32(tmem_cols + ((uint32_t)(lq * 32) << 16) + c0, v0);
-      if (ncols > 32) tmem_ld32(tmem_cols + ((uint32_t)(lq * 32) << 16) + c0 + 32, v1);
-      tmem_ld_wait();
-    }
-    const int n0 = n_base + c0;
-    const bool col_ok = cj * 8 < ncols;
-    if (EPI == EPI_PS_MASK && need_x) {   // reflected rows meet their partners (bias tile area: 2 x 5 slots x 64 floats)
-      const uint32_t xb = smem_u32(bias_s) + ((c0 >> 6) & 1) * 1280;
+    uint32_t v[32];
+    tmem_ld32(taddr + c0, v);
+    tmem_ld_wait();
+    if (EPI == EPI_PS_MASK && need_x) {   // reflected rows meet their partners (bias tile area: 2 halves x 2 x 5 slots x 32 floats)
+      const uint32_t xb = smem_u32(bias_s) + half * 1280 + ((c0 >> 6) & 1) * 640;
       if (R.x_src >= 0) {
 #pragma unroll
-        for (int j4 = 0; j4 < 16; ++j4) sts_v4(xb + R.x_src * 256 + j4 * 16, make_uint4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]));
+        for (int j4 = 0; j4 < 8; ++j4) sts_v4(xb + R.x_src * 128 + j4 * 16, make_uint4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]));
       }
-      epi_bar();
+      epi_bar_half(half);
       if (R.x_par >= 0) {
 #pragma unroll
-        for (int j4 = 0; j4 < 16; ++j4) {
-          const uint4 o = lds_v4(xb + R.x_par * 256 + j4 * 16);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const uint4 o = lds_v4(xb + R.x_par * 128 + j4 * 16);
           v[j4 * 4] = __float_as_uint(__uint_as_float(v[j4 * 4]) + __uint_as_float(o.x));
           v[j4 * 4 + 1] = __float_as_uint(__uint_as_float(v[j4 * 4 + 1]) + __uint_as_float(o.y));
           v[j4 * 4 + 2] = __float_as_uint(__uint_as_float(v[j4 * 4 + 2]) + __uint_as_float(o.z));
@@ -387,8 +401,8 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
       cp_async_wait_all();
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint4 mv = lds_v4(stg_s + lane * 128 + ((j ^ (lane & 7)) << 4));
+      for (int j = 0; j < 4; ++j) {
+        const uint4 mv = lds_v4(my_st + ((j ^ msw) << 4));
         const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
         for (int w2 = 0; w2 < 4; ++w2) {
@@ -405,33 +419,33 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
       bf16* aux = reinterpret_cast<bf16*>(p.aux);
       if (aux) {   // pre-norm activations for the backward pass, through the same coalescing transpose
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           float x[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j * 8 + e]) + bias_s[c0 + j * 8 + e];
           uint4 o;
           o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
           o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
-          sts_v4(stg_s + lane * 128 + ((j ^ (lane & 7)) << 4), o);
+          sts_v4(my_st + ((j ^ msw) << 4), o);
         }
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + (lane >> 3);
-          const uint4 o = lds_v4(stg_s + rr * 128 + ((cj ^ (rr & 7)) << 4));
-          if (R.off[i] >= 0 && col_ok) *reinterpret_cast<uint4*>(aux + R.base + R.off[i] + n0 + cj * 8) = o;
+        for (int i = 0; i < 4; ++i) {
+          const uint4 o = lds_v4(stg_addr(stg_s, i * 8 + crow, cj));
+          if (R.off[i] >= 0) *reinterpret_cast<uint4*>(aux + R.base + R.off[i] + n0 + cj * 8) = o;
         }
         __syncwarp();
       }
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const float x = __uint_as_float(v[j]) + bias_s[c0 + j];
-        v[j] = __float_as_uint(lrelu((x - ln_mean) * ln_rstd * gamma_s[c0 + j] + beta_s[c0 + j]));   // pads: gamma = beta = 0
+      for (int j = 0; j < 32; ++j) {
+        const float a = ln_rstd * gamma_s[c0 + j];                        // pads: gamma = beta = 0
+        const float d = fmaf(bias_s[c0 + j] - ln_mean, a, beta_s[c0 + j]);
+        v[j] = __float_as_uint(lrelu(fmaf(__uint_as_float(v[j]), a, d)));
       }
     }
     if (EPI == EPI_BIAS || EPI == EPI_BIAS_LRELU || EPI == EPI_BIAS_SIGMOID) {
 #pragma unroll
-      for (int j4 = 0; j4 < 16; ++j4) {
+      for (int j4 = 0; j4 < 8; ++j4) {
         const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + j4 * 4);   // smem broadcast
         const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
@@ -445,50 +459,48 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
     }
     if (EPI == EPI_NONE && p.sumsq) {
 #pragma unroll
-      for (int j = 0; j < 64; ++j)
-        if (j < ncols) ssq = fmaf(__uint_as_float(v[j]), __uint_as_float(v[j]), ssq);
+      for (int j = 0; j < 32; ++j) ssq = fmaf(__uint_as_float(v[j]), __uint_as_float(v[j]), ssq);
     }
-    if (p.out32) {   // unpadded fp32 copy (generator head only): 32x32 fp32 transpose through the staging buffer so
-                     // every warp store writes 32 consecutive floats of one output row
+    if (p.out32) {   // unpadded fp32 copy (generic generator head): two 32 x 16 fp32 transposes through the staging buffer so
+                     // every warp store writes 16 consecutive floats of two output rows
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        if (h * 32 < ncols) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sts_f32(stg_s + (lane * 32 + (j ^ lane)) * 4, __uint_as_float(v[h * 32 + j]));
-          __syncwarp();
-          const int n = n0 + h * 32 + lane;
-          const bool n_ok = n < p.n_real;
-#pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
-            const float val = lds_f32(stg_s + (rr * 32 + (lane ^ rr)) * 4);
-            if (R.uniform) {   // all 32 rows belong to one sample: plain address arithmetic (3 SHFL per row made this shuffle-bound)
-              if (R.my_ok && n_ok) p.out32[R.o32_base + (long long)rr * p.o32_rs + n] = val;
-            } else {
-              const long long o = __shfl_sync(0xffffffffu, R.my_o32, rr);
-              const int ok = __shfl_sync(0xffffffffu, (int)R.my_ok, rr);
-              if (ok && n_ok) p.out32[o + n] = val;
-            }
+        for (int j = 0; j < 16; ++j) sts_f32(stg_s + (lane * 16 + (j ^ (lane & 15))) * 4, __uint_as_float(v[h * 16 + j]));
+        __syncwarp();
+        const int n = n0 + h * 16 + (lane & 15);
+        const bool n_ok = n < p.n_real;
+#pragma unroll 4
+        for (int it = 0; it < 16; ++it) {
+          const int rr = 2 * it + (lane >> 4);
+          const float val = lds_f32(stg_s + (rr * 16 + ((lane & 15) ^ (rr & 15))) * 4);
+          if (R.uniform) {   // all 32 rows belong to one sample: plain address arithmetic
+            if (R.my_ok && n_ok) p.out32[R.o32_base + (long long)rr * p.o32_rs + n] = val;
+          } else {
+            const long long o = __shfl_sync(0xffffffffu, R.my_o32, rr);
+            const int ok = __shfl_sync(0xffffffffu, (int)R.my_ok, rr);
+            if (ok && n_ok) p.out32[o + n] = val;
           }
-          __syncwarp();
         }
+        __syncwarp();
       }
     }
     if (out || psx) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
         uint4 o;
         o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
         o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
         o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
         o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
-        sts_v4(stg_s + lane * 128 + ((j ^ (lane & 7)) << 4), o);
+        sts_v4(my_st + ((j ^ msw) << 4), o);
       }
       __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = i * 4 + (lane >> 3);
-        const uint4 o = lds_v4(stg_s + rr * 128 + ((cj ^ (rr & 7)) << 4));
-        if (R.off[i] >= 0 && col_ok) {
+      for (int i = 0; i < 4; ++i) {
+        const int rr = i * 8 + crow;
+        const uint4 o = lds_v4(stg_addr(stg_s, rr, cj));
+        if (R.off[i] >= 0) {
           if (out) *reinterpret_cast<uint4*>(out + R.base + R.off[i] + n0 + cj * 8) = o;
           if (psx) {   // scatter form of the PhaseShuffle gather: row q feeds every t with ps_index(t) == q
             const int q = ps_q0 + lq * 32 + rr, w = p.ps_w;
@@ -503,9 +515,10 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
       }
       __syncwarp();
     }
-  }
-  if (EPI == EPI_PS_MASK && R.x_zero && R.my_ok) {   // times no t maps to
-    for (int c = 0; c < BN; c += 8) *reinterpret_cast<uint4*>(out + R.base + R.my_off + n_base + c) = make_uint4(0u, 0u, 0u, 0u);
+    if (EPI == EPI_PS_MASK && R.x_zero && R.my_ok) {   // times no t maps to
+#pragma unroll
+      for (int c = 0; c < 32; c += 8) *reinterpret_cast<uint4*>(out + R.base + R.my_off + n0 + c) = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
   if (EPI == EPI_NONE && p.sumsq) {
     if (R.uniform) {   // all 32 rows of the warp belong to one sample
@@ -517,18 +530,18 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
   }
 }
 
-// stage bias[n_base .. n_base+BN) (zero beyond n_real) into smem for the 4 epilogue warps
+// stage bias[n_base .. n_base+BN) (zero beyond n_real) into smem for the 8 epilogue warps (tid = 0..255)
 template <int EPI>
-__device__ __forceinline__ void epi_load_bias(const RsParams& p, float* bias_s, int n_base, int BN, int tid128) {
+__device__ __forceinline__ void epi_load_bias(const RsParams& p, float* bias_s, int n_base, int BN, int tid) {
   if (EPI == EPI_BIAS || EPI == EPI_BIAS_LRELU || EPI == EPI_BIAS_SIGMOID || EPI == EPI_BIAS_LN_LRELU) {
     epi_bar();   // previous tile's readers are done
-    for (int i = tid128; i < 256; i += 128) {
-      const int n = n_base + i;
-      const bool ok = i < BN && n < p.n_real;
-      bias_s[i] = ok ? __ldg(&p.bias[n]) : 0.f;
+    {
+      const int n = n_base + tid;
+      const bool ok = tid < BN && n < p.n_real;
+      bias_s[tid] = ok ? __ldg(&p.bias[n]) : 0.f;
       if (EPI == EPI_BIAS_LN_LRELU) {
-        bias_s[256 + i] = ok ? __ldg(&p.gamma[n]) : 0.f;
-        bias_s[512 + i] = ok ? __ldg(&p.beta[n]) : 0.f;
+        bias_s[256 + tid] = ok ? __ldg(&p.gamma[n]) : 0.f;
+        bias_s[512 + tid] = ok ? __ldg(&p.beta[n]) : 0.f;
       }
     }
     epi_bar();
@@ -562,7 +575,7 @@ rsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   uint8_t* stage_buf = smem + (size_t)stages * stage_bytes + 512;   // 4 x kStgBytes epilogue staging + bias tile
-  float* bias_s = reinterpret_cast<float*>(stage_buf + 4 * kStgBytes);
+  float* bias_s = reinterpret_cast<float*>(stage_buf + kEpiWarps * kStgBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -571,7 +584,7 @@ rsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
     for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -649,8 +662,9 @@ rsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  == tile rows
-    const int lq = warp & 3;
+    const int lq = warp & 3, half = (warp - 2) >> 2;
     uint8_t* stg = stage_buf + (warp - 2) * kStgBytes;
+    uint8_t* stg_partner = stage_buf + ((warp - 2) ^ 4) * kStgBytes;
     int rpt_log2 = 7;
     if (P.tiles_per_sample == 0) { rpt_log2 = 0; while ((1 << rpt_log2) < P.rpt) ++rpt_log2; }
     int it = 0, last_nt = -1;
@@ -670,7 +684,7 @@ rsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tfull[acc], ((uint32_t)it >> 1) & 1);
       const long long te1 = clock64();
       tc_fence_after();
-      epilogue_block<EPI>(p, tmem_base + acc * kAccStride, BN, nt * BN, R, bias_s, stg, lq, lane);
+      epilogue_block<EPI>(p, tmem_base + acc * kAccStride, BN, nt * BN, R, bias_s, stg, stg_partner, lq, lane, half);
       if (P.dbg && blockIdx.x == 0 && threadIdx.x == 64) {
         atomicAdd((unsigned long long*)&P.dbg[6], (unsigned long long)(te1 - te0));
         atomicAdd((unsigned long long*)&P.dbg[7], (unsigned long long)(clock64() - te1));
@@ -716,194 +730,6 @@ struct RsTc2Params {
   long long* dbg;   // optional role cycle counters of CTA 0 (CG_TC_TIMING=1)
 };
 
-template <int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
-rsgemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                  const __grid_constant__ RsTc2Params P) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const RsParams& p = P.p;
-  const int BN = P.BN, MB = P.MB;
-  const int SS = P.slab_stages, BS = P.b_stages;
-  const int b_bytes = BN * 128;
-  uint8_t* slabs = smem;
-  uint8_t* btiles = smem + (size_t)SS * P.slab_bytes;
-  uint64_t* s_full = reinterpret_cast<uint64_t*>(btiles + (size_t)BS * b_bytes);
-  uint64_t* s_empty = s_full + SS;
-  uint64_t* b_full = s_empty + SS;
-  uint64_t* b_empty = b_full + BS;
-  uint64_t* tfull = b_empty + BS;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint8_t* stage_buf = btiles + (size_t)BS * b_bytes + 512;   // 4 x kStgBytes epilogue staging + bias tile
-  float* bias_s = reinterpret_cast<float*>(stage_buf + 4 * kStgBytes);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmW);
-    for (int i = 0; i < SS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
-    for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int total_tiles = p.seg.nphase * P.n_tiles * P.m_tiles;
-  const int acc_stride = MB * BN;
-
-  if (warp == 0) {
-    int ss = 0, bs = 0;
-    uint32_t sph = 0, bph = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int mt = t % P.m_tiles;
-      const int rest = t / P.m_tiles;
-      const int nt = rest % P.n_tiles;
-      const int phase = rest / P.n_tiles;
-      for (int kc = 0; kc < P.kchunks; ++kc) {
-        for (int g = 0; g < P.ngroups[phase]; ++g) {
-          const SlabGroup& G = P.grp[phase][g];
-          long long tq = clock64();
-          mbar_wait(&s_empty[ss], sph ^ 1);
-          CG_DBG_ADD(0, tq);
-          if (elect_one()) {
-            uint8_t* sl = slabs + (size_t)ss * P.slab_bytes;
-            mbar_expect_tx(&s_full[ss], (uint32_t)P.slab_bytes);
-            for (int mb = 0; mb < MB; ++mb) {
-              const int blk = mt * MB + mb;
-              const int b = blk / P.blocks_per_sample;
-              const int q0 = (blk % P.blocks_per_sample) * 128;
-              tma_load_3d(sl + (size_t)mb * P.box_bytes, &tmA, &s_full[ss], G.acol + kc * 64, q0 + G.min_shift, b);
-            }
-          }
-          if (++ss == SS) { ss = 0; sph ^= 1; }
-          for (int s = 0; s < G.nseg; ++s) {
-            tq = clock64();
-            mbar_wait(&b_empty[bs], bph ^ 1);
-            CG_DBG_ADD(1, tq);
-            if (elect_one()) {
-              mbar_expect_tx(&b_full[bs], (uint32_t)b_bytes);
-              tma_load_2d(btiles + (size_t)bs * b_bytes, &tmW, &b_full[bs], G.wk[s] + kc * 64, nt * BN);
-            }
-            if (++bs == BS) { bs = 0; bph ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    const uint32_t idesc = make_idesc(128, BN, 0, 0);
-    const uint32_t hi = desc_hi(1024);
-    const uint32_t slab_lo0 = desc_lo(smem_u32(slabs), 16), b_lo0 = desc_lo(smem_u32(btiles), 16);
-    const uint32_t slab_step = (uint32_t)P.slab_bytes >> 4, b_step = (uint32_t)b_bytes >> 4;
-    const uint32_t box_step = (uint32_t)P.box_bytes >> 4;
-    int ss = 0, bs = 0;
-    uint32_t sph = 0, bph = 0;
-    int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int phase = (t / P.m_tiles) / P.n_tiles;
-      const int acc = P.double_acc ? (it & 1) : 0;
-      const uint32_t use = P.double_acc ? ((uint32_t)it >> 1) : (uint32_t)it;
-      long long tq = clock64();
-      mbar_wait(&tempty[acc], (use & 1) ^ 1);
-      CG_DBG_ADD(2, tq);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * acc_stride;
-      uint32_t accum = 0;
-      for (int kc = 0; kc < P.kchunks; ++kc) {
-        for (int g = 0; g < P.ngroups[phase]; ++g) {
-          const SlabGroup& G = P.grp[phase][g];
-          tq = clock64();
-          mbar_wait(&s_full[ss], sph);
-          CG_DBG_ADD(3, tq);
-          tc_fence_after();
-          const uint32_t sl_lo = slab_lo0 + ss * slab_step;
-          for (int s = 0; s < G.nseg; ++s) {
-            tq = clock64();
-            mbar_wait(&b_full[bs], bph);
-            CG_DBG_ADD(4, tq);
-            tc_fence_after();
-            const uint32_t b_lo = b_lo0 + bs * b_step;
-            const uint32_t a_lo = sl_lo + (uint32_t)G.shift_rel[s] * 8;   // one row = 128 B = 8 x 16 B
-            if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, accum | (uint32_t)k);
-              if (MB == 2) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16_lohi(d_tmem + BN, a_lo + box_step + 2 * k, b_lo + 2 * k, hi, idesc, accum | (uint32_t)k);
-              }
-              umma_commit(&b_empty[bs]);
-            }
-            __syncwarp();
-            accum = 1;
-            if (++bs == BS) { bs = 0; bph ^= 1; }
-          }
-          if (elect_one()) umma_commit(&s_empty[ss]);
-          __syncwarp();
-          if (++ss == SS) { ss = 0; sph ^= 1; }
-        }
-      }
-      if (elect_one()) umma_commit(&tfull[acc]);
-      __syncwarp();
-    }
-  } else {
-    const int lq = warp & 3;
-    uint8_t* stg = stage_buf + (warp - 2) * kStgBytes;
-    int it = 0, last_nt = -1;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int mt = t % P.m_tiles;
-      const int rest = t / P.m_tiles;
-      const int nt = rest % P.n_tiles;
-      const int phase = rest / P.n_tiles;
-      EpiRows R[2];
-#pragma unroll
-      for (int mb = 0; mb < 2; ++mb) {
-        if (mb < MB) {
-          const int blk = mt * MB + mb;   // blocks past the end map to samples >= B and are masked
-          epi_rows(p, blk / P.blocks_per_sample, (blk % P.blocks_per_sample) * 128, 7, phase, lq, lane, R[mb]);
-        }
-      }
-      if (nt != last_nt) { epi_load_bias<EPI>(p, bias_s, nt * BN, BN, threadIdx.x - 64); last_nt = nt; }
-      const int acc = P.double_acc ? (it & 1) : 0;
-      const uint32_t use = P.double_acc ? ((uint32_t)it >> 1) : (uint32_t)it;
-      long long tq = clock64();
-      mbar_wait(&tfull[acc], use & 1);
-      if (warp == 2) CG_DBG_ADD(5, tq);
-      tq = clock64();
-      tc_fence_after();
-      {
-        const int blk0 = mt * MB, blk1 = mt * MB + 1;
-        const int bq0 = blk0 / P.blocks_per_sample, bq1 = blk1 / P.blocks_per_sample;
-        const int s0 = p.ps_out ? p.ps_shift[(bq0 < p.B ? bq0 : 0) / p.ps_group_b] : 0;
-        const int s1 = p.ps_out ? p.ps_shift[(bq1 < p.B ? bq1 : 0) / p.ps_group_b] : 0;
-        epilogue_block<EPI>(p, tmem_base + acc * acc_stride, BN, nt * BN, R[0], bias_s, stg, lq, lane,
-                            (blk0 % P.blocks_per_sample) * 128, s0);
-        if (MB == 2)
-          epilogue_block<EPI>(p, tmem_base + acc * acc_stride + BN, BN, nt * BN, R[1], bias_s, stg, lq, lane,
-                              (blk1 % P.blocks_per_sample) * 128, s1);
-      }
-      if (warp == 2) CG_DBG_ADD(6, tq);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
 // =============================================================================================
 // rsgemm3_tc: CTA-pair (cta_group::2) version of rsgemm2. A cluster of two CTAs computes a 256-row x BN tile:
 // each CTA owns one 128-row block (its own slab, its own TMEM accumulator and epilogue) and HALF of every weight
@@ -935,7 +761,7 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   uint8_t* stage_buf = btiles + (size_t)BS * b_bytes + 512;
-  float* bias_s = reinterpret_cast<float*>(stage_buf + 4 * kStgBytes);
+  float* bias_s = reinterpret_cast<float*>(stage_buf + kEpiWarps * kStgBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -947,7 +773,7 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     prefetch_tmap(&tmW);
     for (int i = 0; i < SS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
     for (int i = 0; i < BS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc2(tmem_slot, kTmemCols);
@@ -1108,8 +934,9 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    const int lq = warp & 3;
+    const int lq = warp & 3, half = (warp - 2) >> 2;
     uint8_t* stg = stage_buf + (warp - 2) * kStgBytes;
+    uint8_t* stg_partner = stage_buf + ((warp - 2) ^ 4) * kStgBytes;
     const uint32_t tempty_leader[2] = {mapa_u32(smem_u32(&tempty[0]), 0), mapa_u32(smem_u32(&tempty[1]), 0)};
     int it = 0, last_nt = -1;
     for (int t = pair; t < total_tiles; t += npairs, ++it) {
@@ -1135,7 +962,7 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (warp == 2) CG_DBG_ADD(5, tq);
       tq = clock64();
       tc_fence_after();
-      epilogue_block<EPI>(p, tmem_base + acc * BN, BN, nt * BN, R, bias_s, stg, lq, lane,
+      epilogue_block<EPI>(p, tmem_base + acc * BN, BN, nt * BN, R, bias_s, stg, stg_partner, lq, lane, half,
                           (blk % P.blocks_per_sample) * 128, sft, need_x);
       if (warp == 2) CG_DBG_ADD(6, tq);
       tc_fence_before();
@@ -1164,7 +991,7 @@ struct WgTcParams {
   int rpt, bpt, chunks_per_sample, total_chunks, chunks_per_split, splits, stages;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmP,
                 const __grid_constant__ WgTcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1309,7 +1136,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kWgThreads, 1)
 wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmP,
                  const __grid_constant__ Wg2Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1463,7 +1290,7 @@ struct TcState {
   int sm_count = 148;
   int max_smem = 0;
   bool force_v1 = false;   // CG_TC_V1=1: per-tap boxes everywhere (A/B comparison)
-  bool use_pair = true;    // CG_TC_PAIR=0: single-CTA slab kernel instead of the cta_group::2 kernel
+  const bool use_pair = true;   // the cta_group::2 kernel serves every layer with >= 128 time rows per sample
   bool pair_short = true;  // CG_TC_PAIR_SHORT=0: per-tap single-CTA kernel for layers with < 128 time rows
   std::string err;
 };
@@ -1485,16 +1312,13 @@ static inline int tc_init(TcState* s) {
   s->sm_count = prop.multiProcessorCount;
   s->max_smem = (int)prop.sharedMemPerBlockOptin;
   if (const char* e = getenv("CG_TC_V1")) s->force_v1 = atoi(e) != 0;
-  if (const char* e = getenv("CG_TC_PAIR")) s->use_pair = atoi(e) != 0;
   if (const char* e = getenv("CG_TC_PAIR_SHORT")) s->pair_short = atoi(e) != 0;
   bool ok = true;
 #define CG_SET_SMEM(E)                                                                                                         \
   ok = ok && cudaFuncSetAttribute(tc::rsgemm_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess && \
-       cudaFuncSetAttribute(tc::rsgemm2_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess && \
        cudaFuncSetAttribute(tc::rsgemm3_tc_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess;
   CG_SET_SMEM(EPI_NONE) CG_SET_SMEM(EPI_BIAS) CG_SET_SMEM(EPI_BIAS_LRELU) CG_SET_SMEM(EPI_MASK) CG_SET_SMEM(EPI_BIAS_SIGMOID)
-  ok = ok && cudaFuncSetAttribute(tc::rsgemm2_tc_kernel<EPI_BIAS_LN_LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess &&
-       cudaFuncSetAttribute(tc::rsgemm3_tc_kernel<EPI_BIAS_LN_LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess &&
+  ok = ok && cudaFuncSetAttribute(tc::rsgemm3_tc_kernel<EPI_BIAS_LN_LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess &&
        cudaFuncSetAttribute(tc::rsgemm3_tc_kernel<EPI_PS_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) == cudaSuccess;
 #undef CG_SET_SMEM
   if (!ok ||
@@ -1583,101 +1407,6 @@ static inline bool tc_rsgemm2_supported(const RsParams& p) {
     }
   }
   return true;
-}
-
-static inline int tc_rsgemm2_launch(TcState* s, const RsParams& p, cudaStream_t stream) {
-  tc::RsTc2Params P;
-  memset(&P, 0, sizeof(P));
-  P.p = p;
-  int span = 0;
-  for (int ph = 0; ph < p.seg.nphase; ++ph) {
-    int na = 0;
-    for (int sg = 0; sg < p.seg.nseg[ph]; ++sg) {
-      int g = -1;
-      for (int i = 0; i < na; ++i) if (P.grp[ph][i].acol == p.seg.acol[ph][sg]) g = i;
-      if (g < 0) { g = na++; P.grp[ph][g].acol = p.seg.acol[ph][sg]; P.grp[ph][g].min_shift = 1 << 20; P.grp[ph][g].nseg = 0; }
-      if (p.seg.shift[ph][sg] < P.grp[ph][g].min_shift) P.grp[ph][g].min_shift = p.seg.shift[ph][sg];
-    }
-    P.ngroups[ph] = na;
-    for (int sg = 0; sg < p.seg.nseg[ph]; ++sg) {
-      int g = 0;
-      for (int i = 0; i < na; ++i) if (P.grp[ph][i].acol == p.seg.acol[ph][sg]) g = i;
-      tc::SlabGroup& G = P.grp[ph][g];
-      const int rel = p.seg.shift[ph][sg] - G.min_shift;
-      G.shift_rel[G.nseg] = (unsigned char)rel;
-      G.wk[G.nseg] = p.seg.wk[ph][sg];
-      G.nseg++;
-      if (rel > span) span = rel;
-    }
-  }
-  P.box_rows = (128 + span + 7) / 8 * 8;
-  if (P.box_rows > 256) return cg_tc_set_err("rsgemm2_tc: tap span too large for one TMA box");
-  P.box_bytes = P.box_rows * 128;
-  P.blocks_per_sample = p.Q / 128;
-  P.total_blocks = p.B * P.blocks_per_sample;
-  P.kchunks = p.Kc / 64;
-  int kiters = 0;
-  for (int ph = 0; ph < p.seg.nphase; ++ph) if (p.seg.nseg[ph] > kiters) kiters = p.seg.nseg[ph];
-  // tile shape: minimise (waves x per-tile time) under the L2 -> SMEM model (42 B/clk/SM, 4096 MAC/clk/SM)
-  double best = 1e30;
-  int bestMB = 1, bestBN = 64;
-  for (int MB = 1; MB <= 2; ++MB) {
-    for (int BN = 256; BN >= 64; BN -= 32) {
-      if (p.N % BN) continue;
-      const long long tiles = (long long)p.seg.nphase * (p.N / BN) * ((P.total_blocks + MB - 1) / MB);
-      const double waves = (double)((tiles + s->sm_count - 1) / s->sm_count);
-      const double mma_clk = MB * 128.0 * BN * 64 / 4096.0;                                   // per tap per chunk
-      const double bytes = BN * 128.0 + MB * P.box_bytes / (double)(kiters > 0 ? kiters : 1); // weights + amortised slab
-      const double l2_clk = bytes / 42.0;
-      const double smem_clk = mma_clk * (BN < 128 ? 1.5 : 1.0);                               // N=64: A re-read bound
-      double per = mma_clk > l2_clk ? mma_clk : l2_clk;
-      if (smem_clk > per) per = smem_clk;
-      const double epi = MB * BN * 6.0 * ((2 * MB * BN <= 512) ? 0.25 : 1.0) / (double)(P.kchunks * kiters);
-      const double cost = waves * (per + epi);
-      if (cost < best) { best = cost; bestMB = MB; bestBN = BN; }
-    }
-  }
-  if (p.epi == EPI_BIAS_LN_LRELU) bestBN = p.N;   // the epilogue needs whole channel rows
-  P.MB = bestMB; P.BN = bestBN;
-  P.n_tiles = p.N / P.BN;
-  P.m_tiles = (P.total_blocks + P.MB - 1) / P.MB;
-  P.double_acc = (2 * P.MB * P.BN <= 512) ? 1 : 0;
-  P.slab_bytes = P.MB * P.box_bytes;
-  P.slab_stages = 2;
-  const int b_bytes = P.BN * 128;
-  int bst = (s->max_smem - 1024 - 512 - tc::kEpiSmem - P.slab_stages * P.slab_bytes) / b_bytes;
-  if (bst > 8) bst = 8;
-  if (bst < 2) return cg_tc_set_err("rsgemm2_tc: not enough shared memory");
-  P.b_stages = bst;
-  CUtensorMap tmA, tmW;
-  if (tc_get_map3(s, p.A, p.a_rs, p.a_rows, p.B, p.a_rs, p.a_bs, P.box_rows, 1, &tmA)) return 1;
-  if (tc_get_map2(s, p.W, p.w_ld, p.N, p.w_ld, P.BN, &tmW)) return 1;
-  const int total = p.seg.nphase * P.n_tiles * P.m_tiles;
-  const int grid = total < s->sm_count ? total : s->sm_count;
-  const size_t smem = (size_t)P.slab_stages * P.slab_bytes + (size_t)bst * b_bytes + 1024 + 512 + tc::kEpiSmem;
-  static long long* dbg_buf2 = nullptr;
-  P.dbg = nullptr;
-  if (getenv("CG_TC_TIMING")) {
-    if (!dbg_buf2) cudaMalloc(&dbg_buf2, 16 * sizeof(long long));
-    cudaMemsetAsync(dbg_buf2, 0, 16 * sizeof(long long), stream);
-    P.dbg = dbg_buf2;
-  }
-  switch (p.epi) {
-    case EPI_NONE: tc::rsgemm2_tc_kernel<EPI_NONE><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
-    case EPI_BIAS: tc::rsgemm2_tc_kernel<EPI_BIAS><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
-    case EPI_BIAS_LRELU: tc::rsgemm2_tc_kernel<EPI_BIAS_LRELU><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
-    case EPI_MASK: tc::rsgemm2_tc_kernel<EPI_MASK><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
-    case EPI_BIAS_LN_LRELU: tc::rsgemm2_tc_kernel<EPI_BIAS_LN_LRELU><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
-    default: tc::rsgemm2_tc_kernel<EPI_BIAS_SIGMOID><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
-  }
-  if (P.dbg) {
-    long long h[16];
-    cudaStreamSynchronize(stream);
-    cudaMemcpy(h, dbg_buf2, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[tc2 timing] B=%d Q=%d N=%d Kc=%d epi=%d | MB=%d BN=%d tiles=%d grid=%d bst=%d dacc=%d | prod wait s_empty %lld/%lld b_empty %lld/%lld | mma wait tempty %lld/%lld s_full %lld/%lld b_full %lld/%lld | epi wait %lld/%lld work %lld/%lld\n",
-            p.B, p.Q, p.N, p.Kc, p.epi, P.MB, P.BN, total, grid, bst, P.double_acc, h[0], h[8], h[1], h[9], h[2], h[10], h[3], h[11], h[4], h[12], h[5], h[13], h[6], h[14]);
-  }
-  return 0;
 }
 
 // layer-norm can be fused into the conv epilogue when the slab kernels apply and one n-tile covers the channel row
@@ -1803,7 +1532,8 @@ static inline int tc_rsgemm_launch(TcState* s, const RsParams& p, cudaStream_t s
   if (!s->force_v1 && s->use_pair && (tc_rsgemm2_supported(p) || (s->pair_short && p.Q < 128 && p.B * p.Q >= 256 &&
                                                                 (double)p.B * p.Q * p.N * p.Kc * (p.seg.nseg[0] + p.seg.nseg[1]) >= 8e9)))
     return tc_rsgemm3_launch(s, p, stream);
-  if (!s->force_v1 && tc_rsgemm2_supported(p)) return tc_rsgemm2_launch(s, p, stream);
+  if (p.epi == EPI_BIAS_LN_LRELU || p.epi == EPI_PS_MASK || p.ps_out)
+    return cg_tc_set_err("rsgemm_tc: fused layer-norm / PhaseShuffle epilogues need the CTA-pair kernel");
   tc::RsTcParams P;
   P.p = p;
   P.BN = tc_pick_bn(p.N);
@@ -1935,7 +1665,7 @@ static inline int tc_wgrad2_launch(TcState* s, const WgParams& p, cudaStream_t s
     if (stages < 2) return cg_tc_set_err("wgrad2_tc: not enough shared memory");
     P.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-    tc::wgrad2_tc_kernel<<<items * P.splits, tc::kThreads, smem, stream>>>(tmS, tmP, P);
+    tc::wgrad2_tc_kernel<<<items * P.splits, tc::kWgThreads, smem, stream>>>(tmS, tmP, P);
   }
   return 0;
 }
@@ -1970,7 +1700,7 @@ static inline int tc_wgrad_launch(TcState* s, const WgParams& p, cudaStream_t st
     if (stages < 2) return cg_tc_set_err("wgrad_tc: not enough shared memory");
     P.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-    tc::wgrad_tc_kernel<<<tiles * P.splits, tc::kThreads, smem, stream>>>(tmS, tmP, P);
+    tc::wgrad_tc_kernel<<<tiles * P.splits, tc::kWgThreads, smem, stream>>>(tmS, tmP, P);
   }
   return 0;
 }
