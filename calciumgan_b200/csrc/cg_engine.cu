@@ -874,8 +874,8 @@ static int d_wgrad(cg_ctx* c, int Bt, int nb_bias) {
       for (int l = 1; l <= NL; ++l)
         CK(launch_colsum(c, ops.op[l - 1].X, ops.op[l - 1].out, ops.op[l - 1].rows, ops.op[l - 1].Cp, ops.op[l - 1].c_real));
   }
-  const int tot = c->dl[NL] * c->dc[NL];
-  dim3 hgrid(grid_for(tot), Bt >= 64 ? 16 : 1);
+  const int tot = c->dl[NL] * c->dcp[NL] / (16 / c->esz);
+  dim3 hgrid(grid_for(tot), Bt >= 64 ? 32 : 1);
   DISPATCH_T(c, head_wgrad_kernel<T><<<hgrid, 256, 0, c->stream>>>(
                     (const T*)c->X[NL], c->coef, dgrad(c, 10), dgrad(c, 11), Bt, nb_bias, c->dl[NL], c->dc[NL], c->dcp[NL]));
   CK(post_launch(c, "head_wgrad"));

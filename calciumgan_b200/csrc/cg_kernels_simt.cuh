@@ -464,19 +464,34 @@ __global__ void head_backward_kernel(const T* __restrict__ H5, const float* __re
   }
 }
 
-// dwd[t*c5+c] += sum_b coef[b] * X5[b,t,c];  dbd += sum_{b<nb_bias} coef[b].  grid.y splits the batch.
+// dwd[t*c5+c] += sum_b coef[b] * X5[b,t,c];  dbd += sum_{b<nb_bias} coef[b].  grid.y splits the batch; 16-byte loads.
 template <typename T>
 __global__ void head_wgrad_kernel(const T* __restrict__ X5, const float* __restrict__ coef, float* __restrict__ dwd,
                                   float* __restrict__ dbd, int Bt, int nb_bias, int w5, int c5, int Cp) {
-  const int total = w5 * c5;
+  constexpr int V = Vec16<T>::N;
+  const int nv = w5 * Cp / V;
+  const long long per_sample = (long long)w5 * Cp;
   const int per = (Bt + gridDim.y - 1) / gridDim.y;
   const int b_lo = blockIdx.y * per;
   const int b_hi = b_lo + per < Bt ? b_lo + per : Bt;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c = i % c5, t = i / c5;
-    float acc = 0.f;
-    for (int b = b_lo; b < b_hi; ++b) acc += coef[b] * Elem<T>::to_f(X5[((long long)b * w5 + t) * Cp + c]);
-    atomicAdd(&dwd[i], acc);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) {
+    const int c = (i * V) % Cp, t = (i * V) / Cp;
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+#pragma unroll 4
+    for (int b = b_lo; b < b_hi; ++b) {
+      float v[V];
+      vload<T>(X5 + b * per_sample + (long long)i * V, v);
+      const float cb = coef[b];
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] = fmaf(cb, v[e], acc[e]);
+    }
+    if (b_lo < b_hi) {
+#pragma unroll
+      for (int e = 0; e < V; ++e)
+        if (c + e < c5) atomicAdd(&dwd[t * c5 + c + e], acc[e]);
+    }
   }
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     float s = 0.f;
@@ -734,6 +749,7 @@ __global__ void dense0_forward_kernel(const float* __restrict__ z, const float* 
     if (c < nd) {
       const int j = t * nd + c;
       float acc = b0[j];
+#pragma unroll 8
       for (int k = 0; k < nd; ++k) acc = fmaf(z[b * nd + k], W0[(long long)k * nout + j], acc);
       v = lrelu(acc);
     }
@@ -752,6 +768,7 @@ __global__ void dense0_backward_kernel(const float* __restrict__ z, const T* __r
     const int j = i % nout, k = i / nout;   // k == nd -> bias row
     const int t = j / nd, c = j % nd;
     float acc = 0.f;
+#pragma unroll 8
     for (int b = 0; b < B; ++b) {
       const long long idx = ((long long)b * w0 + t) * Cp + c;
       const float dp = Elem<T>::to_f(DHG0[idx]) * lrelu_slope(Elem<T>::to_f(HG0[idx]));

@@ -722,6 +722,7 @@ struct RsTc2Params {
   RsParams p;
   int BN, n_tiles, m_tiles, MB, blocks_per_sample, total_blocks, kchunks;
   int box_rows, box_bytes, slab_bytes, slab_stages, b_stages, double_acc;
+  int dbg_nk;           // timing experiment: K steps per chunk (0 = all)
   int tps;              // taps per weight stage (pair kernel): more MMAs per barrier round-trip for narrow N
   int per_tap;          // 1: rows per sample < 128 -> no slab reuse: a slab stage holds one 128-row box PER TAP (tps boxes)
   int rpt, bpt, rpt_log2;
@@ -859,6 +860,8 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int ss = 0, bs = 0;
       uint32_t sph = 0, bph = 0;
       int it = 0;
+      int nk_last = (p.k_real - (P.kchunks - 1) * 64 + 15) >> 4;
+      if (nk_last < 1 || nk_last > 4) nk_last = 4;
       for (int t = pair; t < total_tiles; t += npairs, ++it) {
         const int phase = (t / P.m_tiles) / P.n_tiles;
         const int acc = it & 1;
@@ -869,6 +872,8 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t d_tmem = tmem_base + acc * BN;
         uint32_t accum = 0;
         for (int kc = 0; kc < P.kchunks; ++kc) {
+          // K = 16 steps of this 64-channel chunk that hold real channels (the rest multiplies exact zeros: 102 -> 7 of 8)
+          const int nk = P.dbg_nk ? P.dbg_nk : (kc == P.kchunks - 1 ? nk_last : 4);
           if (PT) {
             const int nseg = p.seg.nseg[phase];
             for (int s = 0; s < nseg; s += TPS) {
@@ -884,7 +889,7 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const uint32_t bj = b_lo + j * tap_step;
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
-                    umma2_bf16_lohi(d_tmem, a_lo + 2 * k, bj + 2 * k, hi, idesc, accum | (uint32_t)(j | k));
+                    if (k < nk) umma2_bf16_lohi(d_tmem, a_lo + 2 * k, bj + 2 * k, hi, idesc, accum | (uint32_t)(j | k));
                 }
                 umma2_commit_mc(&b_empty[bs]);
                 umma2_commit_mc(&s_empty[ss]);
@@ -916,7 +921,7 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const uint32_t bj = b_lo + j * tap_step;
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
-                    umma2_bf16_lohi(d_tmem, a_lo + 2 * k, bj + 2 * k, hi, idesc, accum | (uint32_t)(j | k));
+                    if (k < nk) umma2_bf16_lohi(d_tmem, a_lo + 2 * k, bj + 2 * k, hi, idesc, accum | (uint32_t)(j | k));
                 }
                 umma2_commit_mc(&b_empty[bs]);
               }
@@ -1488,6 +1493,7 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   if (P.tps > 6) P.tps = 6;
   if (P.per_tap && P.tps > 3) P.tps = 3;
   if (const char* e = getenv("CG_TC_TPS")) P.tps = atoi(e);
+  if (const char* e = getenv("CG_TC_NK")) P.dbg_nk = atoi(e);
   if (P.per_tap) { P.slab_bytes = P.tps * tc::kABytes; P.slab_stages = 3; }
   const int b_bytes = P.tps * P.BN * 64;
   int bst = (s->max_smem - 1024 - 512 - tc::kEpiSmem - P.slab_stages * P.slab_bytes) / b_bytes;
