@@ -290,6 +290,19 @@ def main():
     kernels = {'wgrad2_tc_kernel': {'achieved_tflops': ach_w, 'frac': ach_w / peak_tf, 'ms_per_step': w['ms'] / 2,
                                    'launches_per_step': w['launches'] / 2},
                'gemm_share_of_step': (g['ms'] + w['ms']) / 2 / ms_per_step}
+    hd = rep.get('head')
+    if hd and hd['launches']:
+      # HBM-bound generator head (dense + sigmoid + fused interpolation), algorithmic bytes per step:
+      # critic sub-steps read activations (rows x 128 bf16) + the real batch (rows x 102 fp32) and write fake + x_hat
+      # (2 x rows x 128 bf16); the generator step reads activations and writes fake bf16 + fake fp32.
+      rows = B * 2048
+      nc = hparams.n_critic
+      step_bytes = nc * rows * (128 * 2 + 102 * 4 + 2 * 128 * 2) + rows * (128 * 2 + 128 * 2 + 102 * 4)
+      hbm = float(peaks.get('hbm_gbs', 6650.0))
+      gbs = step_bytes * 2 / (hd['ms'] * 1e-3) / 1e9
+      kernels['ghead_tc_kernel'] = {'bound': 'hbm', 'achieved_gbs': gbs, 'peak_gbs': hbm, 'frac': gbs / hbm,
+                                    'ms_per_step': hd['ms'] / 2, 'launches_per_step': hd['launches'] / 2,
+                                    'bytes_per_step': step_bytes}
 
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -723,6 +723,7 @@ struct RsTc2Params {
   int BN, n_tiles, m_tiles, MB, blocks_per_sample, total_blocks, kchunks;
   int box_rows, box_bytes, slab_bytes, slab_stages, b_stages, double_acc;
   int dbg_nk;           // timing experiment: K steps per chunk (0 = all)
+  int dbg_flags;        // timing experiment (slab mode): 1 no epilogue, 2 no weight loads, 4 no activation loads
   int tps;              // taps per weight stage (pair kernel): more MMAs per barrier round-trip for narrow N
   int per_tap;          // 1: rows per sample < 128 -> no slab reuse: a slab stage holds one 128-row box PER TAP (tps boxes)
   int rpt, bpt, rpt_log2;
@@ -830,20 +831,26 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const SlabGroup& G = P.grp[phase][g];
           mbar_wait(&s_empty[ss], sph ^ 1);
           if (elect_one()) {
-            if (rank == 0) mbar_expect_tx(&s_full[ss], (uint32_t)(2 * P.slab_bytes));
-            tma2_load_3d(slabs + (size_t)ss * P.slab_bytes, &tmA, mapa_u32(smem_u32(&s_full[ss]), 0), G.acol + kc * 64,
-                         q0 + G.min_shift, b);
+            if (P.dbg_flags & 4) { if (rank == 0) mbar_arrive(&s_full[ss]); }   // timing experiment: no activation loads
+            else {
+              if (rank == 0) mbar_expect_tx(&s_full[ss], (uint32_t)(2 * P.slab_bytes));
+              tma2_load_3d(slabs + (size_t)ss * P.slab_bytes, &tmA, mapa_u32(smem_u32(&s_full[ss]), 0), G.acol + kc * 64,
+                           q0 + G.min_shift, b);
+            }
           }
           if (++ss == SS) { ss = 0; sph ^= 1; }
           for (int s = 0; s < G.nseg; s += TPS) {
             const int cnt = G.nseg - s < TPS ? G.nseg - s : TPS;
             mbar_wait(&b_empty[bs], bph ^ 1);
             if (elect_one()) {
-              if (rank == 0) mbar_expect_tx(&b_full[bs], (uint32_t)(2 * cnt * tap_bytes));
-              const uint32_t bar = mapa_u32(smem_u32(&b_full[bs]), 0);
-              for (int j = 0; j < cnt; ++j)
-                tma2_load_2d(btiles + (size_t)bs * b_bytes + (size_t)j * tap_bytes, &tmW, bar, G.wk[s + j] + kc * 64,
-                             nt * BN + (int)rank * (BN / 2));
+              if (P.dbg_flags & 2) { if (rank == 0) mbar_arrive(&b_full[bs]); }   // timing experiment: no weight loads
+              else {
+                if (rank == 0) mbar_expect_tx(&b_full[bs], (uint32_t)(2 * cnt * tap_bytes));
+                const uint32_t bar = mapa_u32(smem_u32(&b_full[bs]), 0);
+                for (int j = 0; j < cnt; ++j)
+                  tma2_load_2d(btiles + (size_t)bs * b_bytes + (size_t)j * tap_bytes, &tmW, bar, G.wk[s + j] + kc * 64,
+                               nt * BN + (int)rank * (BN / 2));
+              }
             }
             if (++bs == BS) { bs = 0; bph ^= 1; }
           }
@@ -916,6 +923,7 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tc_fence_after();
               const uint32_t b_lo = b_lo0 + bs * b_step;
               if (elect_one()) {
+                const long long tm0 = clock64();
                 for (int j = 0; j < cnt; ++j) {
                   const uint32_t a_lo = sl_lo + (uint32_t)G.shift_rel[s + j] * 8;
                   const uint32_t bj = b_lo + j * tap_step;
@@ -923,7 +931,13 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   for (int k = 0; k < 4; ++k)
                     if (k < nk) umma2_bf16_lohi(d_tmem, a_lo + 2 * k, bj + 2 * k, hi, idesc, accum | (uint32_t)(j | k));
                 }
+                const long long tm1 = clock64();
                 umma2_commit_mc(&b_empty[bs]);
+                if (P.dbg && blockIdx.x == 0) {   // issue time of the MMAs / of the commit of one weight stage
+                  atomicAdd((unsigned long long*)&P.dbg[0], (unsigned long long)(tm1 - tm0));
+                  atomicAdd((unsigned long long*)&P.dbg[1], (unsigned long long)(clock64() - tm1));
+                  atomicAdd((unsigned long long*)&P.dbg[8], 1ull);
+                }
               }
               __syncwarp();
               accum = 1;
@@ -967,8 +981,9 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (warp == 2) CG_DBG_ADD(5, tq);
       tq = clock64();
       tc_fence_after();
-      epilogue_block<EPI>(p, tmem_base + acc * BN, BN, nt * BN, R, bias_s, stg, stg_partner, lq, lane, half,
-                          (blk % P.blocks_per_sample) * 128, sft, need_x);
+      if (!(P.dbg_flags & 1))   // timing experiment bit 1: no epilogue
+        epilogue_block<EPI>(p, tmem_base + acc * BN, BN, nt * BN, R, bias_s, stg, stg_partner, lq, lane, half,
+                            (blk % P.blocks_per_sample) * 128, sft, need_x);
       if (warp == 2) CG_DBG_ADD(6, tq);
       tc_fence_before();
       __syncwarp();
@@ -1490,10 +1505,11 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   if (const char* e = getenv("CG_TC_STAGE_CLK")) stage_clk = atoi(e);
   P.tps = (stage_clk + 2 * P.BN - 1) / (2 * P.BN);
   if (P.tps < 1) P.tps = 1;
-  if (P.tps > 6) P.tps = 6;
+  if (P.tps > 6) P.tps = P.BN <= 64 ? 12 : 6;   // N = 64: a whole 12-tap parity group per weight stage (measured 140 -> 131 us on conv1)
   if (P.per_tap && P.tps > 3) P.tps = 3;
   if (const char* e = getenv("CG_TC_TPS")) P.tps = atoi(e);
   if (const char* e = getenv("CG_TC_NK")) P.dbg_nk = atoi(e);
+  if (const char* e = getenv("CG_TC_DBG")) P.dbg_flags = atoi(e);
   if (P.per_tap) { P.slab_bytes = P.tps * tc::kABytes; P.slab_stages = 3; }
   const int b_bytes = P.tps * P.BN * 64;
   int bst = (s->max_smem - 1024 - 512 - tc::kEpiSmem - P.slab_stages * P.slab_bytes) / b_bytes;
@@ -1528,8 +1544,8 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
     long long h[16];
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, dbg_buf3, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[tc3 timing] B=%d Q=%d N=%d Kc=%d epi=%d | BN=%d tps=%d tiles=%d pairs=%d sst=%d bst=%d pt=%d | total %lld clk | mma wait tempty %lld/%lld s_full %lld/%lld b_full %lld/%lld | epi wait %lld/%lld work %lld/%lld\n",
-            p.B, p.Q, p.N, p.Kc, p.epi, P.BN, P.tps, total, npairs, P.slab_stages, bst, P.per_tap, h[7], h[2], h[10], h[3], h[11], h[4], h[12], h[5], h[13], h[6], h[14]);
+    fprintf(stderr, "[tc3 timing] B=%d Q=%d N=%d Kc=%d epi=%d | BN=%d tps=%d tiles=%d pairs=%d sst=%d bst=%d pt=%d | total %lld clk | mma wait tempty %lld/%lld s_full %lld/%lld b_full %lld/%lld issue %lld commit %lld /%lld | epi wait %lld/%lld work %lld/%lld\n",
+            p.B, p.Q, p.N, p.Kc, p.epi, P.BN, P.tps, total, npairs, P.slab_stages, bst, P.per_tap, h[7], h[2], h[10], h[3], h[11], h[4], h[12], h[0], h[1], h[8], h[5], h[13], h[6], h[14]);
   }
   return 0;
 }
