@@ -13,7 +13,7 @@ FP32, BF16 = 0, 1
 NUM_SCALARS = 16
 S_DIS_LOSS, S_GP, S_REAL_LOSS, S_FAKE_LOSS, S_GEN_LOSS = 0, 1, 2, 3, 4
 S_MET_MIN, S_MET_MAX, S_MET_MEAN, S_MET_STD = 5, 6, 7, 8
-FLAG_NO_UPDATE, FLAG_NO_SYNC, FLAG_SAME_REAL = 1, 2, 4
+FLAG_NO_UPDATE, FLAG_NO_SYNC, FLAG_SAME_REAL, FLAG_NO_FAKE32 = 1, 2, 4, 8
 
 
 class CgConfig(C.Structure):

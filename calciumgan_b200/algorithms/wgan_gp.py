@@ -118,7 +118,8 @@ class WGAN_GP(GAN):
     scal = eng.scalars_tensor()
     for i in range(nc):
       eng.critic_step(real, None if noise is None else noise[i], None if alpha is None else alpha[i],
-                      None if shifts is None else shifts[12 * i:12 * i + 12], update=False, sync=False, same_real=i > 0)
+                      None if shifts is None else shifts[12 * i:12 * i + 12], update=False, sync=False, same_real=i > 0,
+                      want_fake32=False)   # the generator step below rewrites the fp32 output before anything reads it
       hist[i].copy_(scal)
       self._allreduce_buckets(dist, L.DISCRIMINATOR)
       eng.apply_update(L.DISCRIMINATOR)

@@ -1038,7 +1038,7 @@ extern "C" int cg_critic_step(cg_ctx* c, const float* real, int B, const float* 
   CK(check_batch(c, B));
   int32_t shbuf[12];
   CK(prep_random(c, B, noise, &alpha, sh, shbuf, 12));
-  CK(critic_step_impl(c, real, B, noise, alpha, sh, flags, 0, (flags & CG_FLAG_SAME_REAL) != 0));
+  CK(critic_step_impl(c, real, B, noise, alpha, sh, flags, 0, (flags & CG_FLAG_SAME_REAL) != 0, !(flags & CG_FLAG_NO_FAKE32)));
   return fetch_scalars(c, 0, flags, scalars_host);
 }
 

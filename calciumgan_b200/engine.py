@@ -213,7 +213,8 @@ class Engine(object):
     self.set_opt_state(which, None, None, step)
 
   # ---------------------------------------------------------------- hot path
-  def critic_step(self, real, noise=None, alpha=None, shifts=None, update=True, sync=True, same_real=False):
+  def critic_step(self, real, noise=None, alpha=None, shifts=None, update=True, sync=True, same_real=False,
+                  want_fake32=True):
     self._use_stream()
     real = self.to_device(real)
     B = real.shape[0]
@@ -221,6 +222,7 @@ class Engine(object):
     alpha = self.to_device(alpha).reshape(-1) if alpha is not None else None
     sh = self._shifts(shifts, 12)
     flags = (0 if update else L.FLAG_NO_UPDATE) | (0 if sync else L.FLAG_NO_SYNC) | (L.FLAG_SAME_REAL if same_real else 0)
+    flags |= 0 if want_fake32 else L.FLAG_NO_FAKE32
     L.check(self.lib.cg_critic_step(self.ctx, self._ptr(real), B, self._ptr(noise), self._ptr(alpha),
                                     sh[0] if sh else None, flags, self._scal))
     return np.array(self._scal[:], np.float32) if sync else None

@@ -70,8 +70,10 @@ enum {
 enum {
   CG_FLAG_NO_UPDATE = 1,   /* leave gradients in the flat buffer, do not run Adam (DP host allreduces first) */
   CG_FLAG_NO_SYNC = 2,     /* do not copy scalars back / synchronise (scalars_host may be NULL) */
-  CG_FLAG_SAME_REAL = 4    /* real_dev holds the same batch as in the previous cg_critic_step (wgan_gp.py:85-86):
+  CG_FLAG_SAME_REAL = 4,   /* real_dev holds the same batch as in the previous cg_critic_step (wgan_gp.py:85-86):
                               skip its conversion to the compute type */
+  CG_FLAG_NO_FAKE32 = 8    /* cg_critic_step: do not materialise the fp32 generator output (cg_fake_ptr is then stale);
+                              the critic sub-steps of a train step only need the compute-type copies */
 };
 
 int cg_version(void);

@@ -39,8 +39,8 @@ class StubEngine(object):
   def scalars_tensor(self):
     return self.scal
 
-  def critic_step(self, real, noise, alpha, shifts, update=True, sync=True, same_real=False):
-    assert not update and not sync
+  def critic_step(self, real, noise, alpha, shifts, update=True, sync=True, same_real=False, want_fake32=True):
+    assert not update and not sync and not want_fake32
     self.seen_shifts.append(None if shifts is None else np.asarray(shifts).copy())
     self.g[1][:] = float(real.sum()) * torch.arange(1, 7)       # rank-dependent "gradient"
     self.scal[0], self.scal[1] = 10.0 + self.rank, 1.0 + self.rank
