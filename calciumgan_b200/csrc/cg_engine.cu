@@ -710,14 +710,20 @@ static int g_backward(cg_ctx* c, int B) {
     if (c->cfg.layer_norm) {
       const int nvec_b = c->gcp[i] / (16 / c->esz);
       const int lpr_b = nvec_b > 16 ? 32 : (nvec_b > 8 ? 16 : 8);
-      static const int lnb_cap = getenv("CG_LNB_CAP") ? atoi(getenv("CG_LNB_CAP")) : 148 * 2;
-      const int blocks = grid_for(rows * lpr_b, 256, lnb_cap);
-#define CG_LNB(LPRV)                                                                                                 \
-  DISPATCH_T(c, ln_lrelu_backward_kernel<T, LPRV><<<blocks, 256, 2 * c->gcp[i] * sizeof(float), c->stream>>>(          \
+      const int maxv = (nvec_b + lpr_b - 1) / lpr_b;   // channel vectors per lane: sizes the kernel's register arrays
+      if (maxv > 4) return set_err("ln_lrelu_backward: more than 4 channel vectors per lane (Cp %d)", c->gcp[i]);
+      const int blocks = grid_for(rows * lpr_b, 256, 148 * (maxv <= 1 ? 6 : 3));
+#define CG_LNB(LPRV, MV)                                                                                              \
+  DISPATCH_T(c, (ln_lrelu_backward_kernel<T, LPRV, MV>)<<<blocks, 256, 2 * c->gcp[i] * sizeof(float), c->stream>>>(    \
                     (const T*)c->DHG[i], (const T*)c->AG[i], (const T*)c->HG[i], c->MU[i], c->RSTD[i],               \
                     gparam(c, c->g_gam[i]), (T*)c->DAG[i], ggrad(c, c->g_gam[i]), ggrad(c, c->g_bet[i]), rows,       \
                     c->gc[i], c->gcp[i]))
-      if (lpr_b == 32) CG_LNB(32); else if (lpr_b == 16) CG_LNB(16); else CG_LNB(8);
+      if (lpr_b == 8) CG_LNB(8, 1);
+      else if (lpr_b == 16) CG_LNB(16, 1);
+      else if (maxv == 1) CG_LNB(32, 1);
+      else if (maxv == 2) CG_LNB(32, 2);
+      else if (maxv == 3) CG_LNB(32, 3);
+      else CG_LNB(32, 4);
 #undef CG_LNB
       CK(post_launch(c, "ln_bwd"));
     } else {

@@ -639,13 +639,12 @@ __global__ void __launch_bounds__(256) ln_lrelu_forward_kernel(const T* __restri
 // backward of LN + LeakyReLU: DA, dgamma, dbeta. Same sub-warp row layout as the forward kernel; every lane owns fixed
 // channel vectors, so dgamma / dbeta accumulate in registers over all rows of the thread and are reduced once per
 // block through shared memory (the first version did two shared atomics per element).
-template <typename T, int LPR>
-__global__ void __launch_bounds__(256) ln_lrelu_backward_kernel(
+template <typename T, int LPR, int MAXV>   // MAXV >= ceil((Cp / V) / LPR): channel vectors per lane (register arrays)
+__global__ void __launch_bounds__(256, MAXV <= 2 ? 2 : 1) ln_lrelu_backward_kernel(
     const T* __restrict__ DH, const T* __restrict__ A, const T* __restrict__ H, const float* __restrict__ mu_in,
     const float* __restrict__ rstd_in, const float* __restrict__ gamma, T* __restrict__ DA,
     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C, int Cp) {
   constexpr int V = Vec16<T>::N;
-  constexpr int MAXV = 4;
   constexpr int RPW = 32 / LPR;
   extern __shared__ float sm[];   // [2 * Cp]
   for (int i = threadIdx.x; i < 2 * Cp; i += blockDim.x) sm[i] = 0.f;
