@@ -1164,7 +1164,8 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
   const WgParams& p = P.p;
   const int BN = P.BN;
   const int stages = P.stages;
-  const int stage_bytes = P.slab_bytes + BN * 128;
+  const int p_blocks = (BN + 63) >> 6;                  // 64-column MN-major blocks of the P tile (BN = 160 loads 3, uses 2.5)
+  const int stage_bytes = P.slab_bytes + p_blocks * 8192;
   uint8_t* tiles = smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
   uint64_t* empty = full + stages;
@@ -1216,7 +1217,7 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
         uint8_t* sa = tiles + (size_t)stage * stage_bytes;
         mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
         tma_load_3d(sa, &tmS, &full[stage], scol, q0 + P.g_min_shift[g], b0);
-        for (int j = 0; j < BN / 64; ++j)
+        for (int j = 0; j < p_blocks; ++j)
           tma_load_3d(sa + P.slab_bytes + j * 8192, &tmP, &full[stage], n_begin + j * 64, q0, b0);
       }
       if (++stage == stages) { stage = 0; ph ^= 1; }
@@ -1659,13 +1660,24 @@ static inline int tc_wgrad2_launch(TcState* s, const WgParams& p, cudaStream_t s
   CUtensorMap tmS, tmP;
   if (tc_get_map3(s, p.S, p.s_rs, p.s_rows, p.B, p.s_rs, p.s_bs, P.box_rows, 1, &tmS)) return 1;
   if (tc_get_map3(s, p.P, p.p_rs, p.Q, p.B, p.p_rs, p.p_bs, 64, 1, &tmP)) return 1;
+  // 256 < Np <= 512 with Np/2 a multiple of 32 (320 -> 2 x 160): two equal n-tiles in ONE launch instead of a 256-wide
+  // launch plus a 64-wide remainder launch that runs shared-memory bound (measured 33% tensor-pipe activity)
+  const bool halves = p.Np > 256 && p.Np <= 512 && (p.Np / 2) % 32 == 0 && !getenv("CG_WG_NO_HALVES");
   for (int pass = 0; pass < 2; ++pass) {
     const int full_tiles = p.Np / 256, rem = p.Np % 256;
-    if (pass == 0) { if (!full_tiles) continue; P.BN = 256; P.n_origin = 0; P.n_tiles = full_tiles; }
+    if (halves) { if (pass) continue; P.BN = p.Np / 2; P.n_origin = 0; P.n_tiles = 2; }
+    else if (pass == 0) { if (!full_tiles) continue; P.BN = 256; P.n_origin = 0; P.n_tiles = full_tiles; }
     else { if (!rem) continue; P.BN = rem; P.n_origin = full_tiles * 256; P.n_tiles = 1; }
     int max_acc = 512 / P.BN;
     if (max_acc > 8) max_acc = 8;
     P.taps_per_cta = 2 * max_acc;
+    {   // same number of tap subsets, but balanced (12 taps, 8 per CTA: 8 + 4 -> 6 + 6): every CTA loads the same bytes
+      int most = 0;
+      for (int g = 0; g < P.ngroups; ++g) if (P.g_nseg[g] > most) most = P.g_nseg[g];
+      const int nsub = (most + P.taps_per_cta - 1) / P.taps_per_cta;
+      const int even = ((most + nsub - 1) / nsub + 1) / 2 * 2;
+      if (even < P.taps_per_cta && !getenv("CG_WG_NO_BALANCE")) P.taps_per_cta = even;
+    }
     int items = 0;
     for (int g = 0; g < 2; ++g) {
       P.nsub[g] = g < P.ngroups ? (P.g_nseg[g] + P.taps_per_cta - 1) / P.taps_per_cta : 0;
@@ -1681,7 +1693,7 @@ static inline int tc_wgrad2_launch(TcState* s, const WgParams& p, cudaStream_t s
     if (splits < 1) splits = 1;
     P.chunks_per_split = (P.total_chunks + splits - 1) / splits;
     P.splits = (P.total_chunks + P.chunks_per_split - 1) / P.chunks_per_split;
-    const int stage_bytes = P.slab_bytes + P.BN * 128;
+    const int stage_bytes = P.slab_bytes + ((P.BN + 63) / 64) * 8192;
     int stages = (s->max_smem - 2048) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) return cg_tc_set_err("wgrad2_tc: not enough shared memory");
