@@ -1150,6 +1150,8 @@ struct Wg2Params {
   int g_acol[2], g_min_shift[2], g_nseg[2];
   unsigned char g_rel[2][32];                         // shift - min_shift of tap s of group g
   unsigned char g_seg[2][32];                         // original tap index (output slice)
+  int swap;   // 1: operands exchanged (slab = output gradient with negated shifts, P tile = layer input at column g_acol):
+              //    accumulator rows = output channels, columns = input channels, stored transposed
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -1209,7 +1211,8 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
   if (warp == 0) {
     int stage = 0;
     uint32_t ph = 0;
-    const int scol = P.g_acol[g] + mb * 64;
+    const int scol = (P.swap ? 0 : P.g_acol[g]) + mb * 64;
+    const int pcol = (P.swap ? P.g_acol[g] : 0) + n_begin;
     for (int ch = ch_begin; ch < ch_end; ++ch) {
       const int b0 = ch / P.chunks_per_sample, q0 = (ch % P.chunks_per_sample) * 64;
       mbar_wait(&empty[stage], ph ^ 1);
@@ -1218,7 +1221,7 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
         mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
         tma_load_3d(sa, &tmS, &full[stage], scol, q0 + P.g_min_shift[g], b0);
         for (int j = 0; j < p_blocks; ++j)
-          tma_load_3d(sa + P.slab_bytes + j * 8192, &tmP, &full[stage], n_begin + j * 64, q0, b0);
+          tma_load_3d(sa + P.slab_bytes + j * 8192, &tmP, &full[stage], pcol + j * 64, q0, b0);
       }
       if (++stage == stages) { stage = 0; ph ^= 1; }
     }
@@ -1274,7 +1277,14 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + a * BN + c0, v);
         tmem_ld_wait();
-        if (row_ok) {
+        if (row_ok && P.swap) {   // transposed store: element (m = output channel, n = input channel) -> dW[seg][n][m];
+                                  // consecutive lanes hold consecutive m, so every warp instruction is one 128-byte line
+          const int n0 = n_begin + c0;
+          float* dcol = p.dW + ((long long)seg * p.n_real + n0) * p.m_real + m;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.n_real) atomicAdd(dcol + (long long)j * p.m_real, __uint_as_float(v[j]));
+        } else if (row_ok) {
           const int n0 = n_begin + c0;
           if (vec_ok && n0 + 32 <= p.n_real) {
 #pragma unroll
@@ -1626,9 +1636,25 @@ static inline bool tc_wgrad2_supported(const WgParams& p) {
   return true;
 }
 
-static inline int tc_wgrad2_launch(TcState* s, const WgParams& p, cudaStream_t stream) {
+// Output-channel count 64 makes the N = 64 MMA shared-memory bound (A 4 KB + B 2 KB per 128 x 64 x 16 MACs: 48 clk for
+// 32 clk of math). Exchanging the operands -- dW[k][ci][co] = sum_q' X[q'][ci] * dY[q' - shift_k][co] -- puts the 64
+// output channels of TWO taps on M = 128 and the (>= 128) input channels on N: 8 KB per 128 x 128 x 16 MACs = math rate.
+static inline bool tc_wgrad2_swap_pays(const WgParams& p) { return p.Np == 64 && p.Mp >= 128 && p.Mp <= 256 && !getenv("CG_WG_NO_SWAP"); }
+static inline WgParams tc_wgrad2_swapped(const WgParams& p) {
+  WgParams w = p;
+  w.S = p.P; w.s_bs = p.p_bs; w.s_rs = p.p_rs; w.s_rows = p.Q;
+  w.P = p.S; w.p_bs = p.s_bs; w.p_rs = p.s_rs;
+  w.m_real = p.n_real; w.n_real = p.m_real; w.Mp = p.Np; w.Np = p.Mp;
+  for (int k = 0; k < p.nseg; ++k) w.shift[k] = (short)(-p.shift[k]);   // scol[] keeps naming the parity group = P-tile column origin
+  return w;
+}
+
+static inline int tc_wgrad2_launch(TcState* s, const WgParams& p_in, cudaStream_t stream) {
   tc::Wg2Params P;
   memset(&P, 0, sizeof(P));
+  const bool swap = tc_wgrad2_swap_pays(p_in);
+  const WgParams p = swap ? tc_wgrad2_swapped(p_in) : p_in;
+  P.swap = swap ? 1 : 0;
   P.p = p;
   P.mblocks = p.Mp / 64;
   // tap groups (same column offset = same parity), taps sorted by shift so LBO >= 0
@@ -1659,7 +1685,7 @@ static inline int tc_wgrad2_launch(TcState* s, const WgParams& p, cudaStream_t s
   P.total_chunks = p.B * P.chunks_per_sample;
   CUtensorMap tmS, tmP;
   if (tc_get_map3(s, p.S, p.s_rs, p.s_rows, p.B, p.s_rs, p.s_bs, P.box_rows, 1, &tmS)) return 1;
-  if (tc_get_map3(s, p.P, p.p_rs, p.Q, p.B, p.p_rs, p.p_bs, 64, 1, &tmP)) return 1;
+  if (tc_get_map3(s, p.P, p.p_rs, swap ? p_in.s_rows : p.Q, p.B, p.p_rs, p.p_bs, 64, 1, &tmP)) return 1;
   // 256 < Np <= 512 with Np/2 a multiple of 32 (320 -> 2 x 160): two equal n-tiles in ONE launch instead of a 256-wide
   // launch plus a 64-wide remainder launch that runs shared-memory bound (measured 33% tensor-pipe activity)
   const bool halves = p.Np > 256 && p.Np <= 512 && (p.Np / 2) % 32 == 0 && !getenv("CG_WG_NO_HALVES");
