@@ -88,11 +88,13 @@ ghead_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     mbar_init(r_full, 1);
     fence_barrier_init();
   }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * kHeadCp);
+  griddep_wait();      // programmatic dependent launch: the prologue above overlaps the predecessor's tail
+  griddep_launch();
   if (threadIdx.x >= 64 && threadIdx.x < 64 + kHeadCp) {
     const int n = threadIdx.x - 64;
     bias_s[n] = n < P.C ? __ldg(&P.bias[n]) : 0.f;
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * kHeadCp);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -300,6 +302,6 @@ static inline int tc_ghead_launch(TcState* s, const GHeadArgs& a, cudaStream_t s
   if (a.xhat16 && tc_get_map2(s, a.xhat16, a.Cp, rows, a.Cp, 128, &tmX)) return 1;
   const int grid = P.tiles < s->sm_count ? P.tiles : s->sm_count;
   const size_t smem = fixed + (size_t)as * tc::kHeadTileBytes;
-  tc::ghead_tc_kernel<<<grid, tc::kHeadThreads, smem, stream>>>(tmA, tmW, tmF, tmX, P);
+  tc_launch(tc::ghead_tc_kernel, grid, tc::kHeadThreads, smem, stream, tmA, tmW, tmF, tmX, P);
   return 0;
 }

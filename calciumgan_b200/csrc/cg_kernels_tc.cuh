@@ -16,6 +16,7 @@
 #include <map>
 #include <string>
 #include <tuple>
+#include <utility>
 
 #include "cg_common.cuh"
 
@@ -101,6 +102,11 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, u
       ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accum)
       : "memory");
 }
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (and
+// run its prologue: barrier init, TMEM allocation, tensor-map prefetch) while its predecessor in the stream drains;
+// griddep_wait() blocks until the predecessor has completed and its writes are visible (no-op without the attribute).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // one elected lane of a fully converged warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -783,6 +789,8 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   cluster_sync_all();          // barriers of both CTAs initialised before any remote arrive / TMA completion
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();              // everything above overlapped the predecessor's tail; global memory is touched below
+  griddep_launch();
 
   const int total_tiles = p.seg.nphase * P.n_tiles * P.m_tiles;   // m_tiles = ceil(total_blocks / 2)
   const bool PT = P.per_tap != 0;
@@ -1207,6 +1215,8 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch();
 
   if (warp == 0) {
     int stage = 0;
@@ -1409,6 +1419,20 @@ static inline int tc_get_map2(TcState* s, const void* base, long long cols, long
   return 0;
 }
 
+// kernel launch with the programmatic-dependent-launch attribute (see griddep_wait)
+template <typename... KArgs, typename... Args>
+static inline void tc_launch(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
+  static const bool pdl = getenv("CG_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface through cudaGetLastError in post_launch
+}
+
 static inline bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
 // rows of one 128-row M tile must come from whole samples (Q | 128) or one sample (128 | Q)
@@ -1543,13 +1567,13 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   const int grid = 2 * npairs;
   const size_t smem = (size_t)P.slab_stages * P.slab_bytes + (size_t)bst * b_bytes + 1024 + 512 + tc::kEpiSmem;
   switch (p.epi) {
-    case EPI_NONE: tc::rsgemm3_tc_kernel<EPI_NONE><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
-    case EPI_BIAS: tc::rsgemm3_tc_kernel<EPI_BIAS><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
-    case EPI_BIAS_LRELU: tc::rsgemm3_tc_kernel<EPI_BIAS_LRELU><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
-    case EPI_MASK: tc::rsgemm3_tc_kernel<EPI_MASK><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
-    case EPI_BIAS_LN_LRELU: tc::rsgemm3_tc_kernel<EPI_BIAS_LN_LRELU><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
-    case EPI_PS_MASK: tc::rsgemm3_tc_kernel<EPI_PS_MASK><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
-    default: tc::rsgemm3_tc_kernel<EPI_BIAS_SIGMOID><<<grid, tc::kThreads, smem, stream>>>(tmA, tmW, P); break;
+    case EPI_NONE: tc_launch(tc::rsgemm3_tc_kernel<EPI_NONE>, grid, tc::kThreads, smem, stream, tmA, tmW, P); break;
+    case EPI_BIAS: tc_launch(tc::rsgemm3_tc_kernel<EPI_BIAS>, grid, tc::kThreads, smem, stream, tmA, tmW, P); break;
+    case EPI_BIAS_LRELU: tc_launch(tc::rsgemm3_tc_kernel<EPI_BIAS_LRELU>, grid, tc::kThreads, smem, stream, tmA, tmW, P); break;
+    case EPI_MASK: tc_launch(tc::rsgemm3_tc_kernel<EPI_MASK>, grid, tc::kThreads, smem, stream, tmA, tmW, P); break;
+    case EPI_BIAS_LN_LRELU: tc_launch(tc::rsgemm3_tc_kernel<EPI_BIAS_LN_LRELU>, grid, tc::kThreads, smem, stream, tmA, tmW, P); break;
+    case EPI_PS_MASK: tc_launch(tc::rsgemm3_tc_kernel<EPI_PS_MASK>, grid, tc::kThreads, smem, stream, tmA, tmW, P); break;
+    default: tc_launch(tc::rsgemm3_tc_kernel<EPI_BIAS_SIGMOID>, grid, tc::kThreads, smem, stream, tmA, tmW, P); break;
   }
   if (P.dbg) {
     long long h[16];
@@ -1725,7 +1749,7 @@ static inline int tc_wgrad2_launch(TcState* s, const WgParams& p_in, cudaStream_
     if (stages < 2) return cg_tc_set_err("wgrad2_tc: not enough shared memory");
     P.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-    tc::wgrad2_tc_kernel<<<items * P.splits, tc::kWgThreads, smem, stream>>>(tmS, tmP, P);
+    tc_launch(tc::wgrad2_tc_kernel, items * P.splits, tc::kWgThreads, smem, stream, tmS, tmP, P);
   }
   return 0;
 }
