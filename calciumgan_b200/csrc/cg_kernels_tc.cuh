@@ -1423,8 +1423,7 @@ static inline int tc_get_map2(TcState* s, const void* base, long long cols, long
 template <typename... KArgs, typename... Args>
 static inline void tc_launch(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
   static const bool pdl = getenv("CG_NO_PDL") == nullptr;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
