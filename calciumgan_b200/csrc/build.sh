@@ -7,6 +7,6 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -std=c++17 -O3 -lineinfo \
   -gencode arch=compute_100a,code=sm_100a \
   -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function \
-  ${CG_PTXAS_V:+-Xptxas -v} \
+  ${CG_PTXAS_V:+-Xptxas -v} ${CG_TC_INSTRUMENT:+-DCG_TC_INSTRUMENT} \
    -shared -o "$OUT" "$HERE/cg_engine.cu"
 echo "built $OUT"

@@ -20,6 +20,23 @@
 
 #include "cg_common.cuh"
 
+// Role cycle counters (CG_TC_TIMING=1 at run time) need the clock reads compiled in: build with -DCG_TC_INSTRUMENT
+// (CG_TC_INSTRUMENT=1 calciumgan_b200/csrc/build.sh). The shipped build has none: ~350 clock reads per CTA sat on the
+// critical path of the single MMA-issuing thread.
+#ifdef CG_TC_INSTRUMENT
+#define CG_CLK() clock64()
+#define CG_DBG_ON (P.dbg != nullptr)
+#else
+#define CG_CLK() 0LL
+#define CG_DBG_ON false
+#endif
+
+#ifdef CG_TC_INSTRUMENT
+#define CG_TC_INSTRUMENTED 1
+#else
+#define CG_TC_INSTRUMENTED 0
+#endif
+
 #ifndef CG_TC_SPIN_LIMIT
 #define CG_TC_SPIN_LIMIT (1u << 26)   // bounded mbarrier spin: trap instead of hanging the GPU
 #endif
@@ -618,9 +635,9 @@ rsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int acol = p.seg.acol[phase][s];
         const int wk = p.seg.wk[phase][s];
         for (int kc = 0; kc < P.kchunks; ++kc) {
-          const long long tw0 = clock64();
+          const long long tw0 = CG_CLK();
           mbar_wait(&empty[stage], ph ^ 1);
-          if (P.dbg && blockIdx.x == 0 && lane == 0) { atomicAdd((unsigned long long*)&P.dbg[0], (unsigned long long)(clock64() - tw0)); atomicAdd((unsigned long long*)&P.dbg[1], 1ull); }
+          if (CG_DBG_ON && blockIdx.x == 0 && lane == 0) { atomicAdd((unsigned long long*)&P.dbg[0], (unsigned long long)(CG_CLK() - tw0)); atomicAdd((unsigned long long*)&P.dbg[1], 1ull); }
           if (elect_one()) {
             uint8_t* sa = tiles + (size_t)stage * stage_bytes;
             const uint32_t tx = ((P.x_baseoff & 4) ? 0u : (uint32_t)P.a_bytes) + ((P.x_baseoff & 2) ? 0u : (uint32_t)(BN * 128));
@@ -643,16 +660,16 @@ rsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int phase = (t / P.m_tiles) / P.n_tiles;
       const int acc = it & 1;
-      long long tw0 = clock64();
+      long long tw0 = CG_CLK();
       mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1) ^ 1);
-      if (P.dbg && blockIdx.x == 0 && lane == 0) { atomicAdd((unsigned long long*)&P.dbg[2], (unsigned long long)(clock64() - tw0)); atomicAdd((unsigned long long*)&P.dbg[3], 1ull); }
+      if (CG_DBG_ON && blockIdx.x == 0 && lane == 0) { atomicAdd((unsigned long long*)&P.dbg[2], (unsigned long long)(CG_CLK() - tw0)); atomicAdd((unsigned long long*)&P.dbg[3], 1ull); }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * kAccStride;
       const int kiters = p.seg.nseg[phase] * P.kchunks;
       for (int ki = 0; ki < kiters; ++ki) {
-        tw0 = clock64();
+        tw0 = CG_CLK();
         mbar_wait(&full[stage], ph);
-        if (P.dbg && blockIdx.x == 0 && lane == 0) { atomicAdd((unsigned long long*)&P.dbg[4], (unsigned long long)(clock64() - tw0)); atomicAdd((unsigned long long*)&P.dbg[5], 1ull); }
+        if (CG_DBG_ON && blockIdx.x == 0 && lane == 0) { atomicAdd((unsigned long long*)&P.dbg[4], (unsigned long long)(CG_CLK() - tw0)); atomicAdd((unsigned long long*)&P.dbg[5], 1ull); }
         tc_fence_after();
         const uint32_t a_lo = lo0 + stage * stage_step;
         if (elect_one()) {
@@ -686,14 +703,14 @@ rsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       epi_rows(p, b0, q0, rpt_log2, phase, lq, lane, R);
       if (nt != last_nt) { epi_load_bias<EPI>(p, bias_s, nt * BN, BN, threadIdx.x - 64); last_nt = nt; }
       const int acc = it & 1;
-      const long long te0 = clock64();
+      const long long te0 = CG_CLK();
       mbar_wait(&tfull[acc], ((uint32_t)it >> 1) & 1);
-      const long long te1 = clock64();
+      const long long te1 = CG_CLK();
       tc_fence_after();
       epilogue_block<EPI>(p, tmem_base + acc * kAccStride, BN, nt * BN, R, bias_s, stg, stg_partner, lq, lane, half);
-      if (P.dbg && blockIdx.x == 0 && threadIdx.x == 64) {
+      if (CG_DBG_ON && blockIdx.x == 0 && threadIdx.x == 64) {
         atomicAdd((unsigned long long*)&P.dbg[6], (unsigned long long)(te1 - te0));
-        atomicAdd((unsigned long long*)&P.dbg[7], (unsigned long long)(clock64() - te1));
+        atomicAdd((unsigned long long*)&P.dbg[7], (unsigned long long)(CG_CLK() - te1));
         atomicAdd((unsigned long long*)&P.dbg[8], 1ull);
       }
       tc_fence_before();
@@ -718,7 +735,11 @@ rsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //    base_offset = 0 - verified on B200). Activation traffic from L2 drops by the number of taps per group.
 //  * MB (1|2) accumulators of 128 rows share each weight tile, halving weight bytes per MAC.
 // =============================================================================================
-#define CG_DBG_ADD(i, t0) do { if (P.dbg && blockIdx.x == 0 && lane == 0) { atomicAdd((unsigned long long*)&P.dbg[i], (unsigned long long)(clock64() - (t0))); atomicAdd((unsigned long long*)&P.dbg[(i) + 8], 1ull); } } while (0)
+#ifdef CG_TC_INSTRUMENT
+#define CG_DBG_ADD(i, t0) do { if (CG_DBG_ON && blockIdx.x == 0 && lane == 0) { atomicAdd((unsigned long long*)&P.dbg[i], (unsigned long long)(CG_CLK() - (t0))); atomicAdd((unsigned long long*)&P.dbg[(i) + 8], 1ull); } } while (0)
+#else
+#define CG_DBG_ADD(i, t0) do { (void)(t0); } while (0)
+#endif
 struct SlabGroup {
   int acol, min_shift, nseg;
   unsigned char shift_rel[32];
@@ -797,7 +818,7 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // stage structure: slab mode  -> groups = tap-parity groups, each split into weight stages of TPS taps sharing one slab;
   //                  per-tap mode -> groups = ceil(nseg / TPS) bundles of TPS taps, each tap with its own 16 KB box
 
-  const long long t_kernel0 = clock64();
+  const long long t_kernel0 = CG_CLK();
   if (warp == 0) {
     int ss = 0, bs = 0;
     uint32_t sph = 0, bph = 0;
@@ -880,7 +901,7 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int t = pair; t < total_tiles; t += npairs, ++it) {
         const int phase = (t / P.m_tiles) / P.n_tiles;
         const int acc = it & 1;
-        long long tq = clock64();
+        long long tq = CG_CLK();
         mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1) ^ 1);
         CG_DBG_ADD(2, tq);
         tc_fence_after();
@@ -918,20 +939,20 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           for (int g = 0; g < P.ngroups[phase]; ++g) {
             const SlabGroup& G = P.grp[phase][g];
-            tq = clock64();
+            tq = CG_CLK();
             mbar_wait(&s_full[ss], sph);
             CG_DBG_ADD(3, tq);
             tc_fence_after();
             const uint32_t sl_lo = slab_lo0 + ss * slab_step;
             for (int s = 0; s < G.nseg; s += TPS) {
               const int cnt = G.nseg - s < TPS ? G.nseg - s : TPS;
-              tq = clock64();
+              tq = CG_CLK();
               mbar_wait(&b_full[bs], bph);
               CG_DBG_ADD(4, tq);
               tc_fence_after();
               const uint32_t b_lo = b_lo0 + bs * b_step;
               if (elect_one()) {
-                const long long tm0 = clock64();
+                const long long tm0 = CG_CLK();
                 for (int j = 0; j < cnt; ++j) {
                   const uint32_t a_lo = sl_lo + (uint32_t)G.shift_rel[s + j] * 8;
                   const uint32_t bj = b_lo + j * tap_step;
@@ -939,11 +960,11 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   for (int k = 0; k < 4; ++k)
                     if (k < nk) umma2_bf16_lohi(d_tmem, a_lo + 2 * k, bj + 2 * k, hi, idesc, accum | (uint32_t)(j | k));
                 }
-                const long long tm1 = clock64();
+                const long long tm1 = CG_CLK();
                 umma2_commit_mc(&b_empty[bs]);
-                if (P.dbg && blockIdx.x == 0) {   // issue time of the MMAs / of the commit of one weight stage
+                if (CG_DBG_ON && blockIdx.x == 0) {   // issue time of the MMAs / of the commit of one weight stage
                   atomicAdd((unsigned long long*)&P.dbg[0], (unsigned long long)(tm1 - tm0));
-                  atomicAdd((unsigned long long*)&P.dbg[1], (unsigned long long)(clock64() - tm1));
+                  atomicAdd((unsigned long long*)&P.dbg[1], (unsigned long long)(CG_CLK() - tm1));
                   atomicAdd((unsigned long long*)&P.dbg[8], 1ull);
                 }
               }
@@ -984,10 +1005,10 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       else epi_rows(p, bq, (blk % P.blocks_per_sample) * 128, 7, phase, lq, lane, R);
       if (nt != last_nt) { epi_load_bias<EPI>(p, bias_s, nt * BN, BN, threadIdx.x - 64); last_nt = nt; }
       const int acc = it & 1;
-      long long tq = clock64();
+      long long tq = CG_CLK();
       mbar_wait(&tfull[acc], ((uint32_t)it >> 1) & 1);
       if (warp == 2) CG_DBG_ADD(5, tq);
-      tq = clock64();
+      tq = CG_CLK();
       tc_fence_after();
       if (!(P.dbg_flags & 1))   // timing experiment bit 1: no epilogue
         epilogue_block<EPI>(p, tmem_base + acc * BN, BN, nt * BN, R, bias_s, stg, stg_partner, lq, lane, half,
@@ -999,7 +1020,7 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   }
 
-  if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[7] = clock64() - t_kernel0;
+  if (CG_DBG_ON && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[7] = CG_CLK() - t_kernel0;
   tc_fence_before();
   cluster_sync_all();          // nobody may exit (or free TMEM) while the peer can still signal / read
   if (warp == 1) {
@@ -1552,7 +1573,7 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   P.b_stages = bst;
   static long long* dbg_buf3 = nullptr;
   P.dbg = nullptr;
-  if (getenv("CG_TC_TIMING")) {
+  if (CG_TC_INSTRUMENTED && getenv("CG_TC_TIMING") != nullptr) {
     if (!dbg_buf3) cudaMalloc(&dbg_buf3, 16 * sizeof(long long));
     cudaMemsetAsync(dbg_buf3, 0, 16 * sizeof(long long), stream);
     P.dbg = dbg_buf3;
@@ -1615,7 +1636,7 @@ static inline int tc_rsgemm_launch(TcState* s, const RsParams& p, cudaStream_t s
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 512 + tc::kEpiSmem;
   static long long* dbg_buf = nullptr;
   P.dbg = nullptr;
-  if (getenv("CG_TC_TIMING")) {
+  if (CG_TC_INSTRUMENTED && getenv("CG_TC_TIMING") != nullptr) {
     if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
     cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), stream);
     P.dbg = dbg_buf;
