@@ -736,9 +736,15 @@ rsgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //  * MB (1|2) accumulators of 128 rows share each weight tile, halving weight bytes per MAC.
 // =============================================================================================
 #ifdef CG_TC_INSTRUMENT
-#define CG_DBG_ADD(i, t0) do { if (CG_DBG_ON && blockIdx.x == 0 && lane == 0) { atomicAdd((unsigned long long*)&P.dbg[i], (unsigned long long)(CG_CLK() - (t0))); atomicAdd((unsigned long long*)&P.dbg[(i) + 8], 1ull); } } while (0)
+// counters accumulate in registers and are flushed once at kernel end: per-stage global atomics from the single
+// MMA-issuing thread perturbed the pipeline they were measuring (~900 clk per weight stage)
+#define CG_DBG_ADD(i, t0) do { dacc[i] += CG_CLK() - (t0); dacc[(i) + 8] += 1; } while (0)
+#define CG_DBG_DECL long long dacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define CG_DBG_FLUSH do { if (CG_DBG_ON && blockIdx.x == 0 && lane == 0) { _Pragma("unroll") for (int q_ = 0; q_ < 16; ++q_) if (q_ != 7 && dacc[q_]) atomicAdd((unsigned long long*)&P.dbg[q_], (unsigned long long)dacc[q_]); } } while (0)
 #else
 #define CG_DBG_ADD(i, t0) do { (void)(t0); } while (0)
+#define CG_DBG_DECL
+#define CG_DBG_FLUSH do { } while (0)
 #endif
 struct SlabGroup {
   int acol, min_shift, nseg;
@@ -819,6 +825,7 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   //                  per-tap mode -> groups = ceil(nseg / TPS) bundles of TPS taps, each tap with its own 16 KB box
 
   const long long t_kernel0 = CG_CLK();
+  CG_DBG_DECL
   if (warp == 0) {
     int ss = 0, bs = 0;
     uint32_t sph = 0, bph = 0;
@@ -952,7 +959,7 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tc_fence_after();
               const uint32_t b_lo = b_lo0 + bs * b_step;
               if (elect_one()) {
-                const long long tm0 = CG_CLK();
+                const long long tm0 = CG_CLK(); (void)tm0;
                 for (int j = 0; j < cnt; ++j) {
                   const uint32_t a_lo = sl_lo + (uint32_t)G.shift_rel[s + j] * 8;
                   const uint32_t bj = b_lo + j * tap_step;
@@ -960,13 +967,11 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   for (int k = 0; k < 4; ++k)
                     if (k < nk) umma2_bf16_lohi(d_tmem, a_lo + 2 * k, bj + 2 * k, hi, idesc, accum | (uint32_t)(j | k));
                 }
-                const long long tm1 = CG_CLK();
+                const long long tm1 = CG_CLK(); (void)tm1;
                 umma2_commit_mc(&b_empty[bs]);
-                if (CG_DBG_ON && blockIdx.x == 0) {   // issue time of the MMAs / of the commit of one weight stage
-                  atomicAdd((unsigned long long*)&P.dbg[0], (unsigned long long)(tm1 - tm0));
-                  atomicAdd((unsigned long long*)&P.dbg[1], (unsigned long long)(CG_CLK() - tm1));
-                  atomicAdd((unsigned long long*)&P.dbg[8], 1ull);
-                }
+#ifdef CG_TC_INSTRUMENT
+                dacc[0] += tm1 - tm0; dacc[1] += CG_CLK() - tm1; dacc[8] += 1;   // issue / commit time of one weight stage
+#endif
               }
               __syncwarp();
               accum = 1;
@@ -1021,6 +1026,7 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 
   if (CG_DBG_ON && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[7] = CG_CLK() - t_kernel0;
+  if (warp == 1 || warp == 2) CG_DBG_FLUSH;
   tc_fence_before();
   cluster_sync_all();          // nobody may exit (or free TMEM) while the peer can still signal / read
   if (warp == 1) {
