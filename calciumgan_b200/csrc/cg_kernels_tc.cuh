@@ -1552,6 +1552,7 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
     const double cost = waves * per;
     if (cost < best) { best = cost; bestBN = BN; }
   }
+  if (const char* e = getenv("CG_TC_BN")) { const int bn = atoi(e); if (bn >= 32 && bn % 32 == 0 && p.N % bn == 0) bestBN = bn; }   // tuning experiments
   if (p.epi == EPI_BIAS_LN_LRELU) bestBN = p.N;   // the epilogue needs whole channel rows
   P.BN = bestBN;
   P.n_tiles = p.N / P.BN;

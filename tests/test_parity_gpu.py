@@ -350,6 +350,13 @@ def test_generator_head_kernel_modes_bf16(monkeypatch):
     s = gan.engine.critic_step(real, noises[0], alphas[0], shifts[:12], update=False)
     r['c_scal'], r['c_fake'] = np.array(s[:5]), gan.engine.fake(B).cpu().numpy()
     r['c_scores'], r['c_grads'] = gan.engine.scores(3 * B).cpu().numpy(), gan.engine.get_grads(1)
+    if mode == 'fused':   # CG_FLAG_NO_FAKE32 (data-parallel critic sub-steps): same scalars and gradients, fp32 copy untouched
+      before = gan.engine.fake(B).cpu().numpy().copy()
+      s2 = gan.engine.critic_step(real, noises[1], alphas[1], shifts[:12], update=False, want_fake32=False)
+      np.testing.assert_array_equal(gan.engine.fake(B).cpu().numpy(), before)
+      s3 = gan.engine.critic_step(real, noises[1], alphas[1], shifts[:12], update=False, want_fake32=True)
+      assert rel_err(np.array(s2[:5]), np.array(s3[:5])) <= 1e-6
+      assert not np.array_equal(gan.engine.fake(B).cpu().numpy(), before)
     out = gan.train(real, noise=noises, alpha=alphas, shifts=shifts)
     r['train'] = np.array(out[:3])
     r['gw'], r['dw'] = gan.generator.get_weights(), gan.discriminator.get_weights()
