@@ -1,11 +1,17 @@
 """CPU oracle for the CalciumGAN WGAN-GP training step.  TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED: the reference (bryanlimy/CalciumGAN) ships no tests, golden vectors or
-fixtures, and its arithmetic lives in un-vendored TensorFlow 2.3.1 (setup.sh:26,29), which
-cannot be installed in this image.  This file is therefore a *restatement* of the reference
-algorithm, checked for self-consistency only (naive-loop convolutions vs torch, autograd vs
-the hand-derived 4-pass gradient penalty, finite differences, literal pad+slice PhaseShuffle
-vs the closed form).
+PARITY UNPINNED AT THE TENSORFLOW LEVEL: the reference (bryanlimy/CalciumGAN) ships no tests,
+golden vectors or fixtures, and its arithmetic lives in un-vendored TensorFlow 2.3.1
+(setup.sh:26,29), which cannot be installed in this image.  What IS pinned: the reference's own
+Python files (model builders, PhaseShuffle, WGAN-GP losses / tapes / update order, metrics) are
+executed unmodified from /root/reference over a torch-backed stand-in for the TF / Keras calls
+they make (oracle/tf_shim, oracle/reference_runner.py), and this restatement reproduces their
+train step, validate and generate to 1e-9 in float64 (tests/test_reference_shim.py; committed
+fixture tests/golden/reference_step.npz + its generating script).  The semantics of the TF
+kernels themselves (Keras defaults below) remain restated, here and -- independently -- in the
+stand-in.  Self-consistency checks on top: naive-loop convolutions vs torch, autograd vs the
+hand-derived 4-pass gradient penalty, finite differences, literal pad+slice PhaseShuffle vs
+the closed form.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl
 reference`` legs may import this module.  The product path (``calciumgan_b200``) never does.

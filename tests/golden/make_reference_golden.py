@@ -1,0 +1,57 @@
+"""Generate tests/golden/reference_step.npz by running the reference's own code (files under /root/reference, unmodified)
+over the torch-backed TensorFlow stand-in (oracle/tf_shim, float64): one WGAN_GP.train step (n_critic = 2), one
+validate and one generate on seeded weights / inputs / draws.
+
+  python tests/golden/make_reference_golden.py        # needs /root/reference (build container only)
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import calciumgan_oracle as O  # noqa: E402  (HParams + seeded inputs only)
+from oracle import reference_runner as R  # noqa: E402
+
+HP = dict(signal_shape=(128, 12), noise_dim=4, num_units=8, kernel_size=24, m=3, n_critic=2)
+BATCH, SEED = 3, 1
+
+
+def inputs():
+  hp = O.HParams(**HP)
+  gw, dw = O.init_weights(hp, seed=SEED)
+  gw, dw = O.randomize_weights(gw, SEED + 1), O.randomize_weights(dw, SEED + 2)
+  real, noises, alphas, shifts = O.synthetic_batch(hp, BATCH, seed=SEED + 3)
+  return hp, gw, dw, real, noises, alphas, shifts
+
+
+def main():
+  hp, gw, dw, real, noises, alphas, shifts = inputs()
+  out = {}
+  # validate + generate on the initial weights (gan.py:87-97)
+  mods, gan = R.build(hp, BATCH, gw, dw)
+  mods.tf.random.inject(normal=[noises[0]], uniform=[alphas[0]], ints=[int(s) for s in shifts[:12]])
+  fake, gen_loss, dis_loss, gp, metrics = gan.validate(torch.as_tensor(real, dtype=torch.float64))
+  out['val_fake'] = fake.detach().numpy()
+  out['val_scalars'] = np.array([float(gen_loss.detach()), float(dis_loss.detach()), float(gp.detach())] +
+                                [float(metrics[k].detach()) for k in sorted(metrics)])
+  out['gen_fake'] = gan.generate(torch.as_tensor(noises[1], dtype=torch.float64)).detach().numpy()
+  out['gen_fake_denorm'] = gan.generate(torch.as_tensor(noises[1], dtype=torch.float64), denorm=True).detach().numpy()
+  # one full train step (wgan_gp.py:82-95)
+  r = R.train_step(hp, gw, dw, real, noises, alphas, shifts)
+  out['train_scalars'] = np.array([r['gen_loss'], r['dis_loss'], r['gradient_penalty']] +
+                                  [r['metrics'][k] for k in sorted(r['metrics'])])
+  for i, w in enumerate(r['gen_weights']):
+    out['gen_w_%02d' % i] = w
+  for i, w in enumerate(r['dis_weights']):
+    out['dis_w_%02d' % i] = w
+  out['draw_order'] = np.array(r['draw_order'])
+  path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'reference_step.npz')
+  np.savez_compressed(path, **out)
+  print('wrote', path, {k: v.shape for k, v in out.items() if k.endswith('scalars')})
+
+
+if __name__ == '__main__':
+  main()
