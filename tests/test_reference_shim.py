@@ -30,6 +30,21 @@ def _oracle_step(hp, gw, dw, real, noises, alphas, shifts):
 
 
 @needs_reference
+def test_reference_train_step_paper_architecture():
+  """The exact BASELINE.json architecture (2048 x 102, num_units 64, K 24, m 10), batch 1, one critic + one generator
+  update, reference code vs oracle."""
+  hp = O.HParams(n_critic=1)
+  gw, dw = O.init_weights(hp, seed=21)
+  real, noises, alphas, shifts = O.synthetic_batch(hp, 1, seed=22, n_critic=1)
+  ref = R.train_step(hp, gw, dw, real, noises, alphas, shifts)
+  gen_loss, dis_loss, gp, metrics, g_new, d_new = _oracle_step(hp, gw, dw, real, noises, alphas, shifts)
+  for a, b in ((ref['gen_loss'], gen_loss), (ref['dis_loss'], dis_loss), (ref['gradient_penalty'], gp)):
+    assert abs(a - b) <= TOL * max(1, abs(b))
+  for a, b, w0 in list(zip(ref['gen_weights'], g_new, gw)) + list(zip(ref['dis_weights'], d_new, dw)):
+    assert rel_err(a - w0, b - np.asarray(w0)) <= 1e-6
+
+
+@needs_reference
 @pytest.mark.parametrize('kw', [
     dict(signal_shape=(256, 20), noise_dim=8, num_units=16, kernel_size=24, m=3, n_critic=2),
     dict(signal_shape=(256, 12), noise_dim=4, num_units=8, kernel_size=24, m=10, n_critic=1),
