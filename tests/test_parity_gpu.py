@@ -507,35 +507,39 @@ def test_paper_architecture_full_length_fp32():
   print('fp32 full length: worst gradient rel err critic %.1e generator %.1e' % (wc, wg))
 
 
-def test_cuda_path_matches_reference_code_fixture_fp32():
-  """The CUDA path (fp32, through the C ABI) against tests/golden/reference_step.npz -- outputs of the REFERENCE'S OWN
-  code (gan/models/calciumgan.py, gan/algorithms/wgan_gp.py, ... executed unmodified over the torch-backed TensorFlow
-  stand-in, tests/golden/make_reference_golden.py): validate, generate (+denorm) and one full train step (n_critic 2)
-  incl. the weights after Adam. north_star tolerance 1e-4."""
+@pytest.mark.parametrize('mixed', [False, True])
+def test_cuda_path_matches_reference_code_fixture(mixed):
+  """The CUDA path (through the C ABI; fp32, and bf16 mixed precision) against tests/golden/reference_step.npz -- outputs
+  of the REFERENCE'S OWN code (gan/models/calciumgan.py, gan/algorithms/wgan_gp.py, ... executed unmodified over the
+  torch-backed TensorFlow stand-in, tests/golden/make_reference_golden.py): validate, generate (+denorm) and one full
+  train step (n_critic 2) incl. the weights after Adam. north_star tolerances: 1e-4 in fp32, 2e-2 in bf16."""
   import sys
   sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
   import make_reference_golden as G
+  tol = BF16_TOL if mixed else FP32_TOL
   gold = np.load(os.path.join(os.path.dirname(GOLD), 'reference_step.npz'))
   hp, gw, dw, real, noises, alphas, shifts = G.inputs()
-  ns, gan = build(hp, G.BATCH)
+  ns, gan = build(hp, G.BATCH, mixed=mixed)
   gan.generator.set_weights(gw)
   gan.discriminator.set_weights(dw)
   fake, gl, dl, gp, met = gan.validate(real, noise=noises[0], alpha=alphas[0], shifts=shifts[:12])
-  assert rel_err(fake.cpu().numpy(), gold['val_fake']) <= FP32_TOL
+  assert rel_err(fake.cpu().numpy(), gold['val_fake']) <= tol
   got = np.array([gl, dl, gp] + [met[k] for k in sorted(met)])
-  assert np.abs(got - gold['val_scalars']).max() <= FP32_TOL * max(1.0, np.abs(gold['val_scalars']).max())
-  assert rel_err(gan.generate(noises[1]).cpu().numpy(), gold['gen_fake']) <= FP32_TOL
-  assert rel_err(gan.generate(noises[1], denorm=True).cpu().numpy(), gold['gen_fake_denorm']) <= FP32_TOL
+  assert np.abs(got - gold['val_scalars']).max() <= tol * max(1.0, np.abs(gold['val_scalars']).max())
+  assert rel_err(gan.generate(noises[1]).cpu().numpy(), gold['gen_fake']) <= tol
+  assert rel_err(gan.generate(noises[1], denorm=True).cpu().numpy(), gold['gen_fake_denorm']) <= tol
   out = gan.train(real, noise=noises, alpha=alphas, shifts=shifts)
   got = np.array(list(out[:3]) + [out[3][k] for k in sorted(out[3])])
-  assert np.abs(got - gold['train_scalars']).max() <= FP32_TOL * max(1.0, np.abs(gold['train_scalars']).max())
-  # weights after n_critic critic updates / one generator update: compare the update (Adam's first steps are
-  # sign-like, so near-zero gradient elements dominate a relative error on the update; bound it loosely and the
-  # weights tightly)
+  assert np.abs(got - gold['train_scalars']).max() <= tol * max(1.0, np.abs(gold['train_scalars']).max())
+  # weights after n_critic critic updates / one generator update. Adam's first steps are sign-like (lr * g / |g|), so
+  # near-zero gradient elements dominate a relative error on the UPDATE: the weights are held to the tolerance, the
+  # update loosely in fp32 (the critic's output bias has an exactly-zero gradient, -1 + 1 + 0: rounding noise) and by
+  # its size only in bf16 (|update| <= (n_critic or 1) * lr per element whatever the gradient noise)
   for name, new, w0 in (('gen', gan.generator.get_weights(), gw), ('dis', gan.discriminator.get_weights(), dw)):
     for i, (a, b0) in enumerate(zip(new, w0)):
       ref = gold['%s_w_%02d' % (name, i)]
-      # (the critic's output bias has an exactly-zero gradient, -1 + 1 + 0: its fp32 Adam direction is rounding noise)
-      assert np.abs(a - ref).max() <= FP32_TOL * max(1.0, np.abs(ref).max()), (name, i, np.abs(a - ref).max())
-      if float(np.abs(ref - b0).max()) > 1e-6:
+      assert np.abs(a - ref).max() <= tol * max(1.0, np.abs(ref).max()), (name, i, np.abs(a - ref).max())
+      if not mixed and float(np.abs(ref - b0).max()) > 1e-6:
         assert rel_err(a - b0, ref - b0) <= 5e-2, (name, i, rel_err(a - b0, ref - b0))
+      if mixed:
+        assert np.abs(a - b0).max() <= 2.001 * hp.learning_rate * 1.01 + 1e-7, (name, i)
