@@ -27,7 +27,44 @@ def inputs():
   return hp, gw, dw, real, noises, alphas, shifts
 
 
+# a second, larger case (critic layers with >= 128 time rows: the slab-mode tensor-core kernels, fused PhaseShuffle in
+# both directions, m = 10): outputs only, no weights, to keep the fixture small
+HP_MEDIUM = dict(signal_shape=(512, 102), noise_dim=8, num_units=32, kernel_size=24, m=10, n_critic=1)
+BATCH_MEDIUM, SEED_MEDIUM = 4, 7
+
+
+def inputs_medium():
+  hp = O.HParams(**HP_MEDIUM)
+  gw, dw = O.init_weights(hp, seed=SEED_MEDIUM)
+  gw, dw = O.randomize_weights(gw, SEED_MEDIUM + 1), O.randomize_weights(dw, SEED_MEDIUM + 2)
+  real, noises, alphas, shifts = O.synthetic_batch(hp, BATCH_MEDIUM, seed=SEED_MEDIUM + 3, n_critic=1)
+  shifts = np.asarray(shifts).copy()
+  shifts[:12] = [10, -10, 7, -3, -10, 10, -1, 4, 9, -9, 10, -10]
+  return hp, gw, dw, real, noises, alphas, shifts
+
+
+def main_medium():
+  hp, gw, dw, real, noises, alphas, shifts = inputs_medium()
+  out = {}
+  mods, gan = R.build(hp, BATCH_MEDIUM, gw, dw)
+  mods.tf.random.inject(normal=[noises[0]], uniform=[alphas[0]], ints=[int(s) for s in shifts[:12]])
+  fake, gen_loss, dis_loss, gp, metrics = gan.validate(torch.as_tensor(real, dtype=torch.float64))
+  out['val_fake'] = fake.detach().numpy().astype(np.float32)
+  out['val_scalars'] = np.array([float(gen_loss.detach()), float(dis_loss.detach()), float(gp.detach())] +
+                                [float(metrics[k].detach()) for k in sorted(metrics)])
+  r = R.train_step(hp, gw, dw, real, noises, alphas, shifts)
+  out['train_scalars'] = np.array([r['gen_loss'], r['dis_loss'], r['gradient_penalty']] +
+                                  [r['metrics'][k] for k in sorted(r['metrics'])])
+  # per-tensor norms of the weight updates: a compact check of every gradient's scale after Adam
+  out['gen_update_norms'] = np.array([np.linalg.norm(a - b) for a, b in zip(r['gen_weights'], gw)])
+  out['dis_update_norms'] = np.array([np.linalg.norm(a - b) for a, b in zip(r['dis_weights'], dw)])
+  path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'reference_medium.npz')
+  np.savez_compressed(path, **out)
+  print('wrote', path)
+
+
 def main():
+  main_medium()
   hp, gw, dw, real, noises, alphas, shifts = inputs()
   out = {}
   # validate + generate on the initial weights (gan.py:87-97)

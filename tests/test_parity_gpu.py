@@ -543,3 +543,34 @@ def test_cuda_path_matches_reference_code_fixture(mixed):
         assert rel_err(a - b0, ref - b0) <= 5e-2, (name, i, rel_err(a - b0, ref - b0))
       if mixed:
         assert np.abs(a - b0).max() <= 2.001 * hp.learning_rate * 1.01 + 1e-7, (name, i)
+
+
+@pytest.mark.parametrize('mixed', [False, True])
+def test_cuda_path_matches_reference_code_fixture_medium(mixed):
+  """Second fixture from the reference's own code (tests/golden/reference_medium.npz: 512 x 102, num_units 32, m 10 with
+  shifts at the extremes): the slab-mode tensor-core kernels with both fused PhaseShuffle directions in bf16, the
+  CUDA-core path in fp32. validate outputs + the scalars of one train step."""
+  import sys
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+  import make_reference_golden as G
+  tol = BF16_TOL if mixed else FP32_TOL
+  gold = np.load(os.path.join(os.path.dirname(GOLD), 'reference_medium.npz'))
+  hp, gw, dw, real, noises, alphas, shifts = G.inputs_medium()
+  ns, gan = build(hp, G.BATCH_MEDIUM, mixed=mixed)
+  gan.generator.set_weights(gw)
+  gan.discriminator.set_weights(dw)
+  fake, gl, dl, gp, met = gan.validate(real, noise=noises[0], alpha=alphas[0], shifts=shifts[:12])
+  assert rel_err(fake.cpu().numpy(), gold['val_fake']) <= max(tol, 2e-7 * 10)   # fixture stored as float32
+  got = np.array([gl, dl, gp] + [met[k] for k in sorted(met)])
+  assert np.abs(got - gold['val_scalars']).max() <= tol * max(1.0, np.abs(gold['val_scalars']).max()), (got, gold['val_scalars'])
+  out = gan.train(real, noise=noises, alpha=alphas, shifts=shifts)
+  got = np.array(list(out[:3]) + [out[3][k] for k in sorted(out[3])])
+  assert np.abs(got - gold['train_scalars']).max() <= tol * max(1.0, np.abs(gold['train_scalars']).max()), (got, gold['train_scalars'])
+  if mixed:
+    assert gan.engine.tc_launch_count() > 0
+  else:   # update norms: every tensor moved as far as in the reference run (Adam: ~lr * sqrt(#elements) on the first step)
+    for name, new, w0, key in (('gen', gan.generator.get_weights(), gw, 'gen_update_norms'),
+                               ('dis', gan.discriminator.get_weights(), dw, 'dis_update_norms')):
+      norms = np.array([np.linalg.norm(a - np.asarray(b)) for a, b in zip(new, w0)])
+      ok = gold[key] > 1e-6
+      assert np.abs(norms[ok] / gold[key][ok] - 1).max() <= 2e-2, (name, norms, gold[key])
