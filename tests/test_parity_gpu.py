@@ -574,3 +574,32 @@ def test_cuda_path_matches_reference_code_fixture_medium(mixed):
       norms = np.array([np.linalg.norm(a - np.asarray(b)) for a, b in zip(new, w0)])
       ok = gold[key] > 1e-6
       assert np.abs(norms[ok] / gold[key][ok] - 1).max() <= 2e-2, (name, norms, gold[key])
+
+
+@pytest.mark.parametrize('B', [1, 7, 128])
+def test_paper_config_tensor_core_vs_cuda_core_paths(B):
+  """BASELINE.json configs[1] at its FULL batch (128) and at ragged batches: the bf16 tensor-core path against the fp32
+  CUDA-core path of the same engine on identical weights / inputs / draws (the two share no GEMM, epilogue or head
+  code; the fp32 path is the one held to 1e-4 against the oracle). north_star bf16 tolerance 2e-2."""
+  hp = O.HParams()
+  gw, dw = O.init_weights(hp, seed=3)
+  gw, dw = O.randomize_weights(gw, 4), O.randomize_weights(dw, 5)
+  real, noises, alphas, shifts = O.synthetic_batch(hp, B, seed=6 + B, n_critic=1)
+  res = {}
+  for mixed in (False, True):
+    ns, gan = build(hp, B, mixed=mixed)
+    gan.generator.set_weights(gw)
+    gan.discriminator.set_weights(dw)
+    s = gan.engine.critic_step(real, noises[0], alphas[0], shifts[:12], update=False)
+    scores = gan.engine.scores(3 * B).cpu().numpy()[:2 * B]
+    fake = gan.engine.fake(B).cpu().numpy()
+    s2 = gan.engine.generator_step(real, noises[1], shifts[12:16], update=False)
+    res[mixed] = (np.array(s[:4]), scores, fake, np.array(s2[4:9]))
+    if mixed:
+      assert gan.engine.tc_launch_count() > 0
+    gan.engine.close()
+  a, b = res[True], res[False]
+  assert np.abs(a[0] - b[0]).max() <= BF16_TOL * max(1.0, np.abs(b[0]).max())     # dis_loss, GP, real / fake loss
+  assert np.abs(a[1] - b[1]).max() <= BF16_TOL * max(1.0, np.abs(b[1]).max())     # critic scores
+  assert rel_err(a[2], b[2]) <= BF16_TOL                                          # generator output
+  assert np.abs(a[3] - b[3]).max() <= BF16_TOL * max(1.0, np.abs(b[3]).max())     # gen_loss + signal metrics
