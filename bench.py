@@ -284,7 +284,7 @@ def main():
             'peak_kind': peak_kind + ' sustained cuBLAS bf16',
             # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the launches captured with
             # `ncu --set full` in profiles/r1_final.md (tensor-bound kernel: informative only)
-            'traffic': 64.3e6, 'traffic_source': 'profiles/r1_final.md',
+            'traffic': 63.7e6, 'traffic_source': 'profiles/r1_final.md',
             'launches_per_step': g['launches'] / 2, 'ms_per_step_in_kernel': g['ms'] / 2}
     ach_w = w['flops'] / (w['ms'] * 1e-3) / 1e12 if w['ms'] > 0 else 0.0
     kernels = {'wgrad2_tc_kernel': {'achieved_tflops': ach_w, 'frac': ach_w / peak_tf, 'ms_per_step': w['ms'] / 2,
