@@ -14,6 +14,8 @@ NUM_SCALARS = 16
 S_DIS_LOSS, S_GP, S_REAL_LOSS, S_FAKE_LOSS, S_GEN_LOSS = 0, 1, 2, 3, 4
 S_MET_MIN, S_MET_MAX, S_MET_MEAN, S_MET_STD = 5, 6, 7, 8
 FLAG_NO_UPDATE, FLAG_NO_SYNC, FLAG_SAME_REAL, FLAG_NO_FAKE32 = 1, 2, 4, 8
+DEBUG_NO_PS_FUSE, DEBUG_NO_PS_BWD_FUSE, DEBUG_NO_GHEAD, DEBUG_NO_ADAM_FUSE = 1, 2, 4, 8
+BUF_X, BUF_H, BUF_DA, BUF_HG, BUF_AG, BUF_DAG = 0, 1, 2, 3, 4, 5
 
 
 class CgConfig(C.Structure):
@@ -24,7 +26,7 @@ class CgConfig(C.Structure):
       ('max_batch', C.c_int32), ('n_critic', C.c_int32), ('precision', C.c_int32),
       ('gp_lambda', C.c_float), ('learning_rate', C.c_float), ('signals_min', C.c_float),
       ('signals_max', C.c_float), ('world_size', C.c_int32), ('rank', C.c_int32),
-      ('force_simt', C.c_int32), ('reserved', C.c_int32 * 7),
+      ('force_simt', C.c_int32), ('debug_flags', C.c_int32), ('reserved', C.c_int32 * 6),
   ]
 
 
@@ -49,6 +51,8 @@ SIGNATURES = {
     'cg_num_buckets': (_I, [_P, _I]),
     'cg_bucket_info': (_I, [_P, _I, _I, C.POINTER(_I64), C.POINTER(_I64)]),
     'cg_stream_wait_bucket': (_I, [_P, _I, _I, _P]),
+    'cg_set_grads': (_I, [_P, _I, _P]),
+    'cg_skipped_updates': (_I64, [_P, _I]),
     'cg_get_opt_state': (_I, [_P, _I, _P, _P, C.POINTER(_I64)]),
     'cg_set_opt_state': (_I, [_P, _I, _P, _P, _I64]),
     'cg_seed': (_I, [_P, C.c_uint64]),
@@ -62,7 +66,13 @@ SIGNATURES = {
     'cg_debug_gp': (_I, [_P, _P, _I, _I32P, _P, _P]),
     'cg_debug_layer': (_I, [_P, _I, _I, _I, _P, _P, _I, _P]),
     'cg_debug_phase_shuffle': (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    'cg_debug_read': (_I, [_P, _I, _I, _I, _P]),
+    'cg_debug_buffer_shape': (_I, [_P, _I, _I, C.POINTER(_I64), C.POINTER(_I64)]),
+    'cg_debug_last_draws': (_I, [_P, _P, _I64, _P, _I64, _I32P, _I]),
+    'cg_debug_dgrad_ps': (_I, [_P, _I, _P, _P, _I, _I, _I32P, _P]),
     'cg_phase_shuffle_index': (_I, [_I, _I, _I32P]),
+    'cg_phase_shuffle_scatter_index': (_I, [_I, _I, _I32P, _I32P]),
+    'cg_phase_shuffle_adjoint_plan': (_I, [_I, _I, _I32P, _I32P, _I32P, _I32P]),
     'cg_fake_ptr': (_P, [_P]),
     'cg_scores_ptr': (_P, [_P]),
     'cg_scalars_ptr': (_P, [_P]),

@@ -71,6 +71,37 @@ __host__ __device__ __forceinline__ int ps_index(int t, int shift, int w) {
   return j;
 }
 
+// Scatter form of the same map, as used by the fused conv epilogue (cg_kernels_tc.cuh): source row q is the value of
+// output row t1 (direct: t1 + shift == q) and of at most one reflected output row t2; -1 = none.
+// Checked against ps_index for every (w, shift) on the host (cg_phase_shuffle_scatter_index, tests/test_boundary_cpu.py).
+__host__ __device__ __forceinline__ void ps_scatter_targets(int q, int shift, int w, int& t1, int& t2) {
+  t1 = q - shift;
+  if (t1 < 0 || t1 >= w) t1 = -1;
+  t2 = -1;
+  if (shift > 0) { t2 = 2 * (w - 1) - q - shift; if (!(t2 >= 0 && t2 < w && t2 + shift > w - 1)) t2 = -1; }
+  else if (shift < 0) { t2 = -q - shift; if (!(t2 >= 0 && t2 < w && t2 + shift < 0)) t2 = -1; }
+}
+// Adjoint (gradient) of the gather as the fused data-gradient epilogue runs it: accumulator row t goes to output row
+// dest = t + shift when that lies in [0, w); a row pushed over an edge (dest = -1) is reflected onto the output row
+// of a partner row of the same parity: it deposits its value in exchange slot x_src, the partner adds slot x_par.
+// Output rows nobody maps to (x_zero, tested on the row with the same index) are written as zeros.
+__host__ __device__ __forceinline__ void ps_adjoint_row(int t, int shift, int w, int& dest, int& x_src, int& x_par,
+                                                        bool& x_zero) {
+  dest = t + shift;
+  if (dest < 0 || dest > w - 1) dest = -1;
+  x_src = -1; x_par = -1;
+  if (shift > 0) {
+    if (t + shift > w - 1) x_src = (w - 1 - t) >> 1;
+    const int tp = 2 * (w - 1) - t - 2 * shift;
+    if (tp <= w - 1 && tp + shift > w - 1) x_par = (w - 1 - tp) >> 1;
+  } else if (shift < 0) {
+    if (t + shift < 0) x_src = t >> 1;
+    const int tp = -t - 2 * shift;
+    if (tp >= 0 && tp + shift < 0) x_par = tp >> 1;
+  }
+  x_zero = t - shift < 0 || t - shift > w - 1;
+}
+
 // ---- implicit-GEMM operand addressing ("row-shift GEMM") -----------------------------------
 // out[b, q, phase*o_phase_col + n] = epi( sum_{seg in phase} sum_{c<Kc}
 //        A[b, q + shift(seg), acol(seg) + c] * W[n, wk(seg) + c] )      (rows outside [0,a_rows) read 0)

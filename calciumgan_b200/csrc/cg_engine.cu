@@ -68,7 +68,7 @@ struct Model {
   std::vector<ParamInfo> params;
   int64_t total = 0;
   float *w = nullptr, *m = nullptr, *v = nullptr, *g = nullptr;   // flat fp32
-  int64_t steps = 0;                                               // optimizer.iterations
+  OptState* opt = nullptr;                                         // device: optimizer.iterations, skipped updates, lr_t
   void add(std::initializer_list<int64_t> shp) {
     ParamInfo p{};
     p.ndim = (int)shp.size();
@@ -115,7 +115,16 @@ struct cg_ctx {
   float *alpha_buf, *noise_buf;
   float* d_scal;        // [n_critic+1][CG_NUM_SCALARS]
   float* h_scal;        // pinned
-  uint64_t seed = 1234, rng_counter = 0;
+  // Random streams (all functions of (seed, number of step calls so far), never of what the caller injected):
+  // noise / alpha are rank-specific Philox streams, PhaseShuffle shifts one rank-SHARED stream (per-call scalars,
+  // calciumgan.py:121-124) -- every step function advances each counter by a fixed amount whether or not it used it
+  uint64_t seed = 1234, noise_calls = 0, alpha_calls = 0, shift_draws = 0;
+  // draws of the last step function (cg_debug_last_draws): device pointers into caller / library buffers, host shifts
+  const float *last_noise = nullptr, *last_alpha = nullptr;
+  int64_t last_n_noise = 0, last_n_alpha = 0;
+  std::vector<int32_t> last_shifts;
+  int dbg_flags = 0;                       // CG_DEBUG_* (cfg.debug_flags | environment, fixed at cg_create)
+  AdamPlan adam_plan[2];
   static const int NB = 3;                 // gradient buckets per model (ready order: last layers first)
   cudaEvent_t bucket_evt[2][NB] = {};
   int64_t bucket_off[2][NB + 1] = {};
@@ -295,6 +304,45 @@ static int repack(cg_ctx* c, int which) {
   return post_launch(c, "pack_weights");
 }
 
+// one-pass Adam + re-pack: GEMM kernels as 32 x 32 tiles per tap, everything between them as element-wise ranges
+static void build_adam_plans(cg_ctx* c) {
+  for (int which = 0; which < 2; ++which) {
+    AdamPlan& pl = c->adam_plan[which];
+    memset(&pl, 0, sizeof(pl));
+    Model& M = which == CG_GENERATOR ? c->gen : c->dis;
+    std::vector<bool> is_gemm(M.params.size(), false);
+    auto add_tensor = [&](int idx, int K, int A, int B, int Ap, int Bp, void* direct, void* trans) {
+      AdamTensor& t = pl.t[pl.nt++];
+      t.off = M.params[idx].offset; t.K = K; t.A = A; t.B = B; t.Ap = Ap; t.Bp = Bp; t.direct = direct; t.trans = trans;
+      t.tiles_a = (A + 31) / 32; t.tiles_b = (B + 31) / 32;
+      t.item0 = pl.tile_items;
+      pl.tile_items += (long long)K * t.tiles_a * t.tiles_b;
+      is_gemm[idx] = true;
+    };
+    if (which == CG_DISCRIMINATOR) {
+      for (int l = 1; l <= NL; ++l)   // (K, Cin, Cout): a = ci, b = co; Wb_d = [ci][k*Coutp + co], Wf_d = [co][k*Cinp + ci]
+        add_tensor(2 * (l - 1), c->K, c->dc[l - 1], c->dc[l], c->dcp[l - 1], c->dcp[l], c->Wb_d[l], c->Wf_d[l]);
+    } else {
+      for (int i = 1; i <= NL; ++i)   // (K, 1, Cout, Cin): a = co, b = ci; Wf_g = [co][k*Cinp + ci], Wb_g = [ci][k*Coutp + co]
+        add_tensor(c->g_k[i], c->K, c->gc[i], c->gc[i - 1], c->gcp[i], c->gcp[i - 1], c->Wf_g[i], c->Wb_g[i]);
+      // output dense (C_in, C_out): a = in, b = out; Wb_d1 = [in][out], Wf_d1 = [out][in]
+      add_tensor(c->g_d1k, 1, c->C, c->C, c->gcp[NL], c->gcp[NL], c->Wb_d1, c->Wf_d1);
+    }
+    long long items = pl.tile_items;
+    for (size_t i = 0; i < M.params.size();) {
+      if (is_gemm[i]) { ++i; continue; }
+      size_t j = i;
+      long long len = 0;
+      while (j < M.params.size() && !is_gemm[j]) { len += M.params[j].size; ++j; }
+      AdamRange& r = pl.r[pl.nr++];
+      r.off = M.params[i].offset; r.len = len; r.item0 = items - pl.tile_items;
+      items += (len + 1023) / 1024;
+      i = j;
+    }
+    pl.items = items;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ create
 extern "C" int cg_version(void) { return CG_VERSION; }
 extern "C" const char* cg_last_error(void) { return g_err.c_str(); }
@@ -330,6 +378,11 @@ extern "C" int cg_create(const cg_config* cfg, cg_ctx** out) {
   c->cfg = *cfg;
   if (c->cfg.world_size < 1) c->cfg.world_size = 1;
   if (c->cfg.n_critic < 1) c->cfg.n_critic = 1;
+  c->dbg_flags = cfg->debug_flags;
+  if (getenv("CG_NO_PS_FUSE")) c->dbg_flags |= CG_DEBUG_NO_PS_FUSE;
+  if (getenv("CG_NO_PS_BWD_FUSE")) c->dbg_flags |= CG_DEBUG_NO_PS_BWD_FUSE;
+  if (getenv("CG_NO_GHEAD")) c->dbg_flags |= CG_DEBUG_NO_GHEAD;
+  if (getenv("CG_NO_ADAM_FUSE")) c->dbg_flags |= CG_DEBUG_NO_ADAM_FUSE;
   c->bf = cfg->precision == CG_BF16;
   c->esz = c->bf ? 2 : 4;
   c->use_tc = c->bf && !cfg->force_simt;
@@ -382,6 +435,7 @@ extern "C" int cg_create(const cg_config* cfg, cg_ctx** out) {
   } while (0)
   for (Model* m : {&G, &D}) {
     DA_(m->w, m->total * 4); DA_(m->m, m->total * 4); DA_(m->v, m->total * 4); DA_(m->g, m->total * 4);
+    DA_(m->opt, sizeof(OptState));
   }
   const size_t es = c->esz;
   const size_t Bt = 3 * (size_t)c->Bmax, Bm = c->Bmax;
@@ -421,6 +475,7 @@ extern "C" int cg_create(const cg_config* cfg, cg_ctx** out) {
     cg_destroy(c);
     return set_err("cudaMallocHost failed");
   }
+  build_adam_plans(c);
   if (c->use_tc && tc_init(&c->tc)) { cg_destroy(c); return 1; }
   if (cudaStreamSynchronize(c->stream) != cudaSuccess) { cg_destroy(c); return set_err("arena init failed"); }
   *out = c;
@@ -484,21 +539,47 @@ extern "C" int cg_stream_wait_bucket(cg_ctx* c, int which, int bucket, void* str
 }
 extern "C" int cg_get_opt_state(cg_ctx* c, int which, float* hm, float* hv, int64_t* step) {
   Model* m = model_of(c, which);
+  OptState st;
   if (hm) CU(cudaMemcpyAsync(hm, m->m, m->total * 4, cudaMemcpyDeviceToHost, c->stream));
   if (hv) CU(cudaMemcpyAsync(hv, m->v, m->total * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&st, m->opt, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  if (step) *step = m->steps;
+  if (step) *step = st.steps;
   return 0;
 }
 extern "C" int cg_set_opt_state(cg_ctx* c, int which, const float* hm, const float* hv, int64_t step) {
   Model* m = model_of(c, which);
   if (hm) CU(cudaMemcpyAsync(m->m, hm, m->total * 4, cudaMemcpyHostToDevice, c->stream));
   if (hv) CU(cudaMemcpyAsync(m->v, hv, m->total * 4, cudaMemcpyHostToDevice, c->stream));
+  OptState st;
+  memset(&st, 0, sizeof(st));
+  CU(cudaMemcpyAsync(&st, m->opt, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
-  m->steps = step;
+  st.steps = step;
+  CU(cudaMemcpyAsync(m->opt, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
-extern "C" int cg_seed(cg_ctx* c, uint64_t seed) { c->seed = seed; c->rng_counter = 0; return 0; }
+extern "C" int64_t cg_skipped_updates(cg_ctx* c, int which) {
+  OptState st;
+  memset(&st, 0, sizeof(st));
+  if (cudaMemcpyAsync(&st, model_of(c, which)->opt, sizeof(st), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+      cudaStreamSynchronize(c->stream) != cudaSuccess)
+    return -1;
+  return st.skipped;
+}
+extern "C" int cg_set_grads(cg_ctx* c, int which, const float* host) {
+  Model* m = model_of(c, which);
+  if (!host) return set_err("cg_set_grads: null pointer");
+  CU(cudaMemcpyAsync(m->g, host, m->total * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int cg_seed(cg_ctx* c, uint64_t seed) {
+  c->seed = seed;
+  c->noise_calls = c->alpha_calls = c->shift_draws = 0;
+  return 0;
+}
 
 static uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;
@@ -533,7 +614,7 @@ extern "C" int cg_init_weights(cg_ctx* c, uint64_t seed) {
     CK(cg_set_weights(c, which, h.data()));
     CU(cudaMemsetAsync(m->m, 0, m->total * 4, c->stream));
     CU(cudaMemsetAsync(m->v, 0, m->total * 4, c->stream));
-    m->steps = 0;
+    CU(cudaMemsetAsync(m->opt, 0, sizeof(OptState), c->stream));
   }
   CU(cudaStreamSynchronize(c->stream));
   return 0;
@@ -623,7 +704,7 @@ static int g_forward(cg_ctx* c, const float* noise, int B, void* fake_slot = nul
   }
   const int Cp = c->gcp[NL];
   if (xhat_done) *xhat_done = false;
-  if (c->use_tc && !c->tc.force_v1 && !getenv("CG_NO_GHEAD")) {   // dedicated HBM-bound head kernel (cg_kernels_head.cuh)
+  if (c->use_tc && !c->tc.force_v1 && !(c->dbg_flags & CG_DEBUG_NO_GHEAD)) {   // dedicated HBM-bound head kernel (cg_kernels_head.cuh)
     GHeadArgs a;
     memset(&a, 0, sizeof(a));
     a.A = c->HG[NL]; a.W = c->Wf_d1; a.bias = gparam(c, c->g_d1b);
@@ -770,8 +851,7 @@ static RsParams conv_fwd_params(cg_ctx* c, int l, const void* A, void* out, int 
 
 // calciumgan.py:141-192 on X[0][0:Bt]; groups of B samples share PhaseShuffle shifts sh[g*4 + layer-1]
 static bool ps_fusable(cg_ctx* c, const RsParams& p) {
-  static const bool off_ = getenv("CG_NO_PS_FUSE") != nullptr;
-  return !off_ && c->use_tc && !c->tc.force_v1 && tc_rsgemm2_supported(p);
+  return !(c->dbg_flags & CG_DEBUG_NO_PS_FUSE) && c->use_tc && !c->tc.force_v1 && tc_rsgemm2_supported(p);
 }
 static void set_ps(RsParams& p, void* X, int w, int group_b, const int32_t* sh, int groups, int layer) {
   p.ps_out = X; p.ps_w = w; p.ps_group_b = group_b;
@@ -802,7 +882,7 @@ static int d_forward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh) {
 // data-gradient of conv layer l: DA[l] (rows dl[l]) -> out (rows dl[l-1]) for samples [b0, b0+nb)
 static RsParams d_dgrad_params(cg_ctx* c, int l, int b0, int nb, void* out);
 static bool d_dgrad_ps_fusable(cg_ctx* c, int l, int Bt) {
-  if (getenv("CG_NO_PS_BWD_FUSE") || !c->use_tc || c->tc.force_v1 || !c->tc.use_pair || c->cfg.phase_m > 10) return false;
+  if ((c->dbg_flags & CG_DEBUG_NO_PS_BWD_FUSE) || !c->use_tc || c->tc.force_v1 || !c->tc.use_pair || c->cfg.phase_m > 10) return false;
   const RsParams p = d_dgrad_params(c, l, 0, Bt, nullptr);
   return tc_rsgemm_supported(p) && tc_rsgemm2_supported(p) && p.seg.nphase == 2;
 }
@@ -896,17 +976,18 @@ static int d_wgrad(cg_ctx* c, int Bt, int nb_bias) {
 }
 
 // ------------------------------------------------------------------------------------------ rng
-static int draw(cg_ctx* c, float* out, long long n, int mode) {
-  const uint64_t stream = (c->rng_counter++) * 2654435761ull + (uint64_t)(c->cfg.rank + 1) * 0x100000001B3ull;
-  rng_fill_kernel<<<grid_for((n + 3) / 4), 256, 0, c->stream>>>(out, n, c->seed, stream, mode);
+// `calls` consecutive draws of n floats each (out + call * n); draw number (first_call + call) of this rank's stream
+static int draw(cg_ctx* c, float* out, long long n, int calls, uint64_t first_call, int mode) {
+  const uint64_t stream0 = (first_call << 24) | ((uint64_t)(c->cfg.rank & 0xFFFFF) << 4) | (uint64_t)mode;
+  dim3 grid(grid_for((n + 3) / 4), calls);
+  rng_fill_kernel<<<grid, 256, 0, c->stream>>>(out, n, c->seed, stream0, mode);
   return post_launch(c, "rng_fill");
 }
-static void draw_shifts(cg_ctx* c, int32_t* out, int n) {   // identical on every rank (shared per-call scalars)
+// shift number i of the run: identical on every rank (per-call scalars shared by the whole batch, calciumgan.py:121-124)
+static int32_t shift_draw(const cg_ctx* c, uint64_t i) {
   const int m = c->cfg.phase_m;
-  for (int i = 0; i < n; ++i) {
-    const uint64_t r = splitmix64(c->seed * 0x9E3779B97F4A7C15ull + 0xABCDull + (c->rng_counter++));
-    out[i] = (int32_t)(r % (uint64_t)(2 * m + 1)) - m;
-  }
+  const uint64_t r = splitmix64(splitmix64(c->seed ^ 0x5048415345ull) + i);
+  return (int32_t)(r % (uint64_t)(2 * m + 1)) - m;
 }
 
 static int check_batch(cg_ctx* c, int B) {
@@ -917,13 +998,20 @@ static int check_batch(cg_ctx* c, int B) {
 // ------------------------------------------------------------------------------------------ Adam
 extern "C" int cg_apply_update(cg_ctx* c, int which) {
   Model* m = model_of(c, which);
-  m->steps += 1;
-  const double t = (double)m->steps, b1 = 0.9, b2 = 0.999;
-  const float lr_t = (float)(c->cfg.learning_rate * std::sqrt(1.0 - std::pow(b2, t)) / (1.0 - std::pow(b1, t)));
-  adam_kernel<<<grid_for(m->total), 256, 0, c->stream>>>(m->w, m->m, m->v, m->g, m->total, lr_t, 0.9f, 0.999f, 1e-7f,
-                                                        1.0f / (float)c->cfg.world_size);
-  CK(post_launch(c, "adam"));
-  return repack(c, which);
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-7f, gscale = 1.0f / (float)c->cfg.world_size;
+  // pass 1 (reads the gradient once): non-finite check; the last block advances `iterations` and computes lr_t
+  adam_prepare_kernel<<<grid_for(m->total / 4, 256, 148 * 4), 256, 0, c->stream>>>(m->g, m->total, m->opt,
+                                                                                  c->cfg.learning_rate, b1, b2);
+  CK(post_launch(c, "adam_prepare"));
+  if (c->dbg_flags & CG_DEBUG_NO_ADAM_FUSE) {
+    adam_kernel<<<grid_for(m->total), 256, 0, c->stream>>>(m->w, m->m, m->v, m->g, m->total, m->opt, b1, b2, eps, gscale);
+    CK(post_launch(c, "adam"));
+    return repack(c, which);
+  }
+  const AdamPlan& pl = c->adam_plan[which];
+  DISPATCH_T(c, adam_pack_kernel<T><<<grid_for(pl.items * 256, 256, 148 * 8), 256, 0, c->stream>>>(
+                    m->w, m->m, m->v, m->g, pl, m->opt, b1, b2, eps, gscale));
+  return post_launch(c, "adam_pack");
 }
 
 static int fetch_scalars(cg_ctx* c, int slot, int flags, float* scalars_host) {
@@ -1019,23 +1107,33 @@ static int critic_step_impl(cg_ctx* c, const float* real, int B, const float* no
   return 0;
 }
 
-static int prep_random(cg_ctx* c, int B, const float*& noise, const float** alpha, const int32_t*& sh, int32_t* shbuf,
-                       int nsh) {
+// Random inputs of one step function: `noise_calls` draws of (B, nd) noise, `alpha_calls` draws of (B) alpha and nsh
+// PhaseShuffle shifts. Injected values are used as given; the stream positions advance by the same amount either way,
+// so a rank that injects and a rank that does not stay in step, and the shared shift stream never depends on what a
+// caller injected (two ranks making the same sequence of calls always see the same shifts).
+static int prep_random(cg_ctx* c, int B, const float*& noise, int noise_calls, const float** alpha, int alpha_calls,
+                       const int32_t*& sh, int32_t* shbuf, int nsh) {
   if (!noise) {
-    CK(draw(c, c->noise_buf, (long long)B * c->nd, 0));
+    CK(draw(c, c->noise_buf, (long long)B * c->nd, noise_calls, c->noise_calls, 0));
     noise = c->noise_buf;
   }
+  c->noise_calls += (uint64_t)noise_calls;
   if (alpha && !*alpha) {
-    CK(draw(c, c->alpha_buf, B, 1));
+    CK(draw(c, c->alpha_buf, B, alpha_calls, c->alpha_calls, 1));
     *alpha = c->alpha_buf;
   }
+  c->alpha_calls += (uint64_t)alpha_calls;
   if (!sh) {
-    draw_shifts(c, shbuf, nsh);
+    for (int i = 0; i < nsh; ++i) shbuf[i] = shift_draw(c, c->shift_draws + (uint64_t)i);
     sh = shbuf;
   }
+  c->shift_draws += (uint64_t)nsh;
   for (int i = 0; i < nsh; ++i)
     if (sh[i] < -c->cfg.phase_m || sh[i] > c->cfg.phase_m)
       return set_err("phase-shuffle shift %d outside [-m, m] (m=%d)", sh[i], c->cfg.phase_m);
+  c->last_noise = noise; c->last_n_noise = (int64_t)noise_calls * B * c->nd;
+  c->last_alpha = alpha ? *alpha : nullptr; c->last_n_alpha = alpha ? (int64_t)alpha_calls * B : 0;
+  c->last_shifts.assign(sh, sh + nsh);
   return 0;
 }
 
@@ -1043,7 +1141,7 @@ extern "C" int cg_critic_step(cg_ctx* c, const float* real, int B, const float* 
                               const int32_t* sh, int flags, float* scalars_host) {
   CK(check_batch(c, B));
   int32_t shbuf[12];
-  CK(prep_random(c, B, noise, &alpha, sh, shbuf, 12));
+  CK(prep_random(c, B, noise, 1, &alpha, 1, sh, shbuf, 12));
   CK(critic_step_impl(c, real, B, noise, alpha, sh, flags, 0, (flags & CG_FLAG_SAME_REAL) != 0, !(flags & CG_FLAG_NO_FAKE32)));
   return fetch_scalars(c, 0, flags, scalars_host);
 }
@@ -1075,7 +1173,7 @@ extern "C" int cg_generator_step(cg_ctx* c, const float* real, int B, const floa
                                  float* scalars_host) {
   CK(check_batch(c, B));
   int32_t shbuf[4];
-  CK(prep_random(c, B, noise, nullptr, sh, shbuf, 4));
+  CK(prep_random(c, B, noise, 1, nullptr, 0, sh, shbuf, 4));
   CK(generator_step_impl(c, real, B, noise, sh, flags, 0));
   return fetch_scalars(c, 0, flags, scalars_host);
 }
@@ -1086,11 +1184,8 @@ extern "C" int cg_train_step(cg_ctx* c, const float* real, int B, const float* n
   CK(check_batch(c, B));
   const int nc = c->cfg.n_critic;
   std::vector<int32_t> shbuf(12 * nc + 4);
-  if (!noise) { CK(draw(c, c->noise_buf, (long long)(nc + 1) * B * c->nd, 0)); noise = c->noise_buf; }
-  if (!alpha) { CK(draw(c, c->alpha_buf, (long long)nc * B, 1)); alpha = c->alpha_buf; }
-  if (!sh) { draw_shifts(c, shbuf.data(), 12 * nc + 4); sh = shbuf.data(); }
-  for (int i = 0; i < 12 * nc + 4; ++i)
-    if (sh[i] < -c->cfg.phase_m || sh[i] > c->cfg.phase_m) return set_err("phase-shuffle shift out of range");
+  // same stream positions as nc cg_critic_step calls followed by one cg_generator_step (the data-parallel host path)
+  CK(prep_random(c, B, noise, nc + 1, &alpha, nc, sh, shbuf.data(), 12 * nc + 4));
   for (int i = 0; i < nc; ++i)
     CK(critic_step_impl(c, real, B, noise + (size_t)i * B * c->nd, alpha + (size_t)i * B, sh + 12 * i, 0, i, i > 0,
                         /*want_fake32=*/false));   // the generator step rewrites FAKE32 before anything reads it
@@ -1114,7 +1209,7 @@ extern "C" int cg_validate(cg_ctx* c, const float* real, int B, const float* noi
                            const int32_t* sh, float* fake_out, float* scalars_host) {
   CK(check_batch(c, B));
   int32_t shbuf[12];
-  CK(prep_random(c, B, noise, &alpha, sh, shbuf, 12));
+  CK(prep_random(c, B, noise, 1, &alpha, 1, sh, shbuf, 12));
   CK(critic_forward_gp(c, real, B, noise, alpha, sh, 0));
   float* scal = c->d_scal;
   gen_loss_kernel<<<1, 256, 0, c->stream>>>(c->scores + B, scal, B);   // -mean D(fake)
@@ -1242,12 +1337,110 @@ extern "C" int cg_phase_shuffle_index(int w, int shift, int32_t* idx) {
   return 0;
 }
 
+extern "C" int cg_phase_shuffle_scatter_index(int w, int shift, int32_t* t1, int32_t* t2) {
+  if (w < 1 || !t1 || !t2) return set_err("cg_phase_shuffle_scatter_index: bad arguments");
+  if (shift > w - 1 || shift < -(w - 1)) return set_err("cg_phase_shuffle_scatter_index: |shift| must be < w");
+  for (int q = 0; q < w; ++q) { int a, b; ps_scatter_targets(q, shift, w, a, b); t1[q] = a; t2[q] = b; }
+  return 0;
+}
+extern "C" int cg_phase_shuffle_adjoint_plan(int w, int shift, int32_t* dest, int32_t* src_slot, int32_t* par_slot,
+                                             int32_t* zero) {
+  if (w < 2 || (w & 1) || !dest || !src_slot || !par_slot || !zero) return set_err("cg_phase_shuffle_adjoint_plan: bad arguments");
+  if (shift > w - 1 || shift < -(w - 1)) return set_err("cg_phase_shuffle_adjoint_plan: |shift| must be < w");
+  for (int t = 0; t < w; ++t) {
+    int d, xs, xp; bool xz;
+    ps_adjoint_row(t, shift, w, d, xs, xp, xz);
+    dest[t] = d; src_slot[t] = xs; par_slot[t] = xp; zero[t] = xz ? 1 : 0;
+  }
+  return 0;
+}
+
 extern "C" int cg_debug_phase_shuffle(cg_ctx* c, const float* x, int B, int w, int ch, int shift, float* out) {
   if (!x || !out || B < 1 || w < 1 || ch < 4 || ch % 4) return set_err("cg_debug_phase_shuffle: bad arguments");
   if (shift > w - 1 || shift < -(w - 1)) return set_err("cg_debug_phase_shuffle: |shift| must be < w");
   GroupShifts g; g.s[0] = shift; g.s[1] = g.s[2] = g.s[3] = 0;
   ps_gather_kernel<float><<<grid_for((long long)B * w * ch / 4), 256, 0, c->stream>>>(x, out, B, B, w, ch, g);
   CK(post_launch(c, "ps_gather_debug"));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static int debug_buffer(cg_ctx* c, int buffer, int layer, const void** ptr, int64_t* rows, int* ch, int* chp, int* cap) {
+  const bool critic = buffer == CG_BUF_X || buffer == CG_BUF_H || buffer == CG_BUF_DA;
+  const int lo = (buffer == CG_BUF_X || buffer == CG_BUF_HG) ? 0 : 1;
+  if (layer < lo || layer > NL) return set_err("cg_debug_read: layer %d out of range for buffer %d", layer, buffer);
+  switch (buffer) {
+    case CG_BUF_X: *ptr = c->X[layer]; break;
+    case CG_BUF_H: *ptr = c->H[layer]; break;
+    case CG_BUF_DA: *ptr = c->DA[layer]; break;
+    case CG_BUF_HG: *ptr = c->HG[layer]; break;
+    case CG_BUF_AG: *ptr = c->AG[layer]; break;
+    case CG_BUF_DAG: *ptr = c->DAG[layer]; break;
+    default: return set_err("cg_debug_read: unknown buffer %d", buffer);
+  }
+  if (critic) { *rows = c->dl[layer]; *ch = c->dc[layer]; *chp = c->dcp[layer]; *cap = 3 * c->Bmax; }
+  else { *rows = c->gl[layer]; *ch = c->gc[layer]; *chp = c->gcp[layer]; *cap = c->Bmax; }
+  return 0;
+}
+extern "C" int cg_debug_buffer_shape(cg_ctx* c, int buffer, int layer, int64_t* rows, int64_t* channels) {
+  const void* ptr = nullptr; int64_t r = 0; int ch = 0, chp = 0, cap = 0;
+  CK(debug_buffer(c, buffer, layer, &ptr, &r, &ch, &chp, &cap));
+  if (rows) *rows = r;
+  if (channels) *channels = ch;
+  return 0;
+}
+extern "C" int cg_debug_read(cg_ctx* c, int buffer, int layer, int batch, float* out) {
+  const void* ptr = nullptr; int64_t rows = 0; int ch = 0, chp = 0, cap = 0;
+  CK(debug_buffer(c, buffer, layer, &ptr, &rows, &ch, &chp, &cap));
+  if (!out || batch < 1 || batch > cap) return set_err("cg_debug_read: bad batch %d (capacity %d)", batch, cap);
+  CK(pad_out(c, ptr, out, (long long)batch * rows, ch, chp));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int cg_debug_last_draws(cg_ctx* c, float* noise_out, int64_t n_noise, float* alpha_out, int64_t n_alpha,
+                                   int32_t* shifts_out, int n_shifts) {
+  if (noise_out) {
+    if (!c->last_noise || n_noise > c->last_n_noise) return set_err("cg_debug_last_draws: the last step used %lld noise values", (long long)c->last_n_noise);
+    CU(cudaMemcpyAsync(noise_out, c->last_noise, (size_t)n_noise * 4, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  if (alpha_out) {
+    if (!c->last_alpha || n_alpha > c->last_n_alpha) return set_err("cg_debug_last_draws: the last step used %lld alpha values", (long long)c->last_n_alpha);
+    CU(cudaMemcpyAsync(alpha_out, c->last_alpha, (size_t)n_alpha * 4, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  if (shifts_out) {
+    if (n_shifts > (int)c->last_shifts.size()) return set_err("cg_debug_last_draws: the last step used %d shifts", (int)c->last_shifts.size());
+    memcpy(shifts_out, c->last_shifts.data(), (size_t)n_shifts * 4);
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// DA[l] -> DA[l-1]: data gradient, PhaseShuffle adjoint, LeakyReLU slope (one link of d_backward, in isolation)
+extern "C" int cg_debug_dgrad_ps(cg_ctx* c, int layer, const float* dy, const float* h, int B, int group_b,
+                                 const int32_t* shifts, float* out) {
+  const int l = layer;
+  if (l < 2 || l > NL || !dy || !h || !shifts || !out) return set_err("cg_debug_dgrad_ps: bad arguments");
+  if (B < 1 || B > 3 * c->Bmax || group_b < 1) return set_err("cg_debug_dgrad_ps: batch out of range");
+  const int groups = (B + group_b - 1) / group_b;
+  if (groups > 3) return set_err("cg_debug_dgrad_ps: at most 3 shift groups");
+  int32_t sh[12] = {0};
+  for (int g = 0; g < groups; ++g) {
+    if (shifts[g] < -c->cfg.phase_m || shifts[g] > c->cfg.phase_m) return set_err("cg_debug_dgrad_ps: shift outside [-m, m]");
+    sh[g * 4 + (l - 2)] = shifts[g];
+  }
+  CK(pad_in(c, dy, c->DA[l], B, c->dl[l], c->dc[l], c->dcp[l]));
+  CK(pad_in(c, h, c->H[l - 1], B, c->dl[l - 1], c->dc[l - 1], c->dcp[l - 1]));
+  if (d_dgrad_ps_fusable(c, l, B)) {
+    CK(d_dgrad_layer(c, l, 0, B, c->DA[l - 1], nullptr, c->H[l - 1], group_b, sh, groups));
+  } else {
+    CK(d_dgrad_layer(c, l, 0, B, c->DX[l - 1]));
+    const long long tot = (long long)B * c->dl[l - 1] * c->dcp[l - 1] / (16 / c->esz);
+    DISPATCH_T(c, ps_scatter_mask_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
+                      (const T*)c->DX[l - 1], (const T*)c->H[l - 1], (T*)c->DA[l - 1], B, group_b, c->dl[l - 1],
+                      c->dcp[l - 1], group_shifts(sh, groups, l - 1)));
+    CK(post_launch(c, "ps_scatter_mask"));
+  }
+  CK(pad_out(c, c->DA[l - 1], out, (long long)B * c->dl[l - 1], c->dc[l - 1], c->dcp[l - 1]));
   CU(cudaStreamSynchronize(c->stream));
   return 0;
 }

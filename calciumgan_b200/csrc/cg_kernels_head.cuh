@@ -276,11 +276,10 @@ static inline bool tc_ghead_supported(const GHeadArgs& a) {
 }
 
 static inline int tc_ghead_launch(TcState* s, const GHeadArgs& a, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!s->ghead_attr_set) {   // function attributes are per device: once per context, not once per process
     if (cudaFuncSetAttribute(tc::ghead_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) != cudaSuccess)
       return cg_tc_set_err("cudaFuncSetAttribute(ghead_tc_kernel) failed");
-    attr_set = true;
+    s->ghead_attr_set = true;
   }
   tc::GHeadParams P;
   memset(&P, 0, sizeof(P));

@@ -1034,19 +1034,162 @@ __global__ void denorm_kernel(const float* __restrict__ x, float* __restrict__ o
 }
 
 // =============================================================================================
-// Fused Adam (Keras form, optimizer.py:9,34): fp32 master weights + moments, gradient pre-scaled.
+// Adam (Keras form, optimizer.py:9,34): fp32 master weights + moments; w -= lr_t * m / (sqrt(v) + eps_hat),
+// lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t). The iteration counter lives on the device so that a step whose gradient
+// holds a non-finite value can be skipped (what the reference's LossScaleOptimizer does, optimizer.py:10-12) without
+// a host round trip, and so that no kernel argument changes from step to step.
 // =============================================================================================
+struct OptState {
+  long long steps;        // optimizer.iterations
+  long long skipped;      // updates skipped because of a non-finite gradient
+  float lr_t;             // bias-corrected step size of the update in flight
+  int do_update;          // 0: the update in flight is skipped
+  unsigned int bad;       // scratch: a non-finite gradient was seen
+  unsigned int done;      // scratch: blocks of adam_prepare_kernel that have finished
+};
+
+// Pass 1 over the gradient: any non-finite value? The last block to finish advances the counters and computes lr_t.
+__global__ void __launch_bounds__(256) adam_prepare_kernel(const float* __restrict__ g, long long n, OptState* st, float lr,
+                                                           float b1, float b2) {
+  unsigned int bad = 0;
+  const long long n4 = n >> 2;
+  const uint4* g4 = reinterpret_cast<const uint4*>(g);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = g4[i];
+    bad |= ((v.x & 0x7f800000u) == 0x7f800000u) | ((v.y & 0x7f800000u) == 0x7f800000u) |
+           ((v.z & 0x7f800000u) == 0x7f800000u) | ((v.w & 0x7f800000u) == 0x7f800000u);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3))
+    bad |= (__float_as_uint(g[(n4 << 2) + threadIdx.x]) & 0x7f800000u) == 0x7f800000u;
+  bad = __syncthreads_or((int)bad);
+  __shared__ unsigned int ticket;
+  if (threadIdx.x == 0) {
+    if (bad) atomicOr(&st->bad, 1u);
+    __threadfence();
+    ticket = atomicAdd(&st->done, 1u);
+  }
+  __syncthreads();
+  if (ticket == gridDim.x - 1 && threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int any_bad = atomicOr(&st->bad, 0u);
+    if (any_bad) {
+      st->skipped += 1;
+      st->do_update = 0;
+    } else {
+      st->steps += 1;
+      const double t = (double)st->steps;
+      st->lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+      st->do_update = 1;
+    }
+    st->bad = 0u;
+    st->done = 0u;
+  }
+}
+
+__device__ __forceinline__ void adam_elem(float& w, float& m, float& v, float g, float lr_t, float b1, float b2, float eps) {
+  m = b1 * m + (1.f - b1) * g;
+  v = b2 * v + (1.f - b2) * g * g;
+  w -= lr_t * m / (sqrtf(v) + eps);
+}
+
 __global__ void adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
-                            const float* __restrict__ g, long long n, float lr_t, float b1, float b2, float eps,
-                            float gscale) {
+                            const float* __restrict__ g, long long n, const OptState* __restrict__ st, float b1,
+                            float b2, float eps, float gscale) {
+  if (!st->do_update) return;
+  const float lr_t = st->lr_t;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i] * gscale;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    float wi = w[i], mi = m[i], vi = v[i];
+    adam_elem(wi, mi, vi, g[i] * gscale, lr_t, b1, b2, eps);
+    m[i] = mi; v[i] = vi; w[i] = wi;
+  }
+}
+
+// Adam and the refresh of the packed low-precision GEMM operands in ONE pass over the parameters. GEMM kernels are
+// walked as 32 x 32 tiles of one tap's (a, b) plane (b = the Keras layout's fastest axis): w, m, v, g are read and
+// written coalesced along b, the packed copy whose rows run along b is written from registers, the one whose rows run
+// along a through a shared-memory transpose. Everything else (biases, layer-norm parameters, the two small dense
+// layers) is a plain element-wise range. Padded rows / columns of the packed copies are never touched (they are zero
+// from cg_create / the last full re-pack and no update changes them).
+struct AdamTensor {
+  long long off;          // offset in the flat parameter arrays
+  int K, A, B;            // taps, slow and fast extent of one tap's plane: element (k, a, b) at off + (k*A + a)*B + b
+  int Ap, Bp;             // padded extents in the packed copies
+  void* direct;           // [a][k*Bp + b]
+  void* trans;            // [b][k*Ap + a]
+  int tiles_a, tiles_b;
+  long long item0;        // first work item of this tensor
+};
+struct AdamRange { long long off, len, item0; };
+struct AdamPlan {
+  int nt, nr;
+  AdamTensor t[8];
+  AdamRange r[16];
+  long long items;        // tile items first, then 1024-element chunks of the ranges
+  long long tile_items;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) adam_pack_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v,
+                                                        const float* __restrict__ g, const __grid_constant__ AdamPlan plan,
+                                                        const OptState* __restrict__ st, float b1, float b2, float eps,
+                                                        float gscale) {
+  if (!st->do_update) return;
+  const float lr_t = st->lr_t;
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (long long it = blockIdx.x; it < plan.items; it += gridDim.x) {
+    if (it < plan.tile_items) {
+      int ti = 0;
+#pragma unroll
+      for (int j = 1; j < 8; ++j) if (j < plan.nt && it >= plan.t[j].item0) ti = j;
+      const AdamTensor& t = plan.t[ti];
+      int r = (int)(it - t.item0);
+      const int tb = r % t.tiles_b; r /= t.tiles_b;
+      const int ta = r % t.tiles_a;
+      const int k = r / t.tiles_a;
+      const int a0 = ta * 32, b = tb * 32 + tx;
+      T* direct = reinterpret_cast<T*>(t.direct);
+      T* trans = reinterpret_cast<T*>(t.trans);
+      __syncthreads();   // the previous item's transposed reads are done
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int a = a0 + ty + 8 * j;
+        float wi = 0.f;
+        if (a < t.A && b < t.B) {
+          const long long i = t.off + ((long long)k * t.A + a) * t.B + b;
+          wi = w[i];
+          float mi = m[i], vi = v[i];
+          adam_elem(wi, mi, vi, g[i] * gscale, lr_t, b1, b2, eps);
+          m[i] = mi; v[i] = vi; w[i] = wi;
+          direct[((long long)a * t.K + k) * t.Bp + b] = Elem<T>::from_f(wi);
+        }
+        tile[ty + 8 * j][tx] = wi;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int bb = tb * 32 + ty + 8 * j, a = a0 + tx;
+        if (bb < t.B && a < t.A) trans[((long long)bb * t.K + k) * t.Ap + a] = Elem<T>::from_f(tile[tx][ty + 8 * j]);
+      }
+    } else {
+      const long long e = it - plan.tile_items;
+      int ri = 0;
+#pragma unroll
+      for (int j = 1; j < 16; ++j) if (j < plan.nr && e >= plan.r[j].item0) ri = j;
+      const AdamRange& rg = plan.r[ri];
+      const long long base = (e - rg.item0) * 1024;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long o = base + j * 256 + threadIdx.x;
+        if (o < rg.len) {
+          const long long i = rg.off + o;
+          float wi = w[i], mi = m[i], vi = v[i];
+          adam_elem(wi, mi, vi, g[i] * gscale, lr_t, b1, b2, eps);
+          m[i] = mi; v[i] = vi; w[i] = wi;
+        }
+      }
+    }
   }
 }
 
@@ -1068,8 +1211,10 @@ __device__ __forceinline__ void philox4x32(uint64_t seed, uint64_t stream, uint6
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
 }
-// mode 0: standard normal (Box-Muller); mode 1: uniform [0,1)
-__global__ void rng_fill_kernel(float* __restrict__ out, long long n, uint64_t seed, uint64_t stream, int mode) {
+// mode 0: standard normal (Box-Muller); mode 1: uniform [0,1). blockIdx.y = draw number: out + y * n, stream0 + (y << 24)
+__global__ void rng_fill_kernel(float* __restrict__ out_all, long long n, uint64_t seed, uint64_t stream0, int mode) {
+  float* out = out_all + (long long)blockIdx.y * n;
+  const uint64_t stream = stream0 + ((uint64_t)blockIdx.y << 24);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i * 4 < n;
        i += (long long)gridDim.x * blockDim.x) {
     uint32_t c[4];

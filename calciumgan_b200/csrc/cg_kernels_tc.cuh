@@ -4,7 +4,7 @@
 //              strided Conv1D fwd, Conv1DTranspose fwd, their data gradients, GP linearised fwd, Dense.
 //              A tiles are tap-shifted 3-D TMA boxes (batch is its own dim -> per-sample zero fill),
 //              W tiles 2-D TMA boxes, both K-major SWIZZLE_128B; D (128 x BN fp32) lives in TMEM,
-//              double buffered; warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue.
+//              double buffered; warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = epilogue (two per TMEM lane quarter).
 //  wgrad_tc  : dW[tap][m][n] += sum_{b,q} S[b, q+shift(tap), scol(tap)+m] * P[b,q,n]
 //              both operands MN-major (reduction runs over time rows), split over rows, fp32 red.add.
 #pragma once
@@ -321,25 +321,17 @@ __device__ __forceinline__ void epi_rows_ps(const RsParams& p, int b, int q0, in
   R.base = (long long)b * p.o_bs;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int j = (q0 + lq * 32 + i * 8 + crow) * 2 + phase + s;
-    R.off[i] = (bok && j >= 0 && j < w) ? (j >> 1) * p.o_rs + (j & 1) * p.o_phase_col : -1;
+    int j, xs, xp; bool xz;
+    ps_adjoint_row((q0 + lq * 32 + i * 8 + crow) * 2 + phase, s, w, j, xs, xp, xz);
+    R.off[i] = (bok && j >= 0) ? (j >> 1) * p.o_rs + (j & 1) * p.o_phase_col : -1;
   }
   const int q = q0 + lq * 32 + lane;
   const int t = q * 2 + phase;
   R.my_ok = bok;
   R.my_off = q * p.o_rs + phase * p.o_phase_col;
   R.my_o32 = 0; R.my_row = 0; R.o32_base = 0; R.uniform = true;
-  R.x_src = -1; R.x_par = -1;
-  if (s > 0) {
-    if (t + s > w - 1) R.x_src = (w - 1 - t) >> 1;
-    const int tp = 2 * (w - 1) - t - 2 * s;
-    if (tp <= w - 1 && tp + s > w - 1) R.x_par = (w - 1 - tp) >> 1;
-  } else if (s < 0) {
-    if (t + s < 0) R.x_src = t >> 1;
-    const int tp = -t - 2 * s;
-    if (tp >= 0 && tp + s < 0) R.x_par = tp >> 1;
-  }
-  R.x_zero = t - s < 0 || t - s > w - 1;
+  int dest;
+  ps_adjoint_row(t, s, w, dest, R.x_src, R.x_par, R.x_zero);
 }
 
 // The 32-column chunks c0 = 32 * half, 32 * half + 64, ... of one 128-row x BN-column accumulator block:
@@ -526,12 +518,10 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
         if (R.off[i] >= 0) {
           if (out) *reinterpret_cast<uint4*>(out + R.base + R.off[i] + n0 + cj * 8) = o;
           if (psx) {   // scatter form of the PhaseShuffle gather: row q feeds every t with ps_index(t) == q
-            const int q = ps_q0 + lq * 32 + rr, w = p.ps_w;
-            const int t1 = q - ps_s;
-            if (t1 >= 0 && t1 < w) *reinterpret_cast<uint4*>(psx + R.base + (R.off[i] + (t1 - q) * p.o_rs + n0 + cj * 8)) = o;
-            int t2 = -1;
-            if (ps_s > 0) { t2 = 2 * (w - 1) - q - ps_s; if (!(t2 >= 0 && t2 < w && t2 + ps_s > w - 1)) t2 = -1; }
-            else if (ps_s < 0) { t2 = -q - ps_s; if (!(t2 >= 0 && t2 < w && t2 + ps_s < 0)) t2 = -1; }
+            const int q = ps_q0 + lq * 32 + rr;
+            int t1, t2;
+            ps_scatter_targets(q, ps_s, p.ps_w, t1, t2);
+            if (t1 >= 0) *reinterpret_cast<uint4*>(psx + R.base + (R.off[i] + (t1 - q) * p.o_rs + n0 + cj * 8)) = o;
             if (t2 >= 0) *reinterpret_cast<uint4*>(psx + R.base + (R.off[i] + (t2 - q) * p.o_rs + n0 + cj * 8)) = o;
           }
         }
@@ -1360,6 +1350,8 @@ struct TcState {
   bool force_v1 = false;   // CG_TC_V1=1: per-tap boxes everywhere (A/B comparison)
   const bool use_pair = true;   // the cta_group::2 kernel serves every layer with >= 128 time rows per sample
   bool pair_short = true;  // CG_TC_PAIR_SHORT=0: per-tap single-CTA kernel for layers with < 128 time rows
+  bool ghead_attr_set = false;
+  long long *dbg_buf = nullptr, *dbg_buf3 = nullptr;   // role cycle counters (instrumented builds only), per context / device
   std::string err;
 };
 
@@ -1395,7 +1387,12 @@ static inline int tc_init(TcState* s) {
     return cg_tc_set_err("cudaFuncSetAttribute(max dynamic smem) failed");
   return 0;
 }
-static inline void tc_destroy(TcState* s) { s->cache.clear(); }
+static inline void tc_destroy(TcState* s) {
+  s->cache.clear();
+  if (s->dbg_buf) cudaFree(s->dbg_buf);
+  if (s->dbg_buf3) cudaFree(s->dbg_buf3);
+  s->dbg_buf = s->dbg_buf3 = nullptr;
+}
 
 // 3-D map over a bf16 tensor viewed as (batch, rows, cols) with box (64 cols, box_rows, box_batch), SWIZZLE_128B
 static inline int tc_get_map3(TcState* s, const void* base, long long cols, long long rows, long long batch,
@@ -1578,12 +1575,11 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   if (bst > 10) bst = 10;
   if (bst < 2) return cg_tc_set_err("rsgemm3_tc: not enough shared memory");
   P.b_stages = bst;
-  static long long* dbg_buf3 = nullptr;
   P.dbg = nullptr;
   if (CG_TC_INSTRUMENTED && getenv("CG_TC_TIMING") != nullptr) {
-    if (!dbg_buf3) cudaMalloc(&dbg_buf3, 16 * sizeof(long long));
-    cudaMemsetAsync(dbg_buf3, 0, 16 * sizeof(long long), stream);
-    P.dbg = dbg_buf3;
+    if (!s->dbg_buf3) cudaMalloc(&s->dbg_buf3, 16 * sizeof(long long));
+    cudaMemsetAsync(s->dbg_buf3, 0, 16 * sizeof(long long), stream);
+    P.dbg = s->dbg_buf3;
   }
   CUtensorMap tmA, tmW;
   if (P.per_tap) { if (tc_get_map3(s, p.A, p.a_rs, p.a_rows, p.B, p.a_rs, p.a_bs, P.rpt, P.bpt, &tmA)) return 1; }
@@ -1605,7 +1601,7 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   if (P.dbg) {
     long long h[16];
     cudaStreamSynchronize(stream);
-    cudaMemcpy(h, dbg_buf3, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaMemcpy(h, s->dbg_buf3, sizeof(h), cudaMemcpyDeviceToHost);
     fprintf(stderr, "[tc3 timing] B=%d Q=%d N=%d Kc=%d epi=%d | BN=%d tps=%d tiles=%d pairs=%d sst=%d bst=%d pt=%d | total %lld clk | mma wait tempty %lld/%lld s_full %lld/%lld b_full %lld/%lld issue %lld commit %lld /%lld | epi wait %lld/%lld work %lld/%lld\n",
             p.B, p.Q, p.N, p.Kc, p.epi, P.BN, P.tps, total, npairs, P.slab_stages, bst, P.per_tap, h[7], h[2], h[10], h[3], h[11], h[4], h[12], h[0], h[1], h[8], h[5], h[13], h[6], h[14]);
   }
@@ -1641,12 +1637,11 @@ static inline int tc_rsgemm_launch(TcState* s, const RsParams& p, cudaStream_t s
   const int total = p.seg.nphase * P.n_tiles * P.m_tiles;
   const int grid = total < s->sm_count ? total : s->sm_count;
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 512 + tc::kEpiSmem;
-  static long long* dbg_buf = nullptr;
   P.dbg = nullptr;
   if (CG_TC_INSTRUMENTED && getenv("CG_TC_TIMING") != nullptr) {
-    if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
-    cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), stream);
-    P.dbg = dbg_buf;
+    if (!s->dbg_buf) cudaMalloc(&s->dbg_buf, 16 * sizeof(long long));
+    cudaMemsetAsync(s->dbg_buf, 0, 16 * sizeof(long long), stream);
+    P.dbg = s->dbg_buf;
   }
   const long long t_host0 = 0;
   (void)t_host0;
@@ -1660,7 +1655,7 @@ static inline int tc_rsgemm_launch(TcState* s, const RsParams& p, cudaStream_t s
   if (P.dbg) {
     long long h[16];
     cudaStreamSynchronize(stream);
-    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaMemcpy(h, s->dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
     fprintf(stderr, "[tc timing] N=%d BN=%d Q=%d tiles=%d grid=%d stages=%d | producer wait-empty %lld clk/%lld | mma wait-tempty %lld/%lld, wait-full %lld/%lld | epi wait-tfull %lld, work %lld over %lld tiles\n",
             p.N, P.BN, p.Q, total, grid, stages, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8]);
   }

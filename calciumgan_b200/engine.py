@@ -11,7 +11,7 @@ import torch
 from . import _lib as L
 
 
-def hparams_to_config(hparams, max_batch=None, world_size=1, rank=0, force_simt=False):
+def hparams_to_config(hparams, max_batch=None, world_size=1, rank=0, force_simt=False, debug_flags=0):
   """Map the reference's hparams Namespace (main.py:229-261 + dataset_helper.py:84-91) to cg_config."""
   if getattr(hparams, 'batch_norm', False):
     raise NotImplementedError('--batch_norm couples samples and is out of scope (SURVEY §3.6-6)')
@@ -39,6 +39,7 @@ def hparams_to_config(hparams, max_batch=None, world_size=1, rank=0, force_simt=
   cfg.world_size = int(world_size)
   cfg.rank = int(rank)
   cfg.force_simt = int(bool(force_simt))
+  cfg.debug_flags = int(debug_flags)
   return cfg
 
 
@@ -163,6 +164,14 @@ class Engine(object):
     flat = np.empty(self.num_params(which), np.float32)
     L.check(self.lib.cg_get_grads(self.ctx, which, flat.ctypes.data_as(C.c_void_p)))
     return self._split(which, flat)
+
+  def set_grads(self, which, arrays):
+    """Overwrite the flat gradient buffer (parity test of apply_update alone)."""
+    flat = self._join(which, arrays)
+    L.check(self.lib.cg_set_grads(self.ctx, which, flat.ctypes.data_as(C.c_void_p)))
+
+  def skipped_updates(self, which):
+    return int(self.lib.cg_skipped_updates(self.ctx, which))
 
   def grad_tensor(self, which):
     """Flat fp32 CUDA tensor aliasing the library's gradient buffer (for the NCCL all-reduce)."""
@@ -321,6 +330,35 @@ class Engine(object):
     B, w, ch = x.shape
     out = torch.empty_like(x)
     L.check(self.lib.cg_debug_phase_shuffle(self.ctx, self._ptr(x), B, w, ch, int(shift), self._ptr(out)))
+    return out
+
+  def debug_read(self, buffer, layer, batch):
+    """Internal activation buffer of the last step as an unpadded fp32 CUDA tensor (batch, rows, channels)."""
+    self._use_stream()
+    rows, ch = C.c_int64(), C.c_int64()
+    L.check(self.lib.cg_debug_buffer_shape(self.ctx, buffer, layer, C.byref(rows), C.byref(ch)))
+    out = torch.empty((batch, rows.value, ch.value), device=self.device, dtype=torch.float32)
+    L.check(self.lib.cg_debug_read(self.ctx, buffer, layer, batch, self._ptr(out)))
+    return out
+
+  def last_draws(self, n_noise=0, n_alpha=0, n_shifts=0):
+    """(noise, alpha, shifts) of the last step function, injected or library-drawn."""
+    self._use_stream()
+    noise = torch.empty((n_noise,), device=self.device, dtype=torch.float32) if n_noise else None
+    alpha = torch.empty((n_alpha,), device=self.device, dtype=torch.float32) if n_alpha else None
+    sh = np.zeros(max(n_shifts, 1), np.int32)
+    L.check(self.lib.cg_debug_last_draws(self.ctx, self._ptr(noise), n_noise, self._ptr(alpha), n_alpha,
+                                         sh.ctypes.data_as(C.POINTER(C.c_int32)) if n_shifts else None, n_shifts))
+    return noise, alpha, sh[:n_shifts]
+
+  def dgrad_ps(self, layer, dy, h, group_b, shifts):
+    """DA[l] -> DA[l-1] in isolation: data gradient + PhaseShuffle adjoint + LeakyReLU slope (cg_debug_dgrad_ps)."""
+    self._use_stream()
+    dy, h = self.to_device(dy), self.to_device(h)
+    sh = np.ascontiguousarray(np.asarray(shifts, np.int32).reshape(-1))
+    out = torch.empty_like(h)
+    L.check(self.lib.cg_debug_dgrad_ps(self.ctx, layer, self._ptr(dy), self._ptr(h), dy.shape[0], int(group_b),
+                                       sh.ctypes.data_as(C.POINTER(C.c_int32)), self._ptr(out)))
     return out
 
   def fake(self, batch):

@@ -97,7 +97,8 @@ def build_engine(hparams):
   world, rank = (dist.get_world_size(), dist.get_rank()) if dist.is_available() and dist.is_initialized() else (1, 0)
   calculate_noise_shape(hparams.signal_shape, hparams.noise_dim, 5, hparams.strides)
   cfg = hparams_to_config(hparams, world_size=world, rank=rank,
-                          force_simt=getattr(hparams, 'force_simt', False))
+                          force_simt=getattr(hparams, 'force_simt', False),
+                          debug_flags=getattr(hparams, 'debug_flags', 0))
   engine = Engine(cfg)
   seed = int(getattr(hparams, 'seed', 1234))   # main.py:11-12
   engine.init_weights(seed)

@@ -53,8 +53,17 @@ typedef struct cg_config {
   int32_t world_size;     /* data-parallel ranks (gradients are scaled 1/world_size in cg_apply_update) */
   int32_t rank;
   int32_t force_simt;     /* debug: run the CUDA-core kernels even in bf16 mode */
-  int32_t reserved[7];
+  int32_t debug_flags;    /* CG_DEBUG_* bits: run the unfused reference form of a fused kernel (parity tests) */
+  int32_t reserved[6];
 } cg_config;
+
+/* cg_config.debug_flags (the environment variables of the same name, read once in cg_create, set the same bits) */
+enum {
+  CG_DEBUG_NO_PS_FUSE = 1,      /* CG_NO_PS_FUSE: PhaseShuffle gather as its own kernel after the conv GEMM            */
+  CG_DEBUG_NO_PS_BWD_FUSE = 2,  /* CG_NO_PS_BWD_FUSE: PhaseShuffle adjoint + slope mask as its own kernel               */
+  CG_DEBUG_NO_GHEAD = 4,        /* CG_NO_GHEAD: generic GEMM + interpolation kernel instead of the generator-head kernel */
+  CG_DEBUG_NO_ADAM_FUSE = 8     /* CG_NO_ADAM_FUSE: Adam and the bf16 weight re-pack as two kernels                       */
+};
 
 typedef struct cg_ctx cg_ctx;
 
@@ -103,6 +112,11 @@ void* cg_grad_ptr(cg_ctx* ctx, int which);
 int cg_num_buckets(cg_ctx* ctx, int which);
 int cg_bucket_info(cg_ctx* ctx, int which, int bucket, int64_t* offset, int64_t* count);
 int cg_stream_wait_bucket(cg_ctx* ctx, int which, int bucket, void* cuda_stream);
+/* overwrite the flat gradient buffer (parity test of cg_apply_update alone; Keras get_weights() order) */
+int cg_set_grads(cg_ctx* ctx, int which, const float* host_flat);
+/* updates skipped because a gradient was not finite (the reference's LossScaleOptimizer skips such steps,
+ * optimizer.py:10-12; here the step is skipped and `iterations` is not advanced) */
+int64_t cg_skipped_updates(cg_ctx* ctx, int which);
 /* Adam moments + iteration counter (optimizer.py:15-21; extra checkpoint keys) */
 int cg_get_opt_state(cg_ctx* ctx, int which, float* host_m, float* host_v, int64_t* step);
 int cg_set_opt_state(cg_ctx* ctx, int which, const float* host_m, const float* host_v, int64_t step);
@@ -163,7 +177,41 @@ int cg_debug_layer(cg_ctx* ctx, int which, int layer, int pass, const float* x_d
  * bit-exact index arithmetic. cg_phase_shuffle_index fills host idx[w] with the source row of each
  * output row (no GPU needed). */
 int cg_debug_phase_shuffle(cg_ctx* ctx, const float* x_dev, int batch, int w, int ch, int shift, float* out_dev);
+/* Internal activation buffer of the last step as an unpadded fp32 tensor (bf16 -> fp32 is exact, so bit-level
+ * comparisons of the stored values are possible). Critic buffers hold `batch` <= 3*max_batch samples in group order
+ * [real; fake; xhat]; layer 0 = network input.
+ *   CG_BUF_X   critic layer input  X[l]  (batch, L/2^l, C_l)   l = 0..5  (l >= 1: PhaseShuffle output, calciumgan.py:151)
+ *   CG_BUF_H   critic activation   H[l]  (batch, L/2^l, C_l)   l = 1..5  (LeakyReLU output; its sign is the slope mask)
+ *   CG_BUF_DA  critic d/d(pre-activation) of layer l           l = 1..5
+ *   CG_BUF_HG  generator activation HG[i] (batch, w*2^i, C_i)  i = 0..5  (LeakyReLU output)
+ *   CG_BUF_AG  generator pre-norm conv-transpose output        i = 1..5
+ *   CG_BUF_DAG generator d/d(conv-transpose output)            i = 1..5  */
+enum { CG_BUF_X = 0, CG_BUF_H = 1, CG_BUF_DA = 2, CG_BUF_HG = 3, CG_BUF_AG = 4, CG_BUF_DAG = 5 };
+int cg_debug_read(cg_ctx* ctx, int buffer, int layer, int batch, float* out_dev);
+/* shape of that tensor without the batch dimension */
+int cg_debug_buffer_shape(cg_ctx* ctx, int buffer, int layer, int64_t* rows, int64_t* channels);
+/* The random draws of the last step function, whether injected or drawn by the library: noise (n_noise floats,
+ * device), alpha (n_alpha floats, device), shifts (n_shifts int32, host). Any pointer may be NULL. Returns an error
+ * if more values are requested than the last step used. */
+int cg_debug_last_draws(cg_ctx* ctx, float* noise_out_dev, int64_t n_noise, float* alpha_out_dev, int64_t n_alpha,
+                        int32_t* shifts_out_host, int n_shifts);
+/* Data gradient of critic conv layer `layer` (2..5) followed by the PhaseShuffle adjoint and the LeakyReLU slope of the
+ * layer below (the step between DA[l] and DA[l-1] of the backward chain), in isolation:
+ *   dy (batch, L/2^l, C_l) fp32, h (batch, L/2^(l-1), C_(l-1)) fp32 (sign = slope source), group_b samples per shift,
+ *   shifts_host[ceil(batch / group_b)] -> out (batch, L/2^(l-1), C_(l-1)) fp32.
+ * Runs the fused epilogue (EPI_PS_MASK) or, with CG_DEBUG_NO_PS_BWD_FUSE, the two-kernel form. */
+int cg_debug_dgrad_ps(cg_ctx* ctx, int layer, const float* dy_dev, const float* h_dev, int batch, int group_b,
+                      const int32_t* shifts_host, float* out_dev);
 int cg_phase_shuffle_index(int w, int shift, int32_t* idx_host);
+/* The same map in the two forms the fused tensor-core epilogues use (host copies of the device functions, so the
+ * index arithmetic of the hot path can be checked bit for bit without a GPU):
+ *   scatter form (forward): source row q is output row t1[q] and, when reflected, also t2[q] (-1 = none);
+ *   adjoint plan (data gradient): accumulator row t is stored to output row dest[t] (-1: pushed over an edge), deposits
+ *   its value in exchange slot src_slot[t] and adds exchange slot par_slot[t] (slots are per row parity; -1 = none);
+ *   zero[t] = 1 when no row maps to output row t. */
+int cg_phase_shuffle_scatter_index(int w, int shift, int32_t* t1_host, int32_t* t2_host);
+int cg_phase_shuffle_adjoint_plan(int w, int shift, int32_t* dest_host, int32_t* src_slot_host, int32_t* par_slot_host,
+                                  int32_t* zero_host);
 /* device pointer to the generator output (batch, seq_len, channels) fp32 of the last step */
 void* cg_fake_ptr(cg_ctx* ctx);
 /* device pointer to the critic scores of the last critic forward (groups x batch) fp32 */

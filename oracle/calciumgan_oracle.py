@@ -168,8 +168,21 @@ def randomize_weights(weights: Sequence[np.ndarray], seed: int, scale: float = 0
 
 # ----------------------------------------------------------------------------- layers
 
-def leaky_relu(x):
+def leaky_relu(x, slope=None):
+  """LeakyReLU; with ``slope`` (a tensor of 1 / LEAKY_ALPHA per element) the branch of every element is IMPOSED
+  instead of read from the sign of x. That turns the network into a smooth function of its rounding errors
+  (LeakyReLU's slope is its only discontinuity), which is how the parity tests separate "an activation rounded
+  across zero" from "a kernel bug": the CUDA path exports its own branch decisions (sign of the stored activation)
+  and the oracle is evaluated on the same branches."""
+  if slope is not None:
+    return x * slope
   return torch.where(x > 0, x, LEAKY_ALPHA * x)
+
+
+def slopes_from_activation(h):
+  """Branch decisions of a stored LeakyReLU output (sign(h) == sign(pre-activation); 0 counts as negative, as in
+  the engine's lrelu_slope)."""
+  return torch.where(h > 0, torch.ones_like(h), torch.full_like(h, LEAKY_ALPHA))
 
 
 def same_pad_left(K: int, s: int) -> int:
@@ -217,7 +230,7 @@ def phase_shuffle_index(w: int, shift: int) -> np.ndarray:
 
 
 def phase_shuffle(x, shift: int):
-  idx = torch.from_numpy(phase_shuffle_index(x.shape[1], shift).astype(np.int64))
+  idx = torch.from_numpy(phase_shuffle_index(x.shape[1], shift).astype(np.int64)).to(x.device)
   return x.index_select(1, idx)
 
 
@@ -233,17 +246,33 @@ def phase_shuffle_literal(x: np.ndarray, shift: int) -> np.ndarray:
 
 # ----------------------------------------------------------------------------- models
 
+_DEVICE = None   # tests may evaluate the oracle with torch float64 on the CUDA device for batch-128 cases (set_device)
+
+
+def set_device(device):
+  """Where the oracle's tensors live. Default (None) = CPU. The arithmetic is the same torch code either way; the
+  full-batch parity test moves it to the GPU because a batch-128 float64 double backward takes minutes on the host."""
+  global _DEVICE
+  _DEVICE = device
+
+
 def _t(a, dtype):
-  return a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a), dtype=dtype)
+  if isinstance(a, torch.Tensor):
+    return a.to(device=_DEVICE, dtype=dtype) if (_DEVICE is not None or a.dtype != dtype) else a
+  return torch.as_tensor(np.asarray(a), dtype=dtype, device=_DEVICE)
 
 
-def generator_forward(gw, noise, hp: HParams, taps: Optional[dict] = None):
-  """calciumgan.py:22-103. gw = list of tensors in get_weights() order."""
+def generator_forward(gw, noise, hp: HParams, taps: Optional[dict] = None, slopes=None):
+  """calciumgan.py:22-103. gw = list of tensors in get_weights() order.
+  slopes: optional imposed LeakyReLU branches [dense, convT1 .. convT5] (see leaky_relu)."""
   if hp.batch_norm:
     raise NotImplementedError('batch_norm is out of scope (SURVEY §3.6-6)')
   w, nd = calculate_noise_shape(hp.signal_shape, hp.noise_dim, NUM_LAYERS, hp.strides)
   i = 0
-  x = leaky_relu(noise @ gw[0] + gw[1])
+  x = noise @ gw[0] + gw[1]
+  x = leaky_relu(x, None if slopes is None else slopes[0].reshape(x.shape))
+  if taps is not None:
+    taps['g0'] = x
   i = 2
   x = x.reshape(x.shape[0], w, nd)
   for l in range(NUM_LAYERS):
@@ -254,15 +283,18 @@ def generator_forward(gw, noise, hp: HParams, taps: Optional[dict] = None):
     if hp.layer_norm:
       x = layer_norm(x, gw[i], gw[i + 1])
       i += 2
-    x = leaky_relu(x)
+    x = leaky_relu(x, None if slopes is None else slopes[l + 1])
+    if taps is not None:
+      taps['g%d' % (l + 1)] = x
   x = x @ gw[i] + gw[i + 1]
   return torch.sigmoid(x) if hp.normalize else x
 
 
-def discriminator_forward(dw, x, shifts: Sequence[int], hp: HParams, taps: Optional[dict] = None):
-  """calciumgan.py:141-192; ``shifts`` = the 4 PhaseShuffle draws of this call."""
+def discriminator_forward(dw, x, shifts: Sequence[int], hp: HParams, taps: Optional[dict] = None, slopes=None):
+  """calciumgan.py:141-192; ``shifts`` = the 4 PhaseShuffle draws of this call.
+  slopes: optional imposed LeakyReLU branches [conv1 .. conv5] (see leaky_relu)."""
   for l in range(NUM_LAYERS):
-    x = leaky_relu(conv1d_same(x, dw[2 * l], dw[2 * l + 1], hp.strides))
+    x = leaky_relu(conv1d_same(x, dw[2 * l], dw[2 * l + 1], hp.strides), None if slopes is None else slopes[l])
     if taps is not None:
       taps['h%d' % (l + 1)] = x
     if l < NUM_LAYERS - 1:
@@ -294,26 +326,30 @@ def signals_metrics(real, fake, hp: HParams) -> Dict[str, float]:
   }
 
 
-def gradient_penalty(dw, real, fake, alpha, shifts, hp, create_graph=True):
+def gradient_penalty(dw, real, fake, alpha, shifts, hp, create_graph=True, slopes=None, taps=None):
   """wgan_gp.py:38-50. alpha (B,1,1)."""
   xhat = (alpha * real + (1 - alpha) * fake).detach().requires_grad_(True)
-  out = discriminator_forward(dw, xhat, shifts, hp)
+  out = discriminator_forward(dw, xhat, shifts, hp, taps, slopes)
   (g,) = torch.autograd.grad(out.sum(), xhat, create_graph=create_graph)
   norm = torch.sqrt((g.reshape(g.shape[0], -1)**2).sum(dim=1))
   return ((norm - 1.0)**2).mean(), g, norm
 
 
-def critic_step(gw, dw, real, noise, alpha, shifts, hp: HParams, dtype=torch.float64):
+def critic_step(gw, dw, real, noise, alpha, shifts, hp: HParams, dtype=torch.float64, slopes=None, fake=None):
   """wgan_gp.py:64-80 without the optimizer: returns losses + per-parameter gradients.
-  shifts: (3, 4) ints = draws of D(real), D(fake), D(xhat) in that call order."""
+  shifts: (3, 4) ints = draws of D(real), D(fake), D(xhat) in that call order.
+  slopes: optional {'real' | 'fake' | 'xhat': [5 tensors]} imposed LeakyReLU branches of the three critic calls
+  (and 'gen': [6 tensors] for the generator forward); the free-running branch decisions are returned under 'acts'."""
   gw = [_t(a, dtype) for a in gw]
   dw = [_t(a, dtype).clone().requires_grad_(True) for a in dw]
   real, noise, alpha = _t(real, dtype), _t(noise, dtype), _t(alpha, dtype).reshape(-1, 1, 1)
+  sl = slopes or {}
+  taps = {'real': {}, 'fake': {}, 'xhat': {}}
   with torch.no_grad():
-    fake = generator_forward(gw, noise, hp)
-  real_out = discriminator_forward(dw, real, shifts[0], hp)
-  fake_out = discriminator_forward(dw, fake, shifts[1], hp)
-  gp, g, norm = gradient_penalty(dw, real, fake, alpha, shifts[2], hp)
+    fake = generator_forward(gw, noise, hp, slopes=sl.get('gen')) if fake is None else _t(fake, dtype)
+  real_out = discriminator_forward(dw, real, shifts[0], hp, taps['real'], sl.get('real'))
+  fake_out = discriminator_forward(dw, fake, shifts[1], hp, taps['fake'], sl.get('fake'))
+  gp, g, norm = gradient_penalty(dw, real, fake, alpha, shifts[2], hp, slopes=sl.get('xhat'), taps=taps['xhat'])
   loss = -real_out.mean() + fake_out.mean() + hp.gradient_penalty * gp
   grads = torch.autograd.grad(loss, dw)
   return {
@@ -321,20 +357,26 @@ def critic_step(gw, dw, real, noise, alpha, shifts, hp: HParams, dtype=torch.flo
       'fake': fake.detach(), 'real_out': real_out.detach(), 'fake_out': fake_out.detach(),
       'gp_grad': g.detach(), 'gp_norm': norm.detach(),
       'grads': [x.detach() for x in grads],
+      'acts': {k: [v['h%d' % (l + 1)].detach() for l in range(NUM_LAYERS)] for k, v in taps.items()},
   }
 
 
-def generator_step(gw, dw, real, noise, shifts, hp: HParams, dtype=torch.float64):
-  """wgan_gp.py:22-36 without the optimizer. shifts: 4 ints (draws of D(fake))."""
+def generator_step(gw, dw, real, noise, shifts, hp: HParams, dtype=torch.float64, slopes=None):
+  """wgan_gp.py:22-36 without the optimizer. shifts: 4 ints (draws of D(fake)).
+  slopes: optional {'gen': [6 tensors], 'fake': [5 tensors]} imposed LeakyReLU branches (see leaky_relu)."""
   gw = [_t(a, dtype).clone().requires_grad_(True) for a in gw]
   dw = [_t(a, dtype) for a in dw]
   noise = _t(noise, dtype)
-  fake = generator_forward(gw, noise, hp)
-  fake_out = discriminator_forward(dw, fake, shifts, hp)
+  sl = slopes or {}
+  gtaps, dtaps = {}, {}
+  fake = generator_forward(gw, noise, hp, gtaps, sl.get('gen'))
+  fake_out = discriminator_forward(dw, fake, shifts, hp, dtaps, sl.get('fake'))
   loss = -fake_out.mean()
   grads = torch.autograd.grad(loss, gw)
   out = {'gen_loss': float(loss.detach()), 'fake': fake.detach(), 'fake_out': fake_out.detach(),
-         'grads': [x.detach() for x in grads]}
+         'grads': [x.detach() for x in grads],
+         'acts': {'gen': [gtaps['g%d' % l].detach() for l in range(NUM_LAYERS + 1)],
+                  'fake': [dtaps['h%d' % (l + 1)].detach() for l in range(NUM_LAYERS)]}}
   if real is not None:
     out['metrics'] = signals_metrics(_t(real, dtype), fake.detach(), hp)
   return out
@@ -413,7 +455,7 @@ def validate_step(gw, dw, real, noise, alpha, shifts, hp: HParams, dtype=torch.f
 def _ps_transpose(dx, shift):
   """Adjoint of phase_shuffle: scatter-add along the same index map."""
   w = dx.shape[1]
-  idx = torch.from_numpy(phase_shuffle_index(w, shift).astype(np.int64))
+  idx = torch.from_numpy(phase_shuffle_index(w, shift).astype(np.int64)).to(dx.device)
   out = torch.zeros_like(dx)
   return out.index_add(1, idx, dx)
 
@@ -642,4 +684,4 @@ def critic_step_mixed(gw, dw, real, noise, alpha, shifts, hp: HParams, dtype=tor
   real_loss, fake_loss = -scores[:B].mean(), scores[B:2 * B].mean()
   return {'dis_loss': float(real_loss + fake_loss + hp.gradient_penalty * gp), 'gradient_penalty': float(gp),
           'fake': fake, 'real_out': scores[:B], 'fake_out': scores[B:2 * B], 'gp_grad': g, 'gp_norm': n,
-          'grads': grads}
+          'grads': grads, 'H': H, 'X': X}

@@ -1,0 +1,195 @@
+"""Per-parameter gradient parity at the north_star tolerances (rel <= 1e-4 in fp32, <= 2e-2 in bf16), with evidence
+instead of looser bounds.
+
+LeakyReLU's slope is the only discontinuity of the WGAN-GP step. An activation that rounds across zero in the CUDA
+path takes the other branch than in the float64 oracle and moves every gradient below it by O(1/sqrt(#elements)):
+that, not kernel error, is why a free-running bf16 (or, at the full paper size, fp32) evaluation differs from float64
+by several percent. These tests remove the ambiguity: the engine exports the branch decisions it actually took
+(cg_debug_read: sign of every stored activation H[l] / HG[l]) and the oracle is evaluated ON THE SAME BRANCHES
+(oracle.leaky_relu(slope=...)). With the branches imposed the whole step is a smooth function of the rounding errors,
+so every per-parameter gradient has to meet the north_star number -- a wrong tap at a sample edge, a dropped reflected
+PhaseShuffle row or a mis-scaled bucket cannot hide behind "slope flips" any more. The fraction of branch decisions
+that differ from the free-running float64 evaluation is measured and bounded as well.
+
+Reference semantics: gan/algorithms/wgan_gp.py:22-36,64-80 (losses, tapes), gan/algorithms/optimizer.py:31-34
+(gradients w.r.t. model.trainable_variables), gan/models/calciumgan.py (both networks)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import calciumgan_oracle as O
+from calciumgan_b200 import _lib as L
+from tests.util import namespace_from_oracle, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4   # north_star
+BF16_TOL = 2e-2   # north_star
+# LeakyReLU branch decisions that may differ from the free-running float64 evaluation: bf16 storage moves every
+# pre-activation by up to 2^-9 relative of the layer's inputs (measured 0.5e-3 .. 2e-3 of the elements per layer);
+# in fp32 it is a handful of elements per evaluation
+BF16_FLIP_FRACTION = 1e-2
+FP32_FLIP_COUNT = 16
+
+
+def build(hp, batch, mixed, **kw):
+  from calciumgan_b200.algorithms.registry import get_algorithm
+  from calciumgan_b200.models.registry import get_models
+  ns = namespace_from_oracle(hp, batch, mixed_precision=mixed, **kw)
+  g, d = get_models(ns, None)
+  return get_algorithm(ns, g, d, None)
+
+
+def _np(t):
+  return t.detach().cpu().numpy() if hasattr(t, 'detach') else np.asarray(t)
+
+
+def critic_slopes(eng, B, groups=('real', 'fake', 'xhat'), dtype=torch.float64, device=None):
+  """The engine's own LeakyReLU branches of the last critic forward, per critic call."""
+  out = {k: [] for k in groups}
+  for l in range(1, 6):
+    h = eng.debug_read(L.BUF_H, l, len(groups) * B).to(dtype)
+    h = h.cpu() if device is None else h.to(device)
+    for g, k in enumerate(groups):
+      out[k].append(O.slopes_from_activation(h[g * B:(g + 1) * B]))
+  return out
+
+
+def generator_slopes(eng, B, dtype=torch.float64, device=None):
+  out = []
+  for i in range(0, 6):
+    h = eng.debug_read(L.BUF_HG, i, B).to(dtype)
+    out.append(O.slopes_from_activation(h.cpu() if device is None else h.to(device)))
+  return out
+
+
+def flips(acts, slopes):
+  """elements whose imposed branch differs from the oracle's free-running one: (worst layer's share, total count)"""
+  worst, count = 0.0, 0
+  for a, s in zip(acts, slopes):
+    d = O.slopes_from_activation(a).reshape(s.shape) != s
+    worst, count = max(worst, float(d.double().mean())), count + int(d.sum())
+  return worst, count
+
+
+def check_flips(pairs, mixed, report, key):
+  frac = max(flips(a, s)[0] for a, s in pairs)
+  count = sum(flips(a, s)[1] for a, s in pairs)
+  report[key + '_flip_share'], report[key + '_flip_count'] = frac, float(count)
+  if mixed:
+    assert frac <= BF16_FLIP_FRACTION, report
+  else:
+    assert count <= FP32_FLIP_COUNT, report
+
+
+def check_grads(got, ref, tol, what):
+  worst = 0.0
+  for i, (a, b) in enumerate(zip(got, ref)):
+    b = _np(b)
+    assert a.shape == tuple(b.shape)
+    if float(np.abs(b).max()) == 0.0:
+      assert float(np.abs(a).max()) <= 1e-6, (what, i, 'expected exact zeros')
+      continue
+    e = rel_err(a, b)
+    worst = max(worst, e)
+    assert e <= tol, '%s[%d] shape %s: rel err %.3e > %.1e (branches imposed)' % (what, i, a.shape, e, tol)
+  return worst
+
+
+def run_masked(hp, B, mixed, seed, force_simt=False, device=None, check_generator=True):
+  """One critic step and one generator step of the CUDA path against the float64 oracle on the engine's branches."""
+  tol = BF16_TOL if mixed else FP32_TOL
+  gan = build(hp, B, mixed, force_simt=force_simt)
+  eng = gan.engine
+  gw, dw = O.init_weights(hp, seed=seed)
+  gw, dw = O.randomize_weights(gw, seed + 1), O.randomize_weights(dw, seed + 2)
+  gan.generator.set_weights(gw)
+  gan.discriminator.set_weights(dw)
+  real, noises, alphas, shifts = O.synthetic_batch(hp, B, seed=seed + 3, n_critic=1)
+  report = {}
+
+  s = eng.critic_step(real, noises[0], alphas[0], shifts[:12], update=False)
+  grads = eng.get_grads(L.DISCRIMINATOR)
+  sl = critic_slopes(eng, B, device=device)
+  sl['gen'] = generator_slopes(eng, B, device=device)
+  ref = O.critic_step(gw, dw, real, noises[0], alphas[0], shifts[:12].reshape(3, 4), hp, slopes=sl)
+  free = O.critic_step(gw, dw, real, noises[0], alphas[0], shifts[:12].reshape(3, 4), hp)
+  check_flips([(free['acts'][k], sl[k]) for k in ('real', 'fake', 'xhat')], mixed, report, 'critic')
+  assert abs(s[L.S_GP] - ref['gradient_penalty']) <= tol * max(1.0, ref['gradient_penalty'])
+  assert abs(s[L.S_DIS_LOSS] - ref['dis_loss']) <= tol * max(1.0, abs(ref['dis_loss']))
+  assert rel_err(eng.fake(B).cpu().numpy(), _np(ref['fake'])) <= tol
+  report['critic'] = check_grads(grads, ref['grads'], tol, 'critic gradient')
+  report['critic_free'] = max(rel_err(a, _np(b)) for a, b in zip(grads, free['grads']) if float(_np(b).any()))
+
+  if check_generator:
+    s = eng.generator_step(real, noises[1], shifts[12:16], update=False)
+    grads = eng.get_grads(L.GENERATOR)
+    sl = {'gen': generator_slopes(eng, B, device=device), 'fake': critic_slopes(eng, B, ('fake',), device=device)['fake']}
+    ref = O.generator_step(gw, dw, None, noises[1], shifts[12:16], hp, slopes=sl)
+    free = O.generator_step(gw, dw, None, noises[1], shifts[12:16], hp)
+    check_flips([(free['acts']['gen'], sl['gen']), (free['acts']['fake'], sl['fake'])], mixed, report, 'generator')
+    assert abs(s[L.S_GEN_LOSS] - ref['gen_loss']) <= tol * max(1.0, abs(ref['gen_loss']))
+    report['generator'] = check_grads(grads, ref['grads'], tol, 'generator gradient')
+    report['generator_free'] = max(rel_err(a, _np(b)) for a, b in zip(grads, free['grads']) if float(_np(b).any()))
+  eng.close()
+  return report
+
+
+def _medium_hp(**kw):
+  d = dict(signal_shape=(512, 102), noise_dim=8, num_units=32, kernel_size=24, m=3, n_critic=1)
+  d.update(kw)
+  return O.HParams(**d)
+
+
+@pytest.mark.parametrize('mixed,force_simt', [(False, False), (True, True), (True, False)])
+@pytest.mark.parametrize('layer_norm', [True, False])
+def test_gradients_on_imposed_branches_medium(mixed, force_simt, layer_norm):
+  """512 x 102, num_units 32: fp32 CUDA-core path, bf16 CUDA-core path and bf16 tensor-core path, with and without
+  layer norm. Every per-parameter gradient of a critic step and of a generator step within the north_star tolerance."""
+  rep = run_masked(_medium_hp(layer_norm=layer_norm), 8, mixed, seed=7, force_simt=force_simt)
+  print('imposed-branch gradient parity (medium, mixed=%s simt=%s ln=%s): %s' % (mixed, force_simt, layer_norm,
+        {k: '%.2e' % v for k, v in rep.items()}))
+
+
+@pytest.mark.parametrize('mixed,B', [(True, 3), (True, 8), (False, 2)])
+def test_gradients_on_imposed_branches_paper_architecture(mixed, B):
+  """The exact BASELINE.json architecture (noise_dim 32, num_units 64, kernel 24, strides 2, layer_norm, m = 10,
+  2048 x 102): per-parameter gradients <= 2e-2 (bf16 tensor-core path) / <= 1e-4 (fp32 path), critic and generator
+  step, single seed (no best-of)."""
+  rep = run_masked(O.HParams(), B, mixed, seed=40 + B)
+  print('imposed-branch gradient parity (paper architecture, mixed=%s B=%d): %s' % (mixed, B,
+        {k: '%.2e' % v for k, v in rep.items()}))
+
+
+def test_gradients_on_imposed_branches_headline_batch_128():
+  """BASELINE.json configs[1] exactly as benchmarked: batch 128, bf16 tensor-core path. The oracle is the same torch
+  float64 code, evaluated on the CUDA device for this one case (a batch-128 float64 double backward takes minutes on
+  the host cores): scalars, generator output and every per-parameter gradient of a critic step and a generator step
+  within 2e-2."""
+  O.set_device('cuda')
+  try:
+    rep = run_masked(O.HParams(), 128, True, seed=3, device='cuda')
+  finally:
+    O.set_device(None)
+  print('imposed-branch gradient parity (paper config, batch 128, bf16): %s' % {k: '%.2e' % v for k, v in rep.items()})
+
+
+def test_shift_extremes_on_imposed_branches_bf16():
+  """Every PhaseShuffle draw at +-m (both reflection branches of calciumgan.py:126-133 in the fused forward scatter and
+  the fused adjoint of every layer), paper architecture, bf16: critic gradients <= 2e-2 on the engine's branches."""
+  hp, B = O.HParams(), 2
+  gan = build(hp, B, True)
+  eng = gan.engine
+  gw, dw = O.init_weights(hp, seed=51)
+  gw, dw = O.randomize_weights(gw, 52), O.randomize_weights(dw, 53)
+  gan.generator.set_weights(gw)
+  gan.discriminator.set_weights(dw)
+  real, noises, alphas, _ = O.synthetic_batch(hp, B, seed=54, n_critic=1)
+  for shifts in (np.array([10, -10, 10, -10, -10, 10, -10, 10, 10, 10, -10, -10], np.int32),
+                 np.array([-10, -10, -10, -10, 10, 10, 10, 10, -9, 9, -10, 10], np.int32)):
+    eng.critic_step(real, noises[0], alphas[0], shifts, update=False)
+    grads = eng.get_grads(L.DISCRIMINATOR)
+    sl = critic_slopes(eng, B)
+    ref = O.critic_step(gw, dw, real, noises[0], alphas[0], shifts.reshape(3, 4), hp, slopes=sl, fake=eng.fake(B).cpu())
+    worst = check_grads(grads, ref['grads'], BF16_TOL, 'critic gradient, shifts %s' % shifts[:4])
+    print('shift extremes %s: worst %.2e' % (shifts[:4], worst))

@@ -168,6 +168,7 @@ def test_medium_fp32(layer_norm, K):
 # The GEMM kernels themselves are held to bf16 rounding in tests/test_layers_gpu.py.
 BF16_VS_FP64_GRAD_BOUND = 0.15
 BF16_POLICY_GRAD_BOUND = 0.10   # small (bias-sized) tensors average less of the noise
+BF16_FREE_RUNNING_GRAD_BOUND = 0.10   # batch 128: more samples average more of the flip noise than batch 3 .. 8
 
 
 @pytest.mark.parametrize('force_simt', [True, False])
@@ -603,3 +604,52 @@ def test_paper_config_tensor_core_vs_cuda_core_paths(B):
   assert np.abs(a[1] - b[1]).max() <= BF16_TOL * max(1.0, np.abs(b[1]).max())     # critic scores
   assert rel_err(a[2], b[2]) <= BF16_TOL                                          # generator output
   assert np.abs(a[3] - b[3]).max() <= BF16_TOL * max(1.0, np.abs(b[3]).max())     # gen_loss + signal metrics
+
+
+def test_headline_batch_128_against_cpu_fixture():
+  """BASELINE.json configs[1] as benchmarked (batch 128, bf16 tensor-core path) against tests/golden/paper_b128.npz, the
+  float64 CPU oracle's free-running evaluation (tests/golden/make_b128_golden.py): scalars, scores and the generator
+  output at the north_star 2e-2; every per-parameter gradient's norm, direction and a strided sample of its elements
+  within the slope-flip noise floor (the tight, branch-imposed check of the same case is
+  tests/test_gradient_parity_gpu.py::test_gradients_on_imposed_branches_headline_batch_128)."""
+  import sys
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+  import make_b128_golden as G
+  gold = np.load(os.path.join(os.path.dirname(GOLD), 'paper_b128.npz'))
+  hp, gw, dw, real, noises, alphas, shifts = G.inputs()
+  B = G.BATCH
+  ns, gan = build(hp, B, mixed=True)
+  gan.generator.set_weights(gw)
+  gan.discriminator.set_weights(dw)
+  s = gan.engine.critic_step(real, noises[0], alphas[0], shifts[:12], update=False)
+  assert gan.engine.tc_launch_count() > 0
+  assert np.abs(np.array(s[:2]) - gold['c_scalars']).max() <= BF16_TOL * max(1.0, np.abs(gold['c_scalars']).max())
+  scores = gan.engine.scores(3 * B).cpu().numpy()[:2 * B]
+  assert np.abs(scores - gold['c_scores']).max() <= BF16_TOL * max(1.0, np.abs(gold['c_scores']).max())
+  fake = gan.engine.fake(B).cpu().numpy().reshape(-1)[::100003]
+  assert rel_err(fake, gold['c_fake_sample']) <= BF16_TOL
+
+  def check(grads, prefix):
+    worst = 0.0
+    for i, a in enumerate(grads):
+      ref, norm = gold['%s_grad%02d' % (prefix, i)], gold['%s_grad_norms' % prefix][i]
+      if norm == 0:
+        assert np.abs(a).max() <= 1e-6
+        continue
+      assert abs(np.linalg.norm(a.astype(np.float64)) / norm - 1.0) <= BF16_TOL, (prefix, i)
+      got = a.reshape(-1)[::G.STRIDE].astype(np.float64)
+      e = rel_err(got, ref)
+      worst = max(worst, e)
+      assert e <= BF16_FREE_RUNNING_GRAD_BOUND, (prefix, i, e)
+      if ref.size >= 16:
+        assert float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref))) >= 0.995, (prefix, i)
+    return worst
+
+  wc = check(gan.engine.get_grads(1), 'c')
+  s = gan.engine.generator_step(real, noises[1], shifts[12:16], update=False)
+  got = np.array([s[4], s[6], s[7], s[5], s[8]])     # gen_loss, then metrics sorted: max, mean, min, std
+  assert np.abs(got - gold['g_scalars']).max() <= BF16_TOL * max(1.0, np.abs(gold['g_scalars']).max())
+  assert np.abs(gan.engine.scores(B).cpu().numpy() - gold['g_scores']).max() <= BF16_TOL * max(1.0, np.abs(gold['g_scores']).max())
+  wg = check(gan.engine.get_grads(0), 'g')
+  print('batch 128 vs float64 CPU fixture (free-running branches): worst sampled gradient rel err critic %.2e generator %.2e'
+        % (wc, wg))
