@@ -106,6 +106,7 @@ struct cg_ctx {
   void *Wf_d1, *Wb_d1;                   // generator output dense: [C][Cp], transposed
   // critic activations (capacity 3*Bmax)
   void *X[NL + 1], *H[NL + 1], *DX[NL + 1], *DA[NL + 1];
+  void* V5;                                // gradient penalty: linearised forward output of the last conv layer (Bmax samples)
   float *scores, *coef, *sumsq, *ucoef, *norms;
   // generator activations (capacity Bmax)
   float* Z;
@@ -455,6 +456,7 @@ extern "C" int cg_create(const cg_config* cfg, cg_ctx** out) {
     DA_(c->H[l], n); DA_(c->DA[l], n);
     if (l < NL) { DA_(c->X[l], n); DA_(c->DX[l], n); } else { c->X[l] = c->H[l]; c->DX[l] = nullptr; }
   }
+  DA_(c->V5, Bm * c->dl[NL] * c->dcp[NL] * es);
   DA_(c->scores, Bt * 4); DA_(c->coef, Bt * 4); DA_(c->sumsq, Bm * 4); DA_(c->ucoef, Bm * 4); DA_(c->norms, Bm * 4);
   DA_(c->Z, Bm * c->nd * 4);
   for (int i = 0; i <= NL; ++i) {
@@ -945,7 +947,7 @@ static WgParams conv_wgrad_params(cg_ctx* c, int l, int Bt) {
 }
 
 // all critic weight gradients from X[l-1] x DA[l] over Bt samples; biases from the first nb_bias samples
-static int d_wgrad(cg_ctx* c, int Bt, int nb_bias) {
+static int d_wgrad(cg_ctx* c, int Bt, int nb_bias, int tail_from) {   // samples >= tail_from: head input = V5
   if (nb_bias > 0) {   // all five bias gradients in one launch
     ColsumOps ops;
     ops.n = NL;
@@ -963,7 +965,8 @@ static int d_wgrad(cg_ctx* c, int Bt, int nb_bias) {
   const int tot = c->dl[NL] * c->dcp[NL] / (16 / c->esz);
   dim3 hgrid(grid_for(tot), Bt >= 64 ? 32 : 1);
   DISPATCH_T(c, head_wgrad_kernel<T><<<hgrid, 256, 0, c->stream>>>(
-                    (const T*)c->X[NL], c->coef, dgrad(c, 10), dgrad(c, 11), Bt, nb_bias, c->dl[NL], c->dc[NL], c->dcp[NL]));
+                    (const T*)c->X[NL], (const T*)c->V5, tail_from, c->coef, dgrad(c, 10), dgrad(c, 11), Bt, nb_bias, c->dl[NL],
+                    c->dc[NL], c->dcp[NL]));
   CK(post_launch(c, "head_wgrad"));
   // reverse layer order: the data-parallel host all-reduces bucket b as soon as its last writer has finished
   for (int l = NL; l >= 1; --l) {
@@ -1085,7 +1088,7 @@ static int critic_step_impl(cg_ctx* c, const float* real, int B, const float* no
   const int32_t* sh2 = sh + 8;
   for (int l = 1; l <= NL; ++l) {
     const long long gin = 2LL * B * c->dl[l - 1] * c->dcp[l - 1], gout = 2LL * B * c->dl[l] * c->dcp[l];
-    void* dst = l < NL ? off(c, c->DX[l], gout) : off(c, c->X[l], gout);
+    void* dst = l < NL ? off(c, c->DX[l], gout) : c->V5;   // H[l] of the x_hat group stays intact (slope masks, debug taps)
     RsParams p = conv_fwd_params(c, l, off(c, c->X[l - 1], gin), dst, B, EPI_MASK, off(c, c->H[l], gout));
     if (l < NL && ps_fusable(c, p)) {   // v_l = PS(M_l * conv(v_{l-1})) written straight into the xhat group's X_l slot
       p.out = nullptr;
@@ -1102,7 +1105,7 @@ static int critic_step_impl(cg_ctx* c, const float* real, int B, const float* no
       CK(post_launch(c, "ps_gather_lin"));
     }
   }
-  CK(d_wgrad(c, 3 * B, 2 * B));
+  CK(d_wgrad(c, 3 * B, 2 * B, 2 * B));
   if (!(flags & CG_FLAG_NO_UPDATE)) CK(cg_apply_update(c, CG_DISCRIMINATOR));
   return 0;
 }

@@ -465,8 +465,11 @@ __global__ void head_backward_kernel(const T* __restrict__ H5, const float* __re
 }
 
 // dwd[t*c5+c] += sum_b coef[b] * X5[b,t,c];  dbd += sum_{b<nb_bias} coef[b].  grid.y splits the batch; 16-byte loads.
+// Samples b >= tail_from are read from X5_tail[b - tail_from] (the gradient penalty's linearised forward v_5, which
+// must not overwrite the x_hat group's stored activation: its sign is that group's slope mask).
 template <typename T>
-__global__ void head_wgrad_kernel(const T* __restrict__ X5, const float* __restrict__ coef, float* __restrict__ dwd,
+__global__ void head_wgrad_kernel(const T* __restrict__ X5, const T* __restrict__ X5_tail, int tail_from,
+                                  const float* __restrict__ coef, float* __restrict__ dwd,
                                   float* __restrict__ dbd, int Bt, int nb_bias, int w5, int c5, int Cp) {
   constexpr int V = Vec16<T>::N;
   const int nv = w5 * Cp / V;
@@ -482,7 +485,7 @@ __global__ void head_wgrad_kernel(const T* __restrict__ X5, const float* __restr
 #pragma unroll 4
     for (int b = b_lo; b < b_hi; ++b) {
       float v[V];
-      vload<T>(X5 + b * per_sample + (long long)i * V, v);
+      vload<T>((b < tail_from ? X5 + b * per_sample : X5_tail + (b - tail_from) * per_sample) + (long long)i * V, v);
       const float cb = coef[b];
 #pragma unroll
       for (int e = 0; e < V; ++e) acc[e] = fmaf(cb, v[e], acc[e]);

@@ -382,11 +382,11 @@ def generator_step(gw, dw, real, noise, shifts, hp: HParams, dtype=torch.float64
   return out
 
 
-def adam_update(w, m, v, g, t: int, lr: float):
+def adam_update(w, m, v, g, t: int, lr: float, b1: float = ADAM_B1, b2: float = ADAM_B2):
   """Keras Adam dense update at iteration t (1-based, i.e. iterations+1) (optimizer.py:34)."""
-  lr_t = lr * math.sqrt(1.0 - ADAM_B2**t) / (1.0 - ADAM_B1**t)
-  m = ADAM_B1 * m + (1 - ADAM_B1) * g
-  v = ADAM_B2 * v + (1 - ADAM_B2) * g * g
+  lr_t = lr * math.sqrt(1.0 - b2**t) / (1.0 - b1**t)
+  m = b1 * m + (1 - b1) * g
+  v = b2 * v + (1 - b2) * g * g
   w = w - lr_t * m / (torch.sqrt(v) + ADAM_EPS)
   return w, m, v
 

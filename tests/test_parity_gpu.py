@@ -166,8 +166,12 @@ def test_medium_fp32(layer_norm, K):
 # and two evaluations under the same bf16 policy (e.g. the oracle's own fp32- vs fp64-accumulated
 # restatement) differ by 2-3e-2 at this point; see oracle/calciumgan_oracle.py and DESIGN.md.
 # The GEMM kernels themselves are held to bf16 rounding in tests/test_layers_gpu.py.
-BF16_VS_FP64_GRAD_BOUND = 0.15
-BF16_POLICY_GRAD_BOUND = 0.10   # small (bias-sized) tensors average less of the noise
+# These are FREE-RUNNING comparisons (each side takes its own LeakyReLU branches): bounds = measured worst case + 20%
+# (0.114 vs fp64 at the paper architecture, batch 3; 0.066 vs the bf16-policy oracle). The north_star tolerance itself
+# (2e-2 on every per-parameter gradient) is asserted in tests/test_gradient_parity_gpu.py, where the oracle is evaluated
+# on the branches the engine took.
+BF16_VS_FP64_GRAD_BOUND = 0.14
+BF16_POLICY_GRAD_BOUND = 0.08
 BF16_FREE_RUNNING_GRAD_BOUND = 0.10   # batch 128: more samples average more of the flip noise than batch 3 .. 8
 
 
@@ -469,26 +473,24 @@ def _fp32_outputs_ok(B, ref_c, got_c, ref_g, got_g):
 # gradient below it moves by ~|dy_e| / ||dy|| ~ 1/sqrt(#elements) (2e-6 above the flipped layer, 1e-3 .. 1e-2 from there
 # down; tools/fp32_paper_errs.py prints the step pattern, torch fp32 behaves the same). The flip probability per
 # evaluation grows with the number of activations: ~0.5% for the medium configs, ~5% at sequence length 256 with the paper
-# widths, ~50% at the full 2048 x 102 x batch 2. Hence: per-tensor 1e-4 on the best of two seeds at length 256, and a
-# flip-tolerant bound plus a direction check at the full length (outputs and losses are held to 1e-4 everywhere).
+# widths, ~50% at the full 2048 x 102 x batch 2. Hence, for these FREE-RUNNING comparisons, a flip-tolerant bound plus a
+# direction check on gradients (outputs and losses are held to 1e-4 everywhere); with the branches imposed the same
+# gradients agree to 4e-6 (tests/test_gradient_parity_gpu.py).
 FP32_FLIP_BOUND = 2e-2
 
 
 def test_paper_architecture_fp32():
   """Paper layer widths / kernel / strides / m (noise_dim 32, num_units 64, K 24, 102 channels) in fp32, the reference's
-  default precision, at sequence length 256: north_star tolerance 1e-4 on outputs, losses and every gradient."""
+  default precision, at sequence length 256, free-running: outputs and losses to 1e-4, gradients to the slope-flip bound
+  (single seed; the 1e-4 gradient tolerance is asserted on imposed branches at the FULL length in
+  tests/test_gradient_parity_gpu.py::test_gradients_on_imposed_branches_paper_architecture[False-2])."""
   hp = O.HParams(signal_shape=(256, 102))
   B = 2
-  best = None
-  for seed in (61, 64):
-    ref_c, got_c, ref_g, got_g, _ = _run_both(hp, B, mixed=False, seed=seed)
-    _fp32_outputs_ok(B, ref_c, got_c, ref_g, got_g)
-    errs = []
-    for got, ref in ((got_c['grads'], ref_c['grads']), (got_g['grads'], ref_g['grads'])):
-      check_list(got, ref, FP32_FLIP_BOUND, 'grad, seed %d' % seed)
-      errs += [rel_err(a, b.numpy()) if float(b.abs().max()) > 0 else 0.0 for a, b in zip(got, ref)]
-    best = errs if best is None else [min(x, y) for x, y in zip(best, errs)]
-  assert max(best) <= FP32_TOL, ['%.1e' % e for e in best]
+  ref_c, got_c, ref_g, got_g, _ = _run_both(hp, B, mixed=False, seed=61)
+  _fp32_outputs_ok(B, ref_c, got_c, ref_g, got_g)
+  wc = check_list(got_c['grads'], ref_c['grads'], FP32_FLIP_BOUND, 'critic grad')
+  wg = check_list(got_g['grads'], ref_g['grads'], FP32_FLIP_BOUND, 'generator grad')
+  print('fp32 paper widths, length 256, free-running: worst gradient rel err critic %.1e generator %.1e' % (wc, wg))
 
 
 def test_paper_architecture_full_length_fp32():
@@ -637,7 +639,7 @@ def test_headline_batch_128_against_cpu_fixture():
         assert np.abs(a).max() <= 1e-6
         continue
       assert abs(np.linalg.norm(a.astype(np.float64)) / norm - 1.0) <= BF16_TOL, (prefix, i)
-      got = a.reshape(-1)[::G.STRIDE].astype(np.float64)
+      got = a.reshape(-1)[::G.sample_stride(a.size)].astype(np.float64)
       e = rel_err(got, ref)
       worst = max(worst, e)
       assert e <= BF16_FREE_RUNNING_GRAD_BOUND, (prefix, i, e)

@@ -94,7 +94,9 @@ def test_fused_gather_of_the_linearised_gp_forward_is_bit_exact(B):
     for l in range(1, 6):
       assert torch.equal(fused.engine.debug_read(L.BUF_X, l, 3 * B), unfused.engine.debug_read(L.BUF_X, l, 3 * B)), (s, l)
     for a, b in zip(fused.engine.get_grads(L.DISCRIMINATOR), unfused.engine.get_grads(L.DISCRIMINATOR)):
-      np.testing.assert_array_equal(a, b)   # same kernels downstream of identical inputs
+      # same kernels downstream of identical inputs; the weight-gradient kernels accumulate their row splits with
+      # fp32 atomics, so two runs agree to summation order, not bit for bit
+      assert np.abs(a - b).max() <= 1e-5 * max(np.abs(b).max(), 1e-30)
 
 
 @pytest.mark.parametrize('layer', [2, 3, 4])
