@@ -61,6 +61,7 @@ SIGNATURES = {
     'cg_apply_update': (_I, [_P, _I]),
     'cg_train_step': (_I, [_P, _P, _I, _P, _P, _I32P, _F]),
     'cg_validate': (_I, [_P, _P, _I, _P, _P, _I32P, _P, _F]),
+    'cg_metrics': (_I, [_P, _P, _P, _I, _F]),
     'cg_generate': (_I, [_P, _P, _I, _I, _P]),
     'cg_debug_critic_forward': (_I, [_P, _P, _I, _I32P, _P]),
     'cg_debug_gp': (_I, [_P, _P, _I, _I32P, _P, _P]),

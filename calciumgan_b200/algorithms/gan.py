@@ -39,6 +39,18 @@ class GAN(object):
     """gan.py:29-30."""
     return torch.randn((batch_size,) + self.noise_shape, device=self.engine.device)
 
+  def metrics(self, real, fake):
+    """gan.py:32-41: signals_metrics/{min,max,mean,std} of (real, fake), de-normalised when hparams.normalize."""
+    return dict(zip(METRIC_KEYS, self.engine.metrics(real, fake)))
+
+  def _step(self, real, noise, training=True, alpha=None, shifts=None):
+    """gan.py:58-70 -> (fake, gen_loss, dis_loss, gradient_penalty, metrics), with the losses of the subclass
+    (WGAN-GP: wgan_gp.py:19-20,52-62). PhaseShuffle is active whatever `training` says (calciumgan.py:117) and the
+    models have no other train / inference difference (no dropout, no batch norm), so both values run the same
+    kernels; nothing is updated."""
+    fake, s = self.engine.validate(real, noise, alpha, shifts)
+    return (fake, float(s[L.S_GEN_LOSS]), float(s[L.S_DIS_LOSS]), float(s[L.S_GP]), metrics_from_scalars(s))
+
   def generate(self, noise, denorm=False):
     """gan.py:92-97."""
     return self.engine.generate(noise, denorm=denorm)

@@ -1027,12 +1027,13 @@ static int fetch_scalars(cg_ctx* c, int slot, int flags, float* scalars_host) {
 }
 
 // gan.py:32-41 / signals_metrics.py:9-28 on (real, FAKE32); acc[0..3] must be zeroed by the caller
-static int launch_metrics(cg_ctx* c, const float* real, float* acc, long long rows) {
-  if (c->C % 2 == 0 && c->C <= 128 && (reinterpret_cast<uintptr_t>(real) & 7) == 0)
-    metrics8_kernel<<<grid_for(rows * 8, 256, 148 * 8), 256, 0, c->stream>>>(real, c->FAKE32, acc, rows, c->C, c->cfg.signals_min,
+static int launch_metrics(cg_ctx* c, const float* real, float* acc, long long rows, const float* fake = nullptr) {
+  if (!fake) fake = c->FAKE32;
+  if (c->C % 2 == 0 && c->C <= 128 && ((reinterpret_cast<uintptr_t>(real) | reinterpret_cast<uintptr_t>(fake)) & 7) == 0)
+    metrics8_kernel<<<grid_for(rows * 8, 256, 148 * 8), 256, 0, c->stream>>>(real, fake, acc, rows, c->C, c->cfg.signals_min,
                                                                             c->cfg.signals_max, c->cfg.normalize);
   else
-    metrics_kernel<<<grid_for(rows * 32, 256, 148 * 4), 256, 0, c->stream>>>(real, c->FAKE32, acc, rows, c->C, c->cfg.signals_min,
+    metrics_kernel<<<grid_for(rows * 32, 256, 148 * 4), 256, 0, c->stream>>>(real, fake, acc, rows, c->C, c->cfg.signals_min,
                                                                             c->cfg.signals_max, c->cfg.normalize);
   return post_launch(c, "metrics");
 }
@@ -1222,6 +1223,18 @@ extern "C" int cg_validate(cg_ctx* c, const float* real, int B, const float* noi
   CK(launch_metrics(c, real, scal + CG_S_MET_MIN, rows));
   if (fake_out) CU(cudaMemcpyAsync(fake_out, c->FAKE32, (size_t)rows * c->C * 4, cudaMemcpyDeviceToDevice, c->stream));
   return fetch_scalars(c, 0, 0, scalars_host);
+}
+
+// gan.py:32-41 on caller-provided tensors: out_host[4] = min, max, mean, std errors (signals_metrics.py:9-28)
+extern "C" int cg_metrics(cg_ctx* c, const float* real, const float* fake, int B, float* out_host) {
+  if (!real || !fake || !out_host || B < 1) return set_err("cg_metrics: bad arguments");
+  float* scal = c->d_scal;
+  CU(cudaMemsetAsync(scal + CG_S_MET_MIN, 0, 4 * 4, c->stream));
+  CK(launch_metrics(c, real, scal + CG_S_MET_MIN, (long long)B * c->L, fake));
+  CU(cudaMemcpyAsync(c->h_scal, scal, CG_NUM_SCALARS * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 4; ++i) out_host[i] = c->h_scal[CG_S_MET_MIN + i];
+  return 0;
 }
 
 extern "C" int cg_generate(cg_ctx* c, const float* noise, int B, int denorm, float* out) {

@@ -274,6 +274,16 @@ class Engine(object):
                                  sh[0] if sh else None, self._ptr(fake), self._scal))
     return fake, np.array(self._scal[:], np.float32)
 
+  def metrics(self, real, fake):
+    """gan.py:32-41 on caller tensors -> [min, max, mean, std] errors."""
+    self._use_stream()
+    real, fake = self.to_device(real), self.to_device(fake)
+    if real.shape != fake.shape or tuple(real.shape[1:]) != self.signal_shape(1)[1:]:
+      raise ValueError('metrics: expected two (batch, %d, %d) tensors' % self.signal_shape(1)[1:])
+    out = (C.c_float * 4)()
+    L.check(self.lib.cg_metrics(self.ctx, self._ptr(real), self._ptr(fake), real.shape[0], out))
+    return [float(x) for x in out]
+
   def generate(self, noise, denorm=False):
     self._use_stream()
     noise = self.to_device(noise)

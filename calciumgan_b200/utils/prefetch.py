@@ -14,7 +14,7 @@ def prefetch_to_device(batches, device=None, depth=2):
   device = torch.device('cuda', torch.cuda.current_device()) if device is None else device
   copy_stream = torch.cuda.Stream(device=device)
   it = iter(batches)
-  bufs = [dict(dev=None, pinned=None, free=None) for _ in range(depth)]
+  bufs = [dict(dev=None, pinned=None, free=None, ready=None) for _ in range(depth)]
   queue = []
   state = dict(slot=0)
 
@@ -33,10 +33,15 @@ def prefetch_to_device(batches, device=None, depth=2):
     if buf['dev'] is None or buf['dev'].shape[1:] != src.shape[1:] or buf['dev'].shape[0] < n:
       buf['dev'] = torch.empty(src.shape, dtype=torch.float32, device=device)
       buf['pinned'] = None
+      # the block may be recycled from main-stream work still in flight, and is written on copy_stream from now on
+      copy_stream.wait_stream(torch.cuda.current_stream())
+      buf['dev'].record_stream(copy_stream)
     host = src
     if not src.is_pinned():
       if buf['pinned'] is None or buf['pinned'].shape[0] < n:
         buf['pinned'] = torch.empty(buf['dev'].shape, dtype=torch.float32).pin_memory()
+      if buf['ready'] is not None:
+        buf['ready'].synchronize()             # the previous async copy OUT of this staging buffer has finished
       buf['pinned'][:n].copy_(src)
       host = buf['pinned'][:n]
     if buf['free'] is not None:
@@ -45,6 +50,7 @@ def prefetch_to_device(batches, device=None, depth=2):
       buf['dev'][:n].copy_(host, non_blocking=True)
       ready = torch.cuda.Event()
       ready.record(copy_stream)
+    buf['ready'] = ready
     queue.append((slot, n, ready, extra))
 
   for _ in range(depth):

@@ -1,7 +1,10 @@
 """Scalar logging with the reference's TensorBoard tags (gan/utils/summary_helper.py:27-119,559-588).
 
 Only the scalar part of the reference's `Summary` is reproduced (train / validation writers under output_dir,
-`scalar`, `log`); plotting, histograms and the TF profiler hooks are out of scope."""
+`scalar`, `log`) plus the profiler hooks: `profiler_trace` / `profiler_export` (summary_helper.py:115-119, driven by
+main.py:45-52 with --profile) open / close a CUDA profiler capture range (cudaProfilerStart / Stop, i.e. what
+`ncu --profile-from-start off` and `nsys --capture-range=cudaProfilerApi` key on) and an NVTX range around the same
+training batches the reference traces. Plotting and histograms are out of scope."""
 import os
 
 
@@ -34,6 +37,24 @@ class Summary(object):
       self.scalar('elapse', elapse, step=step, training=training)
     if not training and gan is not None and getattr(self._hparams, 'mixed_precision', False):
       self.scalar('model/loss_scale', gan.gen_optimizer.loss_scale, step=step, training=training)
+
+  def profiler_trace(self):
+    """summary_helper.py:115-116 (tf.summary.trace_on): start of the profiled window."""
+    import torch
+    if torch.cuda.is_available():
+      torch.cuda.synchronize()
+      torch.cuda.profiler.start()
+      torch.cuda.nvtx.range_push('calciumgan_b200/train')
+    self._profiling = True
+
+  def profiler_export(self):
+    """summary_helper.py:118-119 (tf.summary.trace_export): end of the profiled window."""
+    import torch
+    if getattr(self, '_profiling', False) and torch.cuda.is_available():
+      torch.cuda.synchronize()
+      torch.cuda.nvtx.range_pop()
+      torch.cuda.profiler.stop()
+    self._profiling = False
 
   def flush(self):
     for w in (self.train_writer, self.val_writer, self.metrics_writer):

@@ -23,6 +23,45 @@ def denormalize(x, x_min, x_max):
   return x * (x_max - x_min) + x_min
 
 
+def get_current_git_hash():
+  """gan/utils/utils.py:66-69; 'unknown' outside a git checkout instead of raising."""
+  import subprocess
+  try:
+    return subprocess.check_output(['git', 'describe', '--always'], stderr=subprocess.DEVNULL).strip().decode()
+  except Exception:
+    return 'unknown'
+
+
+def save_hparams(hparams):
+  """gan/utils/utils.py:72-75: output_dir/hparams.json with every hparams field (+ git_hash). Tuples become lists, as
+  with the reference's json.dump; numpy scalars are converted."""
+  import json
+  hparams.git_hash = get_current_git_hash()
+
+  def plain(v):
+    if isinstance(v, (np.integer,)):
+      return int(v)
+    if isinstance(v, (np.floating,)):
+      return float(v)
+    if isinstance(v, np.ndarray):
+      return v.tolist()
+    raise TypeError('hparams field of type %s is not JSON serialisable' % type(v).__name__)
+
+  with open(os.path.join(hparams.output_dir, 'hparams.json'), 'w') as file:
+    json.dump(hparams.__dict__, file, default=plain)
+
+
+def load_hparams(hparams):
+  """gan/utils/utils.py:78-84: fill in the fields the Namespace does not have yet."""
+  import json
+  filename = os.path.join(hparams.output_dir, 'hparams.json')
+  with open(filename, 'r') as file:
+    content = json.load(file)
+  for key, value in content.items():
+    if not hasattr(hparams, key):
+      setattr(hparams, key, value)
+
+
 def save_models(hparams, gan, epoch, save_optimizer_state=True):
   if not hasattr(hparams, 'ckpt_dir'):
     hparams.ckpt_dir = os.path.join(hparams.output_dir, 'checkpoints')

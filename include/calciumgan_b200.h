@@ -153,6 +153,10 @@ int cg_validate(cg_ctx* ctx, const float* real_dev, int batch, const float* nois
                 const float* alpha_dev, const int32_t* shifts_host, float* fake_out_dev,
                 float* scalars_host);
 
+/* gan.py:32-41 `metrics(real, fake)` on caller tensors (batch, seq_len, channels) fp32: out_host[4] = mean squared
+ * difference of the per-timestep min / max / mean / std over neurons (signals_metrics.py:9-28), after de-normalisation. */
+int cg_metrics(cg_ctx* ctx, const float* real_dev, const float* fake_dev, int batch, float* out_host);
+
 /* gan.py:92-97 `generate(noise, denorm)`. out_dev (batch, seq_len, channels) fp32. */
 int cg_generate(cg_ctx* ctx, const float* noise_dev, int batch, int denorm, float* out_dev);
 

@@ -55,8 +55,14 @@ def train(hparams, train_ds, gan, summary, epoch):
   gen_losses, dis_losses, gradient_penalties = [], [], []
   start = time()
   from calciumgan_b200.utils.prefetch import prefetch_to_device
+  batch_count = 0
   for signal, _ in prefetch_to_device(train_ds()):     # H2D copy of batch i+1 overlaps step i
+    if hparams.profile and batch_count == 2 and epoch == 1:
+      summary.profiler_trace()      # main.py:45-47: the 2nd batch of the 2nd epoch opens the profiled window
     gen_loss, dis_loss, gradient_penalty, metrics = gan.train(signal)
+    if hparams.profile and batch_count == 6 and epoch == 1:
+      summary.profiler_export()     # main.py:51-52
+    batch_count += 1
     gen_losses.append(gen_loss)
     dis_losses.append(dis_loss)
     if gradient_penalty is not None:
@@ -108,6 +114,7 @@ def main(hparams, return_metrics=False):
   generator, discriminator = get_models(hparams, summary)
   gan = get_algorithm(hparams, generator, discriminator, summary)
   utils.load_models(hparams, gan)
+  utils.save_hparams(hparams)       # main.py:184 of the reference
 
   start = time()
   results = {}
@@ -150,7 +157,8 @@ def build_parser():
   parser.add_argument('--plot_weights', action='store_true')
   parser.add_argument('--skip_checkpoints', action='store_true')
   parser.add_argument('--mixed_precision', action='store_true')
-  parser.add_argument('--profile', action='store_true', help='enable profiling (use ncu; see profiles/)')
+  parser.add_argument('--profile', action='store_true',
+                      help='open a cudaProfilerStart/Stop + NVTX window around batches 2-6 of the 2nd epoch')
   parser.add_argument('--dpi', default=120, type=int)
   parser.add_argument('--verbose', default=1, type=int)
   # additions (not in the reference): data source when no TFRecord pipeline is available

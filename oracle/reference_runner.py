@@ -104,4 +104,24 @@ def train_step(hp, gen_weights, dis_weights, real, noises, alphas, shifts):
   return dict(gen_loss=float(gen_loss.detach()), dis_loss=float(dis_loss.detach()), gradient_penalty=float(gp.detach()),
               metrics={k: float(v.detach()) for k, v in metrics.items()},
               gen_weights=gan.generator.get_weights(), dis_weights=gan.discriminator.get_weights(),
+              dis_grads=[[g.numpy() for g in gs] for gs in gan.dis_optimizer.optimizer.gradient_log],
+              gen_grads=[[g.numpy() for g in gs] for gs in gan.gen_optimizer.optimizer.gradient_log],
               draw_order=list(mods.tf.random.log))
+
+
+def sub_step_gradients(hp, gen_weights, dis_weights, real, noise_c, alpha, shifts_c, noise_g, shifts_g):
+  """Per-parameter gradients as the reference's own _train_discriminator / _train_generator compute them on the GIVEN
+  weights (wgan_gp.py:22-36,64-80 -> optimizer.py:31-34: tape.gradient w.r.t. model.trainable_variables), each from a
+  fresh build so that neither sees the other's update."""
+  import torch
+  x = torch.as_tensor(real, dtype=torch.float64)
+  mods, gan = build(hp, real.shape[0], gen_weights, dis_weights)
+  mods.tf.random.inject(normal=[noise_c], uniform=[alpha], ints=[int(s) for s in shifts_c])
+  dis_loss, gp = gan._train_discriminator(x)
+  c = [g.numpy() for g in gan.dis_optimizer.optimizer.gradient_log[0]]
+  mods, gan = build(hp, real.shape[0], gen_weights, dis_weights)
+  mods.tf.random.inject(normal=[noise_g], uniform=[], ints=[int(s) for s in shifts_g])
+  gen_loss, _ = gan._train_generator(x)
+  g = [t.numpy() for t in gan.gen_optimizer.optimizer.gradient_log[0]]
+  return dict(dis_loss=float(dis_loss.detach()), gradient_penalty=float(gp.detach()), gen_loss=float(gen_loss.detach()),
+              dis_grads=c, gen_grads=g)

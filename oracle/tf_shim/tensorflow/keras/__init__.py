@@ -87,8 +87,11 @@ class _Adam(object):
     self.lr, self.b1, self.b2, self.eps = float(learning_rate), beta_1, beta_2, epsilon
     self.iterations = 0
     self.slots = {}
+    self.gradient_log = []     # test hook: the gradients of every apply_gradients call, in variable order
 
   def apply_gradients(self, grads_and_vars):
+    grads_and_vars = list(grads_and_vars)
+    self.gradient_log.append([g.detach().clone() for g, _ in grads_and_vars])
     self.iterations += 1
     t = self.iterations
     lr_t = self.lr * np.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)

@@ -43,6 +43,10 @@ def inputs_medium():
   return hp, gw, dw, real, noises, alphas, shifts
 
 
+def grad_stride(n):
+  return 97 if n > 4096 else 1
+
+
 def main_medium():
   hp, gw, dw, real, noises, alphas, shifts = inputs_medium()
   out = {}
@@ -58,6 +62,13 @@ def main_medium():
   # per-tensor norms of the weight updates: a compact check of every gradient's scale after Adam
   out['gen_update_norms'] = np.array([np.linalg.norm(a - b) for a, b in zip(r['gen_weights'], gw)])
   out['dis_update_norms'] = np.array([np.linalg.norm(a - b) for a, b in zip(r['dis_weights'], dw)])
+  # per-parameter gradients of the reference's own sub-steps on the initial weights: norms + a strided sample
+  sg = R.sub_step_gradients(hp, gw, dw, real, noises[0], alphas[0], shifts[:12], noises[1], shifts[12:16])
+  out['sub_scalars'] = np.array([sg['dis_loss'], sg['gradient_penalty'], sg['gen_loss']])
+  for key, grads in (('c', sg['dis_grads']), ('g', sg['gen_grads'])):
+    out['%s_grad_norms' % key] = np.array([np.linalg.norm(x) for x in grads])
+    for i, x in enumerate(grads):
+      out['%s_grad_%02d' % (key, i)] = x.reshape(-1)[::grad_stride(x.size)].astype(np.float64)
   path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'reference_medium.npz')
   np.savez_compressed(path, **out)
   print('wrote', path)
@@ -85,6 +96,18 @@ def main():
   for i, w in enumerate(r['dis_weights']):
     out['dis_w_%02d' % i] = w
   out['draw_order'] = np.array(r['draw_order'])
+  # per-parameter gradients (optimizer.py:31-34) of the reference's own critic / generator sub-steps on the initial weights
+  sg = R.sub_step_gradients(hp, gw, dw, real, noises[0], alphas[0], shifts[:12], noises[1], shifts[12:16])
+  out['sub_scalars'] = np.array([sg['dis_loss'], sg['gradient_penalty'], sg['gen_loss']])
+  for i, x in enumerate(sg['dis_grads']):
+    out['c_grad_%02d' % i] = x.astype(np.float32)
+  for i, x in enumerate(sg['gen_grads']):
+    out['g_grad_%02d' % i] = x.astype(np.float32)
+  # ... and of the LAST critic update / the generator update inside the full train step above
+  for i, x in enumerate(r['dis_grads'][-1]):
+    out['t_c_grad_%02d' % i] = x.astype(np.float32)
+  for i, x in enumerate(r['gen_grads'][-1]):
+    out['t_g_grad_%02d' % i] = x.astype(np.float32)
   path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'reference_step.npz')
   np.savez_compressed(path, **out)
   print('wrote', path, {k: v.shape for k, v in out.items() if k.endswith('scalars')})

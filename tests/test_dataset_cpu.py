@@ -52,3 +52,77 @@ def test_dataset_layout_to_hparams(tmp_path):
   norm = (signals - signals.min()) / (signals.max() - signals.min())
   np.testing.assert_allclose(val, norm[8:], rtol=1e-6)
   assert val.min() >= 0.0 and val.max() <= 1.0
+
+
+def _tf_example_class():
+  """tf.train.Example built from tensorflow/core/example/{example,feature}.proto's published field numbers with the
+  protobuf runtime (an implementation independent of this repo's reader / writer)."""
+  from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+  F = descriptor_pb2.FieldDescriptorProto
+  fdp = descriptor_pb2.FileDescriptorProto(name='tf_example_for_test.proto', package='tensorflow', syntax='proto3')
+
+  def msg(name, fields=()):
+    m = fdp.message_type.add(name=name)
+    for fname, number, label, ftype, type_name in fields:
+      m.field.add(name=fname, number=number, label=label, type=ftype, type_name=type_name)
+    return m
+
+  msg('BytesList', [('value', 1, F.LABEL_REPEATED, F.TYPE_BYTES, None)])
+  msg('FloatList', [('value', 1, F.LABEL_REPEATED, F.TYPE_FLOAT, None)])
+  msg('Int64List', [('value', 1, F.LABEL_REPEATED, F.TYPE_INT64, None)])
+  feature = msg('Feature')
+  feature.oneof_decl.add(name='kind')
+  for number, (fname, tname) in enumerate((('bytes_list', 'BytesList'), ('float_list', 'FloatList'), ('int64_list', 'Int64List')), 1):
+    feature.field.add(name=fname, number=number, label=F.LABEL_OPTIONAL, type=F.TYPE_MESSAGE, type_name='.tensorflow.' + tname,
+                      oneof_index=0)
+  features = msg('Features')
+  entry = features.nested_type.add(name='FeatureEntry')
+  entry.options.map_entry = True
+  entry.field.add(name='key', number=1, label=F.LABEL_OPTIONAL, type=F.TYPE_STRING)
+  entry.field.add(name='value', number=2, label=F.LABEL_OPTIONAL, type=F.TYPE_MESSAGE, type_name='.tensorflow.Feature')
+  features.field.add(name='feature', number=1, label=F.LABEL_REPEATED, type=F.TYPE_MESSAGE,
+                     type_name='.tensorflow.Features.FeatureEntry')
+  msg('Example', [('features', 1, F.LABEL_OPTIONAL, F.TYPE_MESSAGE, '.tensorflow.Features')])
+  pool = descriptor_pool.DescriptorPool()
+  pool.Add(fdp)
+  return message_factory.GetMessageClass(pool.FindMessageTypeByName('tensorflow.Example'))
+
+
+def test_reader_parses_bytes_written_by_an_independent_protobuf_serializer(tmp_path):
+  """dataset/generate_tfrecords.py:128-139 builds tf.train.Example(features{signal, spike: bytes_list}) and writes it
+  with tf.io.TFRecordWriter. The payload here comes from the protobuf runtime (not from this repo's writer), carries
+  an extra float_list / int64_list feature the reader must skip, and the frame is assembled by hand."""
+  Example = _tf_example_class()
+  rng = np.random.RandomState(3)
+  sig, spk = rng.rand(16, 5).astype(np.float32), (rng.rand(16, 5) > 0.8).astype(np.float32)
+  ex = Example()
+  ex.features.feature['spike'].bytes_list.value.append(spk.tobytes())
+  ex.features.feature['rate'].float_list.value.extend([1.5, 2.5])
+  ex.features.feature['signal'].bytes_list.value.append(sig.tobytes())
+  ex.features.feature['id'].int64_list.value.append(300)
+  payload = ex.SerializeToString()
+  got = D.parse_example(payload)
+  np.testing.assert_array_equal(np.frombuffer(got['signal'], np.float32).reshape(16, 5), sig)
+  np.testing.assert_array_equal(np.frombuffer(got['spike'], np.float32).reshape(16, 5), spk)
+  assert 'rate' not in got and 'id' not in got
+  # and the other direction: the repo's writer produces bytes the protobuf runtime parses to the same message
+  back = Example.FromString(D.serialize_example(sig, spk))
+  assert set(back.features.feature) == {'signal', 'spike'}
+  assert back.features.feature['signal'].bytes_list.value[0] == sig.tobytes()
+  # TFRecord frame: u64 length | masked crc32c(length) | payload | masked crc32c(payload)
+  header = struct.pack('<Q', len(payload))
+  path = str(tmp_path / 'train-001-of-001.record')
+  with open(path, 'wb') as f:
+    f.write(header + struct.pack('<I', D.masked_crc32c(header)) + payload + struct.pack('<I', D.masked_crc32c(payload)))
+  assert list(D.read_records(path, verify_crc=True)) == [payload]
+
+
+def test_hand_assembled_example_known_answer():
+  """Byte-for-byte known answer from the protobuf wire format: Example{1: Features{1: entry{1: "signal", 2: Feature{1:
+  BytesList{1: 01 02 03 04}}}}} = 0A 14 | 0A 12 | 0A 06 'signal' | 12 08 | 0A 06 | 0A 04 01 02 03 04."""
+  raw = bytes([0x0A, 0x14, 0x0A, 0x12, 0x0A, 0x06]) + b'signal' + bytes([0x12, 0x08, 0x0A, 0x06, 0x0A, 0x04, 1, 2, 3, 4])
+  got = D.parse_example(raw)
+  assert set(got) == {'signal'} and bytes(got['signal']) == bytes([1, 2, 3, 4])
+  # masked crc of a known frame header (length 20): standard crc32c, rotated right by 15 and offset 0xa282ead8
+  c = D.crc32c(struct.pack('<Q', 20))
+  assert D.masked_crc32c(struct.pack('<Q', 20)) == ((((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF)

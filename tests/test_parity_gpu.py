@@ -172,7 +172,7 @@ def test_medium_fp32(layer_norm, K):
 # on the branches the engine took.
 BF16_VS_FP64_GRAD_BOUND = 0.14
 BF16_POLICY_GRAD_BOUND = 0.08
-BF16_FREE_RUNNING_GRAD_BOUND = 0.10   # batch 128: more samples average more of the flip noise than batch 3 .. 8
+BF16_FREE_RUNNING_GRAD_BOUND = 0.075   # batch 128 (measured 0.026 critic / 0.062 generator, + 20%): more samples average more flip noise
 
 
 @pytest.mark.parametrize('force_simt', [True, False])
@@ -550,6 +550,57 @@ def test_cuda_path_matches_reference_code_fixture(mixed):
 
 
 @pytest.mark.parametrize('mixed', [False, True])
+def test_gradients_match_reference_code_fixture(mixed):
+  """Per-parameter gradients as the REFERENCE'S OWN _train_discriminator / _train_generator hand them to Adam
+  (wgan_gp.py:22-36,64-80 -> optimizer.py:31-34; captured from the unmodified reference code in
+  tests/golden/reference_step.npz and reference_medium.npz). fp32: rel <= 1e-4 on every tensor. bf16: free-running
+  comparison (slope-flip bound + direction; the 2e-2 tolerance on imposed branches is tests/test_gradient_parity_gpu.py,
+  against the oracle that reproduces these fixtures to 1e-9, tests/test_reference_shim.py)."""
+  import sys
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+  import make_reference_golden as G
+  tol = BF16_TOL if mixed else FP32_TOL
+  gtol = 0.175 if mixed else FP32_TOL      # batch 3 / 4: see the batch-2 bound above
+  # small fixture: whole gradient tensors
+  gold = np.load(os.path.join(os.path.dirname(GOLD), 'reference_step.npz'))
+  hp, gw, dw, real, noises, alphas, shifts = G.inputs()
+  ns, gan = build(hp, G.BATCH, mixed=mixed)
+  gan.generator.set_weights(gw)
+  gan.discriminator.set_weights(dw)
+  s = gan.engine.critic_step(real, noises[0], alphas[0], shifts[:12], update=False)
+  assert abs(s[0] - gold['sub_scalars'][0]) <= tol * max(1.0, abs(gold['sub_scalars'][0]))
+  assert abs(s[1] - gold['sub_scalars'][1]) <= tol * max(1.0, abs(gold['sub_scalars'][1]))
+  wc = check_list(gan.engine.get_grads(1), [gold['c_grad_%02d' % i] for i in range(12)], gtol, 'critic grad vs reference code')
+  s = gan.engine.generator_step(real, noises[1], shifts[12:16], update=False)
+  assert abs(s[4] - gold['sub_scalars'][2]) <= tol * max(1.0, abs(gold['sub_scalars'][2]))
+  wg = check_list(gan.engine.get_grads(0), [gold['g_grad_%02d' % i] for i in range(24)], gtol, 'generator grad vs reference code')
+  # the gradients INSIDE a full train step (last critic update, generator update after the critic's Adam steps); Adam's
+  # first steps are sign-like, so a near-zero gradient element can move a weight the other way: looser in fp32
+  gan.train(real, noise=noises, alpha=alphas, shifts=shifts)
+  check_list(gan.engine.get_grads(1), [gold['t_c_grad_%02d' % i] for i in range(12)], gtol if mixed else 2e-3, 'critic grad in train()')
+  check_list(gan.engine.get_grads(0), [gold['t_g_grad_%02d' % i] for i in range(24)], gtol if mixed else 2e-3, 'generator grad in train()')
+  # medium fixture (512 x 102, shifts at +-10): norms + strided samples
+  gold = np.load(os.path.join(os.path.dirname(GOLD), 'reference_medium.npz'))
+  hp, gw, dw, real, noises, alphas, shifts = G.inputs_medium()
+  ns, gan = build(hp, G.BATCH_MEDIUM, mixed=mixed)
+  gan.generator.set_weights(gw)
+  gan.discriminator.set_weights(dw)
+  gan.engine.critic_step(real, noises[0], alphas[0], shifts[:12], update=False)
+  gc = gan.engine.get_grads(1)
+  gan.engine.generator_step(real, noises[1], shifts[12:16], update=False)
+  gg = gan.engine.get_grads(0)
+  for key, grads in (('c', gc), ('g', gg)):
+    for i, a in enumerate(grads):
+      ref, norm = gold['%s_grad_%02d' % (key, i)], gold['%s_grad_norms' % key][i]
+      if norm == 0:
+        assert np.abs(a).max() <= 1e-6
+        continue
+      assert abs(np.linalg.norm(a.astype(np.float64)) / norm - 1.0) <= tol, (key, i)
+      assert rel_err(a.reshape(-1)[::G.grad_stride(a.size)], ref) <= gtol, (key, i)
+  print('gradients vs reference-code fixture (mixed=%s): worst critic %.2e generator %.2e' % (mixed, wc, wg))
+
+
+@pytest.mark.parametrize('mixed', [False, True])
 def test_cuda_path_matches_reference_code_fixture_medium(mixed):
   """Second fixture from the reference's own code (tests/golden/reference_medium.npz: 512 x 102, num_units 32, m 10 with
   shifts at the extremes): the slab-mode tensor-core kernels with both fused PhaseShuffle directions in bf16, the
@@ -656,3 +707,65 @@ def test_headline_batch_128_against_cpu_fixture():
   wg = check(gan.engine.get_grads(0), 'g')
   print('batch 128 vs float64 CPU fixture (free-running branches): worst sampled gradient rel err critic %.2e generator %.2e'
         % (wc, wg))
+
+
+def test_gan_metrics_and_step_methods():
+  """GAN.metrics(real, fake) (gan.py:32-41) and GAN._step(real, noise, training) (gan.py:58-70) as callable methods of
+  the plugin, against the oracle."""
+  hp = _medium_hp()
+  B = 4
+  ns, gan = build(hp, B)
+  gw, dw = O.init_weights(hp, seed=11)
+  gw, dw = O.randomize_weights(gw, 12), O.randomize_weights(dw, 13)
+  gan.generator.set_weights(gw)
+  gan.discriminator.set_weights(dw)
+  real, noises, alphas, shifts = O.synthetic_batch(hp, B, seed=14, n_critic=1)
+  rng = np.random.RandomState(0)
+  fake = rng.uniform(0, 1, size=real.shape).astype(np.float32)
+  hp2 = hp
+  want = O.signals_metrics(torch.tensor(real, dtype=torch.float64), torch.tensor(fake, dtype=torch.float64), hp2)
+  got = gan.metrics(real, torch.tensor(fake).cuda())
+  assert set(got) == set(want)
+  for k in want:
+    assert abs(got[k] - want[k]) <= 1e-4 * max(1e-3, abs(want[k])), k
+  f, gl, dl, gp, met = O.validate_step(gw, dw, real, noises[0], alphas[0], shifts[:12].reshape(3, 4), hp)
+  f2, gl2, dl2, gp2, met2 = gan._step(real, noises[0], training=False, alpha=alphas[0], shifts=shifts[:12])
+  assert rel_err(f2.cpu().numpy(), f.numpy()) <= FP32_TOL
+  assert abs(gl2 - gl) <= FP32_TOL * max(1, abs(gl)) and abs(dl2 - dl) <= FP32_TOL * max(1, abs(dl))
+  assert abs(gp2 - gp) <= FP32_TOL * max(1, abs(gp))
+  out = gan._step(real, gan.get_noise(B))           # library-drawn alpha / shifts
+  assert len(out) == 5 and np.isfinite(out[1]) and np.isfinite(out[2]) and np.isfinite(out[3])
+
+
+def test_main_profile_flag_and_hparams_json(tmp_path):
+  """--profile opens the cudaProfilerStart/Stop + NVTX window at the reference's batch indices (main.py:45-52,
+  summary_helper.py:115-119) and main() writes output_dir/hparams.json (utils.py:72-75) that load_hparams reads back."""
+  import argparse
+  import json
+  import main as driver
+  from calciumgan_b200.utils import dataset_helper, utils
+  from calciumgan_b200.utils import summary_helper
+  rng = np.random.RandomState(0)
+  data_dir, out_dir = str(tmp_path / 'tfrecords'), str(tmp_path / 'runs')
+  signals = rng.rand(16, 256, 20).astype(np.float32)
+  dataset_helper.write_dataset(data_dir, signals, np.zeros_like(signals), train_size=14, num_per_shard=8)
+  calls = []
+  orig_trace, orig_export = summary_helper.Summary.profiler_trace, summary_helper.Summary.profiler_export
+  summary_helper.Summary.profiler_trace = lambda self: (calls.append(('trace', hp.global_step)), orig_trace(self))
+  summary_helper.Summary.profiler_export = lambda self: (calls.append(('export', hp.global_step)), orig_export(self))
+  try:
+    argv = ['--input_dir', data_dir, '--output_dir', out_dir, '--batch_size', '2', '--num_units', '16', '--kernel_size', '24',
+            '--m', '3', '--epochs', '2', '--noise_dim', '8', '--model', 'calciumgan', '--layer_norm', '--n_critic', '1',
+            '--mixed_precision', '--verbose', '0', '--profile', '--skip_checkpoints']
+    hp = driver.build_parser().parse_args(argv)
+    hp.global_step, hp.surrogate_ds = 0, False
+    driver.main(hp)
+  finally:
+    summary_helper.Summary.profiler_trace, summary_helper.Summary.profiler_export = orig_trace, orig_export
+  # 7 batches per epoch: the window opens before batch 2 and closes after batch 6 of epoch 1 (global steps 9 and 13)
+  assert calls == [('trace', 9), ('export', 13)], calls
+  content = json.load(open(os.path.join(out_dir, 'hparams.json')))
+  assert content['num_units'] == 16 and content['signal_shape'] == [256, 20] and 'git_hash' in content
+  fresh = argparse.Namespace(output_dir=out_dir, num_units=99)
+  utils.load_hparams(fresh)
+  assert fresh.num_units == 99 and fresh.kernel_size == 24 and fresh.noise_dim == 8    # only missing fields are filled

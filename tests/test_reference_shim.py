@@ -121,3 +121,24 @@ def test_oracle_matches_reference_fixture():
     assert rel_err(w - np.asarray(w0), gold['gen_w_%02d' % i] - np.asarray(w0)) <= 1e-7, ('gen', i)
   for i, (w, w0) in enumerate(zip(d_new, dw)):
     assert rel_err(w - np.asarray(w0), gold['dis_w_%02d' % i] - np.asarray(w0)) <= 1e-7, ('dis', i)
+
+
+def test_reference_sub_step_gradients_equal_the_oracle():
+  """The gradients the reference's own _train_discriminator / _train_generator hand to Adam (optimizer.py:31-34),
+  captured from the stand-in optimizer, equal the oracle's per-parameter gradients; the committed fixtures carry them
+  to the GPU box."""
+  import sys
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+  import make_reference_golden as G
+  hp, gw, dw, real, noises, alphas, shifts = G.inputs()
+  sg = R.sub_step_gradients(hp, gw, dw, real, noises[0], alphas[0], shifts[:12], noises[1], shifts[12:16])
+  c = O.critic_step(gw, dw, real, noises[0], alphas[0], shifts[:12].reshape(3, 4), hp)
+  g = O.generator_step(gw, dw, real, noises[1], shifts[12:16], hp)
+  assert len(sg['dis_grads']) == 12 and len(sg['gen_grads']) == 24
+  for a, b in zip(sg['dis_grads'], c['grads']):
+    assert np.abs(a - b.numpy()).max() <= 1e-9 * max(1.0, np.abs(a).max())
+  for a, b in zip(sg['gen_grads'], g['grads']):
+    assert np.abs(a - b.numpy()).max() <= 1e-9 * max(1.0, np.abs(a).max())
+  gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_step.npz'))
+  for i, a in enumerate(sg['dis_grads']):
+    np.testing.assert_allclose(gold['c_grad_%02d' % i], a, rtol=1e-6, atol=1e-12)
