@@ -14,6 +14,7 @@ ap.add_argument('--batch', type=int, default=128)
 ap.add_argument('--iters', type=int, default=20)
 ap.add_argument('--simt', action='store_true')
 ap.add_argument('--fp32', action='store_true')
+ap.add_argument('--only', default='', help='comma list such as D1fwd,D2dgrad,G5fwd')
 a = ap.parse_args()
 hp = O.HParams()
 ns = namespace_from_oracle(hp, a.batch, mixed_precision=not a.fp32, force_simt=a.simt)
@@ -31,6 +32,8 @@ for which, name, batches in ((1, 'D conv', 3 * a.batch), (0, 'G convT', a.batch)
       if which == 0 and pass_ != 0:
         continue
       B = batches
+      if a.only and ('%s%d%s' % (name[0], layer, pn)) not in a.only.split(','):
+        continue
       ms, fl = eng.bench_layer(which, layer, pass_, B, a.iters)
       tf = fl / ms / 1e9
       rows.append((name, layer, pn, B, ms, tf))
