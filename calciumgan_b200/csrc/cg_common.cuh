@@ -131,6 +131,12 @@ struct RsParams {
   void* aux;                                       //   optional pre-norm copy, same indexing as out
   // fused PhaseShuffle (slab kernels, strided-conv form): ps_out[b, t, :] = result[b, ps_index(t, shift[b / ps_group_b]), :]
   void* ps_out; int ps_w; int ps_group_b; int ps_shift[4];
+  // Row-pair form of a strided convolution with 64 output channels (tensor-core path): GEMM row i holds the outputs of
+  // time steps 2i and 2i+1 side by side (N = 128 = [channels of 2i | channels of 2i+1]), the input is read through the
+  // (B, L/4, 4*Cp) view and the weights are two tap-shifted copies of the kernel. An N = 64 MMA reads 4 KB of
+  // activations for 32 clk of math (shared-memory bound); N = 128 does twice the math on the same 4 KB.
+  int row_pairs;                                   // 1: PhaseShuffle scatter / bias index fold the column back to a channel
+  float flop_scale;                                // algorithmic / issued FLOPs (the shifted copies add zero taps); 0 = 1
   int dbg;                                         // timing experiments only
   float* sumsq;                                    // optional: sumsq[b] += sum of squares of the fp32 results of sample b
   int B, Q, N, n_real, Kc, k_real, epi;   // k_real: unpadded channels per tap (algorithmic FLOPs only)

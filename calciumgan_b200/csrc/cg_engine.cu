@@ -104,6 +104,7 @@ struct cg_ctx {
   void *Wf_d[NL + 1], *Wb_d[NL + 1];     // critic conv: forward [Cout][K*Cin_p], dgrad [Cin][K*Cout_p]
   void *Wf_g[NL + 1], *Wb_g[NL + 1];     // generator convT: forward [Cout][K*Cin_p], bwd-data [Cin][K*Cout_p]
   void *Wf_d1, *Wb_d1;                   // generator output dense: [C][Cp], transposed
+  void* Wf2_d[NL + 1];                   // critic conv, row-pair form (64 output channels): [2*64][(K+2)*Cin_p], else null
   // critic activations (capacity 3*Bmax)
   void *X[NL + 1], *H[NL + 1], *DX[NL + 1], *DA[NL + 1];
   void* V5;                                // gradient penalty: linearised forward output of the last conv layer (Bmax samples)
@@ -235,7 +236,7 @@ static int launch_rsgemm(cg_ctx* c, const RsParams& p) {
   for (int i = 0; i < p.seg.nphase; ++i) nseg += p.seg.nseg[i];
   char d[96];
   snprintf(d, sizeof(d), "gemm  B=%d Q=%d N=%d Kc=%d taps=%d ph=%d epi=%d", p.B, p.Q, p.N, p.Kc, nseg, p.seg.nphase, p.epi);
-  CK(prof_begin(c, 0, 2.0 * p.B * p.Q * (double)p.n_real * p.k_real * nseg, d));
+  CK(prof_begin(c, 0, 2.0 * p.B * p.Q * (double)p.n_real * p.k_real * nseg * (p.flop_scale > 0.f ? p.flop_scale : 1.f), d));
   CK(launch_rsgemm_raw(c, p));
   return prof_end(c);
 }
@@ -270,11 +271,13 @@ static int launch_wgrad_raw(cg_ctx* c, WgParams p) {
 }
 
 static void add_pack(PackOps& ops, const float* src, void* dst, int N, int n_real, int nseg, int Cp, int c_real,
-                     long long sk, long long sn, long long sc) {
+                     long long sk, long long sn, long long sc, long long ld = 0) {
   PackOp& o = ops.op[ops.n++];
   o.src = src; o.dst = dst; o.N = N; o.n_real = n_real; o.nseg = nseg; o.Cp = Cp; o.c_real = c_real;
-  o.sk = sk; o.sn = sn; o.sc = sc;
+  o.sk = sk; o.sn = sn; o.sc = sc; o.ld = ld ? ld : (long long)nseg * Cp;
 }
+
+static void* off(cg_ctx* c, void* base, long long elems) { return (char*)base + elems * c->esz; }
 
 // refresh packed T copies of one model's GEMM weights from the fp32 master (one launch)
 static int repack(cg_ctx* c, int which) {
@@ -287,6 +290,12 @@ static int repack(cg_ctx* c, int which) {
       const int ci = c->dc[l - 1], co = c->dc[l], cip = c->dcp[l - 1], cop = c->dcp[l];
       add_pack(ops, w, c->Wf_d[l], cop, co, K, cip, ci, (long long)ci * co, 1, co);
       add_pack(ops, w, c->Wb_d[l], cip, ci, K, cop, co, (long long)ci * co, co, 1);
+      if (c->Wf2_d[l]) {   // row-pair form: rows [g*64, g*64+64) hold the kernel delayed by 2g taps (the other taps stay zero)
+        const long long ld2 = (long long)(K + 2) * cip;
+        for (int g = 0; g < 2; ++g)
+          add_pack(ops, w, off(c, c->Wf2_d[l], (long long)g * 64 * ld2 + 2LL * g * cip), cop, co, K, cip, ci, (long long)ci * co, 1,
+                   co, ld2);
+      }
     }
   } else {
     for (int i = 1; i <= NL; ++i) {
@@ -300,9 +309,17 @@ static int repack(cg_ctx* c, int which) {
     add_pack(ops, w1, c->Wf_d1, Cp, C, 1, Cp, C, 0, 1, C);             // [n=out][c=in]
     add_pack(ops, w1, c->Wb_d1, Cp, C, 1, Cp, C, 0, C, 1);             // [n=in][c=out]
   }
+  if (ops.n > 24) return set_err("repack: too many pack ops");
   dim3 grid(16, c->K, ops.n);
   DISPATCH_T(c, pack_weights_kernel<T><<<grid, 256, 0, c->stream>>>(ops));
   return post_launch(c, "pack_weights");
+}
+
+// Strided critic conv l in row-pair form (RsParams.row_pairs): 64 (padded) output channels, tensor-core path, and at
+// least 128 GEMM rows (pairs of output time steps) per sample in whole 128-row blocks.
+static bool row_pairs_apply(const cg_ctx* c, int l) {
+  if (!c->use_tc || getenv("CG_NO_ROW_PAIRS")) return false;
+  return c->dcp[l] == 64 && c->dl[l] % 256 == 0 && c->K + 2 <= CG_MAX_SEG;
 }
 
 // one-pass Adam + re-pack: GEMM kernels as 32 x 32 tiles per tap, everything between them as element-wise ranges
@@ -312,9 +329,10 @@ static void build_adam_plans(cg_ctx* c) {
     memset(&pl, 0, sizeof(pl));
     Model& M = which == CG_GENERATOR ? c->gen : c->dis;
     std::vector<bool> is_gemm(M.params.size(), false);
-    auto add_tensor = [&](int idx, int K, int A, int B, int Ap, int Bp, void* direct, void* trans) {
+    auto add_tensor = [&](int idx, int K, int A, int B, int Ap, int Bp, void* direct, void* trans, void* trans2 = nullptr) {
       AdamTensor& t = pl.t[pl.nt++];
       t.off = M.params[idx].offset; t.K = K; t.A = A; t.B = B; t.Ap = Ap; t.Bp = Bp; t.direct = direct; t.trans = trans;
+      t.trans2 = trans2;
       t.tiles_a = (A + 31) / 32; t.tiles_b = (B + 31) / 32;
       t.item0 = pl.tile_items;
       pl.tile_items += (long long)K * t.tiles_a * t.tiles_b;
@@ -322,7 +340,7 @@ static void build_adam_plans(cg_ctx* c) {
     };
     if (which == CG_DISCRIMINATOR) {
       for (int l = 1; l <= NL; ++l)   // (K, Cin, Cout): a = ci, b = co; Wb_d = [ci][k*Coutp + co], Wf_d = [co][k*Cinp + ci]
-        add_tensor(2 * (l - 1), c->K, c->dc[l - 1], c->dc[l], c->dcp[l - 1], c->dcp[l], c->Wb_d[l], c->Wf_d[l]);
+        add_tensor(2 * (l - 1), c->K, c->dc[l - 1], c->dc[l], c->dcp[l - 1], c->dcp[l], c->Wb_d[l], c->Wf_d[l], c->Wf2_d[l]);
     } else {
       for (int i = 1; i <= NL; ++i)   // (K, 1, Cout, Cin): a = co, b = ci; Wf_g = [co][k*Cinp + ci], Wb_g = [ci][k*Coutp + co]
         add_tensor(c->g_k[i], c->K, c->gc[i], c->gc[i - 1], c->gcp[i], c->gcp[i - 1], c->Wf_g[i], c->Wb_g[i]);
@@ -445,6 +463,10 @@ extern "C" int cg_create(const cg_config* cfg, cg_ctx** out) {
     DA_(c->Wb_d[l], (size_t)c->dcp[l - 1] * c->K * c->dcp[l] * es);
     DA_(c->Wf_g[l], (size_t)c->gcp[l] * c->K * c->gcp[l - 1] * es);
     DA_(c->Wb_g[l], (size_t)c->gcp[l - 1] * c->K * c->gcp[l] * es);
+  }
+  for (int l = 1; l <= NL; ++l) {
+    c->Wf2_d[l] = nullptr;
+    if (row_pairs_apply(c, l)) DA_(c->Wf2_d[l], (size_t)128 * (c->K + 2) * c->dcp[l - 1] * es);
   }
   DA_(c->Wf_d1, (size_t)c->gcp[NL] * c->gcp[NL] * es);
   DA_(c->Wb_d1, (size_t)c->gcp[NL] * c->gcp[NL] * es);
@@ -830,8 +852,6 @@ static int g_backward(cg_ctx* c, int B) {
 }
 
 // ------------------------------------------------------------------------------------------ critic
-static void* off(cg_ctx* c, void* base, long long elems) { return (char*)base + elems * c->esz; }
-
 static GroupShifts group_shifts(const int32_t* sh, int groups, int layer /*1..4*/) {
   GroupShifts g;
   for (int i = 0; i < 4; ++i) g.s[i] = i < groups ? sh[i * 4 + (layer - 1)] : 0;
@@ -848,6 +868,26 @@ static RsParams conv_fwd_params(cg_ctx* c, int l, const void* A, void* out, int 
   p.mask = mask;
   p.B = Bt; p.Q = c->dl[l]; p.N = c->dcp[l]; p.n_real = c->dc[l]; p.Kc = c->dcp[l - 1]; p.k_real = c->dc[l - 1]; p.epi = epi;
   p.seg = seg_strided(c->K, c->dcp[l - 1]);
+  if (c->Wf2_d[l] && !c->tc.force_v1) {
+    // row-pair form: GEMM row i = output time steps (2i, 2i+1); input through the (B, L/4, 4*Cp) view; tap k' = k + 2g
+    // of the widened kernel reads input time 4i + k' - padL for output 2i + g
+    const int K2 = c->K + 2, Cp = c->dcp[l - 1], padL = (c->K - 2) / 2;
+    p.a_rs = 4 * Cp; p.a_rows = c->dl[l - 1] / 4;
+    p.W = c->Wf2_d[l]; p.w_ld = K2 * Cp;
+    p.o_rs = 2 * c->dcp[l];
+    p.Q = c->dl[l] / 2; p.N = 2 * c->dcp[l];
+    p.row_pairs = 1;
+    p.flop_scale = 2.0f * c->K / K2;
+    memset(&p.seg, 0, sizeof(p.seg));
+    p.seg.nphase = 1;
+    p.seg.nseg[0] = K2;
+    for (int k = 0; k < K2; ++k) {
+      const int d = k - padL, j = d >= 0 ? d / 4 : -((-d + 3) / 4), r = d - 4 * j;
+      p.seg.shift[0][k] = (short)j;
+      p.seg.acol[0][k] = r * Cp;
+      p.seg.wk[0][k] = k * Cp;
+    }
+  }
   return p;
 }
 

@@ -218,7 +218,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict_
 }
 
 // all packed copies of one model in ONE launch: blockIdx.y selects the op
-struct PackOp { const float* src; void* dst; int N, n_real, nseg, Cp, c_real; long long sk, sn, sc; };
+struct PackOp { const float* src; void* dst; int N, n_real, nseg, Cp, c_real; long long sk, sn, sc; long long ld; };   // ld: destination row pitch (elements)
 struct PackOps { int n; PackOp op[24]; };
 // grid (x = 32x32 tiles of the (n, c) plane, y = tap, z = op): reads follow the source's fastest axis, writes follow
 // the destination's (c), transposing through shared memory when they differ.
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + ty + 8 * j, c = c0 + tx;
-      if (n < o.N && c < o.Cp) dst[((long long)n * o.nseg + k) * o.Cp + c] = Elem<T>::from_f(tile[n - n0][c - c0]);
+      if (n < o.N && c < o.Cp) dst[(long long)n * o.ld + (long long)k * o.Cp + c] = Elem<T>::from_f(tile[n - n0][c - c0]);
     }
   }
 }
@@ -1120,6 +1120,7 @@ struct AdamTensor {
   int Ap, Bp;             // padded extents in the packed copies
   void* direct;           // [a][k*Bp + b]
   void* trans;            // [b][k*Ap + a]
+  void* trans2;           // optional row-pair copy [g*Bp + b][(k + 2g)*Ap + a], g = 0, 1, row pitch (K + 2)*Ap (see RsParams.row_pairs)
   int tiles_a, tiles_b;
   long long item0;        // first work item of this tensor
 };
@@ -1173,7 +1174,16 @@ __global__ void __launch_bounds__(256) adam_pack_kernel(float* __restrict__ w, f
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int bb = tb * 32 + ty + 8 * j, a = a0 + tx;
-        if (bb < t.B && a < t.A) trans[((long long)bb * t.K + k) * t.Ap + a] = Elem<T>::from_f(tile[tx][ty + 8 * j]);
+        if (bb < t.B && a < t.A) {
+          const T val = Elem<T>::from_f(tile[tx][ty + 8 * j]);
+          trans[((long long)bb * t.K + k) * t.Ap + a] = val;
+          if (t.trans2) {
+            T* t2 = reinterpret_cast<T*>(t.trans2);
+            const long long ld2 = (long long)(t.K + 2) * t.Ap;
+            t2[(long long)bb * ld2 + (long long)k * t.Ap + a] = val;
+            t2[(long long)(t.Bp + bb) * ld2 + (long long)(k + 2) * t.Ap + a] = val;
+          }
+        }
       }
     } else {
       const long long e = it - plan.tile_items;

@@ -518,11 +518,19 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
         if (R.off[i] >= 0) {
           if (out) *reinterpret_cast<uint4*>(out + R.base + R.off[i] + n0 + cj * 8) = o;
           if (psx) {   // scatter form of the PhaseShuffle gather: row q feeds every t with ps_index(t) == q
-            const int q = ps_q0 + lq * 32 + rr;
             int t1, t2;
-            ps_scatter_targets(q, ps_s, p.ps_w, t1, t2);
-            if (t1 >= 0) *reinterpret_cast<uint4*>(psx + R.base + (R.off[i] + (t1 - q) * p.o_rs + n0 + cj * 8)) = o;
-            if (t2 >= 0) *reinterpret_cast<uint4*>(psx + R.base + (R.off[i] + (t2 - q) * p.o_rs + n0 + cj * 8)) = o;
+            if (p.row_pairs) {   // GEMM row = time steps (2 qs, 2 qs + 1); this 32-column chunk belongs to one of them
+              const int q = 2 * (ps_q0 + lq * 32 + rr) + (n0 >> 6);
+              ps_scatter_targets(q, ps_s, p.ps_w, t1, t2);
+              bf16* dst = psx + R.base + (n0 & 63) + cj * 8;
+              if (t1 >= 0) *reinterpret_cast<uint4*>(dst + t1 * (p.o_rs >> 1)) = o;
+              if (t2 >= 0) *reinterpret_cast<uint4*>(dst + t2 * (p.o_rs >> 1)) = o;
+            } else {
+              const int q = ps_q0 + lq * 32 + rr;
+              ps_scatter_targets(q, ps_s, p.ps_w, t1, t2);
+              if (t1 >= 0) *reinterpret_cast<uint4*>(psx + R.base + (R.off[i] + (t1 - q) * p.o_rs + n0 + cj * 8)) = o;
+              if (t2 >= 0) *reinterpret_cast<uint4*>(psx + R.base + (R.off[i] + (t2 - q) * p.o_rs + n0 + cj * 8)) = o;
+            }
           }
         }
       }
@@ -550,11 +558,12 @@ __device__ __forceinline__ void epi_load_bias(const RsParams& p, float* bias_s, 
     epi_bar();   // previous tile's readers are done
     {
       const int n = n_base + tid;
-      const bool ok = tid < BN && n < p.n_real;
-      bias_s[tid] = ok ? __ldg(&p.bias[n]) : 0.f;
+      const int ch = p.row_pairs ? (n & 63) : n;   // row pairs: column = (time parity, channel)
+      const bool ok = tid < BN && ch < p.n_real;
+      bias_s[tid] = ok ? __ldg(&p.bias[ch]) : 0.f;
       if (EPI == EPI_BIAS_LN_LRELU) {
-        bias_s[256 + tid] = ok ? __ldg(&p.gamma[n]) : 0.f;
-        bias_s[512 + tid] = ok ? __ldg(&p.beta[n]) : 0.f;
+        bias_s[256 + tid] = ok ? __ldg(&p.gamma[ch]) : 0.f;
+        bias_s[512 + tid] = ok ? __ldg(&p.beta[ch]) : 0.f;
       }
     }
     epi_bar();
@@ -751,7 +760,7 @@ struct RsTc2Params {
   int per_tap;          // 1: rows per sample < 128 -> no slab reuse: a slab stage holds one 128-row box PER TAP (tps boxes)
   int rpt, bpt, rpt_log2;
   int ngroups[2];
-  SlabGroup grp[2][2];
+  SlabGroup grp[2][4];   // tap groups sharing one slab (same column offset): 2 for the stride-2 forms, 4 for row pairs
   long long* dbg;   // optional role cycle counters of CTA 0 (CG_TC_TIMING=1)
 };
 
@@ -1476,11 +1485,11 @@ static inline int tc_pick_bn(int N) {
 static inline bool tc_rsgemm2_supported(const RsParams& p) {
   if (p.Q < 128 || p.Q % 128) return false;
   for (int ph = 0; ph < p.seg.nphase; ++ph) {
-    int acols[2], na = 0, cnt[2] = {0, 0};
+    int acols[4], na = 0, cnt[4] = {0, 0, 0, 0};
     for (int s = 0; s < p.seg.nseg[ph]; ++s) {
       int g = -1;
       for (int i = 0; i < na; ++i) if (acols[i] == p.seg.acol[ph][s]) g = i;
-      if (g < 0) { if (na == 2) return false; acols[na] = p.seg.acol[ph][s]; g = na++; }
+      if (g < 0) { if (na == 4) return false; acols[na] = p.seg.acol[ph][s]; g = na++; }
       if (++cnt[g] > 32) return false;
     }
   }
@@ -1559,6 +1568,7 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   for (int ph = 0; ph < p.seg.nphase; ++ph) if (P.ngroups[ph] > groups_per_tile) groups_per_tile = P.ngroups[ph];
   groups_per_tile *= P.kchunks;
   P.slab_stages = groups_per_tile <= 2 ? 4 : (groups_per_tile <= 4 ? 3 : 2);   // short K loops: prefetch the next tile's slabs
+  if (p.row_pairs) P.slab_stages = 3;   // four short tap groups per 64-channel chunk
   // taps per weight stage: enough MMA time per stage (4 MMAs x BN/2 clk per tap) to cover a cross-CTA barrier round-trip
   int stage_clk = 1000;
   if (const char* e = getenv("CG_TC_STAGE_CLK")) stage_clk = atoi(e);

@@ -15,6 +15,11 @@ CONFIGS = {
     'medium': (dict(signal_shape=(512, 102), noise_dim=8, num_units=32, kernel_size=24, m=3, n_critic=1), 6),
     'tiny_ragged': (dict(signal_shape=(64, 6), noise_dim=4, num_units=4, kernel_size=6, m=1, n_critic=1), 5),
     'wide_odd_k': (dict(signal_shape=(256, 70), noise_dim=16, num_units=64, kernel_size=5, m=2, n_critic=1), 3),
+    # BASELINE.json configs[1] architecture (row-pair form of conv1, slab / per-tap modes of every other layer)
+    'paper': (dict(signal_shape=(2048, 102), noise_dim=32, num_units=64, kernel_size=24, m=10, n_critic=1), 2),
+    # BASELINE.json configs[3] widths (num_units 128, 512 channels: N = 640 / 512 tiles, K chunks up to 640, layer norm
+    # over 640 channels outside the GEMM epilogue) at a shorter sequence
+    'scaled_widths': (dict(signal_shape=(1024, 512), noise_dim=32, num_units=128, kernel_size=24, m=10, n_critic=1), 2),
 }
 
 
