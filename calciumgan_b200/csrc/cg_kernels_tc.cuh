@@ -1576,6 +1576,12 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   if (P.tps < 1) P.tps = 1;
   if (P.tps > 6) P.tps = P.BN <= 64 ? 12 : 6;   // N = 64: a whole 12-tap parity group per weight stage (measured 140 -> 131 us on conv1)
   if (P.per_tap && P.tps > 3) P.tps = 3;
+  if (p.row_pairs) {   // one weight stage per tap group (6-7 taps): measured 108 -> 97 us on conv1 forward (tps 4 -> 7)
+    P.tps = 1;
+    for (int ph = 0; ph < p.seg.nphase; ++ph)
+      for (int g = 0; g < P.ngroups[ph]; ++g) if (P.grp[ph][g].nseg > P.tps) P.tps = P.grp[ph][g].nseg;
+    if (P.tps > 8) P.tps = 8;
+  }
   if (const char* e = getenv("CG_TC_TPS")) P.tps = atoi(e);
   if (const char* e = getenv("CG_TC_NK")) P.dbg_nk = atoi(e);
   if (const char* e = getenv("CG_TC_DBG")) P.dbg_flags = atoi(e);

@@ -30,6 +30,8 @@ def _bf(x):
 def _engine(cfg, mixed, force_simt=False):
   from calciumgan_b200.models.registry import get_models
   kw, B = CONFIGS[cfg]
+  if cfg == 'scaled_widths' and not mixed:
+    pytest.skip('the fp32 debug path keeps a layer-norm row in registers: at most 512 channels (config 4 is a bf16 configuration)')
   hp = O.HParams(**kw)
   ns = namespace_from_oracle(hp, B, mixed_precision=mixed, force_simt=force_simt)
   g, d = get_models(ns, None)

@@ -34,7 +34,11 @@ for which, name, batches in ((1, 'D conv', 3 * a.batch), (0, 'G convT', a.batch)
       B = batches
       if a.only and ('%s%d%s' % (name[0], layer, pn)) not in a.only.split(','):
         continue
-      ms, fl = eng.bench_layer(which, layer, pass_, B, a.iters)
+      try:
+        ms, fl = eng.bench_layer(which, layer, pass_, B, a.iters)
+      except Exception as e:
+        print('%-8s L%d %-6s B=%4d  failed: %s' % (name, layer, pn, B, str(e)[:60]))
+        continue
       tf = fl / ms / 1e9
       rows.append((name, layer, pn, B, ms, tf))
       print('%-8s L%d %-6s B=%4d  %8.3f ms  %8.1f TFLOP/s  %5.1f%% of %.0f' % (name, layer, pn, B, ms, tf, 100 * tf / peak, peak))
