@@ -13,7 +13,7 @@ FP32, BF16 = 0, 1
 NUM_SCALARS = 16
 S_DIS_LOSS, S_GP, S_REAL_LOSS, S_FAKE_LOSS, S_GEN_LOSS = 0, 1, 2, 3, 4
 S_MET_MIN, S_MET_MAX, S_MET_MEAN, S_MET_STD = 5, 6, 7, 8
-FLAG_NO_UPDATE, FLAG_NO_SYNC, FLAG_SAME_REAL, FLAG_NO_FAKE32 = 1, 2, 4, 8
+FLAG_NO_UPDATE, FLAG_NO_SYNC, FLAG_SAME_REAL, FLAG_NO_FAKE32, FLAG_GEN_PREFETCHED = 1, 2, 4, 8, 16
 DEBUG_NO_PS_FUSE, DEBUG_NO_PS_BWD_FUSE, DEBUG_NO_GHEAD, DEBUG_NO_ADAM_FUSE = 1, 2, 4, 8
 BUF_X, BUF_H, BUF_DA, BUF_HG, BUF_AG, BUF_DAG = 0, 1, 2, 3, 4, 5
 
@@ -58,13 +58,16 @@ SIGNATURES = {
     'cg_seed': (_I, [_P, C.c_uint64]),
     'cg_critic_step': (_I, [_P, _P, _I, _P, _P, _I32P, _I, _F]),
     'cg_generator_step': (_I, [_P, _P, _I, _P, _I32P, _I, _F]),
+    'cg_prefetch_generator': (_I, [_P, _P, _I, _P, _P, _I, _I]),
     'cg_apply_update': (_I, [_P, _I]),
     'cg_train_step': (_I, [_P, _P, _I, _P, _P, _I32P, _F]),
     'cg_validate': (_I, [_P, _P, _I, _P, _P, _I32P, _P, _F]),
+    'cg_gather_rows': (_I, [_P, _P, _I64, _P, _I, _I64, _P]),
     'cg_metrics': (_I, [_P, _P, _P, _I, _F]),
     'cg_generate': (_I, [_P, _P, _I, _I, _P]),
     'cg_debug_critic_forward': (_I, [_P, _P, _I, _I32P, _P]),
     'cg_debug_gp': (_I, [_P, _P, _I, _I32P, _P, _P]),
+    'cg_gp_gradient': (_I, [_P, _P, _I, _I32P, _I, _F]),
     'cg_debug_layer': (_I, [_P, _I, _I, _I, _P, _P, _I, _P]),
     'cg_debug_phase_shuffle': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'cg_debug_read': (_I, [_P, _I, _I, _I, _P]),

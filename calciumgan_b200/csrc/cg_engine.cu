@@ -126,6 +126,8 @@ struct cg_ctx {
   int64_t last_n_noise = 0, last_n_alpha = 0;
   std::vector<int32_t> last_shifts;
   int dbg_flags = 0;                       // CG_DEBUG_* (cfg.debug_flags | environment, fixed at cg_create)
+  // cg_prefetch_generator: the generator forward of the next sub-step has already run (data parallel overlap)
+  struct { bool valid = false; int for_gen_step = 0, B = 0; const float* noise = nullptr; const float* alpha = nullptr; } pref;
   AdamPlan adam_plan[2];
   static const int NB = 3;                 // gradient buckets per model (ready order: last layers first)
   cudaEvent_t bucket_evt[2][NB] = {};
@@ -1079,26 +1081,34 @@ static int launch_metrics(cg_ctx* c, const float* real, float* acc, long long ro
 }
 
 // ------------------------------------------------------------------------------------------ critic step
-// forward part shared by cg_critic_step and cg_validate: fake, D on [real; fake; xhat], dgrad chain, GP scalars
-static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
-                             const int32_t* sh, int slot, bool real_ready = false, bool train = false,
-                             bool want_fake32 = true) {
+// generator part of a critic sub-step (wgan_gp.py:65-66 + the interpolation of :38-41): reads no critic weight, so the
+// data-parallel host may run it under the all-reduce of the previous critic update (cg_prefetch_generator)
+static int critic_generator_part(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
+                                 bool want_fake32) {
   const long long per = (long long)B * c->L * c->dcp[0];
-  if (train) CU(cudaMemsetAsync(c->dis.g, 0, c->dis.total * 4, c->stream));
   // generator head writes fp32 FAKE32 and the compute-type copy straight into the critic's "fake" slot
   bool xhat_done = false;
   CK(g_forward(c, noise, B, off(c, c->X[0], per), false, off(c, c->X[0], 2 * per), real, alpha, want_fake32, &xhat_done));
-  const long long tot = per / 4;
-  if (!real_ready) {   // the 5 critic sub-steps of one train step share the real batch (wgan_gp.py:85-86)
-    DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(real, nullptr, nullptr, (T*)c->X[0], B,
-                                                                             c->L, c->C, c->dcp[0], 1));
-    CK(post_launch(c, "real_to_x0"));
-  }
   if (!xhat_done) {
-    DISPATCH_T(c, interp_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(real, c->FAKE32, alpha,
-                                                                        (T*)off(c, c->X[0], 2 * per), B, c->L, c->C,
-                                                                        c->dcp[0]));
+    DISPATCH_T(c, interp_kernel<T><<<grid_for(per / 4), 256, 0, c->stream>>>(real, c->FAKE32, alpha,
+                                                                            (T*)off(c, c->X[0], 2 * per), B, c->L, c->C,
+                                                                            c->dcp[0]));
     CK(post_launch(c, "interp"));
+  }
+  return 0;
+}
+
+// forward part shared by cg_critic_step and cg_validate: fake, D on [real; fake; xhat], dgrad chain, GP scalars
+static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
+                             const int32_t* sh, int slot, bool real_ready = false, bool train = false,
+                             bool want_fake32 = true, bool gen_done = false) {
+  const long long per = (long long)B * c->L * c->dcp[0];
+  if (train) CU(cudaMemsetAsync(c->dis.g, 0, c->dis.total * 4, c->stream));
+  if (!gen_done) CK(critic_generator_part(c, real, B, noise, alpha, want_fake32));
+  if (!real_ready) {   // the 5 critic sub-steps of one train step share the real batch (wgan_gp.py:85-86)
+    DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(per / 4), 256, 0, c->stream>>>(real, nullptr, nullptr, (T*)c->X[0], B,
+                                                                                 c->L, c->C, c->dcp[0], 1));
+    CK(post_launch(c, "real_to_x0"));
   }
   CK(d_forward(c, 3 * B, B, 3, sh));
   fill_coef_kernel<<<(3 * B + 255) / 256, 256, 0, c->stream>>>(c->coef, B, 3, 0.f);
@@ -1118,55 +1128,66 @@ static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* n
   return post_launch(c, "critic_scalars");
 }
 
-static int critic_step_impl(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
-                            const int32_t* sh, int flags, int slot, bool real_ready = false, bool want_fake32 = true) {
-  CK(critic_forward_gp(c, real, B, noise, alpha, sh, slot, real_ready, true, want_fake32));
-  // GP second-order term without the second-order graph: v0 = u = d(lambda*GP)/dg
+// GP second-order term without the second-order graph, passes 3 and 4 input: v0 = u = d(lambda*GP)/dg, then
+// the linearised forward v_l = PS(M_l * conv(v_{l-1})) into the activation slots of sample group `xg` (the x_hat group:
+// 2 inside a critic step, 0 in the stand-alone gradient-penalty entry); sh4 = that group's four shifts
+static int gp_linearised_forward(cg_ctx* c, int B, int xg, const int32_t* sh4) {
   const long long per = (long long)c->L * c->dcp[0];
   DISPATCH_T(c, scale_rows_kernel<T><<<grid_for(per * B / (16 / c->esz)), 256, 0, c->stream>>>(
-                    (const T*)c->DX[0], c->ucoef, (T*)off(c, c->X[0], 2 * B * per), per, per * B));
+                    (const T*)c->DX[0], c->ucoef, (T*)off(c, c->X[0], (long long)xg * B * per), per, per * B));
   CK(post_launch(c, "scale_rows"));
-  const int32_t* sh2 = sh + 8;
   for (int l = 1; l <= NL; ++l) {
-    const long long gin = 2LL * B * c->dl[l - 1] * c->dcp[l - 1], gout = 2LL * B * c->dl[l] * c->dcp[l];
+    const long long gin = (long long)xg * B * c->dl[l - 1] * c->dcp[l - 1], gout = (long long)xg * B * c->dl[l] * c->dcp[l];
     void* dst = l < NL ? off(c, c->DX[l], gout) : c->V5;   // H[l] of the x_hat group stays intact (slope masks, debug taps)
     RsParams p = conv_fwd_params(c, l, off(c, c->X[l - 1], gin), dst, B, EPI_MASK, off(c, c->H[l], gout));
     if (l < NL && ps_fusable(c, p)) {   // v_l = PS(M_l * conv(v_{l-1})) written straight into the xhat group's X_l slot
       p.out = nullptr;
-      set_ps(p, off(c, c->X[l], gout), c->dl[l], B, sh2, 1, l);
+      set_ps(p, off(c, c->X[l], gout), c->dl[l], B, sh4, 1, l);
       CK(launch_rsgemm(c, p));
       continue;
     }
     CK(launch_rsgemm(c, p));
     if (l < NL) {
       const long long tot = (long long)B * c->dl[l] * c->dcp[l] / (16 / c->esz);
-      GroupShifts g; g.s[0] = sh2[l - 1]; g.s[1] = g.s[2] = g.s[3] = 0;
+      GroupShifts g; g.s[0] = sh4[l - 1]; g.s[1] = g.s[2] = g.s[3] = 0;
       DISPATCH_T(c, ps_gather_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
                         (const T*)dst, (T*)off(c, c->X[l], gout), B, B, c->dl[l], c->dcp[l], g));
       CK(post_launch(c, "ps_gather_lin"));
     }
   }
+  return 0;
+}
+
+static int critic_step_impl(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
+                            const int32_t* sh, int flags, int slot, bool real_ready = false, bool want_fake32 = true) {
+  CK(critic_forward_gp(c, real, B, noise, alpha, sh, slot, real_ready, true, want_fake32,
+                       (flags & CG_FLAG_GEN_PREFETCHED) != 0));
+  CK(gp_linearised_forward(c, B, 2, sh + 8));
   CK(d_wgrad(c, 3 * B, 2 * B, 2 * B));
   if (!(flags & CG_FLAG_NO_UPDATE)) CK(cg_apply_update(c, CG_DISCRIMINATOR));
   return 0;
 }
 
-// Random inputs of one step function: `noise_calls` draws of (B, nd) noise, `alpha_calls` draws of (B) alpha and nsh
+// (prep_random) Random inputs of one step function: `noise_calls` draws of (B, nd) noise, `alpha_calls` draws of (B) alpha and nsh
 // PhaseShuffle shifts. Injected values are used as given; the stream positions advance by the same amount either way,
 // so a rank that injects and a rank that does not stay in step, and the shared shift stream never depends on what a
 // caller injected (two ranks making the same sequence of calls always see the same shifts).
-static int prep_random(cg_ctx* c, int B, const float*& noise, int noise_calls, const float** alpha, int alpha_calls,
-                       const int32_t*& sh, int32_t* shbuf, int nsh) {
-  if (!noise) {
+static int prep_noise_alpha(cg_ctx* c, int B, const float*& noise, int noise_calls, const float** alpha, int alpha_calls) {
+  if (!noise && noise_calls > 0) {
     CK(draw(c, c->noise_buf, (long long)B * c->nd, noise_calls, c->noise_calls, 0));
     noise = c->noise_buf;
   }
   c->noise_calls += (uint64_t)noise_calls;
-  if (alpha && !*alpha) {
+  if (alpha && !*alpha && alpha_calls > 0) {
     CK(draw(c, c->alpha_buf, B, alpha_calls, c->alpha_calls, 1));
     *alpha = c->alpha_buf;
   }
   c->alpha_calls += (uint64_t)alpha_calls;
+  c->last_noise = noise; c->last_n_noise = (int64_t)noise_calls * B * c->nd;
+  c->last_alpha = alpha ? *alpha : nullptr; c->last_n_alpha = alpha ? (int64_t)alpha_calls * B : 0;
+  return 0;
+}
+static int prep_shifts(cg_ctx* c, const int32_t*& sh, int32_t* shbuf, int nsh) {
   if (!sh) {
     for (int i = 0; i < nsh; ++i) shbuf[i] = shift_draw(c, c->shift_draws + (uint64_t)i);
     sh = shbuf;
@@ -1175,9 +1196,23 @@ static int prep_random(cg_ctx* c, int B, const float*& noise, int noise_calls, c
   for (int i = 0; i < nsh; ++i)
     if (sh[i] < -c->cfg.phase_m || sh[i] > c->cfg.phase_m)
       return set_err("phase-shuffle shift %d outside [-m, m] (m=%d)", sh[i], c->cfg.phase_m);
-  c->last_noise = noise; c->last_n_noise = (int64_t)noise_calls * B * c->nd;
-  c->last_alpha = alpha ? *alpha : nullptr; c->last_n_alpha = alpha ? (int64_t)alpha_calls * B : 0;
   c->last_shifts.assign(sh, sh + nsh);
+  return 0;
+}
+static int prep_random(cg_ctx* c, int B, const float*& noise, int noise_calls, const float** alpha, int alpha_calls,
+                       const int32_t*& sh, int32_t* shbuf, int nsh) {
+  CK(prep_noise_alpha(c, B, noise, noise_calls, alpha, alpha_calls));
+  return prep_shifts(c, sh, shbuf, nsh);
+}
+// a step that follows cg_prefetch_generator: noise / alpha were drawn (and the streams advanced) there
+static int take_prefetched(cg_ctx* c, int B, int for_gen_step, const float*& noise, const float** alpha) {
+  if (!c->pref.valid || c->pref.for_gen_step != for_gen_step || c->pref.B != B)
+    return set_err("CG_FLAG_GEN_PREFETCHED without a matching cg_prefetch_generator call");
+  noise = c->pref.noise;
+  if (alpha) *alpha = c->pref.alpha;
+  c->pref.valid = false;
+  c->last_noise = noise; c->last_n_noise = (int64_t)B * c->nd;
+  c->last_alpha = alpha ? *alpha : nullptr; c->last_n_alpha = alpha ? B : 0;
   return 0;
 }
 
@@ -1185,16 +1220,25 @@ extern "C" int cg_critic_step(cg_ctx* c, const float* real, int B, const float* 
                               const int32_t* sh, int flags, float* scalars_host) {
   CK(check_batch(c, B));
   int32_t shbuf[12];
-  CK(prep_random(c, B, noise, 1, &alpha, 1, sh, shbuf, 12));
+  if (flags & CG_FLAG_GEN_PREFETCHED) {
+    CK(take_prefetched(c, B, 0, noise, &alpha));
+    CK(prep_shifts(c, sh, shbuf, 12));
+  } else {
+    CK(prep_random(c, B, noise, 1, &alpha, 1, sh, shbuf, 12));
+  }
   CK(critic_step_impl(c, real, B, noise, alpha, sh, flags, 0, (flags & CG_FLAG_SAME_REAL) != 0, !(flags & CG_FLAG_NO_FAKE32)));
   return fetch_scalars(c, 0, flags, scalars_host);
 }
 
 // ------------------------------------------------------------------------------------------ generator step
+// generator forward of the generator step (wgan_gp.py:23-26): keeps everything its backward pass needs
+static int generator_step_generator_part(cg_ctx* c, int B, const float* noise) {
+  CU(cudaMemcpyAsync(c->Z, noise, (size_t)B * c->nd * 4, cudaMemcpyDeviceToDevice, c->stream));
+  return g_forward(c, c->Z, B, c->X[0]);
+}
 static int generator_step_impl(cg_ctx* c, const float* real, int B, const float* noise, const int32_t* sh, int flags,
                                int slot) {
-  CU(cudaMemcpyAsync(c->Z, noise, (size_t)B * c->nd * 4, cudaMemcpyDeviceToDevice, c->stream));
-  CK(g_forward(c, c->Z, B, c->X[0]));
+  if (!(flags & CG_FLAG_GEN_PREFETCHED)) CK(generator_step_generator_part(c, B, noise));
   CK(d_forward(c, B, B, 1, sh));
   float* scal = c->d_scal + (size_t)slot * CG_NUM_SCALARS;
   gen_loss_kernel<<<1, 256, 0, c->stream>>>(c->scores, scal, B);
@@ -1217,9 +1261,33 @@ extern "C" int cg_generator_step(cg_ctx* c, const float* real, int B, const floa
                                  float* scalars_host) {
   CK(check_batch(c, B));
   int32_t shbuf[4];
-  CK(prep_random(c, B, noise, 1, nullptr, 0, sh, shbuf, 4));
+  if (flags & CG_FLAG_GEN_PREFETCHED) {
+    CK(take_prefetched(c, B, 1, noise, nullptr));
+    CK(prep_shifts(c, sh, shbuf, 4));
+  } else {
+    CK(prep_random(c, B, noise, 1, nullptr, 0, sh, shbuf, 4));
+  }
   CK(generator_step_impl(c, real, B, noise, sh, flags, 0));
   return fetch_scalars(c, 0, flags, scalars_host);
+}
+
+// Data-parallel overlap (no reference counterpart): the generator forward of the NEXT sub-step reads no critic
+// weight, so the host enqueues it before it waits for the all-reduce of the critic gradients of the current one.
+extern "C" int cg_prefetch_generator(cg_ctx* c, const float* real, int B, const float* noise, const float* alpha,
+                                     int for_generator_step, int flags) {
+  CK(check_batch(c, B));
+  if (c->pref.valid) return set_err("cg_prefetch_generator: the previous prefetch has not been consumed");
+  if (for_generator_step) {
+    CK(prep_noise_alpha(c, B, noise, 1, nullptr, 0));
+    CK(generator_step_generator_part(c, B, noise));
+  } else {
+    if (!real) return set_err("cg_prefetch_generator: the critic sub-step needs the real batch (interpolation)");
+    CK(prep_noise_alpha(c, B, noise, 1, &alpha, 1));
+    CK(critic_generator_part(c, real, B, noise, alpha, !(flags & CG_FLAG_NO_FAKE32)));
+  }
+  c->pref.valid = true; c->pref.for_gen_step = for_generator_step ? 1 : 0; c->pref.B = B;
+  c->pref.noise = noise; c->pref.alpha = alpha;
+  return 0;
 }
 
 // wgan_gp.py:82-95
@@ -1263,6 +1331,21 @@ extern "C" int cg_validate(cg_ctx* c, const float* real, int B, const float* noi
   CK(launch_metrics(c, real, scal + CG_S_MET_MIN, rows));
   if (fake_out) CU(cudaMemcpyAsync(fake_out, c->FAKE32, (size_t)rows * c->C * 4, cudaMemcpyDeviceToDevice, c->stream));
   return fetch_scalars(c, 0, 0, scalars_host);
+}
+
+// batch assembly from a device-resident dataset cache: dst[i] = src[idx[i]] (rows of row_elems floats)
+extern "C" int cg_gather_rows(cg_ctx* c, const float* src, int64_t n_src, const int64_t* idx_dev, int n, int64_t row_elems,
+                              float* dst) {
+  if (!src || !idx_dev || !dst || n < 1 || row_elems < 1 || n_src < 1) return set_err("cg_gather_rows: bad arguments");
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) || (row_elems & 3))
+    return set_err("cg_gather_rows: rows must be 16-byte aligned (row_elems %% 4 == 0)");
+  int gx = (int)((row_elems / 4 + 255) / 256);
+  const int cap = (148 * 16 + n - 1) / n;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, n);
+  gather_rows_kernel<<<grid, 256, 0, c->stream>>>(src, (const long long*)idx_dev, dst, row_elems, n_src);
+  return post_launch(c, "gather_rows");
 }
 
 // gan.py:32-41 on caller-provided tensors: out_host[4] = min, max, mean, std errors (signals_metrics.py:9-28)
@@ -1330,6 +1413,37 @@ extern "C" int cg_debug_gp(cg_ctx* c, const float* xhat, int B, const int32_t* s
   }
   CU(cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+// BASELINE.json configs[4]: the gradient penalty alone -- critic forward at x_hat, data-gradient chain to g = dD/dx_hat,
+// GP = mean (||g|| - 1)^2, and its gradient w.r.t. every critic weight through the double backward (linearised forward
+// + weight gradients), i.e. all four passes of wgan_gp.py:43-50 under the outer tape of optimizer.py:32. Leaves
+// lambda * dGP/dW in the critic's gradient buffer (cg_get_grads) and the GP value in scalars_host[CG_S_GP].
+extern "C" int cg_gp_gradient(cg_ctx* c, const float* xhat, int B, const int32_t* sh, int flags, float* scalars_host) {
+  CK(check_batch(c, B));
+  if (!xhat || !sh) return set_err("cg_gp_gradient: null pointer");
+  for (int i = 0; i < 4; ++i)
+    if (sh[i] < -c->cfg.phase_m || sh[i] > c->cfg.phase_m) return set_err("cg_gp_gradient: shift outside [-m, m]");
+  CU(cudaMemsetAsync(c->dis.g, 0, c->dis.total * 4, c->stream));
+  const long long tot = (long long)B * c->L * c->dcp[0] / 4;
+  DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(xhat, nullptr, nullptr, (T*)c->X[0], B,
+                                                                           c->L, c->C, c->dcp[0], 1));
+  CK(post_launch(c, "assemble_x0"));
+  CK(d_forward(c, B, B, 1, sh));                                                    // pass 1: forward, slope masks
+  fill_coef_kernel<<<(B + 255) / 256, 256, 0, c->stream>>>(c->coef, B, 1, 1.f);
+  CK(post_launch(c, "fill_coef"));
+  CU(cudaMemsetAsync(c->sumsq, 0, (size_t)B * 4, c->stream));
+  const bool fuse_norm = c->use_tc && c->dl[1] >= 128 && !c->tc.force_v1;
+  CK(d_backward(c, B, B, 1, sh, 0, B, fuse_norm ? c->sumsq : nullptr));             // pass 2: g and ||g||
+  if (!fuse_norm) {
+    DISPATCH_T(c, sumsq_kernel<T><<<B * 8, 256, 0, c->stream>>>((const T*)c->DX[0], c->sumsq, (long long)c->L * c->dcp[0], 8));
+    CK(post_launch(c, "sumsq"));
+  }
+  critic_scalars_kernel<<<1, 256, 0, c->stream>>>(c->scores, c->sumsq, c->ucoef, c->norms, c->d_scal, B, c->cfg.gp_lambda);
+  CK(post_launch(c, "critic_scalars"));
+  CK(gp_linearised_forward(c, B, 0, sh));                                           // pass 3
+  CK(d_wgrad(c, B, 0, 0));                                                          // pass 4 (dGP/db = 0)
+  return fetch_scalars(c, 0, flags, scalars_host);
 }
 
 static int pad_in(cg_ctx* c, const float* src, void* dst, int B, int rows, int C, int Cp) {

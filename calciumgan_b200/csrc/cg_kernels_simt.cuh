@@ -1028,6 +1028,22 @@ __global__ void __launch_bounds__(256) metrics8_kernel(const float* __restrict__
   }
 }
 
+// dst[i, :] = src[idx[i], :] for a device-resident dataset cache (the reference caches its dataset in host memory,
+// gan/utils/dataset_helper.py:171 `train_ds.cache()`, and shuffles indices): one block column per output row, 16-byte
+// copies; a step then moves a few hundred indices over PCIe instead of the batch.
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx,
+                                                          float* __restrict__ dst, long long row_elems, long long n_src) {
+  const long long i = blockIdx.y;
+  long long r = idx[i];
+  if (r < 0 || r >= n_src) r = 0;   // indices are validated on the host; never read out of bounds
+  const float4* s4 = reinterpret_cast<const float4*>(src + r * row_elems);
+  float4* d4 = reinterpret_cast<float4*>(dst + i * row_elems);
+  const long long n4 = row_elems >> 2;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n4; j += (long long)gridDim.x * blockDim.x) d4[j] = s4[j];
+  if (blockIdx.x == 0 && threadIdx.x < (row_elems & 3))
+    dst[i * row_elems + (n4 << 2) + threadIdx.x] = src[r * row_elems + (n4 << 2) + threadIdx.x];
+}
+
 // out = x*(max-min)+min (gan/utils/utils.py:30-32)
 __global__ void denorm_kernel(const float* __restrict__ x, float* __restrict__ out, long long total, float smin,
                               float smax) {

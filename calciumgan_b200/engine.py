@@ -222,8 +222,19 @@ class Engine(object):
     self.set_opt_state(which, None, None, step)
 
   # ---------------------------------------------------------------- hot path
+  def prefetch_generator(self, real, noise=None, alpha=None, for_generator_step=False, want_fake32=True):
+    """Generator part of the NEXT sub-step, enqueued now (cg_prefetch_generator)."""
+    self._use_stream()
+    real = self.to_device(real)
+    B = real.shape[0]
+    noise = self.to_device(noise, (B, self.cfg.noise_dim)) if noise is not None else None
+    alpha = self.to_device(alpha).reshape(-1) if alpha is not None else None
+    self._pref_keep = (real, noise, alpha)     # the library reads them when the kernels run
+    L.check(self.lib.cg_prefetch_generator(self.ctx, self._ptr(real), B, self._ptr(noise), self._ptr(alpha),
+                                           int(bool(for_generator_step)), 0 if want_fake32 else L.FLAG_NO_FAKE32))
+
   def critic_step(self, real, noise=None, alpha=None, shifts=None, update=True, sync=True, same_real=False,
-                  want_fake32=True):
+                  want_fake32=True, gen_prefetched=False):
     self._use_stream()
     real = self.to_device(real)
     B = real.shape[0]
@@ -232,17 +243,19 @@ class Engine(object):
     sh = self._shifts(shifts, 12)
     flags = (0 if update else L.FLAG_NO_UPDATE) | (0 if sync else L.FLAG_NO_SYNC) | (L.FLAG_SAME_REAL if same_real else 0)
     flags |= 0 if want_fake32 else L.FLAG_NO_FAKE32
+    flags |= L.FLAG_GEN_PREFETCHED if gen_prefetched else 0
     L.check(self.lib.cg_critic_step(self.ctx, self._ptr(real), B, self._ptr(noise), self._ptr(alpha),
                                     sh[0] if sh else None, flags, self._scal))
     return np.array(self._scal[:], np.float32) if sync else None
 
-  def generator_step(self, real, noise=None, shifts=None, update=True, sync=True):
+  def generator_step(self, real, noise=None, shifts=None, update=True, sync=True, gen_prefetched=False):
     self._use_stream()
     real = self.to_device(real)
     B = real.shape[0]
     noise = self.to_device(noise, (B, self.cfg.noise_dim)) if noise is not None else None
     sh = self._shifts(shifts, 4)
     flags = (0 if update else L.FLAG_NO_UPDATE) | (0 if sync else L.FLAG_NO_SYNC)
+    flags |= L.FLAG_GEN_PREFETCHED if gen_prefetched else 0
     L.check(self.lib.cg_generator_step(self.ctx, self._ptr(real), B, self._ptr(noise),
                                        sh[0] if sh else None, flags, self._scal))
     return np.array(self._scal[:], np.float32) if sync else None
@@ -273,6 +286,16 @@ class Engine(object):
     L.check(self.lib.cg_validate(self.ctx, self._ptr(real), B, self._ptr(noise), self._ptr(alpha),
                                  sh[0] if sh else None, self._ptr(fake), self._scal))
     return fake, np.array(self._scal[:], np.float32)
+
+  def gather_rows(self, src, idx, out=None):
+    """out[i] = src[idx[i]] on the device (cg_gather_rows); src (N, ...) fp32 CUDA, idx int64 CUDA."""
+    self._use_stream()
+    n, row = int(idx.numel()), int(src[0].numel())
+    if out is None:
+      out = torch.empty((n,) + tuple(src.shape[1:]), device=self.device, dtype=torch.float32)
+    L.check(self.lib.cg_gather_rows(self.ctx, self._ptr(src), int(src.shape[0]), C.c_void_p(idx.data_ptr()), n, row,
+                                    self._ptr(out)))
+    return out
 
   def metrics(self, real, fake):
     """gan.py:32-41 on caller tensors -> [min, max, mean, std] errors."""
@@ -311,6 +334,14 @@ class Engine(object):
     n2 = torch.empty((B,), device=self.device, dtype=torch.float32)
     L.check(self.lib.cg_debug_gp(self.ctx, self._ptr(x), B, sh[0], self._ptr(g), self._ptr(n2)))
     return g, n2
+
+  def gp_gradient(self, xhat, shifts, sync=True):
+    """Gradient penalty at xhat and gp_lambda * dGP/dW (cg_gp_gradient); returns the GP value (None without sync)."""
+    self._use_stream()
+    x = self.to_device(xhat)
+    sh = self._shifts(shifts, 4)
+    L.check(self.lib.cg_gp_gradient(self.ctx, self._ptr(x), x.shape[0], sh[0], 0 if sync else L.FLAG_NO_SYNC, self._scal))
+    return float(self._scal[L.S_GP]) if sync else None
 
   def debug_layer(self, which, layer, pass_, x=None, dy=None):
     """One conv layer in isolation (cg_debug_layer): fp32 tensors in / out."""

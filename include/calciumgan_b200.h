@@ -81,8 +81,10 @@ enum {
   CG_FLAG_NO_SYNC = 2,     /* do not copy scalars back / synchronise (scalars_host may be NULL) */
   CG_FLAG_SAME_REAL = 4,   /* real_dev holds the same batch as in the previous cg_critic_step (wgan_gp.py:85-86):
                               skip its conversion to the compute type */
-  CG_FLAG_NO_FAKE32 = 8    /* cg_critic_step: do not materialise the fp32 generator output (cg_fake_ptr is then stale);
+  CG_FLAG_NO_FAKE32 = 8,   /* cg_critic_step: do not materialise the fp32 generator output (cg_fake_ptr is then stale);
                               the critic sub-steps of a train step only need the compute-type copies */
+  CG_FLAG_GEN_PREFETCHED = 16  /* the generator forward of this sub-step (and its noise / alpha draws) already ran in
+                              cg_prefetch_generator; noise_dev / alpha_dev are ignored */
 };
 
 int cg_version(void);
@@ -137,6 +139,15 @@ int cg_critic_step(cg_ctx* ctx, const float* real_dev, int batch, const float* n
 int cg_generator_step(cg_ctx* ctx, const float* real_dev, int batch, const float* noise_dev,
                       const int32_t* shifts_host, int flags, float* scalars_host);
 
+/* Data-parallel overlap (no reference counterpart): runs the generator part of the NEXT sub-step now --
+ * for_generator_step = 0: wgan_gp.py:65-66 + the interpolation of :38-41 (fake and x_hat into the critic's input slots);
+ * for_generator_step = 1: wgan_gp.py:23-26 (generator forward keeping what its backward needs). It reads no critic
+ * weight, so the host enqueues it before waiting for the all-reduce of the current critic update's gradients and calls
+ * the next cg_critic_step / cg_generator_step with CG_FLAG_GEN_PREFETCHED. Random streams advance exactly as in the
+ * unsplit call. flags: CG_FLAG_NO_FAKE32. */
+int cg_prefetch_generator(cg_ctx* ctx, const float* real_dev, int batch, const float* noise_dev, const float* alpha_dev,
+                          int for_generator_step, int flags);
+
 /* optimizer.py:31-34 `Optimizer.update` tail: Adam on the flat gradient buffer (scaled by
  * 1/world_size) and refresh of the packed low-precision weight copies. */
 int cg_apply_update(cg_ctx* ctx, int which);
@@ -153,6 +164,13 @@ int cg_validate(cg_ctx* ctx, const float* real_dev, int batch, const float* nois
                 const float* alpha_dev, const int32_t* shifts_host, float* fake_out_dev,
                 float* scalars_host);
 
+/* Batch assembly from a device-resident dataset cache (the reference caches its dataset, dataset_helper.py:171
+ * `train_ds.cache()`, and draws shuffled batches from it): dst_dev[i, :] = src_dev[idx_dev[i], :] for i < n, rows of
+ * row_elems floats (row_elems % 4 == 0, 16-byte aligned pointers), idx_dev int64 on the device, 0 <= idx < n_src.
+ * Asynchronous on the context stream. */
+int cg_gather_rows(cg_ctx* ctx, const float* src_dev, int64_t n_src, const int64_t* idx_dev, int n, int64_t row_elems,
+                   float* dst_dev);
+
 /* gan.py:32-41 `metrics(real, fake)` on caller tensors (batch, seq_len, channels) fp32: out_host[4] = mean squared
  * difference of the per-timestep min / max / mean / std over neurons (signals_metrics.py:9-28), after de-normalisation. */
 int cg_metrics(cg_ctx* ctx, const float* real_dev, const float* fake_dev, int batch, float* out_host);
@@ -168,6 +186,13 @@ int cg_debug_critic_forward(cg_ctx* ctx, const float* x_dev, int batch, const in
  * norms_dev (batch) fp32 | NULL. shifts_host[4]. */
 int cg_debug_gp(cg_ctx* ctx, const float* xhat_dev, int batch, const int32_t* shifts_host,
                 float* grad_dev, float* norms_dev);
+/* The gradient penalty alone (BASELINE.json configs[4]; wgan_gp.py:43-50 under the outer tape of optimizer.py:32): critic
+ * forward at xhat, g = dD/dxhat, GP = mean_b (||g_b|| - 1)^2 and gp_lambda * dGP/dW for every critic tensor through the
+ * double backward -- forward, data-gradient chain, linearised forward, weight gradients; the second-order graph is never
+ * built. Gradients land in the critic's flat gradient buffer (cg_get_grads), GP in scalars_host[CG_S_GP]. shifts_host[4].
+ * flags: CG_FLAG_NO_SYNC. */
+int cg_gp_gradient(cg_ctx* ctx, const float* xhat_dev, int batch, const int32_t* shifts_host, int flags,
+                   float* scalars_host);
 /* One conv layer in isolation, fp32 in / fp32 out (cast to the compute type inside), for kernel-level
  * parity: which = CG_DISCRIMINATOR (Conv1D layer 1..5, calciumgan.py:145-185; forward includes bias +
  * LeakyReLU) or CG_GENERATOR (Conv1DTranspose layer 1..5, models/utils.py:79-89; forward includes bias).

@@ -51,12 +51,24 @@ def get_dataset(hparams):
   return (lambda: batches(train, True)), (lambda: batches(val, False))
 
 
-def train(hparams, train_ds, gan, summary, epoch):
+def _train_batches(hparams, train_ds, cache):
+  """Device batches of one epoch. With the device-resident cache (the reference's `train_ds.cache()`,
+  dataset_helper.py:171, kept in HBM) the first epoch uploads and caches every batch, later epochs only send shuffled
+  indices; otherwise every batch is streamed from pinned host memory with the copy of batch i+1 under step i."""
+  from calciumgan_b200.utils.prefetch import prefetch_to_device
+  if cache is None:
+    return prefetch_to_device(train_ds())
+  if not cache.complete:
+    cache.filled = 0
+    return cache.fill_from(train_ds())
+  return cache.batches(hparams.batch_size, shuffle=True)
+
+
+def train(hparams, train_ds, gan, summary, epoch, cache=None):
   gen_losses, dis_losses, gradient_penalties = [], [], []
   start = time()
-  from calciumgan_b200.utils.prefetch import prefetch_to_device
   batch_count = 0
-  for signal, _ in prefetch_to_device(train_ds()):     # H2D copy of batch i+1 overlaps step i
+  for signal, _ in _train_batches(hparams, train_ds, cache):
     if hparams.profile and batch_count == 2 and epoch == 1:
       summary.profiler_trace()      # main.py:45-47: the 2nd batch of the 2nd epoch opens the profiled window
     gen_loss, dis_loss, gradient_penalty, metrics = gan.train(signal)
@@ -116,10 +128,16 @@ def main(hparams, return_metrics=False):
   utils.load_models(hparams, gan)
   utils.save_hparams(hparams)       # main.py:184 of the reference
 
+  cache = None
+  if not hparams.no_device_cache:
+    from calciumgan_b200.utils.dataset_cache import DeviceDatasetCache
+    if DeviceDatasetCache.fits(hparams.train_size, hparams.signal_shape):
+      cache = DeviceDatasetCache(gan.engine, hparams.train_size, hparams.signal_shape)
+
   start = time()
   results = {}
   for epoch in range(hparams.start_epoch, hparams.epochs):
-    train(hparams, train_ds, gan, summary, epoch)
+    train(hparams, train_ds, gan, summary, epoch, cache)
     results = validate(hparams, validation_ds, gan, summary, epoch)
     if not hparams.skip_checkpoints and (epoch % 10 == 0 or epoch == hparams.epochs - 1):
       utils.save_models(hparams, gan, epoch)
@@ -164,6 +182,8 @@ def build_parser():
   # additions (not in the reference): data source when no TFRecord pipeline is available
   parser.add_argument('--synthetic', action='store_true', help='uniform [0,1) signals of shape (N, 2048, 102)')
   parser.add_argument('--synthetic_size', default=512, type=int)
+  parser.add_argument('--no_device_cache', action='store_true',
+                      help='stream every batch from host memory instead of caching the training set in HBM')
   return parser
 
 

@@ -485,11 +485,11 @@ def conv1d_same_wgrad(x, dy, K, stride=2):
   return torch.stack(out)
 
 
-def gp_four_pass(dw, xhat, shifts, hp: HParams, dtype=torch.float64):
+def gp_four_pass(dw, xhat, shifts, hp: HParams, dtype=torch.float64, slopes=None):
   """The 4-pass gradient-penalty gradient that never builds the second-order graph
   (SURVEY §8a): forward (masks) -> dgrad chain (g) -> linearised forward of u (no biases)
   -> wgrad(v_{l-1}, delta_l).  Returns gp, g, and dGP/dW for all 12 critic tensors
-  (NOT multiplied by the penalty weight)."""
+  (NOT multiplied by the penalty weight). slopes: optional imposed LeakyReLU branches [conv1 .. conv5]."""
   dw = [_t(a, dtype) for a in dw]
   x = _t(xhat, dtype)
   B = x.shape[0]
@@ -498,8 +498,8 @@ def gp_four_pass(dw, xhat, shifts, hp: HParams, dtype=torch.float64):
   for l in range(NUM_LAYERS):
     lens.append(x.shape[1])
     a = conv1d_same(x, dw[2 * l], dw[2 * l + 1])
-    masks.append(torch.where(a > 0, torch.ones_like(a), torch.full_like(a, LEAKY_ALPHA)))
-    x = leaky_relu(a)
+    masks.append(slopes_from_activation(a) if slopes is None else _t(slopes[l], dtype))
+    x = a * masks[-1]
     if l < NUM_LAYERS - 1:
       x = phase_shuffle(x, int(shifts[l]))
   # pass 2: dgrad chain of sum_b D(xhat)_b

@@ -24,7 +24,7 @@ class StubEngine(object):
     self.cfg = argparse.Namespace(n_critic=n_critic, phase_m=2, noise_dim=4)
     self.g = {0: torch.zeros(8), 1: torch.zeros(6)}
     self.scal = torch.zeros(16)
-    self.applied, self.seen_shifts = [], []
+    self.applied, self.seen_shifts, self.calls = [], [], []
 
   def to_device(self, x, shape=None):
     return None if x is None else torch.as_tensor(np.asarray(x), dtype=torch.float32)
@@ -39,20 +39,27 @@ class StubEngine(object):
   def scalars_tensor(self):
     return self.scal
 
-  def critic_step(self, real, noise, alpha, shifts, update=True, sync=True, same_real=False, want_fake32=True):
+  def prefetch_generator(self, real, noise=None, alpha=None, for_generator_step=False, want_fake32=True):
+    self.calls.append('prefetch_g' if for_generator_step else 'prefetch_c')
+
+  def critic_step(self, real, noise, alpha, shifts, update=True, sync=True, same_real=False, want_fake32=True,
+                  gen_prefetched=False):
     assert not update and not sync and not want_fake32
+    self.calls.append('critic+' if gen_prefetched else 'critic')
     self.seen_shifts.append(None if shifts is None else np.asarray(shifts).copy())
     self.g[1][:] = float(real.sum()) * torch.arange(1, 7)       # rank-dependent "gradient"
     self.scal[0], self.scal[1] = 10.0 + self.rank, 1.0 + self.rank
 
-  def generator_step(self, real, noise, shifts, update=True, sync=True):
+  def generator_step(self, real, noise, shifts, update=True, sync=True, gen_prefetched=False):
     assert not update and not sync
+    self.calls.append('generator+' if gen_prefetched else 'generator')
     self.seen_shifts.append(None if shifts is None else np.asarray(shifts).copy())
     self.g[0][:] = float(real.mean()) * torch.arange(1, 9)
     self.scal[4] = -3.0 - self.rank
     self.scal[5:9] = torch.tensor([1.0, 2.0, 3.0, 4.0]) * (self.rank + 1)
 
   def apply_update(self, which):
+    self.calls.append('adam%d' % which)
     self.applied.append((which, self.g[which].clone()))
 
 
@@ -72,7 +79,7 @@ def _worker(rank, world, port, out):
   shifts = np.arange(12 * nc + 4) % 5 - 2
   res = gan.train(real, shifts=shifts)
   out[rank] = dict(res=res, applied=[(w, g.numpy()) for w, g in eng.applied],
-                   shifts=[s.tolist() for s in eng.seen_shifts])
+                   shifts=[s.tolist() for s in eng.seen_shifts], calls=list(eng.calls))
   dist.destroy_process_group()
 
 
@@ -98,3 +105,6 @@ def test_dp_two_ranks_gloo():
   # identical PhaseShuffle draws on every rank, 12 per critic sub-step then 4
   assert r0['shifts'] == r1['shifts']
   assert [len(s) for s in r0['shifts']] == [12, 12, 4]
+  # the generator part of the next sub-step is enqueued before the critic's Adam (it hides the all-reduce tail), and the
+  # sub-step that follows is told that its generator forward already ran
+  assert r0['calls'] == ['critic', 'prefetch_c', 'adam1', 'critic+', 'prefetch_g', 'adam1', 'generator+', 'adam0'], r0['calls']

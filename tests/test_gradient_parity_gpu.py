@@ -193,3 +193,96 @@ def test_shift_extremes_on_imposed_branches_bf16():
     ref = O.critic_step(gw, dw, real, noises[0], alphas[0], shifts.reshape(3, 4), hp, slopes=sl, fake=eng.fake(B).cpu())
     worst = check_grads(grads, ref['grads'], BF16_TOL, 'critic gradient, shifts %s' % shifts[:4])
     print('shift extremes %s: worst %.2e' % (shifts[:4], worst))
+
+
+@pytest.mark.parametrize('mixed', [False, True])
+def test_gradient_penalty_entry_all_four_passes(mixed):
+  """cg_gp_gradient (BASELINE.json configs[4]): GP value and gp_lambda * dGP/dW of every critic tensor from the four
+  passes (forward, data-gradient chain, linearised forward, weight gradients) against the oracle's hand-derived 4-pass
+  form, itself checked against autograd's double backward in tests/test_oracle.py. Paper architecture at length 512,
+  batch 5 (odd), branches imposed."""
+  hp = O.HParams(signal_shape=(512, 102))
+  B = 5
+  tol = BF16_TOL if mixed else FP32_TOL
+  gan = build(hp, B, mixed)
+  eng = gan.engine
+  gw, dw = O.init_weights(hp, seed=71)
+  dw = O.randomize_weights(dw, 72)
+  gan.discriminator.set_weights(dw)
+  rng = np.random.RandomState(73)
+  xhat = rng.uniform(0, 1, size=(B, 512, 102)).astype(np.float32)
+  for sh in ([3, -2, 0, 1], [10, -10, 10, -10]):
+    gp = eng.gp_gradient(xhat, sh)
+    grads = eng.get_grads(L.DISCRIMINATOR)
+    sl = critic_slopes(eng, B, ('xhat',))['xhat']
+    ref_gp, _, ref_grads = O.gp_four_pass(dw, xhat, sh, hp, slopes=sl)
+    assert abs(gp - float(ref_gp)) <= tol * max(1.0, float(ref_gp))
+    worst = check_grads(grads, [hp.gradient_penalty * g for g in ref_grads], tol, 'lambda * dGP/dW')
+    for i in (1, 3, 5, 7, 9, 11):
+      assert not grads[i].any()            # the penalty does not depend on any bias
+    print('gradient-penalty entry (mixed=%s, shifts %s): GP %.5f (oracle %.5f), worst gradient rel err %.2e' %
+          (mixed, sh, gp, float(ref_gp), worst))
+
+
+def test_prefetched_generator_forward_is_the_same_step():
+  """cg_prefetch_generator + CG_FLAG_GEN_PREFETCHED (the data-parallel overlap) against the unsplit calls: same random
+  draws from the library's streams, same scalars, same gradients (to the summation order of the fp32 atomics)."""
+  hp = O.HParams(signal_shape=(512, 102), num_units=32, noise_dim=8, n_critic=2)
+  B = 4
+  real, _, _, _ = O.synthetic_batch(hp, B, seed=9, n_critic=2)
+  a, b = build(hp, B, True).engine, build(hp, B, True).engine
+  b.set_weights(L.GENERATOR, a.get_weights(L.GENERATOR))
+  b.set_weights(L.DISCRIMINATOR, a.get_weights(L.DISCRIMINATOR))
+  a.seed(5)
+  b.seed(5)
+  nd = hp.noise_dim
+  # a: plain sub-steps; b: generator parts enqueued ahead, as WGAN_GP._train_dp does
+  sa, sb, da, db = [], [], [], []
+  sa.append(a.critic_step(real, update=False)); da.append(a.last_draws(B * nd, B, 12)); a.apply_update(L.DISCRIMINATOR)
+  sa.append(a.critic_step(real, update=False)); da.append(a.last_draws(B * nd, B, 12)); a.apply_update(L.DISCRIMINATOR)
+  sa.append(a.generator_step(real, update=False)); da.append(a.last_draws(B * nd, 0, 4))
+  sb.append(b.critic_step(real, update=False)); db.append(b.last_draws(B * nd, B, 12))
+  b.prefetch_generator(real, for_generator_step=False)
+  b.apply_update(L.DISCRIMINATOR)
+  sb.append(b.critic_step(real, update=False, gen_prefetched=True)); db.append(b.last_draws(B * nd, B, 12))
+  b.prefetch_generator(real, for_generator_step=True)
+  b.apply_update(L.DISCRIMINATOR)
+  sb.append(b.generator_step(real, update=False, gen_prefetched=True)); db.append(b.last_draws(B * nd, 0, 4))
+  for (n1, a1, s1), (n2, a2, s2) in zip(da, db):
+    assert torch.equal(n1, n2) and np.array_equal(s1, s2)
+    assert (a1 is None and a2 is None) or torch.equal(a1, a2)
+  for x, y in zip(sa, sb):
+    np.testing.assert_allclose(x[:9], y[:9], rtol=2e-3, atol=1e-5)
+  for which in (L.GENERATOR, L.DISCRIMINATOR):
+    for x, y in zip(a.get_grads(which), b.get_grads(which)):
+      assert rel_err(x, y) <= 2e-2      # bf16: the two critics differ by one Adam step computed from atomically summed gradients
+  from calciumgan_b200._lib import CgError
+  with pytest.raises(CgError, match='PREFETCHED'):
+    b.critic_step(real, update=False, gen_prefetched=True)
+
+
+def test_device_dataset_cache_batches():
+  """DeviceDatasetCache (the reference's train_ds.cache(), dataset_helper.py:171, in HBM): the first epoch uploads and
+  stores every batch, later epochs gather shuffled batches by index on the device; every sample is seen exactly once per
+  epoch, ragged last batch included."""
+  from calciumgan_b200.utils.dataset_cache import DeviceDatasetCache
+  hp = O.HParams(signal_shape=(256, 20), num_units=16, noise_dim=8, n_critic=1, m=3)
+  eng = build(hp, 4, False).engine
+  rng = np.random.RandomState(0)
+  data = rng.uniform(0, 1, size=(11, 256, 20)).astype(np.float32)
+  host_batches = [(data[i:i + 4], i) for i in range(0, 11, 4)]
+  assert DeviceDatasetCache.fits(11, (256, 20))
+  cache = DeviceDatasetCache(eng, 11, (256, 20))
+  seen = [b.cpu().numpy().copy() for b, _ in cache.fill_from(iter(host_batches))]
+  assert cache.complete and [len(s) for s in seen] == [4, 4, 3]
+  np.testing.assert_array_equal(np.concatenate(seen), data)
+  assert cache.h2d_bytes == data.nbytes
+  for epoch in range(2):
+    got = [b.cpu().numpy() for b, _ in cache.batches(4, shuffle=True, rng=np.random.RandomState(epoch))]
+    assert [len(g) for g in got] == [4, 4, 3]
+    allrows = np.concatenate(got)
+    order = np.random.RandomState(epoch).permutation(11)
+    np.testing.assert_array_equal(allrows, data[order])
+  assert cache.h2d_bytes == data.nbytes + 2 * 11 * 8       # two epochs of indices, nothing else
+  with pytest.raises(IndexError):
+    cache.gather([11])
