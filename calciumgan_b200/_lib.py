@@ -85,6 +85,7 @@ SIGNATURES = {
     'cg_device_bytes': (_I64, [_P]),
     'cg_profile': (_I, [_P, _I]),
     'cg_profile_report': (_I, [_P, C.POINTER(C.c_double)]),
+    'cg_profile_report_text': (_I, [_P, C.c_char_p, _I]),
     'cg_bench_layer': (_I, [_P, _I, _I, _I, _I, _I, _F, C.POINTER(C.c_double)]),
 }
 

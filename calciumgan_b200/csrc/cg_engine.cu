@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -90,8 +91,9 @@ struct cg_ctx {
   int64_t launches = 0;
   int64_t tc_launches = 0;
   bool profiling = false;
-  struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; char desc[96]; };
+  struct ProfRec { cudaEvent_t e0, e1; int cls; double flops; double bytes; char desc[96]; };   // cls 3: memory-bound glue
   std::vector<ProfRec> prof;
+  bool glue_open = false;                 // a glue record waits for its launch (closed by post_launch)
   int64_t dev_bytes = 0;
   std::vector<void*> allocs;
 
@@ -202,13 +204,18 @@ static int post_launch(cg_ctx* c, const char* what) {
   c->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_err("launch %s failed: %s", what, cudaGetErrorString(e));
+  if (c->glue_open) {   // live timing of a memory-bound kernel (cg_profile): named after the launch that closes it
+    c->glue_open = false;
+    snprintf(c->prof.back().desc, sizeof(c->prof.back().desc), "%s", what);
+    if (cudaEventRecord(c->prof.back().e1, c->stream) != cudaSuccess) return set_err("cudaEventRecord failed");
+  }
   return 0;
 }
 
 static int prof_begin(cg_ctx* c, int cls, double flops, const char* desc = "") {
   if (!c->profiling) return 0;
   cg_ctx::ProfRec r;
-  r.cls = cls; r.flops = flops;
+  r.cls = cls; r.flops = cls == 3 ? 0.0 : flops; r.bytes = cls == 3 ? flops : 0.0;
   snprintf(r.desc, sizeof(r.desc), "%s", desc);
   CU(cudaEventCreate(&r.e0));
   CU(cudaEventCreate(&r.e1));
@@ -219,6 +226,14 @@ static int prof_begin(cg_ctx* c, int cls, double flops, const char* desc = "") {
 static int prof_end(cg_ctx* c) {
   if (!c->profiling) return 0;
   CU(cudaEventRecord(c->prof.back().e1, c->stream));
+  return 0;
+}
+
+// opens a timing record for the NEXT launch of a memory-bound kernel; `bytes` = its algorithmic HBM traffic
+static int glue(cg_ctx* c, double bytes) {
+  if (!c->profiling) return 0;
+  CK(prof_begin(c, 3, bytes, ""));
+  c->glue_open = true;
   return 0;
 }
 
@@ -313,6 +328,7 @@ static int repack(cg_ctx* c, int which) {
   }
   if (ops.n > 24) return set_err("repack: too many pack ops");
   dim3 grid(16, c->K, ops.n);
+  CK(glue(c, (4.0 + 2.0 * c->esz) * (which == CG_GENERATOR ? c->gen.total : c->dis.total)));
   DISPATCH_T(c, pack_weights_kernel<T><<<grid, 256, 0, c->stream>>>(ops));
   return post_launch(c, "pack_weights");
 }
@@ -695,6 +711,7 @@ static WgParams convT_wgrad_params(cg_ctx* c, int i, int B) {
 static int g_forward(cg_ctx* c, const float* noise, int B, void* fake_slot = nullptr, bool for_backward = true,
                      void* xhat_slot = nullptr, const float* real = nullptr, const float* alpha = nullptr,
                      bool want32 = true, bool* xhat_done = nullptr) {
+  CK(glue(c, (double)B * c->nd * 4 + (double)c->nd * c->w0 * c->nd * 4 + (double)B * c->w0 * c->gcp[0] * c->esz));
   DISPATCH_T(c, dense0_forward_kernel<T><<<grid_for((long long)B * c->w0 * c->gcp[0]), 256, 0, c->stream>>>(
                     noise, gparam(c, 0), gparam(c, 1), (T*)c->HG[0], B, c->nd, c->w0, c->gcp[0]));
   CK(post_launch(c, "dense0_fwd"));
@@ -715,6 +732,7 @@ static int g_forward(cg_ctx* c, const float* noise, int B, void* fake_slot = nul
     if (c->cfg.layer_norm) {
       const int nvec = c->gcp[i] / (16 / c->esz);
       const int lpr = nvec > 16 ? 32 : (nvec > 8 ? 16 : 8);
+CK(glue(c, 2.0 * rows * c->gcp[i] * c->esz + 8.0 * rows));
 #define CG_LN(LPRV)                                                                                              \
   DISPATCH_T(c, ln_lrelu_forward_kernel<T, LPRV><<<grid_for(rows * LPRV), 256, 0, c->stream>>>(                    \
                     (const T*)c->AG[i], gparam(c, c->g_gam[i]), gparam(c, c->g_bet[i]), (T*)c->HG[i], c->MU[i], \
@@ -723,6 +741,7 @@ static int g_forward(cg_ctx* c, const float* noise, int B, void* fake_slot = nul
 #undef CG_LN
       CK(post_launch(c, "ln_fwd"));
     } else {
+      CK(glue(c, 2.0 * rows * c->gcp[i] * c->esz));
       DISPATCH_T(c, lrelu_kernel<T><<<grid_for(rows * c->gcp[i]), 256, 0, c->stream>>>((const T*)c->AG[i],
                                                                                       (T*)c->HG[i], rows * c->gcp[i]));
       CK(post_launch(c, "lrelu"));
@@ -742,6 +761,9 @@ static int g_forward(cg_ctx* c, const float* noise, int B, void* fake_slot = nul
       snprintf(d, sizeof(d), "ghead B=%d L=%d C=%d f=%d x=%d o32=%d", B, c->L, c->C, a.fake16 != nullptr, a.xhat16 != nullptr,
                a.out32 != nullptr);
       CK(prof_begin(c, 2, 2.0 * B * c->L * (double)c->C * c->C, d));
+      if (c->profiling)   // HBM-bound: activations in, [real in], fake [+ x_hat] out in the compute type, [fp32 copy out]
+        c->prof.back().bytes = (double)B * c->L * (Cp * 2.0 + (a.xhat16 ? 4.0 * c->C : 0.0) + (a.fake16 ? Cp * 2.0 : 0.0) +
+                                                  (a.xhat16 ? Cp * 2.0 : 0.0) + (a.out32 ? 4.0 * c->C : 0.0));
       CK(tc_ghead_launch(&c->tc, a, c->stream));
       c->tc_launches++;
       CK(post_launch(c, "ghead_tc"));
@@ -770,6 +792,9 @@ static int launch_colsum_ops(cg_ctx* c, const ColsumOps& ops) {
   for (int i = 0; i < ops.n; ++i)
     if (ops.op[i].Cp / (16 / c->esz) > 256) return set_err("colsum: more than 256 16-byte vectors per row");
   dim3 grid(148 * 2, ops.n);
+  double cs_bytes = 0;
+  for (int i = 0; i < ops.n; ++i) cs_bytes += (double)ops.op[i].rows * ops.op[i].Cp * c->esz;
+  CK(glue(c, cs_bytes));
   DISPATCH_T(c, colsum_multi_kernel<T><<<grid, 256, 0, c->stream>>>(ops));
   return post_launch(c, "colsum");
 }
@@ -778,6 +803,7 @@ static int launch_colsum(cg_ctx* c, const void* X, float* out, long long rows, i
     int gx = (int)((rows + 3) / 4);
     if (gx > 148 * 4) gx = 148 * 4;
     dim3 grid(gx, (c_real + 63) / 64), block(64, 4);
+    CK(glue(c, (double)rows * Cp * c->esz));
     DISPATCH_T(c, colsum_kernel<T><<<grid, block, 0, c->stream>>>((const T*)X, out, rows, Cp, c_real));
     return post_launch(c, "colsum");
   }
@@ -791,6 +817,7 @@ static int launch_colsum(cg_ctx* c, const void* X, float* out, long long rows, i
 static int g_backward(cg_ctx* c, int B) {
   const int Cp = c->gcp[NL];
   const long long rowsL = (long long)B * c->L;
+  CK(glue(c, (double)rowsL * (2.0 * Cp * c->esz + 4.0 * c->C)));
   DISPATCH_T(c, sigmoid_backward_kernel<T><<<grid_for(rowsL * Cp / (16 / c->esz)), 256, 0, c->stream>>>(
                     (const T*)c->DX[0], c->FAKE32, (T*)c->DO, rowsL, c->C, Cp, c->cfg.normalize));
   CK(post_launch(c, "sigmoid_bwd"));
@@ -820,6 +847,7 @@ static int g_backward(cg_ctx* c, int B) {
       const int maxv = (nvec_b + lpr_b - 1) / lpr_b;   // channel vectors per lane: sizes the kernel's register arrays
       if (maxv > 4) return set_err("ln_lrelu_backward: more than 4 channel vectors per lane (Cp %d)", c->gcp[i]);
       const int blocks = grid_for(rows * lpr_b, 256, 148 * (maxv <= 1 ? 6 : 3));
+CK(glue(c, 4.0 * rows * c->gcp[i] * c->esz + 8.0 * rows));
 #define CG_LNB(LPRV, MV)                                                                                              \
   DISPATCH_T(c, (ln_lrelu_backward_kernel<T, LPRV, MV>)<<<blocks, 256, 2 * c->gcp[i] * sizeof(float), c->stream>>>(    \
                     (const T*)c->DHG[i], (const T*)c->AG[i], (const T*)c->HG[i], c->MU[i], c->RSTD[i],               \
@@ -834,6 +862,7 @@ static int g_backward(cg_ctx* c, int B) {
 #undef CG_LNB
       CK(post_launch(c, "ln_bwd"));
     } else {
+      CK(glue(c, 3.0 * rows * c->gcp[i] * c->esz));
       DISPATCH_T(c, mask_mul_kernel<T><<<grid_for(rows * c->gcp[i]), 256, 0, c->stream>>>(
                         (const T*)c->DHG[i], (const T*)c->HG[i], (T*)c->DAG[i], rows * c->gcp[i]));
       CK(post_launch(c, "mask_mul"));
@@ -845,6 +874,7 @@ static int g_backward(cg_ctx* c, int B) {
     CK(launch_rsgemm(c, convT_bwd_params(c, i, B)));
   }
   const int tot = (c->nd + 1) * c->w0 * c->nd;
+  CK(glue(c, 2.0 * B * c->w0 * c->gcp[0] * c->esz + (double)B * c->nd * 4));
   DISPATCH_T(c, dense0_backward_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
                     c->Z, (const T*)c->DHG[0], (const T*)c->HG[0], ggrad(c, 0), ggrad(c, 1), B, c->nd, c->w0,
                     c->gcp[0]));
@@ -913,11 +943,13 @@ static int d_forward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh) {
     CK(launch_rsgemm(c, p));
     if (l < NL) {
       const long long tot = (long long)Bt * c->dl[l] * c->dcp[l] / (16 / c->esz);
+      CK(glue(c, 2.0 * Bt * c->dl[l] * c->dcp[l] * c->esz));
       DISPATCH_T(c, ps_gather_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
                         (const T*)c->H[l], (T*)c->X[l], Bt, B, c->dl[l], c->dcp[l], group_shifts(sh, groups, l)));
       CK(post_launch(c, "ps_gather"));
     }
   }
+  CK(glue(c, (double)Bt * c->dl[NL] * c->dcp[NL] * c->esz + 4.0 * c->dl[NL] * c->dc[NL]));
   DISPATCH_T(c, head_forward_kernel<T><<<Bt, 256, 0, c->stream>>>((const T*)c->X[NL], dparam(c, 10), dparam(c, 11),
                                                                   c->scores, c->dl[NL], c->dc[NL], c->dcp[NL]));
   return post_launch(c, "head_fwd");
@@ -956,6 +988,7 @@ static RsParams d_dgrad_params(cg_ctx* c, int l, int b0, int nb, void* out) {
 // backward chain of sum_b coef[b]*D(x)_b down to DA[1] (and DX[0] for samples [dx0_b0, dx0_b0+dx0_nb))
 static int d_backward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh, int dx0_b0, int dx0_nb,
                       float* sumsq = nullptr) {   // sumsq: per-sample squared norm of dX0, fused into the last GEMM
+  CK(glue(c, 2.0 * Bt * c->dl[NL] * c->dcp[NL] * c->esz + 4.0 * c->dl[NL] * c->dc[NL]));
   DISPATCH_T(c, head_backward_kernel<T><<<grid_for((long long)Bt * c->dl[NL] * c->dcp[NL] / (16 / c->esz)), 256, 0, c->stream>>>(
                     (const T*)c->H[NL], dparam(c, 10), c->coef, (T*)c->DA[NL], Bt, c->dl[NL], c->dc[NL], c->dcp[NL]));
   CK(post_launch(c, "head_bwd"));
@@ -966,6 +999,7 @@ static int d_backward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh, i
     }
     CK(d_dgrad_layer(c, l, 0, Bt, c->DX[l - 1]));
     const long long tot = (long long)Bt * c->dl[l - 1] * c->dcp[l - 1] / (16 / c->esz);
+    CK(glue(c, 3.0 * Bt * c->dl[l - 1] * c->dcp[l - 1] * c->esz));
     DISPATCH_T(c, ps_scatter_mask_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
                       (const T*)c->DX[l - 1], (const T*)c->H[l - 1], (T*)c->DA[l - 1], Bt, B, c->dl[l - 1],
                       c->dcp[l - 1], group_shifts(sh, groups, l - 1)));
@@ -1006,6 +1040,7 @@ static int d_wgrad(cg_ctx* c, int Bt, int nb_bias, int tail_from) {   // samples
   }
   const int tot = c->dl[NL] * c->dcp[NL] / (16 / c->esz);
   dim3 hgrid(grid_for(tot), Bt >= 64 ? 32 : 1);
+  CK(glue(c, (double)Bt * c->dl[NL] * c->dcp[NL] * c->esz));
   DISPATCH_T(c, head_wgrad_kernel<T><<<hgrid, 256, 0, c->stream>>>(
                     (const T*)c->X[NL], (const T*)c->V5, tail_from, c->coef, dgrad(c, 10), dgrad(c, 11), Bt, nb_bias, c->dl[NL],
                     c->dc[NL], c->dcp[NL]));
@@ -1045,15 +1080,18 @@ extern "C" int cg_apply_update(cg_ctx* c, int which) {
   Model* m = model_of(c, which);
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-7f, gscale = 1.0f / (float)c->cfg.world_size;
   // pass 1 (reads the gradient once): non-finite check; the last block advances `iterations` and computes lr_t
+  CK(glue(c, 4.0 * m->total));
   adam_prepare_kernel<<<grid_for(m->total / 4, 256, 148 * 4), 256, 0, c->stream>>>(m->g, m->total, m->opt,
                                                                                   c->cfg.learning_rate, b1, b2);
   CK(post_launch(c, "adam_prepare"));
   if (c->dbg_flags & CG_DEBUG_NO_ADAM_FUSE) {
+    CK(glue(c, 28.0 * m->total));
     adam_kernel<<<grid_for(m->total), 256, 0, c->stream>>>(m->w, m->m, m->v, m->g, m->total, m->opt, b1, b2, eps, gscale);
     CK(post_launch(c, "adam"));
     return repack(c, which);
   }
   const AdamPlan& pl = c->adam_plan[which];
+  CK(glue(c, 28.0 * m->total + 2.0 * c->esz * m->total));
   DISPATCH_T(c, adam_pack_kernel<T><<<grid_for(pl.items * 256, 256, 148 * 8), 256, 0, c->stream>>>(
                     m->w, m->m, m->v, m->g, pl, m->opt, b1, b2, eps, gscale));
   return post_launch(c, "adam_pack");
@@ -1071,6 +1109,7 @@ static int fetch_scalars(cg_ctx* c, int slot, int flags, float* scalars_host) {
 // gan.py:32-41 / signals_metrics.py:9-28 on (real, FAKE32); acc[0..3] must be zeroed by the caller
 static int launch_metrics(cg_ctx* c, const float* real, float* acc, long long rows, const float* fake = nullptr) {
   if (!fake) fake = c->FAKE32;
+  CK(glue(c, 8.0 * rows * c->C));
   if (c->C % 2 == 0 && c->C <= 128 && ((reinterpret_cast<uintptr_t>(real) | reinterpret_cast<uintptr_t>(fake)) & 7) == 0)
     metrics8_kernel<<<grid_for(rows * 8, 256, 148 * 8), 256, 0, c->stream>>>(real, fake, acc, rows, c->C, c->cfg.signals_min,
                                                                             c->cfg.signals_max, c->cfg.normalize);
@@ -1090,6 +1129,7 @@ static int critic_generator_part(cg_ctx* c, const float* real, int B, const floa
   bool xhat_done = false;
   CK(g_forward(c, noise, B, off(c, c->X[0], per), false, off(c, c->X[0], 2 * per), real, alpha, want_fake32, &xhat_done));
   if (!xhat_done) {
+    CK(glue(c, (double)B * c->L * (8.0 * c->C + (double)c->dcp[0] * c->esz)));
     DISPATCH_T(c, interp_kernel<T><<<grid_for(per / 4), 256, 0, c->stream>>>(real, c->FAKE32, alpha,
                                                                             (T*)off(c, c->X[0], 2 * per), B, c->L, c->C,
                                                                             c->dcp[0]));
@@ -1106,6 +1146,7 @@ static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* n
   if (train) CU(cudaMemsetAsync(c->dis.g, 0, c->dis.total * 4, c->stream));
   if (!gen_done) CK(critic_generator_part(c, real, B, noise, alpha, want_fake32));
   if (!real_ready) {   // the 5 critic sub-steps of one train step share the real batch (wgan_gp.py:85-86)
+    CK(glue(c, (double)B * c->L * (4.0 * c->C + (double)c->dcp[0] * c->esz)));
     DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(per / 4), 256, 0, c->stream>>>(real, nullptr, nullptr, (T*)c->X[0], B,
                                                                                  c->L, c->C, c->dcp[0], 1));
     CK(post_launch(c, "real_to_x0"));
@@ -1120,6 +1161,7 @@ static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* n
   if (!fuse_norm) {
     const long long per_sample = (long long)c->L * c->dcp[0];
     const int chunks = 8;
+    CK(glue(c, (double)B * per_sample * c->esz));
     DISPATCH_T(c, sumsq_kernel<T><<<B * chunks, 256, 0, c->stream>>>((const T*)c->DX[0], c->sumsq, per_sample, chunks));
     CK(post_launch(c, "sumsq"));
   }
@@ -1133,6 +1175,7 @@ static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* n
 // 2 inside a critic step, 0 in the stand-alone gradient-penalty entry); sh4 = that group's four shifts
 static int gp_linearised_forward(cg_ctx* c, int B, int xg, const int32_t* sh4) {
   const long long per = (long long)c->L * c->dcp[0];
+  CK(glue(c, 2.0 * B * per * c->esz));
   DISPATCH_T(c, scale_rows_kernel<T><<<grid_for(per * B / (16 / c->esz)), 256, 0, c->stream>>>(
                     (const T*)c->DX[0], c->ucoef, (T*)off(c, c->X[0], (long long)xg * B * per), per, per * B));
   CK(post_launch(c, "scale_rows"));
@@ -1344,6 +1387,7 @@ extern "C" int cg_gather_rows(cg_ctx* c, const float* src, int64_t n_src, const 
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   dim3 grid(gx, n);
+  CK(glue(c, 8.0 * n * row_elems));
   gather_rows_kernel<<<grid, 256, 0, c->stream>>>(src, (const long long*)idx_dev, dst, row_elems, n_src);
   return post_launch(c, "gather_rows");
 }
@@ -1633,6 +1677,41 @@ extern "C" int cg_profile_report(cg_ctx* c, double out[12]) {
     cudaEventDestroy(r.e1);
   }
   c->prof.clear();
+  return 0;
+}
+
+// Per-kernel table of everything timed since cg_profile(ctx, 1): one line per kernel,
+//   name <tab> bound (tensor|hbm) <tab> launches <tab> milliseconds <tab> algorithmic FLOPs <tab> algorithmic bytes
+// Returns the number of bytes written (truncated to cap - 1), clears the accumulators.
+extern "C" int cg_profile_report_text(cg_ctx* c, char* out, int cap) {
+  if (!out || cap < 1) return set_err("cg_profile_report_text: bad arguments");
+  CU(cudaStreamSynchronize(c->stream));
+  struct Agg { int n = 0; double ms = 0, flops = 0, bytes = 0; int cls = 0; };
+  std::map<std::string, Agg> agg;
+  std::vector<std::string> order;
+  static const char* cls_name[3] = {"rsgemm_tc", "wgrad_tc", "ghead_tc"};
+  for (auto& r : c->prof) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    const std::string key = r.cls < 3 ? cls_name[r.cls] : r.desc;
+    if (!agg.count(key)) order.push_back(key);
+    Agg& a = agg[key];
+    a.n++; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes; a.cls = r.cls;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  c->prof.clear();
+  std::string txt;
+  for (auto& k : order) {
+    const Agg& a = agg[k];
+    char line[256];
+    snprintf(line, sizeof(line), "%s\t%s\t%d\t%.6f\t%.6e\t%.6e\n", k.c_str(), (a.cls == 0 || a.cls == 1) ? "tensor" : "hbm", a.n, a.ms,
+             a.flops, a.bytes);
+    txt += line;
+  }
+  const int n = (int)txt.size() < cap - 1 ? (int)txt.size() : cap - 1;
+  memcpy(out, txt.data(), n);
+  out[n] = 0;
   return 0;
 }
 

@@ -439,6 +439,16 @@ class Engine(object):
             'wgrad': {'ms': out[3], 'flops': out[4], 'launches': int(out[5])},
             'head': {'ms': out[6], 'flops': out[7], 'launches': int(out[8])}}
 
+  def profile_table(self):
+    """{kernel: {bound, launches, ms, flops, bytes}} of everything timed since profile(True) (cg_profile_report_text)."""
+    buf = C.create_string_buffer(1 << 16)
+    L.check(self.lib.cg_profile_report_text(self.ctx, buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+      name, bound, n, ms, fl, by = line.split('\t')
+      out[name] = {'bound': bound, 'launches': int(n), 'ms': float(ms), 'flops': float(fl), 'bytes': float(by)}
+    return out
+
   def bench_layer(self, which, layer, pass_, batch, iters=10):
     self._use_stream()
     ms, fl = C.c_float(), C.c_double()

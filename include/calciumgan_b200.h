@@ -260,6 +260,11 @@ int64_t cg_device_bytes(cg_ctx* ctx);
  * accumulated since cg_profile(ctx, 1), then clears the accumulators. */
 int cg_profile(cg_ctx* ctx, int enable);
 int cg_profile_report(cg_ctx* ctx, double out[12]);
+/* The same accumulators as text, one line per kernel -- the tensor-core kernels and every memory-bound kernel of the
+ * step (layer norm, PhaseShuffle adjoint, bias column sums, Adam, metrics, ...):
+ *   name <tab> tensor|hbm <tab> launches <tab> milliseconds <tab> algorithmic FLOPs <tab> algorithmic bytes <newline>
+ * Writes at most cap - 1 characters + NUL, then clears the accumulators (use either report, not both). */
+int cg_profile_report_text(cg_ctx* ctx, char* out, int cap);
 /* microbenchmark hook: time `iters` launches of one conv layer kernel with CUDA events on the
  * context stream. which/layer: CG_DISCRIMINATOR conv 1..5 or CG_GENERATOR convT 1..5; pass: 0 fwd,
  * 1 dgrad, 2 wgrad. Writes avg milliseconds and the algorithmic FLOPs of one launch. */
