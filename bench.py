@@ -447,7 +447,7 @@ def run_gp(args, rank, world):
     for i in range(args.steps):
       gp = eng.gp_gradient(host.cuda(non_blocking=True), shifts[i % 64], sync=True)
     ms_e2e = (time.time() - t0) * 1e3 / args.steps
-    tf = B * W['gf_gp'] / ms / 1e3
+    tf = B * W['gf_gp'] / ms          # GFLOP per millisecond = TFLOP/s
     sweep[str(B)] = {'samples_per_s': world * B / (ms * 1e-3), 'ms': ms, 'tflops': tf, 'frac_of_sustained_bf16': tf / peak_tf,
                      'e2e_samples_per_s': world * B / (ms_e2e * 1e-3), 'gp': gp}
   if rank == 0:

@@ -40,7 +40,14 @@ sl = slice(rank * Bl, (rank + 1) * Bl)
 eng, g, d = make(world, rank)
 g.set_weights(gw); d.set_weights(dw)
 gan = WGAN_GP(ns, g, d, None)
+gan.no_dp_overlap = os.environ.get('CG_NO_DP_OVERLAP') is not None
 out_dp = gan.train(real[sl], noise=noises[:, sl], alpha=alphas[:, sl], shifts=shifts)
+# second step with library-drawn randomness: every rank must have drawn the same PhaseShuffle shifts
+gan.train(real[sl])
+_, _, sh_mine = eng.last_draws(0, 0, 4)
+sh_all = [torch.zeros(4, dtype=torch.int32, device='cuda') for _ in range(world)]
+dist.all_gather(sh_all, torch.as_tensor(sh_mine, device='cuda'))
+assert all(torch.equal(sh_all[0], t) for t in sh_all), 'ranks drew different PhaseShuffle shifts'
 
 # single-process reference on the concatenated batch (bypass the DP branch)
 eng1, g1, d1 = make(1, 0)
