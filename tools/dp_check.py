@@ -42,12 +42,6 @@ g.set_weights(gw); d.set_weights(dw)
 gan = WGAN_GP(ns, g, d, None)
 gan.no_dp_overlap = os.environ.get('CG_NO_DP_OVERLAP') is not None
 out_dp = gan.train(real[sl], noise=noises[:, sl], alpha=alphas[:, sl], shifts=shifts)
-# second step with library-drawn randomness: every rank must have drawn the same PhaseShuffle shifts
-gan.train(real[sl])
-_, _, sh_mine = eng.last_draws(0, 0, 4)
-sh_all = [torch.zeros(4, dtype=torch.int32, device='cuda') for _ in range(world)]
-dist.all_gather(sh_all, torch.as_tensor(sh_mine, device='cuda'))
-assert all(torch.equal(sh_all[0], t) for t in sh_all), 'ranks drew different PhaseShuffle shifts'
 
 # single-process reference on the concatenated batch (bypass the DP branch)
 eng1, g1, d1 = make(1, 0)
@@ -64,6 +58,15 @@ print('rank %d: dp losses %s | single %s | worst update rel err %.3e' %
       (rank, ['%.5f' % x for x in out_dp[:3]], ['%.5f' % float(s[i]) for i in (4, 0, 1)], worst))
 assert worst <= tol, worst
 assert abs(out_dp[1] - float(s[0])) <= (5e-2 if mixed else 1e-3) * max(1, abs(float(s[0])))
+# a further step with library-drawn randomness: every rank must draw the same PhaseShuffle shifts (and different noise)
+gan.train(real[sl])
+n_mine, _, sh_mine = eng.last_draws(Bl * hp.noise_dim, 0, 4)
+sh_all = [torch.zeros(4, dtype=torch.int32, device='cuda') for _ in range(world)]
+dist.all_gather(sh_all, torch.as_tensor(sh_mine, device='cuda'))
+assert all(torch.equal(sh_all[0], t) for t in sh_all), 'ranks drew different PhaseShuffle shifts'
+n_all = [torch.zeros_like(n_mine) for _ in range(world)]
+dist.all_gather(n_all, n_mine)
+assert world == 1 or not torch.equal(n_all[0], n_all[1]), 'ranks drew the same noise'
 dist.barrier()
 if rank == 0:
   print('DP CHECK OK (world %d, %s)' % (world, 'bf16' if mixed else 'fp32'))
