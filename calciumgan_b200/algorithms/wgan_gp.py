@@ -10,6 +10,8 @@ each rank runs its batch shard; the flat fp32 gradient buffer is all-reduced ove
 the fused Adam (which folds in 1/world_size). PhaseShuffle shifts are per-call scalars shared
 by the whole batch, so all ranks draw them from the same seeded stream.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -76,7 +78,12 @@ class WGAN_GP(GAN):
       self._comm_stream = torch.cuda.Stream(device=eng.device)
     works = []
     with torch.cuda.stream(self._comm_stream):
-      for view, b in eng.grad_buckets(which):
+      buckets = eng.grad_buckets(which)
+      if os.environ.get('CG_DP_BUCKETS') == '1':   # experiment: one all-reduce per model after the last writer
+        eng.stream_wait_bucket(which, buckets[-1][1], self._comm_stream)
+        works.append(dist.all_reduce(eng.grad_tensor(which), async_op=True))
+        return works
+      for view, b in buckets:
         eng.stream_wait_bucket(which, b, self._comm_stream)
         works.append(dist.all_reduce(view, async_op=True))
     return works

@@ -1379,6 +1379,10 @@ static inline int tc_init(TcState* s) {
   if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return cg_tc_set_err("cudaGetDeviceProperties failed");
   if (prop.major != 10) return cg_tc_set_err("the bf16 tensor-core path needs an sm_100 device (tcgen05/TMEM)");
   s->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("CG_SM_LIMIT")) {   // experiment: leave SMs free for a concurrent collective
+    const int lim = atoi(e) & ~1;
+    if (lim >= 2 && lim < s->sm_count) s->sm_count = lim;
+  }
   s->max_smem = (int)prop.sharedMemPerBlockOptin;
   if (const char* e = getenv("CG_TC_V1")) s->force_v1 = atoi(e) != 0;
   if (const char* e = getenv("CG_TC_PAIR_SHORT")) s->pair_short = atoi(e) != 0;
