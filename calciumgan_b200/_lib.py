@@ -51,6 +51,10 @@ SIGNATURES = {
     'cg_num_buckets': (_I, [_P, _I]),
     'cg_bucket_info': (_I, [_P, _I, _I, C.POINTER(_I64), C.POINTER(_I64)]),
     'cg_stream_wait_bucket': (_I, [_P, _I, _I, _P]),
+    'cg_set_grad_buffer': (_I, [_P, _I, _P]),
+    'cg_reduce_peer_grads': (_I, [_P, _I, C.POINTER(_P), _I, _P]),
+    'cg_apply_update_reduced': (_I, [_P, _I]),
+    'cg_reduced_grad_ptr': (_P, [_P, _I]),
     'cg_set_grads': (_I, [_P, _I, _P]),
     'cg_skipped_updates': (_I64, [_P, _I]),
     'cg_get_opt_state': (_I, [_P, _I, _P, _P, C.POINTER(_I64)]),

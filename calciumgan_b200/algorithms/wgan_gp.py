@@ -64,6 +64,46 @@ class WGAN_GP(GAN):
     return loss, gradient_penalty
 
   # ------------------------------------------------------------------ steps (wgan_gp.py:22-36,64-95)
+  # ---------------------------------------------------------------- data-parallel gradient exchange
+  def _peer_setup(self, dist):
+    """Gradient buffers in symmetric memory (every rank maps every peer's buffer over NVLink): the exchange is then ONE
+    small kernel of this library (cg_reduce_peer_grads) between two cross-rank barriers instead of an NCCL all-reduce.
+    Returns False (NCCL path) when symmetric memory is unavailable or CG_DP_COMM=nccl."""
+    if hasattr(self, '_peer'):
+      return self._peer is not None
+    self._peer = None
+    eng = self.engine
+    world = dist.get_world_size()
+    if eng.device.type != 'cuda' or os.environ.get('CG_DP_COMM', 'p2p') != 'p2p' or world not in (2, 4, 8):
+      return False
+    try:
+      import torch.distributed._symmetric_memory as symm
+      group = dist.group.WORLD
+      peer = {}
+      for which in (L.GENERATOR, L.DISCRIMINATOR):
+        n = eng.num_params(which)
+        buf = symm.empty((n + 3) // 4 * 4, dtype=torch.float32, device=eng.device)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, group)
+        ptrs = [int(hdl.buffer_ptrs[r]) for r in range(world)]
+        peer[which] = (buf, hdl, ptrs)
+      torch.cuda.synchronize()
+      dist.barrier()
+      for which, (buf, _, _) in peer.items():
+        eng.set_grad_buffer(which, buf)
+      self._peer = peer
+    except Exception as e:   # noqa: BLE001 -- any failure here just means "use NCCL"
+      if dist.get_rank() == 0:
+        print('calciumgan_b200: peer-memory gradient exchange unavailable (%s: %s); using NCCL all-reduce' % (type(e).__name__, e))
+    # every rank must take the same path
+    flag = torch.tensor([1.0 if self._peer is not None else 0.0], device=eng.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if float(flag.item()) == 0.0 and self._peer is not None:
+      for which in self._peer:
+        eng.set_grad_buffer(which, None)
+      self._peer = None
+    return self._peer is not None
+
   def _allreduce_start(self, dist, which):
     """Bucketed gradient all-reduce overlapped with the backward pass: bucket b is reduced on a side stream as soon as
     the library's event for its last writer has fired; the remaining wgrad kernels keep running on the main stream.
@@ -76,6 +116,14 @@ class WGAN_GP(GAN):
       return None
     if not hasattr(self, '_comm_stream'):
       self._comm_stream = torch.cuda.Stream(device=eng.device)
+    if self._peer_setup(dist):
+      buf, hdl, ptrs = self._peer[which]
+      with torch.cuda.stream(self._comm_stream):
+        eng.stream_wait_bucket(which, eng.num_buckets(which) - 1, self._comm_stream)   # the last writer of this model's gradients
+        hdl.barrier(channel=0)                      # every rank's gradients are complete
+        eng.reduce_peer_grads(which, ptrs, self._comm_stream)
+        hdl.barrier(channel=1)                      # every rank has finished reading: buffers may be overwritten
+      return 'peer'
     works = []
     with torch.cuda.stream(self._comm_stream):
       buckets = eng.grad_buckets(which)
@@ -88,16 +136,24 @@ class WGAN_GP(GAN):
         works.append(dist.all_reduce(view, async_op=True))
     return works
 
-  def _allreduce_finish(self, works):
+  def _allreduce_finish(self, works, which):
+    """Make the main stream wait for the exchange, then Adam on the exchanged gradients."""
+    eng = self.engine
     if works is None:
+      eng.apply_update(which)
+      return
+    if works == 'peer':
+      torch.cuda.current_stream().wait_stream(self._comm_stream)
+      eng.apply_update_reduced(which)
       return
     with torch.cuda.stream(self._comm_stream):
       for w in works:
         w.wait()
     torch.cuda.current_stream().wait_stream(self._comm_stream)
+    eng.apply_update(which)
 
   def _allreduce_buckets(self, dist, which):
-    self._allreduce_finish(self._allreduce_start(dist, which))
+    self._allreduce_finish(self._allreduce_start(dist, which), which)
 
   def _train_discriminator(self, inputs, noise=None, alpha=None, shifts=None):
     dist = _dist()
@@ -106,7 +162,6 @@ class WGAN_GP(GAN):
     else:
       s = self.engine.critic_step(inputs, noise, alpha, shifts, update=False)
       self._allreduce_buckets(dist, L.DISCRIMINATOR)
-      self.dis_optimizer.update()
     return float(s[L.S_DIS_LOSS]), float(s[L.S_GP])
 
   def _train_generator(self, inputs, noise=None, shifts=None):
@@ -116,7 +171,6 @@ class WGAN_GP(GAN):
     else:
       s = self.engine.generator_step(inputs, noise, shifts, update=False)
       self._allreduce_buckets(dist, L.GENERATOR)
-      self.gen_optimizer.update()
     return float(s[L.S_GEN_LOSS]), metrics_from_scalars(s)
 
   def train(self, inputs, noise=None, alpha=None, shifts=None):
@@ -153,14 +207,12 @@ class WGAN_GP(GAN):
         else:
           eng.prefetch_generator(real, None if noise is None else noise[nc], None, for_generator_step=True)
         prefetched = True
-      self._allreduce_finish(works)
-      eng.apply_update(L.DISCRIMINATOR)
+      self._allreduce_finish(works, L.DISCRIMINATOR)
     eng.generator_step(real, None if noise is None else noise[nc],
                        None if shifts is None else shifts[12 * nc:12 * nc + 4], update=False, sync=False,
                        gen_prefetched=prefetched)
     hist[nc].copy_(scal)
     self._allreduce_buckets(dist, L.GENERATOR)
-    eng.apply_update(L.GENERATOR)
     out = torch.zeros(L.NUM_SCALARS, device=eng.device)
     out[L.S_DIS_LOSS] = hist[:nc, L.S_DIS_LOSS].mean()
     out[L.S_GP] = hist[:nc, L.S_GP].mean()

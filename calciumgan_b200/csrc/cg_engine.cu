@@ -70,6 +70,8 @@ struct Model {
   int64_t total = 0;
   float *w = nullptr, *m = nullptr, *v = nullptr, *g = nullptr;   // flat fp32
   OptState* opt = nullptr;                                         // device: optimizer.iterations, skipped updates, lr_t
+  float* g_own = nullptr;      // the library's own gradient buffer (g may point at a caller-provided symmetric buffer)
+  float* gr = nullptr;         // data parallel over peer memory: sum of every rank's gradients (cg_reduce_peer_grads)
   void add(std::initializer_list<int64_t> shp) {
     ParamInfo p{};
     p.ndim = (int)shp.size();
@@ -473,6 +475,7 @@ extern "C" int cg_create(const cg_config* cfg, cg_ctx** out) {
   for (Model* m : {&G, &D}) {
     DA_(m->w, m->total * 4); DA_(m->m, m->total * 4); DA_(m->v, m->total * 4); DA_(m->g, m->total * 4);
     DA_(m->opt, sizeof(OptState));
+    m->g_own = m->g;
   }
   const size_t es = c->esz;
   const size_t Bt = 3 * (size_t)c->Bmax, Bm = c->Bmax;
@@ -610,6 +613,39 @@ extern "C" int64_t cg_skipped_updates(cg_ctx* c, int which) {
     return -1;
   return st.skipped;
 }
+// Data parallel over NVLink peer memory: gradients are accumulated straight into a caller-provided buffer that every
+// peer has mapped (symmetric memory); NULL restores the library's own buffer.
+extern "C" int cg_set_grad_buffer(cg_ctx* c, int which, float* dev) {
+  Model* m = model_of(c, which);
+  if (dev && (reinterpret_cast<uintptr_t>(dev) & 15)) return set_err("cg_set_grad_buffer: the buffer must be 16-byte aligned");
+  CU(cudaStreamSynchronize(c->stream));
+  m->g = dev ? dev : m->g_own;
+  return 0;
+}
+// out (library-owned, read by cg_apply_update_reduced) = sum over ranks r = 0 .. world-1 of peer_ptrs[r][0 .. num_params),
+// launched on `cuda_stream`. The caller orders it between two cross-rank barriers (all gradients written / all peers
+// have finished reading) on the same stream.
+extern "C" int cg_reduce_peer_grads(cg_ctx* c, int which, const void* const* peer_ptrs_host, int world, void* cuda_stream) {
+  Model* m = model_of(c, which);
+  if (!peer_ptrs_host || (world != 2 && world != 4 && world != 8)) return set_err("cg_reduce_peer_grads: world must be 2, 4 or 8");
+  if (!m->gr) {
+    if (dalloc(c, (void**)&m->gr, (size_t)m->total * 4)) return 1;
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  PeerPtrs pp;
+  for (int r = 0; r < 8; ++r) {
+    pp.p[r] = (const float*)(r < world ? peer_ptrs_host[r] : peer_ptrs_host[0]);
+    if (reinterpret_cast<uintptr_t>(pp.p[r]) & 15) return set_err("cg_reduce_peer_grads: peer buffers must be 16-byte aligned");
+  }
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int grid = 148 * 2;
+  if (world == 2) peer_sum_kernel<2><<<grid, 128, 0, st>>>(pp, m->gr, m->total);
+  else if (world == 4) peer_sum_kernel<4><<<grid, 128, 0, st>>>(pp, m->gr, m->total);
+  else peer_sum_kernel<8><<<grid, 128, 0, st>>>(pp, m->gr, m->total);
+  return post_launch(c, "peer_sum");
+}
+extern "C" void* cg_reduced_grad_ptr(cg_ctx* c, int which) { return model_of(c, which)->gr; }
+
 extern "C" int cg_set_grads(cg_ctx* c, int which, const float* host) {
   Model* m = model_of(c, which);
   if (!host) return set_err("cg_set_grads: null pointer");
@@ -1076,24 +1112,31 @@ static int check_batch(cg_ctx* c, int B) {
 }
 
 // ------------------------------------------------------------------------------------------ Adam
-extern "C" int cg_apply_update(cg_ctx* c, int which) {
+static int apply_update_from(cg_ctx* c, int which, const float* grad);
+extern "C" int cg_apply_update(cg_ctx* c, int which) { return apply_update_from(c, which, model_of(c, which)->g); }
+extern "C" int cg_apply_update_reduced(cg_ctx* c, int which) {
+  Model* m = model_of(c, which);
+  if (!m->gr) return set_err("cg_apply_update_reduced: no reduced gradient (call cg_reduce_peer_grads first)");
+  return apply_update_from(c, which, m->gr);
+}
+static int apply_update_from(cg_ctx* c, int which, const float* grad) {
   Model* m = model_of(c, which);
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-7f, gscale = 1.0f / (float)c->cfg.world_size;
   // pass 1 (reads the gradient once): non-finite check; the last block advances `iterations` and computes lr_t
   CK(glue(c, 4.0 * m->total));
-  adam_prepare_kernel<<<grid_for(m->total / 4, 256, 148 * 4), 256, 0, c->stream>>>(m->g, m->total, m->opt,
+  adam_prepare_kernel<<<grid_for(m->total / 4, 256, 148 * 4), 256, 0, c->stream>>>(grad, m->total, m->opt,
                                                                                   c->cfg.learning_rate, b1, b2);
   CK(post_launch(c, "adam_prepare"));
   if (c->dbg_flags & CG_DEBUG_NO_ADAM_FUSE) {
     CK(glue(c, 28.0 * m->total));
-    adam_kernel<<<grid_for(m->total), 256, 0, c->stream>>>(m->w, m->m, m->v, m->g, m->total, m->opt, b1, b2, eps, gscale);
+    adam_kernel<<<grid_for(m->total), 256, 0, c->stream>>>(m->w, m->m, m->v, grad, m->total, m->opt, b1, b2, eps, gscale);
     CK(post_launch(c, "adam"));
     return repack(c, which);
   }
   const AdamPlan& pl = c->adam_plan[which];
   CK(glue(c, 28.0 * m->total + 2.0 * c->esz * m->total));
   DISPATCH_T(c, adam_pack_kernel<T><<<grid_for(pl.items * 256, 256, 148 * 8), 256, 0, c->stream>>>(
-                    m->w, m->m, m->v, m->g, pl, m->opt, b1, b2, eps, gscale));
+                    m->w, m->m, m->v, grad, pl, m->opt, b1, b2, eps, gscale));
   return post_launch(c, "adam_pack");
 }
 

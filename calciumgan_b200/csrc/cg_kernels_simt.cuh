@@ -1028,6 +1028,38 @@ __global__ void __launch_bounds__(256) metrics8_kernel(const float* __restrict__
   }
 }
 
+// Data-parallel gradient exchange over NVLink peer memory (no reference counterpart): every rank's flat
+// gradient buffer is mapped into every other rank (symmetric memory); this kernel pulls the W buffers with 16-byte
+// peer loads and writes their sum, always added in rank order 0 .. W-1 so that all ranks produce bit-identical results.
+// Footprint by design: 128 threads, < 64 registers, no shared memory -- it fits beside a resident tcgen05 GEMM CTA on
+// every SM, so it runs UNDER the GEMMs of the next sub-step instead of waiting for an SM to drain (an NCCL all-reduce
+// CTA does not fit beside them and serialises with the persistent kernels).
+struct PeerPtrs { const float* p[8]; };
+template <int W>
+__global__ void __launch_bounds__(128) peer_sum_kernel(const __grid_constant__ PeerPtrs peers, float* __restrict__ out,
+                                                       long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v[W];
+#pragma unroll
+    for (int r = 0; r < W; ++r)
+      asm volatile("ld.global.relaxed.sys.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(v[r].x), "=f"(v[r].y), "=f"(v[r].z), "=f"(v[r].w)
+                   : "l"(reinterpret_cast<const float4*>(peers.p[r]) + i));
+    float4 a = v[0];
+#pragma unroll
+    for (int r = 1; r < W; ++r) { a.x += v[r].x; a.y += v[r].y; a.z += v[r].z; a.w += v[r].w; }
+    reinterpret_cast<float4*>(out)[i] = a;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    float a = 0.f;
+#pragma unroll
+    for (int r = 0; r < W; ++r) a += peers.p[r][i];
+    out[i] = a;
+  }
+}
+
 // dst[i, :] = src[idx[i], :] for a device-resident dataset cache (the reference caches its dataset in host memory,
 // gan/utils/dataset_helper.py:171 `train_ds.cache()`, and shuffles indices): one block column per output row, 16-byte
 // copies; a step then moves a few hundred indices over PCIe instead of the batch.

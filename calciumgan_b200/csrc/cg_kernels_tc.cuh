@@ -1383,7 +1383,9 @@ static inline int tc_init(TcState* s) {
     const int lim = atoi(e) & ~1;
     if (lim >= 2 && lim < s->sm_count) s->sm_count = lim;
   }
-  s->max_smem = (int)prop.sharedMemPerBlockOptin;
+  // 2 KB short of the opt-in maximum: leaves room on every SM for a second, tiny CTA (1 KB of system-reserved shared
+  // memory each) -- the data-parallel peer-memory reduction kernel runs beside the persistent GEMM CTAs
+  s->max_smem = (int)prop.sharedMemPerBlockOptin - 2048;
   if (const char* e = getenv("CG_TC_V1")) s->force_v1 = atoi(e) != 0;
   if (const char* e = getenv("CG_TC_PAIR_SHORT")) s->pair_short = atoi(e) != 0;
   bool ok = true;

@@ -165,6 +165,28 @@ class Engine(object):
     L.check(self.lib.cg_get_grads(self.ctx, which, flat.ctypes.data_as(C.c_void_p)))
     return self._split(which, flat)
 
+  def set_grad_buffer(self, which, tensor):
+    """Accumulate gradients into `tensor` (flat fp32 CUDA, e.g. symmetric memory mapped by every peer); None restores."""
+    if tensor is not None and (tensor.dtype != torch.float32 or tensor.numel() < self.num_params(which)):
+      raise ValueError('gradient buffer must be float32 with at least num_params elements')
+    L.check(self.lib.cg_set_grad_buffer(self.ctx, which, self._ptr(tensor)))
+    self._grad_views.clear()
+    self._ext_grad = getattr(self, '_ext_grad', {})
+    self._ext_grad[which] = tensor
+
+  def reduce_peer_grads(self, which, peer_ptrs, stream):
+    """sum over ranks of the peers' gradient buffers -> the library's reduced buffer, on `stream` (cg_reduce_peer_grads)."""
+    arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+    L.check(self.lib.cg_reduce_peer_grads(self.ctx, which, arr, len(peer_ptrs), C.c_void_p(stream.cuda_stream)))
+
+  def apply_update_reduced(self, which):
+    self._use_stream()
+    L.check(self.lib.cg_apply_update_reduced(self.ctx, which))
+
+  def reduced_grad_tensor(self, which):
+    ptr = self.lib.cg_reduced_grad_ptr(self.ctx, which)
+    return torch.as_tensor(_DevArray(ptr, self.num_params(which)), device=self.device)
+
   def set_grads(self, which, arrays):
     """Overwrite the flat gradient buffer (parity test of apply_update alone)."""
     flat = self._join(which, arrays)
@@ -190,6 +212,9 @@ class Engine(object):
         out.append((g[off.value:off.value + cnt.value], b))
       self._grad_views[('b', which)] = out
     return self._grad_views[('b', which)]
+
+  def num_buckets(self, which):
+    return int(self.lib.cg_num_buckets(self.ctx, which))
 
   def stream_wait_bucket(self, which, bucket, stream):
     L.check(self.lib.cg_stream_wait_bucket(self.ctx, which, bucket, C.c_void_p(stream.cuda_stream)))

@@ -114,6 +114,17 @@ void* cg_grad_ptr(cg_ctx* ctx, int which);
 int cg_num_buckets(cg_ctx* ctx, int which);
 int cg_bucket_info(cg_ctx* ctx, int which, int bucket, int64_t* offset, int64_t* count);
 int cg_stream_wait_bucket(cg_ctx* ctx, int which, int bucket, void* cuda_stream);
+/* Data parallel over NVLink peer memory (no reference counterpart): instead of an NCCL all-reduce, every rank
+ * accumulates its gradients into a buffer all peers have mapped (cg_set_grad_buffer: caller-provided symmetric memory,
+ * num_params floats, 16-byte aligned; NULL = the library's own buffer again), and after a cross-rank barrier
+ * cg_reduce_peer_grads pulls all `world` (2, 4 or 8) buffers with 16-byte peer loads on `cuda_stream` and writes their
+ * sum, added in rank order on every rank (bit-identical replicas), into a library-owned buffer that
+ * cg_apply_update_reduced feeds to Adam (scaled by 1 / world_size). The kernel is sized to sit beside a resident tensor-
+ * core CTA on every SM (128 threads, no shared memory), so it overlaps the next sub-step's generator GEMMs. */
+int cg_set_grad_buffer(cg_ctx* ctx, int which, float* grad_dev);
+int cg_reduce_peer_grads(cg_ctx* ctx, int which, const void* const* peer_ptrs_host, int world, void* cuda_stream);
+int cg_apply_update_reduced(cg_ctx* ctx, int which);
+void* cg_reduced_grad_ptr(cg_ctx* ctx, int which);
 /* overwrite the flat gradient buffer (parity test of cg_apply_update alone; Keras get_weights() order) */
 int cg_set_grads(cg_ctx* ctx, int which, const float* host_flat);
 /* updates skipped because a gradient was not finite (the reference's LossScaleOptimizer skips such steps,

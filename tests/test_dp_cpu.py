@@ -36,6 +36,9 @@ class StubEngine(object):
     g = self.g[which]
     return [(g[4:], 0), (g[2:4], 1), (g[:2], 2)]     # last layers first, contiguous views of the flat buffer
 
+  def num_buckets(self, which):
+    return 3
+
   def scalars_tensor(self):
     return self.scal
 
