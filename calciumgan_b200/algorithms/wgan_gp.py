@@ -85,7 +85,9 @@ class WGAN_GP(GAN):
         buf = symm.empty((n + 3) // 4 * 4, dtype=torch.float32, device=eng.device)
         buf.zero_()
         hdl = symm.rendezvous(buf, group)
-        ptrs = [int(hdl.buffer_ptrs[r]) for r in range(world)]
+        # the tensor may sit at an offset inside a pooled symmetric block: same offset on every rank
+        delta = buf.data_ptr() - int(hdl.buffer_ptrs[dist.get_rank()])
+        ptrs = [int(hdl.buffer_ptrs[r]) + delta for r in range(world)]
         peer[which] = (buf, hdl, ptrs)
       torch.cuda.synchronize()
       dist.barrier()
