@@ -162,6 +162,7 @@ class WGAN_GP(GAN):
     if dist is None:
       s = self.engine.critic_step(inputs, noise, alpha, shifts, update=True)
     else:
+      self._peer_setup(dist)     # before the step: it decides which buffer the gradients are accumulated into
       s = self.engine.critic_step(inputs, noise, alpha, shifts, update=False)
       self._allreduce_buckets(dist, L.DISCRIMINATOR)
     return float(s[L.S_DIS_LOSS]), float(s[L.S_GP])
@@ -171,6 +172,7 @@ class WGAN_GP(GAN):
     if dist is None:
       s = self.engine.generator_step(inputs, noise, shifts, update=True)
     else:
+      self._peer_setup(dist)
       s = self.engine.generator_step(inputs, noise, shifts, update=False)
       self._allreduce_buckets(dist, L.GENERATOR)
     return float(s[L.S_GEN_LOSS]), metrics_from_scalars(s)
@@ -189,6 +191,7 @@ class WGAN_GP(GAN):
     weight: wgan_gp.py:65-66 / :23-26), so the all-reduce tail and the critic's Adam hide under ~0.3 ms of generator
     GEMMs instead of idling the GPU."""
     eng, nc = self.engine, self.n_critic
+    self._peer_setup(dist)       # before the first sub-step: it decides which buffer the gradients are accumulated into
     real = eng.to_device(inputs)
     shifts = None if shifts is None else np.asarray(shifts, np.int32).reshape(-1)
     hist = torch.zeros((nc + 1, L.NUM_SCALARS), device=eng.device)
