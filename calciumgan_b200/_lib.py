@@ -53,6 +53,9 @@ SIGNATURES = {
     'cg_stream_wait_bucket': (_I, [_P, _I, _I, _P]),
     'cg_set_grad_buffer': (_I, [_P, _I, _P]),
     'cg_reduce_peer_grads': (_I, [_P, _I, C.POINTER(_P), _I, _P]),
+    'cg_set_reduced_buffer': (_I, [_P, _I, _P]),
+    'cg_peer_reduce_scatter': (_I, [_P, _I, C.POINTER(_P), _I, _I, _P]),
+    'cg_peer_all_gather': (_I, [_P, _I, C.POINTER(_P), _I, _I, _P]),
     'cg_apply_update_reduced': (_I, [_P, _I]),
     'cg_reduced_grad_ptr': (_P, [_P, _I]),
     'cg_set_grads': (_I, [_P, _I, _P]),

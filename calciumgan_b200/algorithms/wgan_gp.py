@@ -88,11 +88,20 @@ class WGAN_GP(GAN):
         # the tensor may sit at an offset inside a pooled symmetric block: same offset on every rank
         delta = buf.data_ptr() - int(hdl.buffer_ptrs[dist.get_rank()])
         ptrs = [int(hdl.buffer_ptrs[r]) + delta for r in range(world)]
-        peer[which] = (buf, hdl, ptrs)
+        red, rptrs = None, None
+        if world > 2:    # two-phase exchange: the reduced gradient is peer-mapped too
+          red = symm.empty((n + 7) // 4 * 4, dtype=torch.float32, device=eng.device)
+          red.zero_()
+          rh = symm.rendezvous(red, group)
+          rdelta = red.data_ptr() - int(rh.buffer_ptrs[dist.get_rank()])
+          rptrs = [int(rh.buffer_ptrs[r]) + rdelta for r in range(world)]
+        peer[which] = (buf, hdl, ptrs, red, rptrs)
       torch.cuda.synchronize()
       dist.barrier()
-      for which, (buf, _, _) in peer.items():
+      for which, (buf, _, _, red, _) in peer.items():
         eng.set_grad_buffer(which, buf)
+        if red is not None:
+          eng.set_reduced_buffer(which, red)
       self._peer = peer
     except Exception as e:   # noqa: BLE001 -- any failure here just means "use NCCL"
       if dist.get_rank() == 0:
@@ -103,6 +112,7 @@ class WGAN_GP(GAN):
     if float(flag.item()) == 0.0 and self._peer is not None:
       for which in self._peer:
         eng.set_grad_buffer(which, None)
+        eng.set_reduced_buffer(which, None)
       self._peer = None
     return self._peer is not None
 
@@ -119,12 +129,18 @@ class WGAN_GP(GAN):
     if not hasattr(self, '_comm_stream'):
       self._comm_stream = torch.cuda.Stream(device=eng.device)
     if self._peer_setup(dist):
-      buf, hdl, ptrs = self._peer[which]
+      buf, hdl, ptrs, red, rptrs = self._peer[which]
+      rank = dist.get_rank()
       with torch.cuda.stream(self._comm_stream):
         eng.stream_wait_bucket(which, eng.num_buckets(which) - 1, self._comm_stream)   # the last writer of this model's gradients
-        hdl.barrier(channel=0)                      # every rank's gradients are complete
-        eng.reduce_peer_grads(which, ptrs, self._comm_stream)
-        hdl.barrier(channel=1)                      # every rank has finished reading: buffers may be overwritten
+        hdl.barrier(channel=0)                      # every rank's gradients are complete (and its last gather is done)
+        if red is None:                             # 2 ranks: one kernel pulls the peer's buffer
+          eng.reduce_peer_grads(which, ptrs, self._comm_stream)
+          hdl.barrier(channel=1)                    # every rank has finished reading: buffers may be overwritten
+        else:                                       # 4 / 8 ranks: reduce-scatter, barrier, all-gather
+          eng.peer_reduce_scatter(which, ptrs, rank, self._comm_stream)
+          hdl.barrier(channel=1)                    # every slice is complete; gradient buffers may be overwritten
+          eng.peer_all_gather(which, rptrs, rank, self._comm_stream)
       return 'peer'
     works = []
     with torch.cuda.stream(self._comm_stream):

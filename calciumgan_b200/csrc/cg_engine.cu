@@ -622,27 +622,77 @@ extern "C" int cg_set_grad_buffer(cg_ctx* c, int which, float* dev) {
   m->g = dev ? dev : m->g_own;
   return 0;
 }
-// out (library-owned, read by cg_apply_update_reduced) = sum over ranks r = 0 .. world-1 of peer_ptrs[r][0 .. num_params),
+static int peer_ptrs(const void* const* host, int world, PeerPtrs& pp) {
+  if (!host || (world != 2 && world != 4 && world != 8)) return set_err("peer gradient exchange: world must be 2, 4 or 8");
+  for (int r = 0; r < 8; ++r) {
+    pp.p[r] = (const float*)(r < world ? host[r] : host[0]);
+    if (!pp.p[r] || (reinterpret_cast<uintptr_t>(pp.p[r]) & 15)) return set_err("peer gradient exchange: peer buffers must be 16-byte aligned");
+  }
+  return 0;
+}
+static int reduced_buffer(cg_ctx* c, Model* m) {
+  if (m->gr) return 0;
+  if (dalloc(c, (void**)&m->gr, (size_t)(m->total + 4) * 4)) return 1;
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+static long long peer_slice(const Model* m, int world) { return ((m->total + world - 1) / world + 3) / 4 * 4; }
+static int launch_peer_sum(cg_ctx* c, const PeerPtrs& pp, int world, float* out, long long first, long long n, cudaStream_t st) {
+  long long g = (n / 4 + 127) / 128;
+  const int grid = (int)(g < 1 ? 1 : (g > 148 * 2 ? 148 * 2 : g));
+  if (world == 2) peer_sum_kernel<2><<<grid, 128, 0, st>>>(pp, out, first, n);
+  else if (world == 4) peer_sum_kernel<4><<<grid, 128, 0, st>>>(pp, out, first, n);
+  else peer_sum_kernel<8><<<grid, 128, 0, st>>>(pp, out, first, n);
+  return post_launch(c, "peer_sum");
+}
+// one-shot: reduced (read by cg_apply_update_reduced) = sum over ranks r = 0 .. world-1 of peer_ptrs[r][0 .. num_params),
 // launched on `cuda_stream`. The caller orders it between two cross-rank barriers (all gradients written / all peers
-// have finished reading) on the same stream.
+// have finished reading) on the same stream. Pulls (world - 1) x the gradient size: the right form for 2 ranks.
 extern "C" int cg_reduce_peer_grads(cg_ctx* c, int which, const void* const* peer_ptrs_host, int world, void* cuda_stream) {
   Model* m = model_of(c, which);
-  if (!peer_ptrs_host || (world != 2 && world != 4 && world != 8)) return set_err("cg_reduce_peer_grads: world must be 2, 4 or 8");
-  if (!m->gr) {
-    if (dalloc(c, (void**)&m->gr, (size_t)m->total * 4)) return 1;
-    CU(cudaStreamSynchronize(c->stream));
-  }
   PeerPtrs pp;
-  for (int r = 0; r < 8; ++r) {
-    pp.p[r] = (const float*)(r < world ? peer_ptrs_host[r] : peer_ptrs_host[0]);
-    if (reinterpret_cast<uintptr_t>(pp.p[r]) & 15) return set_err("cg_reduce_peer_grads: peer buffers must be 16-byte aligned");
-  }
-  cudaStream_t st = (cudaStream_t)cuda_stream;
-  const int grid = 148 * 2;
-  if (world == 2) peer_sum_kernel<2><<<grid, 128, 0, st>>>(pp, m->gr, m->total);
-  else if (world == 4) peer_sum_kernel<4><<<grid, 128, 0, st>>>(pp, m->gr, m->total);
-  else peer_sum_kernel<8><<<grid, 128, 0, st>>>(pp, m->gr, m->total);
-  return post_launch(c, "peer_sum");
+  CK(peer_ptrs(peer_ptrs_host, world, pp));
+  CK(reduced_buffer(c, m));
+  return launch_peer_sum(c, pp, world, m->gr, 0, m->total, (cudaStream_t)cuda_stream);
+}
+// two-phase form for 4 / 8 ranks (2 x (world - 1) / world x the gradient size per rank instead of (world - 1) x):
+// phase 1, reduce-scatter: this rank sums ITS slice of every peer's gradient buffer into its reduced buffer, which must
+// be peer-mapped too (cg_set_reduced_buffer); phase 2, all-gather: it copies the other slices from their owners'
+// reduced buffers. Barriers: before phase 1 (gradients complete) and between the phases (slices complete; gradient
+// buffers may be overwritten); the next exchange's first barrier also protects the reduced slices.
+extern "C" int cg_peer_reduce_scatter(cg_ctx* c, int which, const void* const* grad_peer_ptrs_host, int world, int rank,
+                                      void* cuda_stream) {
+  Model* m = model_of(c, which);
+  PeerPtrs pp;
+  CK(peer_ptrs(grad_peer_ptrs_host, world, pp));
+  if (rank < 0 || rank >= world || !m->gr) return set_err("cg_peer_reduce_scatter: bad rank or no reduced buffer (cg_set_reduced_buffer)");
+  const long long slice = peer_slice(m, world), first = (long long)rank * slice;
+  long long cnt = m->total - first;
+  if (cnt > slice) cnt = slice;
+  if (cnt <= 0) return 0;
+  return launch_peer_sum(c, pp, world, m->gr, first, cnt, (cudaStream_t)cuda_stream);
+}
+extern "C" int cg_peer_all_gather(cg_ctx* c, int which, const void* const* reduced_peer_ptrs_host, int world, int rank,
+                                  void* cuda_stream) {
+  Model* m = model_of(c, which);
+  PeerPtrs pp;
+  CK(peer_ptrs(reduced_peer_ptrs_host, world, pp));
+  if (rank < 0 || rank >= world || !m->gr) return set_err("cg_peer_all_gather: bad rank or no reduced buffer (cg_set_reduced_buffer)");
+  const long long slice = peer_slice(m, world);
+  long long g = (slice / 4 + 127) / 128;
+  const int gx = (int)(g < 1 ? 1 : (g > 40 ? 40 : g));
+  peer_gather_kernel<<<dim3(gx, world), 128, 0, (cudaStream_t)cuda_stream>>>(pp, m->gr, slice, m->total, rank);
+  return post_launch(c, "peer_gather");
+}
+// the buffer cg_apply_update_reduced reads: caller-provided (peer-mapped, >= num_params + 4 floats) or, with NULL, the
+// library's own
+extern "C" int cg_set_reduced_buffer(cg_ctx* c, int which, float* dev) {
+  Model* m = model_of(c, which);
+  if (dev && (reinterpret_cast<uintptr_t>(dev) & 15)) return set_err("cg_set_reduced_buffer: the buffer must be 16-byte aligned");
+  CU(cudaStreamSynchronize(c->stream));
+  m->gr = dev;
+  if (!dev) CK(reduced_buffer(c, m));
+  return 0;
 }
 extern "C" void* cg_reduced_grad_ptr(cg_ctx* c, int which) { return model_of(c, which)->gr; }
 

@@ -1035,9 +1035,14 @@ __global__ void __launch_bounds__(256) metrics8_kernel(const float* __restrict__
 // every SM, so it runs UNDER the GEMMs of the next sub-step instead of waiting for an SM to drain (an NCCL all-reduce
 // CTA does not fit beside them and serialises with the persistent kernels).
 struct PeerPtrs { const float* p[8]; };
+// out[first .. first + n) = sum_r peers[r][first .. first + n)   (first % 4 == 0)
 template <int W>
-__global__ void __launch_bounds__(128) peer_sum_kernel(const __grid_constant__ PeerPtrs peers, float* __restrict__ out,
-                                                       long long n) {
+__global__ void __launch_bounds__(128) peer_sum_kernel(const __grid_constant__ PeerPtrs peers, float* __restrict__ out_all,
+                                                       long long first, long long n) {
+  PeerPtrs pp = peers;
+#pragma unroll
+  for (int r = 0; r < W; ++r) pp.p[r] += first;
+  float* out = out_all + first;
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v[W];
@@ -1045,7 +1050,7 @@ __global__ void __launch_bounds__(128) peer_sum_kernel(const __grid_constant__ P
     for (int r = 0; r < W; ++r)
       asm volatile("ld.global.relaxed.sys.v4.f32 {%0, %1, %2, %3}, [%4];"
                    : "=f"(v[r].x), "=f"(v[r].y), "=f"(v[r].z), "=f"(v[r].w)
-                   : "l"(reinterpret_cast<const float4*>(peers.p[r]) + i));
+                   : "l"(reinterpret_cast<const float4*>(pp.p[r]) + i));
     float4 a = v[0];
 #pragma unroll
     for (int r = 1; r < W; ++r) { a.x += v[r].x; a.y += v[r].y; a.z += v[r].z; a.w += v[r].w; }
@@ -1055,9 +1060,30 @@ __global__ void __launch_bounds__(128) peer_sum_kernel(const __grid_constant__ P
     const long long i = (n4 << 2) + threadIdx.x;
     float a = 0.f;
 #pragma unroll
-    for (int r = 0; r < W; ++r) a += peers.p[r][i];
+    for (int r = 0; r < W; ++r) a += pp.p[r][i];
     out[i] = a;
   }
+}
+// second phase of the two-phase exchange: slice s of the reduced gradient was summed by rank s; every rank copies the
+// W - 1 slices it does not own from their owners' (peer-mapped) reduced buffers into its own. blockIdx.y = slice.
+__global__ void __launch_bounds__(128) peer_gather_kernel(const __grid_constant__ PeerPtrs peers, float* __restrict__ out,
+                                                          long long slice, long long n, int rank) {
+  const int s = blockIdx.y;
+  if (s == rank) return;
+  const long long first = (long long)s * slice;
+  long long cnt = n - first;
+  if (cnt <= 0) return;
+  if (cnt > slice) cnt = slice;
+  const float* src = peers.p[s] + first;
+  float* dst = out + first;
+  const long long n4 = cnt >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v;
+    asm volatile("ld.global.relaxed.sys.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(reinterpret_cast<const float4*>(src) + i));
+    reinterpret_cast<float4*>(dst)[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(cnt & 3)) dst[(n4 << 2) + threadIdx.x] = src[(n4 << 2) + threadIdx.x];
 }
 
 // dst[i, :] = src[idx[i], :] for a device-resident dataset cache (the reference caches its dataset in host memory,

@@ -179,6 +179,19 @@ class Engine(object):
     arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(p)) for p in peer_ptrs])
     L.check(self.lib.cg_reduce_peer_grads(self.ctx, which, arr, len(peer_ptrs), C.c_void_p(stream.cuda_stream)))
 
+  def set_reduced_buffer(self, which, tensor):
+    L.check(self.lib.cg_set_reduced_buffer(self.ctx, which, self._ptr(tensor)))
+    self._ext_red = getattr(self, '_ext_red', {})
+    self._ext_red[which] = tensor
+
+  def peer_reduce_scatter(self, which, grad_peer_ptrs, rank, stream):
+    arr = (C.c_void_p * len(grad_peer_ptrs))(*[C.c_void_p(int(p)) for p in grad_peer_ptrs])
+    L.check(self.lib.cg_peer_reduce_scatter(self.ctx, which, arr, len(grad_peer_ptrs), int(rank), C.c_void_p(stream.cuda_stream)))
+
+  def peer_all_gather(self, which, reduced_peer_ptrs, rank, stream):
+    arr = (C.c_void_p * len(reduced_peer_ptrs))(*[C.c_void_p(int(p)) for p in reduced_peer_ptrs])
+    L.check(self.lib.cg_peer_all_gather(self.ctx, which, arr, len(reduced_peer_ptrs), int(rank), C.c_void_p(stream.cuda_stream)))
+
   def apply_update_reduced(self, which):
     self._use_stream()
     L.check(self.lib.cg_apply_update_reduced(self.ctx, which))

@@ -123,6 +123,13 @@ int cg_stream_wait_bucket(cg_ctx* ctx, int which, int bucket, void* cuda_stream)
  * core CTA on every SM (128 threads, no shared memory), so it overlaps the next sub-step's generator GEMMs. */
 int cg_set_grad_buffer(cg_ctx* ctx, int which, float* grad_dev);
 int cg_reduce_peer_grads(cg_ctx* ctx, int which, const void* const* peer_ptrs_host, int world, void* cuda_stream);
+/* Two-phase form for 4 / 8 ranks: the reduced buffer is peer-mapped as well (cg_set_reduced_buffer: num_params + 4
+ * floats; NULL = the library's own); cg_peer_reduce_scatter sums this rank's slice (num_params / world, rounded up to 4)
+ * of every peer's gradients into it, cg_peer_all_gather copies the other slices from their owners. Per rank that pulls
+ * 2 (world - 1) / world gradient sizes instead of (world - 1). Barriers: before the first phase and between the phases. */
+int cg_set_reduced_buffer(cg_ctx* ctx, int which, float* reduced_dev);
+int cg_peer_reduce_scatter(cg_ctx* ctx, int which, const void* const* grad_peer_ptrs_host, int world, int rank, void* cuda_stream);
+int cg_peer_all_gather(cg_ctx* ctx, int which, const void* const* reduced_peer_ptrs_host, int world, int rank, void* cuda_stream);
 int cg_apply_update_reduced(cg_ctx* ctx, int which);
 void* cg_reduced_grad_ptr(cg_ctx* ctx, int which);
 /* overwrite the flat gradient buffer (parity test of cg_apply_update alone; Keras get_weights() order) */

@@ -24,7 +24,7 @@ real = torch.from_numpy(np.random.RandomState(rank).uniform(0, 1, (B, 2048, 102)
 for which, step in ((L.DISCRIMINATOR, lambda: eng.critic_step(real, update=False)), (L.GENERATOR, lambda: eng.generator_step(real, update=False))):
   for it in range(3):
     step()
-    buf, hdl, ptrs = gan._peer[which]
+    buf, hdl, ptrs, red_buf, rptrs = gan._peer[which]
     n = eng.num_params(which)
     own = torch.as_tensor(np.concatenate([x.ravel() for x in eng.get_grads(which)])).cuda()
     print('rank %d which %d it %d: |buf - get_grads| %.3e, buf norm %.4e, ptr ok %s' % (
