@@ -128,6 +128,8 @@ class WGAN_GP(GAN):
       return None
     if not hasattr(self, '_comm_stream'):
       self._comm_stream = torch.cuda.Stream(device=eng.device)
+    if os.environ.get('CG_DP_COMM') == 'none':     # timing experiment only: no exchange at all (replicas diverge)
+      return None
     if self._peer_setup(dist):
       buf, hdl, ptrs, red, rptrs = self._peer[which]
       rank = dist.get_rank()
