@@ -638,11 +638,12 @@ static int reduced_buffer(cg_ctx* c, Model* m) {
 }
 static long long peer_slice(const Model* m, int world) { return ((m->total + world - 1) / world + 3) / 4 * 4; }
 static int launch_peer_sum(cg_ctx* c, const PeerPtrs& pp, int world, float* out, long long first, long long n, cudaStream_t st) {
-  long long g = (n / 4 + 127) / 128;
-  const int grid = (int)(g < 1 ? 1 : (g > 148 * 2 ? 148 * 2 : g));
-  if (world == 2) peer_sum_kernel<2><<<grid, 128, 0, st>>>(pp, out, first, n);
-  else if (world == 4) peer_sum_kernel<4><<<grid, 128, 0, st>>>(pp, out, first, n);
-  else peer_sum_kernel<8><<<grid, 128, 0, st>>>(pp, out, first, n);
+  static const int ctas = getenv("CG_PEER_CTAS") ? atoi(getenv("CG_PEER_CTAS")) : 64;
+  long long g = (n / 4 + 63) / 64;
+  const int grid = (int)(g < 1 ? 1 : (g > ctas ? ctas : g));
+  if (world == 2) peer_sum_kernel<2, 4><<<grid, 64, 0, st>>>(pp, out, first, n);
+  else if (world == 4) peer_sum_kernel<4, 2><<<grid, 64, 0, st>>>(pp, out, first, n);
+  else peer_sum_kernel<8, 1><<<grid, 64, 0, st>>>(pp, out, first, n);
   return post_launch(c, "peer_sum");
 }
 // one-shot: reduced (read by cg_apply_update_reduced) = sum over ranks r = 0 .. world-1 of peer_ptrs[r][0 .. num_params),
@@ -679,9 +680,12 @@ extern "C" int cg_peer_all_gather(cg_ctx* c, int which, const void* const* reduc
   CK(peer_ptrs(reduced_peer_ptrs_host, world, pp));
   if (rank < 0 || rank >= world || !m->gr) return set_err("cg_peer_all_gather: bad rank or no reduced buffer (cg_set_reduced_buffer)");
   const long long slice = peer_slice(m, world);
-  long long g = (slice / 4 + 127) / 128;
-  const int gx = (int)(g < 1 ? 1 : (g > 40 ? 40 : g));
-  peer_gather_kernel<<<dim3(gx, world), 128, 0, (cudaStream_t)cuda_stream>>>(pp, m->gr, slice, m->total, rank);
+  static const int ctas = getenv("CG_PEER_CTAS") ? atoi(getenv("CG_PEER_CTAS")) : 64;
+  long long g = (slice / 4 + 63) / 64;
+  int gx = ctas / world;
+  if (gx < 1) gx = 1;
+  if (gx > g) gx = (int)g;
+  peer_gather_kernel<<<dim3(gx, world), 64, 0, (cudaStream_t)cuda_stream>>>(pp, m->gr, slice, m->total, rank);
   return post_launch(c, "peer_gather");
 }
 // the buffer cg_apply_update_reduced reads: caller-provided (peer-mapped, >= num_params + 4 floats) or, with NULL, the

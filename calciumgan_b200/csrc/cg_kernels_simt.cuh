@@ -1031,30 +1031,44 @@ __global__ void __launch_bounds__(256) metrics8_kernel(const float* __restrict__
 // Data-parallel gradient exchange over NVLink peer memory (no reference counterpart): every rank's flat
 // gradient buffer is mapped into every other rank (symmetric memory); this kernel pulls the W buffers with 16-byte
 // peer loads and writes their sum, always added in rank order 0 .. W-1 so that all ranks produce bit-identical results.
-// Footprint by design: 128 threads, < 64 registers, no shared memory -- it fits beside a resident tcgen05 GEMM CTA on
-// every SM, so it runs UNDER the GEMMs of the next sub-step instead of waiting for an SM to drain (an NCCL all-reduce
-// CTA does not fit beside them and serialises with the persistent kernels).
+// Footprint by design: 64 threads (<= 128 registers each = 8 K of the ~11.7 K registers a resident tcgen05 GEMM CTA leaves
+// free), no shared memory -- a CTA of it fits beside a GEMM CTA, so the exchange runs UNDER the GEMMs of the next
+// sub-step's generator forward instead of waiting for an SM to drain.
 struct PeerPtrs { const float* p[8]; };
-// out[first .. first + n) = sum_r peers[r][first .. first + n)   (first % 4 == 0)
-template <int W>
-__global__ void __launch_bounds__(128) peer_sum_kernel(const __grid_constant__ PeerPtrs peers, float* __restrict__ out_all,
+// out[first .. first + n) = sum_r peers[r][first .. first + n)   (first % 4 == 0). Few CTAs, U vectors per peer in flight
+// per thread: the kernel shares every SM it lands on with a GEMM CTA, so it is sized to disturb few of them.
+template <int W, int U>
+__global__ void __launch_bounds__(64) peer_sum_kernel(const __grid_constant__ PeerPtrs peers, float* __restrict__ out_all,
                                                        long long first, long long n) {
   PeerPtrs pp = peers;
 #pragma unroll
   for (int r = 0; r < W; ++r) pp.p[r] += first;
   float* out = out_all + first;
   const long long n4 = n >> 2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 v[W];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
+    float4 v[U][W];
 #pragma unroll
-    for (int r = 0; r < W; ++r)
-      asm volatile("ld.global.relaxed.sys.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(v[r].x), "=f"(v[r].y), "=f"(v[r].z), "=f"(v[r].w)
-                   : "l"(reinterpret_cast<const float4*>(pp.p[r]) + i));
-    float4 a = v[0];
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
 #pragma unroll
-    for (int r = 1; r < W; ++r) { a.x += v[r].x; a.y += v[r].y; a.z += v[r].z; a.w += v[r].w; }
-    reinterpret_cast<float4*>(out)[i] = a;
+        for (int r = 0; r < W; ++r)
+          asm volatile("ld.global.relaxed.sys.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(v[u][r].x), "=f"(v[u][r].y), "=f"(v[u][r].z), "=f"(v[u][r].w)
+                       : "l"(reinterpret_cast<const float4*>(pp.p[r]) + i));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        float4 a = v[u][0];
+#pragma unroll
+        for (int r = 1; r < W; ++r) { a.x += v[u][r].x; a.y += v[u][r].y; a.z += v[u][r].z; a.w += v[u][r].w; }
+        reinterpret_cast<float4*>(out)[i] = a;
+      }
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) {
     const long long i = (n4 << 2) + threadIdx.x;
@@ -1066,7 +1080,7 @@ __global__ void __launch_bounds__(128) peer_sum_kernel(const __grid_constant__ P
 }
 // second phase of the two-phase exchange: slice s of the reduced gradient was summed by rank s; every rank copies the
 // W - 1 slices it does not own from their owners' (peer-mapped) reduced buffers into its own. blockIdx.y = slice.
-__global__ void __launch_bounds__(128) peer_gather_kernel(const __grid_constant__ PeerPtrs peers, float* __restrict__ out,
+__global__ void __launch_bounds__(64) peer_gather_kernel(const __grid_constant__ PeerPtrs peers, float* __restrict__ out,
                                                           long long slice, long long n, int rank) {
   const int s = blockIdx.y;
   if (s == rank) return;
@@ -1077,11 +1091,18 @@ __global__ void __launch_bounds__(128) peer_gather_kernel(const __grid_constant_
   const float* src = peers.p[s] + first;
   float* dst = out + first;
   const long long n4 = cnt >> 2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 v;
-    asm volatile("ld.global.relaxed.sys.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(reinterpret_cast<const float4*>(src) + i));
-    reinterpret_cast<float4*>(dst)[i] = v;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (i0 + u * stride < n4)
+        asm volatile("ld.global.relaxed.sys.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                     : "l"(reinterpret_cast<const float4*>(src) + i0 + u * stride));
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (i0 + u * stride < n4) reinterpret_cast<float4*>(dst)[i0 + u * stride] = v[u];
   }
   if (blockIdx.x == 0 && threadIdx.x < (int)(cnt & 3)) dst[(n4 << 2) + threadIdx.x] = src[(n4 << 2) + threadIdx.x];
 }
