@@ -136,6 +136,10 @@ struct RsParams {
   // (B, L/4, 4*Cp) view and the weights are two tap-shifted copies of the kernel. An N = 64 MMA reads 4 KB of
   // activations for 32 clk of math (shared-memory bound); N = 128 does twice the math on the same 4 KB.
   int row_pairs;                                   // 1: PhaseShuffle scatter / bias index fold the column back to a channel
+  // Merged output phases of a transposed-form GEMM with 64 output channels (tensor-core path): both phases read the same
+  // input rows, so one N = 128 MMA per input window computes [phase 0 | phase 1] with the two phases' taps stacked in the
+  // weight tile (13 windows instead of 2 x 12 taps). Column half = output phase; o_phase_col keeps the phase offset.
+  int merged_phases;
   float flop_scale;                                // algorithmic / issued FLOPs (the shifted copies add zero taps); 0 = 1
   int dbg;                                         // timing experiments only
   float* sumsq;                                    // optional: sumsq[b] += sum of squares of the fp32 results of sample b

@@ -109,6 +109,8 @@ struct cg_ctx {
   void *Wf_g[NL + 1], *Wb_g[NL + 1];     // generator convT: forward [Cout][K*Cin_p], bwd-data [Cin][K*Cout_p]
   void *Wf_d1, *Wb_d1;                   // generator output dense: [C][Cp], transposed
   void* Wf2_d[NL + 1];                   // critic conv, row-pair form (64 output channels): [2*64][(K+2)*Cin_p], else null
+  void* Wb2_d[NL + 1];                   // critic conv data gradient, merged output phases (64 input channels): [2*64][K2*Cout_p], else null
+  int mp_emin = 0, mp_K2 = 0;            // merged phases: first input-window shift and number of windows (K = 24: -6, 13)
   // critic activations (capacity 3*Bmax)
   void *X[NL + 1], *H[NL + 1], *DX[NL + 1], *DA[NL + 1];
   void* V5;                                // gradient penalty: linearised forward output of the last conv layer (Bmax samples)
@@ -290,10 +292,12 @@ static int launch_wgrad_raw(cg_ctx* c, WgParams p) {
 }
 
 static void add_pack(PackOps& ops, const float* src, void* dst, int N, int n_real, int nseg, int Cp, int c_real,
-                     long long sk, long long sn, long long sc, long long ld = 0) {
+                     long long sk, long long sn, long long sc, long long ld = 0, int k0 = 0, int kstep = 1, int slot0 = 0,
+                     int slotstep = 1) {
   PackOp& o = ops.op[ops.n++];
   o.src = src; o.dst = dst; o.N = N; o.n_real = n_real; o.nseg = nseg; o.Cp = Cp; o.c_real = c_real;
   o.sk = sk; o.sn = sn; o.sc = sc; o.ld = ld ? ld : (long long)nseg * Cp;
+  o.k0 = k0; o.kstep = kstep; o.slot0 = slot0; o.slotstep = slotstep;
 }
 
 static void* off(cg_ctx* c, void* base, long long elems) { return (char*)base + elems * c->esz; }
@@ -314,6 +318,16 @@ static int repack(cg_ctx* c, int which) {
         for (int g = 0; g < 2; ++g)
           add_pack(ops, w, off(c, c->Wf2_d[l], (long long)g * 64 * ld2 + 2LL * g * cip), cop, co, K, cip, ci, (long long)ci * co, 1,
                    co, ld2);
+      }
+      if (c->Wb2_d[l]) {   // merged phases: rows [g*64, g*64+64) = the taps of output phase g, each in its input window's slot
+        const int padL = (K - 2) / 2;
+        const long long ld2 = (long long)c->mp_K2 * cop;
+        for (int g = 0; g < 2; ++g) {
+          const int k0 = (padL & 1) == g ? 0 : 1;                    // first tap with (padL - k) & 1 == g
+          const int d0 = padL - k0, slot0 = ((d0 + g) >> 1) - c->mp_emin;
+          add_pack(ops, w, off(c, c->Wb2_d[l], (long long)g * 64 * ld2), cip, ci, (K - k0 + 1) / 2, cop, co, (long long)ci * co, co, 1,
+                   ld2, k0, 2, slot0, -1);
+        }
       }
     }
   } else {
@@ -342,6 +356,13 @@ static bool row_pairs_apply(const cg_ctx* c, int l) {
   return c->dcp[l] == 64 && c->dl[l] % 256 == 0 && c->K + 2 <= CG_MAX_SEG;
 }
 
+// Data gradient of critic conv l with merged output phases (RsParams.merged_phases): 64 (padded) input channels, tensor-
+// core path, whole 128-row blocks per sample.
+static bool merged_phases_apply(const cg_ctx* c, int l) {
+  if (!c->use_tc || getenv("CG_NO_MERGED_PHASES") || l < 2) return false;
+  return c->dcp[l - 1] == 64 && c->dl[l] >= 128 && c->dl[l] % 128 == 0 && c->mp_K2 <= 32;
+}
+
 // one-pass Adam + re-pack: GEMM kernels as 32 x 32 tiles per tap, everything between them as element-wise ranges
 static void build_adam_plans(cg_ctx* c) {
   for (int which = 0; which < 2; ++which) {
@@ -349,10 +370,11 @@ static void build_adam_plans(cg_ctx* c) {
     memset(&pl, 0, sizeof(pl));
     Model& M = which == CG_GENERATOR ? c->gen : c->dis;
     std::vector<bool> is_gemm(M.params.size(), false);
-    auto add_tensor = [&](int idx, int K, int A, int B, int Ap, int Bp, void* direct, void* trans, void* trans2 = nullptr) {
+    auto add_tensor = [&](int idx, int K, int A, int B, int Ap, int Bp, void* direct, void* trans, void* trans2 = nullptr,
+                          void* direct2 = nullptr) {
       AdamTensor& t = pl.t[pl.nt++];
       t.off = M.params[idx].offset; t.K = K; t.A = A; t.B = B; t.Ap = Ap; t.Bp = Bp; t.direct = direct; t.trans = trans;
-      t.trans2 = trans2;
+      t.trans2 = trans2; t.direct2 = direct2; t.d2_emin = c->mp_emin; t.d2_K2 = c->mp_K2;
       t.tiles_a = (A + 31) / 32; t.tiles_b = (B + 31) / 32;
       t.item0 = pl.tile_items;
       pl.tile_items += (long long)K * t.tiles_a * t.tiles_b;
@@ -360,7 +382,8 @@ static void build_adam_plans(cg_ctx* c) {
     };
     if (which == CG_DISCRIMINATOR) {
       for (int l = 1; l <= NL; ++l)   // (K, Cin, Cout): a = ci, b = co; Wb_d = [ci][k*Coutp + co], Wf_d = [co][k*Cinp + ci]
-        add_tensor(2 * (l - 1), c->K, c->dc[l - 1], c->dc[l], c->dcp[l - 1], c->dcp[l], c->Wb_d[l], c->Wf_d[l], c->Wf2_d[l]);
+        add_tensor(2 * (l - 1), c->K, c->dc[l - 1], c->dc[l], c->dcp[l - 1], c->dcp[l], c->Wb_d[l], c->Wf_d[l], c->Wf2_d[l],
+                   c->Wb2_d[l]);
     } else {
       for (int i = 1; i <= NL; ++i)   // (K, 1, Cout, Cin): a = co, b = ci; Wf_g = [co][k*Cinp + ci], Wb_g = [ci][k*Coutp + co]
         add_tensor(c->g_k[i], c->K, c->gc[i], c->gc[i - 1], c->gcp[i], c->gcp[i - 1], c->Wf_g[i], c->Wb_g[i]);
@@ -485,9 +508,15 @@ extern "C" int cg_create(const cg_config* cfg, cg_ctx** out) {
     DA_(c->Wf_g[l], (size_t)c->gcp[l] * c->K * c->gcp[l - 1] * es);
     DA_(c->Wb_g[l], (size_t)c->gcp[l - 1] * c->K * c->gcp[l] * es);
   }
+  {
+    const int padL = (c->K - 2) / 2, dlo = padL - (c->K - 1);
+    c->mp_emin = (dlo + (dlo & 1)) >> 1;                              // K = 24: windows e = -6 .. 6
+    c->mp_K2 = ((padL + (padL & 1)) >> 1) - c->mp_emin + 1;
+  }
   for (int l = 1; l <= NL; ++l) {
-    c->Wf2_d[l] = nullptr;
+    c->Wf2_d[l] = c->Wb2_d[l] = nullptr;
     if (row_pairs_apply(c, l)) DA_(c->Wf2_d[l], (size_t)128 * (c->K + 2) * c->dcp[l - 1] * es);
+    if (merged_phases_apply(c, l)) DA_(c->Wb2_d[l], (size_t)128 * c->mp_K2 * c->dcp[l] * es);
   }
   DA_(c->Wf_d1, (size_t)c->gcp[NL] * c->gcp[NL] * es);
   DA_(c->Wb_d1, (size_t)c->gcp[NL] * c->gcp[NL] * es);
@@ -1050,7 +1079,7 @@ static RsParams d_dgrad_params(cg_ctx* c, int l, int b0, int nb, void* out);
 static bool d_dgrad_ps_fusable(cg_ctx* c, int l, int Bt) {
   if ((c->dbg_flags & CG_DEBUG_NO_PS_BWD_FUSE) || !c->use_tc || c->tc.force_v1 || !c->tc.use_pair || c->cfg.phase_m > 10) return false;
   const RsParams p = d_dgrad_params(c, l, 0, Bt, nullptr);
-  return tc_rsgemm_supported(p) && tc_rsgemm2_supported(p) && p.seg.nphase == 2;
+  return tc_rsgemm_supported(p) && tc_rsgemm2_supported(p) && (p.seg.nphase == 2 || p.merged_phases);
 }
 static int d_dgrad_layer(cg_ctx* c, int l, int b0, int nb, void* out, float* sumsq = nullptr, const void* ps_mask = nullptr,
                          int group_b = 0, const int32_t* sh = nullptr, int groups = 0) {
@@ -1072,6 +1101,22 @@ static RsParams d_dgrad_params(cg_ctx* c, int l, int b0, int nb, void* out) {
   p.out = out; p.o_bs = (long long)c->dl[l - 1] * c->dcp[l - 1]; p.o_rs = 2 * c->dcp[l - 1]; p.o_phase_col = c->dcp[l - 1];
   p.B = nb; p.Q = c->dl[l]; p.N = c->dcp[l - 1]; p.n_real = c->dc[l - 1]; p.Kc = c->dcp[l]; p.k_real = c->dc[l]; p.epi = EPI_NONE;
   p.seg = seg_transposed(c->K, c->dcp[l]);
+  if (c->Wb2_d[l] && !c->tc.force_v1) {
+    // merged phases: one N = 128 GEMM, columns [phase 0 | phase 1] = the contiguous (B, L/2, 2*Cp) output row; input
+    // window j (shift emin + j) carries phase 0's tap k = padL - 2e and phase 1's tap k = padL + 1 - 2e
+    p.W = c->Wb2_d[l]; p.w_ld = c->mp_K2 * c->dcp[l];
+    p.N = 2 * c->dcp[l - 1];
+    p.merged_phases = 1;
+    p.flop_scale = (float)c->K / (float)c->mp_K2;
+    memset(&p.seg, 0, sizeof(p.seg));
+    p.seg.nphase = 1;
+    p.seg.nseg[0] = c->mp_K2;
+    for (int j = 0; j < c->mp_K2; ++j) {
+      p.seg.shift[0][j] = (short)(c->mp_emin + j);
+      p.seg.acol[0][j] = 0;
+      p.seg.wk[0][j] = j * c->dcp[l];
+    }
+  }
   return p;
 }
 
@@ -1207,7 +1252,15 @@ static int fetch_scalars(cg_ctx* c, int slot, int flags, float* scalars_host) {
 static int launch_metrics(cg_ctx* c, const float* real, float* acc, long long rows, const float* fake = nullptr) {
   if (!fake) fake = c->FAKE32;
   CK(glue(c, 8.0 * rows * c->C));
-  if (c->C % 2 == 0 && c->C <= 128 && ((reinterpret_cast<uintptr_t>(real) | reinterpret_cast<uintptr_t>(fake)) & 7) == 0)
+  if (((reinterpret_cast<uintptr_t>(real) | reinterpret_cast<uintptr_t>(fake)) & 15) == 0 && c->C <= 256 && !getenv("CG_NO_METRICS_SMEM")) {
+    const size_t smem = (size_t)2 * 32 * c->C * sizeof(float);
+    if (smem > 48 * 1024)   // per device, so not cached in a process-wide static; once per step
+      CU(cudaFuncSetAttribute(metrics_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    const long long nchunks = (rows + 31) / 32;
+    const int grid = (int)(nchunks < 148 * 8 ? nchunks : 148 * 8);
+    metrics_smem_kernel<<<grid, 256, smem, c->stream>>>(real, fake, acc, rows, c->C, c->cfg.signals_min, c->cfg.signals_max,
+                                                        c->cfg.normalize);
+  } else if (c->C % 2 == 0 && c->C <= 128 && ((reinterpret_cast<uintptr_t>(real) | reinterpret_cast<uintptr_t>(fake)) & 7) == 0)
     metrics8_kernel<<<grid_for(rows * 8, 256, 148 * 8), 256, 0, c->stream>>>(real, fake, acc, rows, c->C, c->cfg.signals_min,
                                                                             c->cfg.signals_max, c->cfg.normalize);
   else

@@ -218,7 +218,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict_
 }
 
 // all packed copies of one model in ONE launch: blockIdx.y selects the op
-struct PackOp { const float* src; void* dst; int N, n_real, nseg, Cp, c_real; long long sk, sn, sc; long long ld; };   // ld: destination row pitch (elements)
+// ld: destination row pitch (elements); op tap i < nseg reads source tap k0 + i*kstep and writes tap slot slot0 + i*slotstep
+struct PackOp { const float* src; void* dst; int N, n_real, nseg, Cp, c_real; long long sk, sn, sc; long long ld; int k0, kstep, slot0, slotstep; };
 struct PackOps { int n; PackOp op[24]; };
 // grid (x = 32x32 tiles of the (n, c) plane, y = tap, z = op): reads follow the source's fastest axis, writes follow
 // the destination's (c), transposing through shared memory when they differ.
@@ -226,8 +227,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackOps ops) {
   __shared__ float tile[32][33];
   const PackOp& o = ops.op[blockIdx.z];
-  const int k = blockIdx.y;
-  if (k >= o.nseg) return;
+  if ((int)blockIdx.y >= o.nseg) return;
+  const int k = o.k0 + (int)blockIdx.y * o.kstep, slot = o.slot0 + (int)blockIdx.y * o.slotstep;
   const int ct = (o.Cp + 31) / 32, ntl = (o.N + 31) / 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
   T* dst = reinterpret_cast<T*>(o.dst);
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + ty + 8 * j, c = c0 + tx;
-      if (n < o.N && c < o.Cp) dst[(long long)n * o.ld + (long long)k * o.Cp + c] = Elem<T>::from_f(tile[n - n0][c - c0]);
+      if (n < o.N && c < o.Cp) dst[(long long)n * o.ld + (long long)slot * o.Cp + c] = Elem<T>::from_f(tile[n - n0][c - c0]);
     }
   }
 }
@@ -1123,6 +1124,80 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
     dst[i * row_elems + (n4 << 2) + threadIdx.x] = src[r * row_elems + (n4 << 2) + threadIdx.x];
 }
 
+// Same statistics, staged through shared memory: a block copies 32 consecutive rows of both tensors (32 * C floats, a
+// multiple of 16 bytes for every C) with fully coalesced 16-byte loads, then 8 lanes per row reduce from shared memory.
+// The unpadded rows are 408 bytes at C = 102, so per-row global loads can be at most 8 bytes wide and leave half of
+// every 32-byte sector request unused; this form reads each byte once at full width (measured 102 -> ~45 us per step).
+__global__ void __launch_bounds__(256) metrics_smem_kernel(const float* __restrict__ real, const float* __restrict__ fake,
+                                                           float* __restrict__ acc, long long rows, int C, float smin,
+                                                           float smax, int normalize) {
+  extern __shared__ __align__(16) float msm[];   // [2][32 * C]
+  const float sc = normalize ? (smax - smin) : 1.f, of = normalize ? smin : 0.f;
+  const int sub = threadIdx.x & 7, rloc = threadIdx.x >> 3;   // 32 rows x 8 lanes
+  const int chunk_f = 32 * C, chunk_v = chunk_f >> 2;
+  const long long nchunks = (rows + 31) >> 5;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const long long r0 = ch << 5;
+    const int nrow = rows - r0 < 32 ? (int)(rows - r0) : 32;
+    const int nv = (nrow * C) >> 2, tail = (nrow * C) & 3;
+    __syncthreads();   // the previous chunk has been consumed
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const float* src = (w == 0 ? real : fake) + r0 * C;
+      float4* dst = reinterpret_cast<float4*>(msm + w * chunk_f);
+      for (int i = threadIdx.x; i < nv; i += 256) dst[i] = reinterpret_cast<const float4*>(src)[i];
+      if (threadIdx.x < tail) msm[w * chunk_f + (nv << 2) + threadIdx.x] = src[(nv << 2) + threadIdx.x];
+    }
+    (void)chunk_v;
+    __syncthreads();
+    float st[2][4];
+    const bool rok = rloc < nrow;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const float* x = msm + w * chunk_f + rloc * C;
+      float mn = INFINITY, mx = -INFINITY, s = 0.f;
+      if (rok)
+        for (int c = sub; c < C; c += 8) {
+          const float v = x[c] * sc + of;
+          mn = fminf(mn, v); mx = fmaxf(mx, v); s += v;
+        }
+#pragma unroll
+      for (int o = 4; o >= 1; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+      }
+      const float mean = s / C;
+      float q = 0.f;
+      if (rok)
+        for (int c = sub; c < C; c += 8) {
+          const float d = x[c] * sc + of - mean;
+          q = fmaf(d, d, q);
+        }
+#pragma unroll
+      for (int o = 4; o >= 1; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      st[w][0] = mn; st[w][1] = mx; st[w][2] = mean; st[w][3] = sqrtf(q / C);
+    }
+    if (rok && sub == 0) {
+      a0 += (st[0][0] - st[1][0]) * (st[0][0] - st[1][0]);
+      a1 += (st[0][1] - st[1][1]) * (st[0][1] - st[1][1]);
+      a2 += (st[0][2] - st[1][2]) * (st[0][2] - st[1][2]);
+      a3 += (st[0][3] - st[1][3]) * (st[0][3] - st[1][3]);
+    }
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+  __shared__ float red[8][4];
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = a0; red[threadIdx.x >> 5][1] = a1; red[threadIdx.x >> 5][2] = a2; red[threadIdx.x >> 5][3] = a3; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(&acc[threadIdx.x], t / (float)rows);
+  }
+}
+
 // out = x*(max-min)+min (gan/utils/utils.py:30-32)
 __global__ void denorm_kernel(const float* __restrict__ x, float* __restrict__ out, long long total, float smin,
                               float smax) {
@@ -1216,6 +1291,8 @@ struct AdamTensor {
   void* direct;           // [a][k*Bp + b]
   void* trans;            // [b][k*Ap + a]
   void* trans2;           // optional row-pair copy [g*Bp + b][(k + 2g)*Ap + a], g = 0, 1, row pitch (K + 2)*Ap (see RsParams.row_pairs)
+  void* direct2;          // optional merged-phase copy [g*Ap + a][j*Bp + b]: tap k belongs to output phase g and input window j
+  int d2_emin, d2_K2;     //   (RsParams.merged_phases): d = padL - k, g = d & 1, j = (d + g)/2 - emin, row pitch K2*Bp
   int tiles_a, tiles_b;
   long long item0;        // first work item of this tensor
 };
@@ -1262,6 +1339,10 @@ __global__ void __launch_bounds__(256) adam_pack_kernel(float* __restrict__ w, f
           adam_elem(wi, mi, vi, g[i] * gscale, lr_t, b1, b2, eps);
           m[i] = mi; v[i] = vi; w[i] = wi;
           direct[((long long)a * t.K + k) * t.Bp + b] = Elem<T>::from_f(wi);
+          if (t.direct2) {
+            const int d = (t.K - 2) / 2 - k, g2 = d & 1, j = ((d + g2) >> 1) - t.d2_emin;
+            reinterpret_cast<T*>(t.direct2)[((long long)(g2 * t.Ap + a) * t.d2_K2 + j) * t.Bp + b] = Elem<T>::from_f(wi);
+          }
         }
         tile[ty + 8 * j][tx] = wi;
       }

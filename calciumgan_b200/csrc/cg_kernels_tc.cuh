@@ -342,8 +342,9 @@ __device__ __forceinline__ void epi_rows_ps(const RsParams& p, int b, int q0, in
 // weight rows and the staged bias are zero.
 template <int EPI>
 __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_cols, int BN, int n_base,
-                                               const EpiRows& R, const float* bias_s, uint8_t* stg, uint8_t* stg_partner,
-                                               int lq, int lane, int half, int ps_q0 = 0, int ps_s = 0, bool need_x = false) {
+                                               EpiRows& R, const float* bias_s, uint8_t* stg, uint8_t* stg_partner,
+                                               int lq, int lane, int half, int ps_q0 = 0, int ps_s = 0, bool need_x = false,
+                                               int ps_b = 0) {
   // ps_q0: time index of tile row 0 (single-sample blocks); ps_s: this sample's PhaseShuffle shift
   bf16* out = reinterpret_cast<bf16*>(p.out);
   bf16* psx = reinterpret_cast<bf16*>(p.ps_out);
@@ -382,7 +383,11 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
     if (half == 0 && p.mu && R.my_ok) { p.mu[R.my_row] = ln_mean; p.rstd[R.my_row] = ln_rstd; }
   }
   for (int c0 = half * 32; c0 < BN; c0 += 64) {
-    const int n0 = n_base + c0;
+    int n0 = n_base + c0;
+    if (EPI == EPI_PS_MASK && p.merged_phases) {   // column half = output phase: this chunk's rows follow that phase's map
+      epi_rows_ps(p, ps_b, ps_q0, n0 >> 6, ps_s, lq, lane, R);
+      n0 &= 63;
+    }
     if (EPI == EPI_MASK || EPI == EPI_PS_MASK) {   // coalesced, register-free read of the slope source (same indexing as out) into the staging tile
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -394,6 +399,10 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
     uint32_t v[32];
     tmem_ld32(taddr + c0, v);
     tmem_ld_wait();
+    if (c0 + 32 > BN) {   // BN is a multiple of 16, not of 32 (e.g. 112 for 102 channels): columns past the tile are not ours
+#pragma unroll
+      for (int j = 16; j < 32; ++j) v[j] = 0u;
+    }
     if (EPI == EPI_PS_MASK && need_x) {   // reflected rows meet their partners (bias tile area: 2 halves x 2 x 5 slots x 32 floats)
       const uint32_t xb = smem_u32(bias_s) + half * 1280 + ((c0 >> 6) & 1) * 640;
       if (R.x_src >= 0) {
@@ -754,6 +763,7 @@ struct RsTc2Params {
   RsParams p;
   int BN, n_tiles, m_tiles, MB, blocks_per_sample, total_blocks, kchunks;
   int box_rows, box_bytes, slab_bytes, slab_stages, b_stages, double_acc;
+  int acc_stride;       // TMEM columns between the two accumulator buffers (BN rounded up to 32)
   int dbg_nk;           // timing experiment: K steps per chunk (0 = all)
   int dbg_flags;        // timing experiment (slab mode): 1 no epilogue, 2 no weight loads, 4 no activation loads
   int tps;              // taps per weight stage (pair kernel): more MMAs per barrier round-trip for narrow N
@@ -911,7 +921,7 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1) ^ 1);
         CG_DBG_ADD(2, tq);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * P.acc_stride;
         uint32_t accum = 0;
         for (int kc = 0; kc < P.kchunks; ++kc) {
           // K = 16 steps of this 64-channel chunk that hold real channels (the rest multiplies exact zeros: 102 -> 7 of 8)
@@ -1015,8 +1025,8 @@ rsgemm3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tq = CG_CLK();
       tc_fence_after();
       if (!(P.dbg_flags & 1))   // timing experiment bit 1: no epilogue
-        epilogue_block<EPI>(p, tmem_base + acc * BN, BN, nt * BN, R, bias_s, stg, stg_partner, lq, lane, half,
-                            (blk % P.blocks_per_sample) * 128, sft, need_x);
+        epilogue_block<EPI>(p, tmem_base + acc * P.acc_stride, BN, nt * BN, R, bias_s, stg, stg_partner, lq, lane, half,
+                            (blk % P.blocks_per_sample) * 128, sft, need_x, bq);
       if (warp == 2) CG_DBG_ADD(6, tq);
       tc_fence_before();
       __syncwarp();
@@ -1511,7 +1521,7 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   memset(&P, 0, sizeof(P));
   P.p = p;
   P.per_tap = p.Q < 128 ? 1 : 0;
-  if (p.epi == EPI_PS_MASK && (P.per_tap || p.seg.nphase != 2 || !p.mask || p.ps_w != 2 * p.Q))
+  if (p.epi == EPI_PS_MASK && (P.per_tap || (p.seg.nphase != 2 && !p.merged_phases) || !p.mask || p.ps_w != 2 * p.Q))
     return cg_tc_set_err("rsgemm3_tc: EPI_PS_MASK needs single-sample blocks (Q % 128 == 0) and the two-phase data-gradient form");
   int span = 0;
   for (int ph = 0; ph < p.seg.nphase; ++ph) {
@@ -1568,6 +1578,14 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   if (p.epi == EPI_BIAS_LN_LRELU) bestBN = p.N;   // the epilogue needs whole channel rows
   P.BN = bestBN;
   P.n_tiles = p.N / P.BN;
+  // One n-tile whose real channels end well before the 64-channel padding (102 of 128): issue N = 112 MMAs (any multiple
+  // of 16 is a legal cta_group::2 shape) instead of multiplying 26 all-zero weight rows -- 12% fewer tensor cycles on the
+  // generator's last conv-transpose and the critic's first data gradient.
+  if (P.n_tiles == 1 && !p.row_pairs && !p.merged_phases && !getenv("CG_TC_NO_TRIM")) {
+    const int trimmed = (p.n_real + 15) / 16 * 16;
+    if (trimmed >= 32 && trimmed < P.BN) P.BN = trimmed;
+  }
+  P.acc_stride = (P.BN + 31) / 32 * 32;
   P.double_acc = 1;
   P.slab_bytes = P.box_bytes;
   int groups_per_tile = 0;
@@ -1582,11 +1600,12 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   if (P.tps < 1) P.tps = 1;
   if (P.tps > 6) P.tps = P.BN <= 64 ? 12 : 6;   // N = 64: a whole 12-tap parity group per weight stage (measured 140 -> 131 us on conv1)
   if (P.per_tap && P.tps > 3) P.tps = 3;
-  if (p.row_pairs) {   // one weight stage per tap group (6-7 taps): measured 108 -> 97 us on conv1 forward (tps 4 -> 7)
-    P.tps = 1;
+  if (p.row_pairs || p.merged_phases) {   // few, equal weight stages per tap group (6-7 taps each): measured 108 -> 97 us on
+    int most = 1;                         // conv1 forward (tps 4 -> 7)
     for (int ph = 0; ph < p.seg.nphase; ++ph)
-      for (int g = 0; g < P.ngroups[ph]; ++g) if (P.grp[ph][g].nseg > P.tps) P.tps = P.grp[ph][g].nseg;
-    if (P.tps > 8) P.tps = 8;
+      for (int g = 0; g < P.ngroups[ph]; ++g) if (P.grp[ph][g].nseg > most) most = P.grp[ph][g].nseg;
+    const int nst = (most + 7) / 8;
+    P.tps = (most + nst - 1) / nst;
   }
   if (const char* e = getenv("CG_TC_TPS")) P.tps = atoi(e);
   if (const char* e = getenv("CG_TC_NK")) P.dbg_nk = atoi(e);
