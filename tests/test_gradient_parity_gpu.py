@@ -161,6 +161,15 @@ def test_gradients_on_imposed_branches_paper_architecture(mixed, B):
         {k: '%.2e' % v for k, v in rep.items()}))
 
 
+def test_gradients_on_imposed_branches_scaled_widths():
+  """BASELINE.json configs[3] widths (num_units 128, 512 channels: N = 640 / 512 tiles, layer norm over 640 channels
+  outside the GEMM epilogue, K chunks up to 640) at sequence length 512, bf16 tensor-core path: one critic step and one
+  generator step, every per-parameter gradient <= 2e-2 on the engine's branches."""
+  hp = O.HParams(signal_shape=(512, 512), num_units=128)
+  rep = run_masked(hp, 2, True, seed=81)
+  print('imposed-branch gradient parity (scaled widths, bf16): %s' % {k: '%.2e' % v for k, v in rep.items()})
+
+
 def test_gradients_on_imposed_branches_headline_batch_128():
   """BASELINE.json configs[1] exactly as benchmarked: batch 128, bf16 tensor-core path. The oracle is the same torch
   float64 code, evaluated on the CUDA device for this one case (a batch-128 float64 double backward takes minutes on
