@@ -1593,6 +1593,7 @@ static inline int tc_rsgemm3_launch(TcState* s, const RsParams& p, cudaStream_t 
   groups_per_tile *= P.kchunks;
   P.slab_stages = groups_per_tile <= 2 ? 4 : (groups_per_tile <= 4 ? 3 : 2);   // short K loops: prefetch the next tile's slabs
   if (p.row_pairs) P.slab_stages = 3;   // four short tap groups per 64-channel chunk
+  if (const char* e = getenv("CG_TC_SST")) { const int v = atoi(e); if (v >= 2 && v <= 6 && !P.per_tap) P.slab_stages = v; }   // tuning experiments
   // taps per weight stage: enough MMA time per stage (4 MMAs x BN/2 clk per tap) to cover a cross-CTA barrier round-trip
   int stage_clk = 1000;
   if (const char* e = getenv("CG_TC_STAGE_CLK")) stage_clk = atoi(e);
