@@ -132,6 +132,10 @@ struct cg_ctx {
   int64_t last_n_noise = 0, last_n_alpha = 0;
   std::vector<int32_t> last_shifts;
   int dbg_flags = 0;                       // CG_DEBUG_* (cfg.debug_flags | environment, fixed at cg_create)
+  // side stream for memory-bound work that has no consumer until the end of the step (signal metrics): a 128-thread
+  // block of it fits beside a resident tensor-core CTA, so it runs UNDER the generator's backward GEMMs
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // cg_prefetch_generator: the generator forward of the next sub-step has already run (data parallel overlap)
   struct { bool valid = false; int for_gen_step = 0, B = 0; const float* noise = nullptr; const float* alpha = nullptr; } pref;
   AdamPlan adam_plan[2];
@@ -418,6 +422,9 @@ extern "C" void cg_destroy(cg_ctx* c) {
     for (int b = 0; b < cg_ctx::NB; ++b)
       if (c->bucket_evt[w][b]) cudaEventDestroy(c->bucket_evt[w][b]);
   if (c->h_scal) cudaFreeHost(c->h_scal);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->side) cudaStreamDestroy(c->side);
   delete c;
 }
 
@@ -1423,6 +1430,33 @@ extern "C" int cg_critic_step(cg_ctx* c, const float* real, int B, const float* 
   return fetch_scalars(c, 0, flags, scalars_host);
 }
 
+// gan.py:32-41 on a side stream, forked from the main stream now (FAKE32 is final) and joined by side_metrics_join: the
+// metrics have no consumer before the scalars are read, and the kernel (no shared memory, 128-thread blocks) is small
+// enough to be resident beside the tensor-core CTAs of the backward pass instead of taking its own 70 us of the step
+static bool side_metrics_ok(cg_ctx* c, const float* real) {
+  return c->use_tc && !c->profiling && !getenv("CG_NO_SIDE_METRICS") && c->C % 2 == 0 && c->C <= 128 &&
+         ((reinterpret_cast<uintptr_t>(real) | reinterpret_cast<uintptr_t>(c->FAKE32)) & 7) == 0;
+}
+static int side_metrics_fork(cg_ctx* c, const float* real, float* acc, long long rows) {
+  if (!c->side) {
+    CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  }
+  CU(cudaMemsetAsync(acc, 0, 4 * 4, c->stream));
+  CU(cudaEventRecord(c->ev_fork, c->stream));
+  CU(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+  metrics8_kernel<<<grid_for(rows * 8, 128, 148 * 4), 128, 0, c->side>>>(real, c->FAKE32, acc, rows, c->C, c->cfg.signals_min,
+                                                                       c->cfg.signals_max, c->cfg.normalize);
+  CK(post_launch(c, "metrics_side"));
+  CU(cudaEventRecord(c->ev_join, c->side));
+  return 0;
+}
+static int side_metrics_join(cg_ctx* c) {
+  CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ generator step
 // generator forward of the generator step (wgan_gp.py:23-26): keeps everything its backward pass needs
 static int generator_step_generator_part(cg_ctx* c, int B, const float* noise) {
@@ -1432,8 +1466,10 @@ static int generator_step_generator_part(cg_ctx* c, int B, const float* noise) {
 static int generator_step_impl(cg_ctx* c, const float* real, int B, const float* noise, const int32_t* sh, int flags,
                                int slot) {
   if (!(flags & CG_FLAG_GEN_PREFETCHED)) CK(generator_step_generator_part(c, B, noise));
-  CK(d_forward(c, B, B, 1, sh));
   float* scal = c->d_scal + (size_t)slot * CG_NUM_SCALARS;
+  const bool side = real && side_metrics_ok(c, real);
+  if (side) CK(side_metrics_fork(c, real, scal + CG_S_MET_MIN, (long long)B * c->L));
+  CK(d_forward(c, B, B, 1, sh));
   gen_loss_kernel<<<1, 256, 0, c->stream>>>(c->scores, scal, B);
   CK(post_launch(c, "gen_loss"));
   fill_coef_kernel<<<(B + 255) / 256, 256, 0, c->stream>>>(c->coef, B, 1, -1.f / B);
@@ -1441,7 +1477,8 @@ static int generator_step_impl(cg_ctx* c, const float* real, int B, const float*
   CK(d_backward(c, B, B, 1, sh, 0, B));
   CU(cudaMemsetAsync(c->gen.g, 0, c->gen.total * 4, c->stream));
   CK(g_backward(c, B));
-  if (real) {
+  if (side) CK(side_metrics_join(c));
+  else if (real) {
     CU(cudaMemsetAsync(scal + CG_S_MET_MIN, 0, 4 * 4, c->stream));
     const long long rows = (long long)B * c->L;
     CK(launch_metrics(c, real, scal + CG_S_MET_MIN, rows));
