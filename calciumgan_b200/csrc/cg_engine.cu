@@ -1164,8 +1164,48 @@ static WgParams conv_wgrad_params(cg_ctx* c, int l, int Bt) {
   return w;
 }
 
-// all critic weight gradients from X[l-1] x DA[l] over Bt samples; biases from the first nb_bias samples
-static int d_wgrad(cg_ctx* c, int Bt, int nb_bias, int tail_from) {   // samples >= tail_from: head input = V5
+static bool side_ok(cg_ctx* c);
+static int side_fork(cg_ctx* c);
+static int side_join(cg_ctx* c);
+// bias gradients (column sums of DA[1..5] over the first nb_bias samples) on the side stream, under the GEMMs that follow
+static bool side_glue_ok(cg_ctx* c) {
+  if (!side_ok(c) || !c->bf || getenv("CG_NO_SIDE_GLUE")) return false;
+  for (int l = 1; l <= NL; ++l) if (c->dcp[l] / 8 > 128) return false;
+  return true;
+}
+static int side_colsum(cg_ctx* c, int nb_bias) {
+  ColsumOps ops;
+  ops.n = NL;
+  for (int l = 1; l <= NL; ++l) {
+    ops.op[l - 1].X = c->DA[l]; ops.op[l - 1].out = dgrad(c, 2 * (l - 1) + 1);
+    ops.op[l - 1].rows = (long long)nb_bias * c->dl[l]; ops.op[l - 1].Cp = c->dcp[l]; ops.op[l - 1].c_real = c->dc[l];
+  }
+  CK(side_fork(c));
+  colsum_light_kernel<bf16><<<dim3(148, ops.n), 128, 0, c->side>>>(ops);
+  return post_launch(c, "colsum_side");
+}
+static int side_head_wgrad(cg_ctx* c, int Bt, int nb_bias, int tail_from) {
+  const int tot = c->dl[NL] * c->dcp[NL] / 8;
+  dim3 hgrid(grid_for(tot, 128), Bt >= 64 ? 32 : 1);
+  CK(side_fork(c));
+  head_wgrad_kernel<bf16><<<hgrid, 128, 0, c->side>>>((const bf16*)c->X[NL], (const bf16*)c->V5, tail_from, c->coef, dgrad(c, 10),
+                                                     dgrad(c, 11), Bt, nb_bias, c->dl[NL], c->dc[NL], c->dcp[NL]);
+  return post_launch(c, "head_wgrad_side");
+}
+
+// all critic weight gradients from X[l-1] x DA[l] over Bt samples; biases from the first nb_bias samples.
+// side_glue: the bias column sums and the head's weight gradient already run on the side stream (side_colsum /
+// side_head_wgrad); they are joined after the first GEMM, before the first gradient bucket is declared complete
+static int d_wgrad(cg_ctx* c, int Bt, int nb_bias, int tail_from, bool side_glue = false) {   // samples >= tail_from: head input = V5
+  if (side_glue) {
+    for (int l = NL; l >= 1; --l) {
+      CK(launch_wgrad(c, conv_wgrad_params(c, l, Bt)));
+      if (l == NL) { CK(side_join(c)); CU(cudaEventRecord(c->bucket_evt[CG_DISCRIMINATOR][0], c->stream)); }
+      if (l == NL - 1) CU(cudaEventRecord(c->bucket_evt[CG_DISCRIMINATOR][1], c->stream));
+    }
+    CU(cudaEventRecord(c->bucket_evt[CG_DISCRIMINATOR][2], c->stream));
+    return 0;
+  }
   if (nb_bias > 0) {   // all five bias gradients in one launch
     ColsumOps ops;
     ops.n = NL;
@@ -1362,8 +1402,13 @@ static int critic_step_impl(cg_ctx* c, const float* real, int B, const float* no
                             const int32_t* sh, int flags, int slot, bool real_ready = false, bool want_fake32 = true) {
   CK(critic_forward_gp(c, real, B, noise, alpha, sh, slot, real_ready, true, want_fake32,
                        (flags & CG_FLAG_GEN_PREFETCHED) != 0));
+  // memory-bound by-products with no consumer before Adam go to the side stream, where their small CTAs are resident
+  // beside the tensor-core CTAs of the gradient-penalty passes: bias gradients now, the head's weight gradient once v_5 exists
+  const bool side = side_glue_ok(c);
+  if (side) CK(side_colsum(c, 2 * B));
   CK(gp_linearised_forward(c, B, 2, sh + 8));
-  CK(d_wgrad(c, 3 * B, 2 * B, 2 * B));
+  if (side) CK(side_head_wgrad(c, 3 * B, 2 * B, 2 * B));
+  CK(d_wgrad(c, 3 * B, 2 * B, 2 * B, side));
   if (!(flags & CG_FLAG_NO_UPDATE)) CK(cg_apply_update(c, CG_DISCRIMINATOR));
   return 0;
 }
@@ -1433,29 +1478,35 @@ extern "C" int cg_critic_step(cg_ctx* c, const float* real, int B, const float* 
 // gan.py:32-41 on a side stream, forked from the main stream now (FAKE32 is final) and joined by side_metrics_join: the
 // metrics have no consumer before the scalars are read, and the kernel (no shared memory, 128-thread blocks) is small
 // enough to be resident beside the tensor-core CTAs of the backward pass instead of taking its own 70 us of the step
+static bool side_ok(cg_ctx* c) { return c->use_tc && !c->profiling && !getenv("CG_NO_SIDE_STREAM"); }
 static bool side_metrics_ok(cg_ctx* c, const float* real) {
-  return c->use_tc && !c->profiling && !getenv("CG_NO_SIDE_METRICS") && c->C % 2 == 0 && c->C <= 128 &&
+  return side_ok(c) && !getenv("CG_NO_SIDE_METRICS") && c->C % 2 == 0 && c->C <= 128 &&
          ((reinterpret_cast<uintptr_t>(real) | reinterpret_cast<uintptr_t>(c->FAKE32)) & 7) == 0;
 }
-static int side_metrics_fork(cg_ctx* c, const float* real, float* acc, long long rows) {
+// side stream starts after everything enqueued on the main stream so far / main stream waits for the side stream
+static int side_fork(cg_ctx* c) {
   if (!c->side) {
     CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   }
-  CU(cudaMemsetAsync(acc, 0, 4 * 4, c->stream));
   CU(cudaEventRecord(c->ev_fork, c->stream));
   CU(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
-  metrics8_kernel<<<grid_for(rows * 8, 128, 148 * 4), 128, 0, c->side>>>(real, c->FAKE32, acc, rows, c->C, c->cfg.signals_min,
-                                                                       c->cfg.signals_max, c->cfg.normalize);
-  CK(post_launch(c, "metrics_side"));
-  CU(cudaEventRecord(c->ev_join, c->side));
   return 0;
 }
-static int side_metrics_join(cg_ctx* c) {
+static int side_join(cg_ctx* c) {
+  CU(cudaEventRecord(c->ev_join, c->side));
   CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
   return 0;
 }
+static int side_metrics_fork(cg_ctx* c, const float* real, float* acc, long long rows) {
+  CU(cudaMemsetAsync(acc, 0, 4 * 4, c->stream));
+  CK(side_fork(c));
+  metrics8_kernel<<<grid_for(rows * 8, 128, 148 * 4), 128, 0, c->side>>>(real, c->FAKE32, acc, rows, c->C, c->cfg.signals_min,
+                                                                       c->cfg.signals_max, c->cfg.normalize);
+  return post_launch(c, "metrics_side");
+}
+static int side_metrics_join(cg_ctx* c) { return side_join(c); }
 
 // ------------------------------------------------------------------------------------------ generator step
 // generator forward of the generator step (wgan_gp.py:23-26): keeps everything its backward pass needs

@@ -570,6 +570,41 @@ __global__ void __launch_bounds__(256) colsum_multi_kernel(const __grid_constant
   }
 }
 
+// The same sums with a footprint that fits beside a resident tensor-core CTA (128 threads, no shared memory): partial sums
+// go straight to the output with one atomicAdd per channel and thread. Runs on the engine's side stream under the GEMMs
+// of the gradient-penalty passes; nobody reads the bias gradients before Adam.
+template <typename T>
+__global__ void __launch_bounds__(128) colsum_light_kernel(const __grid_constant__ ColsumOps ops) {
+  constexpr int V = Vec16<T>::N;
+  const auto& o = ops.op[blockIdx.y];
+  const int cv = o.Cp / V;                 // host: cv <= 128
+  const int rpp = 128 / cv;
+  const int tr = threadIdx.x / cv, tc = threadIdx.x - tr * cv;
+  if (tr >= rpp) return;
+  const T* X = reinterpret_cast<const T*>(o.X);
+  float acc[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) acc[e] = 0.f;
+  const long long step = (long long)gridDim.x * rpp;
+  long long r = (long long)blockIdx.x * rpp + tr;
+  for (; r + step < o.rows; r += 2 * step) {
+    float t0[V], t1[V];
+    vload<T>(X + r * o.Cp + tc * V, t0);
+    vload<T>(X + (r + step) * o.Cp + tc * V, t1);
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] += t0[e] + t1[e];
+  }
+  for (; r < o.rows; r += step) {
+    float t0[V];
+    vload<T>(X + r * o.Cp + tc * V, t0);
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] += t0[e];
+  }
+#pragma unroll
+  for (int e = 0; e < V; ++e)
+    if (tc * V + e < o.c_real) atomicAdd(&o.out[tc * V + e], acc[e]);
+}
+
 // =============================================================================================
 // Generator layer-norm + LeakyReLU (calciumgan.py:45-46): one warp per (b,t) row, channels C of Cp.
 // =============================================================================================
