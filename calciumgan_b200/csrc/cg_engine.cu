@@ -1167,9 +1167,13 @@ static WgParams conv_wgrad_params(cg_ctx* c, int l, int Bt) {
 static bool side_ok(cg_ctx* c);
 static int side_fork(cg_ctx* c);
 static int side_join(cg_ctx* c);
-// bias gradients (column sums of DA[1..5] over the first nb_bias samples) on the side stream, under the GEMMs that follow
+// bias gradients (column sums of DA[1..5] over the first nb_bias samples) on the side stream, under the GEMMs that follow.
+// Opt-in experiment (CG_SIDE_GLUE=1): measured same-box 12.05 / 12.12 ms per step with it against 11.80 / 11.93 without --
+// the small CTAs do become resident beside the tensor-core CTAs, but they take issue slots and L2 bandwidth from kernels
+// that are statically partitioned over the SMs, and the slowest SM sets each GEMM's time. The signal metrics (one launch
+// per step, under the generator's backward pass) are the only by-product kept on the side stream.
 static bool side_glue_ok(cg_ctx* c) {
-  if (!side_ok(c) || !c->bf || getenv("CG_NO_SIDE_GLUE")) return false;
+  if (!side_ok(c) || !c->bf || !getenv("CG_SIDE_GLUE")) return false;
   for (int l = 1; l <= NL; ++l) if (c->dcp[l] / 8 > 128) return false;
   return true;
 }
