@@ -43,6 +43,15 @@ template <> __device__ __forceinline__ void load4<bf16>(const bf16* p, float (&v
   }
 }
 
+// Programmatic dependent launch for the memory-bound kernels between the GEMMs: a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may be scheduled while its predecessor drains; pdl_enter() lets ITS
+// successor do the same and then blocks until the predecessor has completed and its writes are visible. Must be the first
+// statement of every kernel launched that way; a no-op under a plain launch.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : CG_LRELU_ALPHA * x; }
 __device__ __forceinline__ float lrelu_slope(float h) { return h > 0.f ? 1.f : CG_LRELU_ALPHA; }
 

@@ -237,6 +237,20 @@ static int prof_end(cg_ctx* c) {
   return 0;
 }
 
+// Launch of a memory-bound kernel with the programmatic-dependent-launch attribute (its first statement is pdl_enter()):
+// the kernel is scheduled while its predecessor -- usually a persistent tensor-core kernel that triggered early -- drains.
+template <typename... KArgs, typename... Args>
+static inline void glue_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  static const bool pdl = getenv("CG_NO_GLUE_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface through cudaGetLastError in post_launch
+}
+
 // opens a timing record for the NEXT launch of a memory-bound kernel; `bytes` = its algorithmic HBM traffic
 static int glue(cg_ctx* c, double bytes) {
   if (!c->profiling) return 0;
@@ -838,7 +852,7 @@ static int g_forward(cg_ctx* c, const float* noise, int B, void* fake_slot = nul
                      void* xhat_slot = nullptr, const float* real = nullptr, const float* alpha = nullptr,
                      bool want32 = true, bool* xhat_done = nullptr) {
   CK(glue(c, (double)B * c->nd * 4 + (double)c->nd * c->w0 * c->nd * 4 + (double)B * c->w0 * c->gcp[0] * c->esz));
-  DISPATCH_T(c, dense0_forward_kernel<T><<<grid_for((long long)B * c->w0 * c->gcp[0]), 256, 0, c->stream>>>(
+  DISPATCH_T(c, glue_launch(dense0_forward_kernel<T>, dim3(grid_for((long long)B * c->w0 * c->gcp[0])), dim3(256), 0, c->stream, 
                     noise, gparam(c, 0), gparam(c, 1), (T*)c->HG[0], B, c->nd, c->w0, c->gcp[0]));
   CK(post_launch(c, "dense0_fwd"));
   for (int i = 1; i <= NL; ++i) {
@@ -860,7 +874,7 @@ static int g_forward(cg_ctx* c, const float* noise, int B, void* fake_slot = nul
       const int lpr = nvec > 16 ? 32 : (nvec > 8 ? 16 : 8);
 CK(glue(c, 2.0 * rows * c->gcp[i] * c->esz + 8.0 * rows));
 #define CG_LN(LPRV)                                                                                              \
-  DISPATCH_T(c, ln_lrelu_forward_kernel<T, LPRV><<<grid_for(rows * LPRV), 256, 0, c->stream>>>(                    \
+  DISPATCH_T(c, glue_launch(ln_lrelu_forward_kernel<T, LPRV>, dim3(grid_for(rows * LPRV)), dim3(256), 0, c->stream,                     \
                     (const T*)c->AG[i], gparam(c, c->g_gam[i]), gparam(c, c->g_bet[i]), (T*)c->HG[i], c->MU[i], \
                     c->RSTD[i], rows, c->gc[i], c->gcp[i]))
       if (lpr == 32) CG_LN(32); else if (lpr == 16) CG_LN(16); else CG_LN(8);
@@ -921,7 +935,7 @@ static int launch_colsum_ops(cg_ctx* c, const ColsumOps& ops) {
   double cs_bytes = 0;
   for (int i = 0; i < ops.n; ++i) cs_bytes += (double)ops.op[i].rows * ops.op[i].Cp * c->esz;
   CK(glue(c, cs_bytes));
-  DISPATCH_T(c, colsum_multi_kernel<T><<<grid, 256, 0, c->stream>>>(ops));
+  DISPATCH_T(c, glue_launch(colsum_multi_kernel<T>, dim3(grid), dim3(256), 0, c->stream, ops));
   return post_launch(c, "colsum");
 }
 static int launch_colsum(cg_ctx* c, const void* X, float* out, long long rows, int Cp, int c_real) {
@@ -944,7 +958,7 @@ static int g_backward(cg_ctx* c, int B) {
   const int Cp = c->gcp[NL];
   const long long rowsL = (long long)B * c->L;
   CK(glue(c, (double)rowsL * (2.0 * Cp * c->esz + 4.0 * c->C)));
-  DISPATCH_T(c, sigmoid_backward_kernel<T><<<grid_for(rowsL * Cp / (16 / c->esz)), 256, 0, c->stream>>>(
+  DISPATCH_T(c, glue_launch(sigmoid_backward_kernel<T>, dim3(grid_for(rowsL * Cp / (16 / c->esz))), dim3(256), 0, c->stream, 
                     (const T*)c->DX[0], c->FAKE32, (T*)c->DO, rowsL, c->C, Cp, c->cfg.normalize));
   CK(post_launch(c, "sigmoid_bwd"));
   {  // output dense: dW1[c_in][c_out] = sum_rows HG5[row,c_in] * DO[row,c_out]
@@ -975,7 +989,7 @@ static int g_backward(cg_ctx* c, int B) {
       const int blocks = grid_for(rows * lpr_b, 256, 148 * (maxv <= 1 ? 6 : 3));
 CK(glue(c, 4.0 * rows * c->gcp[i] * c->esz + 8.0 * rows));
 #define CG_LNB(LPRV, MV)                                                                                              \
-  DISPATCH_T(c, (ln_lrelu_backward_kernel<T, LPRV, MV>)<<<blocks, 256, 2 * c->gcp[i] * sizeof(float), c->stream>>>(    \
+  DISPATCH_T(c, glue_launch(ln_lrelu_backward_kernel<T, LPRV, MV>, dim3(blocks), dim3(256), 2 * c->gcp[i] * sizeof(float), c->stream,     \
                     (const T*)c->DHG[i], (const T*)c->AG[i], (const T*)c->HG[i], c->MU[i], c->RSTD[i],               \
                     gparam(c, c->g_gam[i]), (T*)c->DAG[i], ggrad(c, c->g_gam[i]), ggrad(c, c->g_bet[i]), rows,       \
                     c->gc[i], c->gcp[i]))
@@ -1001,7 +1015,7 @@ CK(glue(c, 4.0 * rows * c->gcp[i] * c->esz + 8.0 * rows));
   }
   const int tot = (c->nd + 1) * c->w0 * c->nd;
   CK(glue(c, 2.0 * B * c->w0 * c->gcp[0] * c->esz + (double)B * c->nd * 4));
-  DISPATCH_T(c, dense0_backward_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
+  DISPATCH_T(c, glue_launch(dense0_backward_kernel<T>, dim3(grid_for(tot)), dim3(256), 0, c->stream, 
                     c->Z, (const T*)c->DHG[0], (const T*)c->HG[0], ggrad(c, 0), ggrad(c, 1), B, c->nd, c->w0,
                     c->gcp[0]));
   CK(post_launch(c, "dense0_bwd"));
@@ -1076,7 +1090,7 @@ static int d_forward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh) {
     }
   }
   CK(glue(c, (double)Bt * c->dl[NL] * c->dcp[NL] * c->esz + 4.0 * c->dl[NL] * c->dc[NL]));
-  DISPATCH_T(c, head_forward_kernel<T><<<Bt, 256, 0, c->stream>>>((const T*)c->X[NL], dparam(c, 10), dparam(c, 11),
+  DISPATCH_T(c, glue_launch(head_forward_kernel<T>, dim3(Bt), dim3(256), 0, c->stream, (const T*)c->X[NL], dparam(c, 10), dparam(c, 11),
                                                                   c->scores, c->dl[NL], c->dc[NL], c->dcp[NL]));
   return post_launch(c, "head_fwd");
 }
@@ -1131,7 +1145,7 @@ static RsParams d_dgrad_params(cg_ctx* c, int l, int b0, int nb, void* out) {
 static int d_backward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh, int dx0_b0, int dx0_nb,
                       float* sumsq = nullptr) {   // sumsq: per-sample squared norm of dX0, fused into the last GEMM
   CK(glue(c, 2.0 * Bt * c->dl[NL] * c->dcp[NL] * c->esz + 4.0 * c->dl[NL] * c->dc[NL]));
-  DISPATCH_T(c, head_backward_kernel<T><<<grid_for((long long)Bt * c->dl[NL] * c->dcp[NL] / (16 / c->esz)), 256, 0, c->stream>>>(
+  DISPATCH_T(c, glue_launch(head_backward_kernel<T>, dim3(grid_for((long long)Bt * c->dl[NL] * c->dcp[NL] / (16 / c->esz))), dim3(256), 0, c->stream, 
                     (const T*)c->H[NL], dparam(c, 10), c->coef, (T*)c->DA[NL], Bt, c->dl[NL], c->dc[NL], c->dcp[NL]));
   CK(post_launch(c, "head_bwd"));
   for (int l = NL; l >= 2; --l) {
@@ -1142,7 +1156,7 @@ static int d_backward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh, i
     CK(d_dgrad_layer(c, l, 0, Bt, c->DX[l - 1]));
     const long long tot = (long long)Bt * c->dl[l - 1] * c->dcp[l - 1] / (16 / c->esz);
     CK(glue(c, 3.0 * Bt * c->dl[l - 1] * c->dcp[l - 1] * c->esz));
-    DISPATCH_T(c, ps_scatter_mask_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
+    DISPATCH_T(c, glue_launch(ps_scatter_mask_kernel<T>, dim3(grid_for(tot)), dim3(256), 0, c->stream, 
                       (const T*)c->DX[l - 1], (const T*)c->H[l - 1], (T*)c->DA[l - 1], Bt, B, c->dl[l - 1],
                       c->dcp[l - 1], group_shifts(sh, groups, l - 1)));
     CK(post_launch(c, "ps_scatter_mask"));
@@ -1227,7 +1241,7 @@ static int d_wgrad(cg_ctx* c, int Bt, int nb_bias, int tail_from, bool side_glue
   const int tot = c->dl[NL] * c->dcp[NL] / (16 / c->esz);
   dim3 hgrid(grid_for(tot), Bt >= 64 ? 32 : 1);
   CK(glue(c, (double)Bt * c->dl[NL] * c->dcp[NL] * c->esz));
-  DISPATCH_T(c, head_wgrad_kernel<T><<<hgrid, 256, 0, c->stream>>>(
+  DISPATCH_T(c, glue_launch(head_wgrad_kernel<T>, dim3(hgrid), dim3(256), 0, c->stream, 
                     (const T*)c->X[NL], (const T*)c->V5, tail_from, c->coef, dgrad(c, 10), dgrad(c, 11), Bt, nb_bias, c->dl[NL],
                     c->dc[NL], c->dcp[NL]));
   CK(post_launch(c, "head_wgrad"));
@@ -1274,7 +1288,7 @@ static int apply_update_from(cg_ctx* c, int which, const float* grad) {
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-7f, gscale = 1.0f / (float)c->cfg.world_size;
   // pass 1 (reads the gradient once): non-finite check; the last block advances `iterations` and computes lr_t
   CK(glue(c, 4.0 * m->total));
-  adam_prepare_kernel<<<grid_for(m->total / 4, 256, 148 * 4), 256, 0, c->stream>>>(grad, m->total, m->opt,
+  glue_launch(adam_prepare_kernel, dim3(grid_for(m->total / 4, 256, 148 * 4)), dim3(256), 0, c->stream, grad, m->total, m->opt,
                                                                                   c->cfg.learning_rate, b1, b2);
   CK(post_launch(c, "adam_prepare"));
   if (c->dbg_flags & CG_DEBUG_NO_ADAM_FUSE) {
@@ -1285,7 +1299,7 @@ static int apply_update_from(cg_ctx* c, int which, const float* grad) {
   }
   const AdamPlan& pl = c->adam_plan[which];
   CK(glue(c, 28.0 * m->total + 2.0 * c->esz * m->total));
-  DISPATCH_T(c, adam_pack_kernel<T><<<grid_for(pl.items * 256, 256, 148 * 8), 256, 0, c->stream>>>(
+  DISPATCH_T(c, glue_launch(adam_pack_kernel<T>, dim3(grid_for(pl.items * 256, 256, 148 * 8)), dim3(256), 0, c->stream, 
                     m->w, m->m, m->v, grad, pl, m->opt, b1, b2, eps, gscale));
   return post_launch(c, "adam_pack");
 }
@@ -1348,12 +1362,12 @@ static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* n
   if (!gen_done) CK(critic_generator_part(c, real, B, noise, alpha, want_fake32));
   if (!real_ready) {   // the 5 critic sub-steps of one train step share the real batch (wgan_gp.py:85-86)
     CK(glue(c, (double)B * c->L * (4.0 * c->C + (double)c->dcp[0] * c->esz)));
-    DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(per / 4), 256, 0, c->stream>>>(real, nullptr, nullptr, (T*)c->X[0], B,
+    DISPATCH_T(c, glue_launch(assemble_x0_kernel<T>, dim3(grid_for(per / 4)), dim3(256), 0, c->stream, real, nullptr, nullptr, (T*)c->X[0], B,
                                                                                  c->L, c->C, c->dcp[0], 1));
     CK(post_launch(c, "real_to_x0"));
   }
   CK(d_forward(c, 3 * B, B, 3, sh));
-  fill_coef_kernel<<<(3 * B + 255) / 256, 256, 0, c->stream>>>(c->coef, B, 3, 0.f);
+  glue_launch(fill_coef_kernel, dim3((3 * B + 255) / 256), dim3(256), 0, c->stream, c->coef, B, 3, 0.f);
   CK(post_launch(c, "fill_coef"));
   CU(cudaMemsetAsync(c->sumsq, 0, (size_t)B * 4, c->stream));
   // tensor-core path: ||g_b||^2 accumulates in the epilogue of the last data-gradient GEMM (fp32 accumulators)
@@ -1366,7 +1380,7 @@ static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* n
     DISPATCH_T(c, sumsq_kernel<T><<<B * chunks, 256, 0, c->stream>>>((const T*)c->DX[0], c->sumsq, per_sample, chunks));
     CK(post_launch(c, "sumsq"));
   }
-  critic_scalars_kernel<<<1, 256, 0, c->stream>>>(c->scores, c->sumsq, c->ucoef, c->norms,
+  glue_launch(critic_scalars_kernel, dim3(1), dim3(256), 0, c->stream, c->scores, c->sumsq, c->ucoef, c->norms,
                                                   c->d_scal + (size_t)slot * CG_NUM_SCALARS, B, c->cfg.gp_lambda);
   return post_launch(c, "critic_scalars");
 }
@@ -1377,7 +1391,7 @@ static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* n
 static int gp_linearised_forward(cg_ctx* c, int B, int xg, const int32_t* sh4) {
   const long long per = (long long)c->L * c->dcp[0];
   CK(glue(c, 2.0 * B * per * c->esz));
-  DISPATCH_T(c, scale_rows_kernel<T><<<grid_for(per * B / (16 / c->esz)), 256, 0, c->stream>>>(
+  DISPATCH_T(c, glue_launch(scale_rows_kernel<T>, dim3(grid_for(per * B / (16 / c->esz))), dim3(256), 0, c->stream, 
                     (const T*)c->DX[0], c->ucoef, (T*)off(c, c->X[0], (long long)xg * B * per), per, per * B));
   CK(post_launch(c, "scale_rows"));
   for (int l = 1; l <= NL; ++l) {
@@ -1525,9 +1539,9 @@ static int generator_step_impl(cg_ctx* c, const float* real, int B, const float*
   const bool side = real && side_metrics_ok(c, real);
   if (side) CK(side_metrics_fork(c, real, scal + CG_S_MET_MIN, (long long)B * c->L));
   CK(d_forward(c, B, B, 1, sh));
-  gen_loss_kernel<<<1, 256, 0, c->stream>>>(c->scores, scal, B);
+  glue_launch(gen_loss_kernel, dim3(1), dim3(256), 0, c->stream, c->scores, scal, B);
   CK(post_launch(c, "gen_loss"));
-  fill_coef_kernel<<<(B + 255) / 256, 256, 0, c->stream>>>(c->coef, B, 1, -1.f / B);
+  glue_launch(fill_coef_kernel, dim3((B + 255) / 256), dim3(256), 0, c->stream, c->coef, B, 1, -1.f / B);
   CK(post_launch(c, "fill_coef"));
   CK(d_backward(c, B, B, 1, sh, 0, B));
   CU(cudaMemsetAsync(c->gen.g, 0, c->gen.total * 4, c->stream));
@@ -1609,7 +1623,7 @@ extern "C" int cg_validate(cg_ctx* c, const float* real, int B, const float* noi
   CK(prep_random(c, B, noise, 1, &alpha, 1, sh, shbuf, 12));
   CK(critic_forward_gp(c, real, B, noise, alpha, sh, 0));
   float* scal = c->d_scal;
-  gen_loss_kernel<<<1, 256, 0, c->stream>>>(c->scores + B, scal, B);   // -mean D(fake)
+  glue_launch(gen_loss_kernel, dim3(1), dim3(256), 0, c->stream, c->scores + B, scal, B);   // -mean D(fake)
   CK(post_launch(c, "gen_loss"));
   CU(cudaMemsetAsync(scal + CG_S_MET_MIN, 0, 4 * 4, c->stream));
   const long long rows = (long long)B * c->L;
@@ -1666,7 +1680,7 @@ extern "C" int cg_debug_critic_forward(cg_ctx* c, const float* x, int B, const i
   CK(check_batch(c, B));
   if (!x || !sh || !scores_dev) return set_err("cg_debug_critic_forward: null pointer");
   const long long tot = (long long)B * c->L * c->dcp[0] / 4;
-  DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(x, nullptr, nullptr, (T*)c->X[0], B, c->L,
+  DISPATCH_T(c, glue_launch(assemble_x0_kernel<T>, dim3(grid_for(tot)), dim3(256), 0, c->stream, x, nullptr, nullptr, (T*)c->X[0], B, c->L,
                                                                            c->C, c->dcp[0], 1));
   CK(post_launch(c, "assemble_x0"));
   CK(d_forward(c, B, B, 1, sh));
@@ -1679,11 +1693,11 @@ extern "C" int cg_debug_gp(cg_ctx* c, const float* xhat, int B, const int32_t* s
   CK(check_batch(c, B));
   if (!xhat || !sh) return set_err("cg_debug_gp: null pointer");
   const long long tot = (long long)B * c->L * c->dcp[0] / 4;
-  DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(xhat, nullptr, nullptr, (T*)c->X[0], B,
+  DISPATCH_T(c, glue_launch(assemble_x0_kernel<T>, dim3(grid_for(tot)), dim3(256), 0, c->stream, xhat, nullptr, nullptr, (T*)c->X[0], B,
                                                                            c->L, c->C, c->dcp[0], 1));
   CK(post_launch(c, "assemble_x0"));
   CK(d_forward(c, B, B, 1, sh));
-  fill_coef_kernel<<<(B + 255) / 256, 256, 0, c->stream>>>(c->coef, B, 1, 1.f);
+  glue_launch(fill_coef_kernel, dim3((B + 255) / 256), dim3(256), 0, c->stream, c->coef, B, 1, 1.f);
   CK(post_launch(c, "fill_coef"));
   CK(d_backward(c, B, B, 1, sh, 0, B));
   if (grad_dev) {
@@ -1712,11 +1726,11 @@ extern "C" int cg_gp_gradient(cg_ctx* c, const float* xhat, int B, const int32_t
     if (sh[i] < -c->cfg.phase_m || sh[i] > c->cfg.phase_m) return set_err("cg_gp_gradient: shift outside [-m, m]");
   CU(cudaMemsetAsync(c->dis.g, 0, c->dis.total * 4, c->stream));
   const long long tot = (long long)B * c->L * c->dcp[0] / 4;
-  DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(xhat, nullptr, nullptr, (T*)c->X[0], B,
+  DISPATCH_T(c, glue_launch(assemble_x0_kernel<T>, dim3(grid_for(tot)), dim3(256), 0, c->stream, xhat, nullptr, nullptr, (T*)c->X[0], B,
                                                                            c->L, c->C, c->dcp[0], 1));
   CK(post_launch(c, "assemble_x0"));
   CK(d_forward(c, B, B, 1, sh));                                                    // pass 1: forward, slope masks
-  fill_coef_kernel<<<(B + 255) / 256, 256, 0, c->stream>>>(c->coef, B, 1, 1.f);
+  glue_launch(fill_coef_kernel, dim3((B + 255) / 256), dim3(256), 0, c->stream, c->coef, B, 1, 1.f);
   CK(post_launch(c, "fill_coef"));
   CU(cudaMemsetAsync(c->sumsq, 0, (size_t)B * 4, c->stream));
   const bool fuse_norm = c->use_tc && c->dl[1] >= 128 && !c->tc.force_v1;
@@ -1725,7 +1739,7 @@ extern "C" int cg_gp_gradient(cg_ctx* c, const float* xhat, int B, const int32_t
     DISPATCH_T(c, sumsq_kernel<T><<<B * 8, 256, 0, c->stream>>>((const T*)c->DX[0], c->sumsq, (long long)c->L * c->dcp[0], 8));
     CK(post_launch(c, "sumsq"));
   }
-  critic_scalars_kernel<<<1, 256, 0, c->stream>>>(c->scores, c->sumsq, c->ucoef, c->norms, c->d_scal, B, c->cfg.gp_lambda);
+  glue_launch(critic_scalars_kernel, dim3(1), dim3(256), 0, c->stream, c->scores, c->sumsq, c->ucoef, c->norms, c->d_scal, B, c->cfg.gp_lambda);
   CK(post_launch(c, "critic_scalars"));
   CK(gp_linearised_forward(c, B, 0, sh));                                           // pass 3
   CK(d_wgrad(c, B, 0, 0));                                                          // pass 4 (dGP/db = 0)
@@ -1733,7 +1747,7 @@ extern "C" int cg_gp_gradient(cg_ctx* c, const float* xhat, int B, const int32_t
 }
 
 static int pad_in(cg_ctx* c, const float* src, void* dst, int B, int rows, int C, int Cp) {
-  DISPATCH_T(c, assemble_x0_kernel<T><<<grid_for((long long)B * rows * Cp / 4), 256, 0, c->stream>>>(
+  DISPATCH_T(c, glue_launch(assemble_x0_kernel<T>, dim3(grid_for((long long)B * rows * Cp / 4)), dim3(256), 0, c->stream, 
                     src, nullptr, nullptr, (T*)dst, B, rows, C, Cp, 1));
   return post_launch(c, "pad_in");
 }
@@ -1891,7 +1905,7 @@ extern "C" int cg_debug_dgrad_ps(cg_ctx* c, int layer, const float* dy, const fl
   } else {
     CK(d_dgrad_layer(c, l, 0, B, c->DX[l - 1]));
     const long long tot = (long long)B * c->dl[l - 1] * c->dcp[l - 1] / (16 / c->esz);
-    DISPATCH_T(c, ps_scatter_mask_kernel<T><<<grid_for(tot), 256, 0, c->stream>>>(
+    DISPATCH_T(c, glue_launch(ps_scatter_mask_kernel<T>, dim3(grid_for(tot)), dim3(256), 0, c->stream, 
                       (const T*)c->DX[l - 1], (const T*)c->H[l - 1], (T*)c->DA[l - 1], B, group_b, c->dl[l - 1],
                       c->dcp[l - 1], group_shifts(sh, groups, l - 1)));
     CK(post_launch(c, "ps_scatter_mask"));

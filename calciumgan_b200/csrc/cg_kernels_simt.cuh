@@ -282,6 +282,7 @@ __global__ void ps_gather_kernel(const T* __restrict__ H, T* __restrict__ X, int
 template <typename T>
 __global__ void ps_scatter_mask_kernel(const T* __restrict__ DX, const T* __restrict__ H, T* __restrict__ DA,
                                        int Bt, int group_b, int w, int Cp, GroupShifts sh) {
+  pdl_enter();
   constexpr int V = Vec16<T>::N;
   const int cv = Cp / V;
   const long long total = (long long)Bt * w * cv;
@@ -347,6 +348,7 @@ template <typename T>
 __global__ void assemble_x0_kernel(const float* __restrict__ real, const float* __restrict__ fake,
                                    const float* __restrict__ alpha, T* __restrict__ X0, int B, int L, int C,
                                    int Cp, int mode) {
+  pdl_enter();
   const int c4 = Cp / 4;
   const long long per = (long long)L * Cp;
   const long long total = (long long)B * L * c4;
@@ -418,6 +420,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) head_forward_kernel(const T* __restrict__ X5, const float* __restrict__ wd,
                                                            const float* __restrict__ bd, float* __restrict__ scores,
                                                            int w5, int c5, int Cp) {
+  pdl_enter();
   constexpr int V = Vec16<T>::N;
   __shared__ float red[8];
   const int b = blockIdx.x;
@@ -447,6 +450,7 @@ template <typename T>
 __global__ void head_backward_kernel(const T* __restrict__ H5, const float* __restrict__ wd,
                                      const float* __restrict__ coef, T* __restrict__ DA5, int Bt, int w5, int c5,
                                      int Cp) {
+  pdl_enter();
   constexpr int V = Vec16<T>::N;
   const long long per = (long long)w5 * Cp;
   const long long total = (long long)Bt * per / V;
@@ -472,6 +476,7 @@ template <typename T>
 __global__ void head_wgrad_kernel(const T* __restrict__ X5, const T* __restrict__ X5_tail, int tail_from,
                                   const float* __restrict__ coef, float* __restrict__ dwd,
                                   float* __restrict__ dbd, int Bt, int nb_bias, int w5, int c5, int Cp) {
+  pdl_enter();
   constexpr int V = Vec16<T>::N;
   const int nv = w5 * Cp / V;
   const long long per_sample = (long long)w5 * Cp;
@@ -531,6 +536,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, fl
 struct ColsumOps { int n; struct { const void* X; float* out; long long rows; int Cp, c_real; } op[8]; };
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_multi_kernel(const __grid_constant__ ColsumOps ops) {
+  pdl_enter();
   constexpr int V = Vec16<T>::N;
   const auto& o = ops.op[blockIdx.y];
   const int cv = o.Cp / V;                 // host: cv <= 256
@@ -613,6 +619,7 @@ __global__ void __launch_bounds__(256) ln_lrelu_forward_kernel(const T* __restri
                                                                const float* __restrict__ beta, T* __restrict__ H,
                                                                float* __restrict__ mu_out, float* __restrict__ rstd_out,
                                                                long long rows, int C, int Cp) {
+  pdl_enter();
   constexpr int V = Vec16<T>::N;
   constexpr int MAXV = 4;               // vectors per lane: Cp <= LPR * 4 * V
   constexpr int RPW = 32 / LPR;         // rows per warp
@@ -683,6 +690,7 @@ __global__ void __launch_bounds__(256, MAXV <= 2 ? 2 : 1) ln_lrelu_backward_kern
     const T* __restrict__ DH, const T* __restrict__ A, const T* __restrict__ H, const float* __restrict__ mu_in,
     const float* __restrict__ rstd_in, const float* __restrict__ gamma, T* __restrict__ DA,
     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C, int Cp) {
+  pdl_enter();
   constexpr int V = Vec16<T>::N;
   constexpr int RPW = 32 / LPR;
   extern __shared__ float sm[];   // [2 * Cp]
@@ -776,6 +784,7 @@ template <typename T>
 __global__ void dense0_forward_kernel(const float* __restrict__ z, const float* __restrict__ W0,
                                       const float* __restrict__ b0, T* __restrict__ HG0, int B, int nd, int w0,
                                       int Cp) {
+  pdl_enter();
   const long long total = (long long)B * w0 * Cp;
   const int nout = w0 * nd;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -800,6 +809,7 @@ template <typename T>
 __global__ void dense0_backward_kernel(const float* __restrict__ z, const T* __restrict__ DHG0,
                                        const T* __restrict__ HG0, float* __restrict__ dW0, float* __restrict__ db0,
                                        int B, int nd, int w0, int Cp) {
+  pdl_enter();
   const int nout = w0 * nd;
   const int total = (nd + 1) * nout;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -822,6 +832,7 @@ __global__ void dense0_backward_kernel(const float* __restrict__ z, const T* __r
 template <typename T>
 __global__ void sigmoid_backward_kernel(const T* __restrict__ DX0, const float* __restrict__ fake, T* __restrict__ DO,
                                         long long rows, int C, int Cp, int normalize) {
+  pdl_enter();
   constexpr int V = Vec16<T>::N;
   const int cv = Cp / V;
   const long long total = rows * cv;
@@ -888,6 +899,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ G, flo
 __global__ void critic_scalars_kernel(const float* __restrict__ scores, const float* __restrict__ sumsq,
                                       float* __restrict__ ucoef, float* __restrict__ norms, float* __restrict__ scal,
                                       int B, float lambda) {
+  pdl_enter();
   __shared__ float red[3][32];
   float sr = 0.f, sf = 0.f, sg = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -916,6 +928,7 @@ __global__ void critic_scalars_kernel(const float* __restrict__ scores, const fl
 
 // gen_loss = -mean(scores[0:B]) -> scal[4]
 __global__ void gen_loss_kernel(const float* __restrict__ scores, float* __restrict__ scal, int B) {
+  pdl_enter();
   __shared__ float red[32];
   float s = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) s += scores[b];
@@ -931,6 +944,7 @@ __global__ void gen_loss_kernel(const float* __restrict__ scores, float* __restr
 
 // coef for the concatenated critic batch: [-1/B]*B, [+1/B]*B, [1]*B   (or a constant for 1 group)
 __global__ void fill_coef_kernel(float* coef, int B, int groups, float single) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * groups) return;
   if (groups == 1) coef[i] = single;
@@ -941,6 +955,7 @@ __global__ void fill_coef_kernel(float* coef, int B, int groups, float single) {
 template <typename T>
 __global__ void scale_rows_kernel(const T* __restrict__ G, const float* __restrict__ ucoef, T* __restrict__ V,
                                   long long per_sample, long long total) {
+  pdl_enter();
   constexpr int W = Vec16<T>::N;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * W; i < total;
        i += (long long)gridDim.x * blockDim.x * W) {
@@ -1259,6 +1274,7 @@ struct OptState {
 // Pass 1 over the gradient: any non-finite value? The last block to finish advances the counters and computes lr_t.
 __global__ void __launch_bounds__(256) adam_prepare_kernel(const float* __restrict__ g, long long n, OptState* st, float lr,
                                                            float b1, float b2) {
+  pdl_enter();
   unsigned int bad = 0;
   const long long n4 = n >> 2;
   const uint4* g4 = reinterpret_cast<const uint4*>(g);
@@ -1345,6 +1361,7 @@ __global__ void __launch_bounds__(256) adam_pack_kernel(float* __restrict__ w, f
                                                         const float* __restrict__ g, const __grid_constant__ AdamPlan plan,
                                                         const OptState* __restrict__ st, float b1, float b2, float eps,
                                                         float gscale) {
+  pdl_enter();
   if (!st->do_update) return;
   const float lr_t = st->lr_t;
   __shared__ float tile[32][33];
