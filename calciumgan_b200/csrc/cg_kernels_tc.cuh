@@ -1196,6 +1196,7 @@ struct Wg2Params {
   unsigned char g_seg[2][32];                         // original tap index (output slice)
   int swap;   // 1: operands exchanged (slab = output gradient with negated shifts, P tile = layer input at column g_acol):
               //    accumulator rows = output channels, columns = input channels, stored transposed
+  long long* dbg;   // optional role cycle counters of CTA 0 (instrumented build, CG_TC_TIMING=1)
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -1251,6 +1252,7 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  long long e_t0_w = 0, e_t1_w = 0;   // epilogue timestamps (instrumented build)
   griddep_wait();
   griddep_launch();
 
@@ -1287,9 +1289,14 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
     }
     int stage = 0;
     uint32_t ph = 0;
+    long long w_wait = 0, w_issue = 0;
+    const long long w_t0 = CG_CLK();
     for (int ci = 0; ci < nchunks; ++ci) {
+      const long long tq0 = CG_CLK();
       mbar_wait(&full[stage], ph);
       tc_fence_after();
+      const long long tq1 = CG_CLK();
+      w_wait += tq1 - tq0;
       const uint32_t s_lo = lo0 + stage * stage_step;
       if (elect_one()) {
 #pragma unroll
@@ -1305,15 +1312,21 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
         if (ci == nchunks - 1) umma_commit(&tfull[0]);
       }
       __syncwarp();
+      w_issue += CG_CLK() - tq1;
       if (++stage == stages) { stage = 0; ph ^= 1; }
+    }
+    if (CG_DBG_ON && blockIdx.x == 0 && lane == 0) {
+      P.dbg[0] = w_wait; P.dbg[1] = w_issue; P.dbg[2] = CG_CLK() - w_t0; P.dbg[3] = nchunks; P.dbg[4] = nacc;
     }
   } else {
     const int lq = warp & 3;
     const int r = lq * 32 + lane;       // accumulator row: tap (r / 64) of the pair, channel r % 64
+    e_t0_w = CG_CLK();
     const int m = mb * 64 + (r & 63);
     const bool vec_ok = (p.n_real & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.dW) & 15) == 0);
     mbar_wait(&tfull[0], 0);
     tc_fence_after();
+    e_t1_w = CG_CLK();
     for (int a = 0; a < nacc; ++a) {
       const int ti = tap0 + 2 * a + (r >> 6);
       const bool row_ok = ti < tap0 + ntaps && m < p.m_real;
@@ -1346,6 +1359,7 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
       }
     }
   }
+  if (CG_DBG_ON && blockIdx.x == 0 && threadIdx.x == 64) { P.dbg[5] = CG_CLK() - e_t1_w; P.dbg[6] = e_t1_w - e_t0_w; }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -1813,7 +1827,20 @@ static inline int tc_wgrad2_launch(TcState* s, const WgParams& p_in, cudaStream_
     if (stages < 2) return cg_tc_set_err("wgrad2_tc: not enough shared memory");
     P.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    P.dbg = nullptr;
+    if (CG_TC_INSTRUMENTED && getenv("CG_TC_TIMING") != nullptr) {
+      if (!s->dbg_buf) cudaMalloc(&s->dbg_buf, 16 * sizeof(long long));
+      cudaMemsetAsync(s->dbg_buf, 0, 16 * sizeof(long long), stream);
+      P.dbg = s->dbg_buf;
+    }
     tc_launch(tc::wgrad2_tc_kernel, items * P.splits, tc::kWgThreads, smem, stream, tmS, tmP, P);
+    if (P.dbg) {
+      long long h[16];
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(h, s->dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[wg2 timing] B=%d Q=%d M=%d N=%d swap=%d | BN=%d items=%d splits=%d stages=%d | chunks %lld nacc %lld | mma: wait full %lld issue+commit %lld loop total %lld | epilogue: wait %lld work %lld\n",
+              p.B, p.Q, p.Mp, p.Np, P.swap, P.BN, items, P.splits, stages, h[3], h[4], h[0], h[1], h[2], h[6], h[5]);
+    }
   }
   return 0;
 }
