@@ -231,7 +231,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 
 constexpr int kThreads = 320;               // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int kEpiWarps = 8;
-constexpr int kWgThreads = 192;             // weight-gradient kernels: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kWgThreads = 192;             // weight-gradient kernel v1: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kWg2Threads = 320;            // wgrad2: eight epilogue warps (two per TMEM lane quarter, alternate 32-column chunks):
+                                            // the red.add tail of a CTA, during which its tensor pipe idles, was 12-15 % of the kernel
 constexpr int kABytes = 128 * 128;          // 128 rows x 64 bf16
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;             // columns between the two accumulator buffers
@@ -1197,13 +1199,24 @@ struct Wg2Params {
   int swap;   // 1: operands exchanged (slab = output gradient with negated shifts, P tile = layer input at column g_acol):
               //    accumulator rows = output channels, columns = input channels, stored transposed
   long long* dbg;   // optional role cycle counters of CTA 0 (instrumented build, CG_TC_TIMING=1)
+  int bulk;         // 1: the epilogue stages accumulator rows in the (then idle) stage ring and adds them to dW with one
+                    //    bulk reduce per row segment (TMA engine) instead of red.global.v4 per 16 bytes, whose LSU issue rate
+                    //    (~1.3 clk per lane-op) made the tail 12-15 % of the kernel
 };
+
+__device__ __forceinline__ void bulk_red_add_f32(float* gdst, uint32_t src_s, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(src_s), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(kWgThreads, 1)
+__global__ void __launch_bounds__(kWg2Threads, 1)
 wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmP,
                  const __grid_constant__ Wg2Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1319,7 +1332,7 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
       P.dbg[0] = w_wait; P.dbg[1] = w_issue; P.dbg[2] = CG_CLK() - w_t0; P.dbg[3] = nchunks; P.dbg[4] = nacc;
     }
   } else {
-    const int lq = warp & 3;
+    const int lq = warp & 3, half = (warp - 2) >> 2;
     const int r = lq * 32 + lane;       // accumulator row: tap (r / 64) of the pair, channel r % 64
     e_t0_w = CG_CLK();
     const int m = mb * 64 + (r & 63);
@@ -1327,12 +1340,41 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
     mbar_wait(&tfull[0], 0);
     tc_fence_after();
     e_t1_w = CG_CLK();
+    if (P.bulk) {
+      // row r of every accumulator: this thread's half of the columns -> padded row buffer (conflict-free 16-byte
+      // stores) -> one bulk reduce-add of the whole segment into dW
+      const int nch = BN >> 5, cb = half ? (nch + 1) >> 1 : 0, ce = half ? nch : (nch + 1) >> 1;
+      const uint32_t rowbuf = smem_u32(tiles) + (uint32_t)r * (uint32_t)(BN * 4 + 16);
+      const int n0 = n_begin + cb * 32;
+      int n1 = n_begin + ce * 32;
+      if (n1 > p.n_real) n1 = p.n_real;
+      for (int a = 0; a < nacc; ++a) {
+        const int ti = tap0 + 2 * a + (r >> 6);
+        const bool row_ok = ti < tap0 + ntaps && m < p.m_real;
+        const int seg = P.g_seg[g][ti < 32 ? ti : 0];
+        float* dst = p.dW + ((long long)seg * p.m_real + m) * p.n_real;
+        if (a) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // my previous segment has left shared memory
+        for (int c = cb; c < ce; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + a * BN + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) st_shared_v4(rowbuf + c * 128 + j * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (row_ok && n1 > n0) {
+          fence_proxy_async();
+          bulk_red_add_f32(dst + n0, rowbuf + cb * 128, (uint32_t)(n1 - n0) * 4u);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    } else
     for (int a = 0; a < nacc; ++a) {
       const int ti = tap0 + 2 * a + (r >> 6);
       const bool row_ok = ti < tap0 + ntaps && m < p.m_real;
       const int seg = P.g_seg[g][ti < 32 ? ti : 0];
       float* dst = p.dW + ((long long)seg * p.m_real + m) * p.n_real;
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + a * BN + c0, v);
         tmem_ld_wait();
@@ -1827,19 +1869,24 @@ static inline int tc_wgrad2_launch(TcState* s, const WgParams& p_in, cudaStream_
     if (stages < 2) return cg_tc_set_err("wgrad2_tc: not enough shared memory");
     P.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    // bulk-reduce epilogue: direct (row-major) stores, 16-byte aligned row segments, the row staging area (128 padded
+    // rows) fits in the stage ring
+    P.bulk = (!swap && P.BN % 32 == 0 && p.n_real % 4 == 0 && P.n_origin % 4 == 0 &&
+              (reinterpret_cast<uintptr_t>(p.dW) & 15) == 0 && (size_t)128 * (P.BN * 4 + 16) <= (size_t)stages * stage_bytes &&
+              !getenv("CG_WG_NO_BULK")) ? 1 : 0;
     P.dbg = nullptr;
     if (CG_TC_INSTRUMENTED && getenv("CG_TC_TIMING") != nullptr) {
       if (!s->dbg_buf) cudaMalloc(&s->dbg_buf, 16 * sizeof(long long));
       cudaMemsetAsync(s->dbg_buf, 0, 16 * sizeof(long long), stream);
       P.dbg = s->dbg_buf;
     }
-    tc_launch(tc::wgrad2_tc_kernel, items * P.splits, tc::kWgThreads, smem, stream, tmS, tmP, P);
+    tc_launch(tc::wgrad2_tc_kernel, items * P.splits, tc::kWg2Threads, smem, stream, tmS, tmP, P);
     if (P.dbg) {
       long long h[16];
       cudaStreamSynchronize(stream);
       cudaMemcpy(h, s->dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[wg2 timing] B=%d Q=%d M=%d N=%d swap=%d | BN=%d items=%d splits=%d stages=%d | chunks %lld nacc %lld | mma: wait full %lld issue+commit %lld loop total %lld | epilogue: wait %lld work %lld\n",
-              p.B, p.Q, p.Mp, p.Np, P.swap, P.BN, items, P.splits, stages, h[3], h[4], h[0], h[1], h[2], h[6], h[5]);
+      fprintf(stderr, "[wg2 timing] B=%d Q=%d M=%d N=%d swap=%d bulk=%d | BN=%d items=%d splits=%d stages=%d | chunks %lld nacc %lld | mma: wait full %lld issue+commit %lld loop total %lld | epilogue: wait %lld work %lld\n",
+              p.B, p.Q, p.Mp, p.Np, P.swap, P.bulk, P.BN, items, P.splits, stages, h[3], h[4], h[0], h[1], h[2], h[6], h[5]);
     }
   }
   return 0;
