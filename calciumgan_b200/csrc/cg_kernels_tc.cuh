@@ -1340,7 +1340,41 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
     mbar_wait(&tfull[0], 0);
     tc_fence_after();
     e_t1_w = CG_CLK();
-    if (P.bulk) {
+    if (P.bulk && P.swap) {
+      // transposed store dW[seg][n][m]: stage each accumulator as [tap half][n][64 channels] (lanes = consecutive m, so
+      // the 4-byte stores are conflict-free), then one 256-byte bulk reduce-add per (tap, input channel) row
+      const uint32_t buf = smem_u32(tiles);
+      const int e = (int)threadIdx.x - 64;
+      int mcnt = p.m_real - mb * 64;
+      if (mcnt > 64) mcnt = 64;
+      for (int a = 0; a < nacc; ++a) {
+        if (a) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + a * BN + c0, v);
+          tmem_ld_wait();
+          const uint32_t dst_s = buf + (uint32_t)(((r >> 6) * BN + c0) * 256 + (r & 63) * 4);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst_s + j * 256), "r"(v[j]) : "memory");
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int idx = e; idx < 2 * BN; idx += 256) {
+          const int th = idx / BN, n = idx - th * BN;
+          const int ti = tap0 + 2 * a + th;
+          if (ti < tap0 + ntaps && n_begin + n < p.n_real && mcnt > 0) {
+            const int seg = P.g_seg[g][ti];
+            bulk_red_add_f32(p.dW + ((long long)seg * p.n_real + n_begin + n) * p.m_real + mb * 64,
+                             buf + (uint32_t)(th * BN + n) * 256u, (uint32_t)mcnt * 4u);
+          }
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    } else if (P.bulk) {
       // row r of every accumulator: this thread's half of the columns -> padded row buffer (conflict-free 16-byte
       // stores) -> one bulk reduce-add of the whole segment into dW
       const int nch = BN >> 5, cb = half ? (nch + 1) >> 1 : 0, ce = half ? nch : (nch + 1) >> 1;
@@ -1871,9 +1905,13 @@ static inline int tc_wgrad2_launch(TcState* s, const WgParams& p_in, cudaStream_
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
     // bulk-reduce epilogue: direct (row-major) stores, 16-byte aligned row segments, the row staging area (128 padded
     // rows) fits in the stage ring
-    P.bulk = (!swap && P.BN % 32 == 0 && p.n_real % 4 == 0 && P.n_origin % 4 == 0 &&
-              (reinterpret_cast<uintptr_t>(p.dW) & 15) == 0 && (size_t)128 * (P.BN * 4 + 16) <= (size_t)stages * stage_bytes &&
-              !getenv("CG_WG_NO_BULK")) ? 1 : 0;
+    const bool dw_aligned = (reinterpret_cast<uintptr_t>(p.dW) & 15) == 0 && !getenv("CG_WG_NO_BULK");
+    if (swap)   // transposed store: 64-channel rows of dW[seg][n][:]
+      P.bulk = (dw_aligned && P.BN % 64 == 0 && p.m_real % 4 == 0 && (size_t)2 * P.BN * 256 <= (size_t)stages * stage_bytes &&
+                !getenv("CG_WG_NO_BULK_SWAP")) ? 1 : 0;
+    else
+      P.bulk = (dw_aligned && P.BN % 32 == 0 && p.n_real % 4 == 0 && P.n_origin % 4 == 0 &&
+                (size_t)128 * (P.BN * 4 + 16) <= (size_t)stages * stage_bytes) ? 1 : 0;
     P.dbg = nullptr;
     if (CG_TC_INSTRUMENTED && getenv("CG_TC_TIMING") != nullptr) {
       if (!s->dbg_buf) cudaMalloc(&s->dbg_buf, 16 * sizeof(long long));
