@@ -109,11 +109,12 @@ if d:
   out.append('## fp32 CUDA-core path, BASELINE configs[0] shape (batch 16, fp32) on the GPU\n')
   out.append('%.2f ms per step = %.0f samples/s (the reference-precision path used for the 1e-4 parity tests; CPU oracle port on the same shape: see `cpu_baseline`).\n' % (d['ms_per_step'], d['value']))
 
-for st in ('%sc_scale' % tag, '%sa_scale' % tag, '%sb_scale' % tag):
+stag = sys.argv[2] if len(sys.argv) > 2 else tag   # scaling runs may carry an earlier tag (python tools/make_r2_profile.py r2d r2)
+for st in ('%sc_scale' % stag, '%sa_scale' % stag, '%sb_scale' % stag):
   rows = [load('%s_n%d.json' % (st, n)) for n in (1, 2, 4, 8)]
   if all(rows):
     what = {'c': 'final build: overlap + NCCL above 2 ranks, peer memory at 2 (= profiles/r2_scale_n*.json)', 'a': 'earlier build of this round: overlap + NCCL at every size',
-            'b': 'earlier build: ONE-SHOT peer-memory exchange at every size (7 x 16 MB pulled per rank at 8 GPUs)'}[st[len(tag)]]
+            'b': 'earlier build: ONE-SHOT peer-memory exchange at every size (7 x 16 MB pulled per rank at 8 GPUs)'}[st[len(stag)]]
     out.append('## Scaling on one 8-GPU box (`tools/scale_run.sh`, 128 samples per GPU) -- %s\n' % what)
     out.append('| GPUs | ms/step | samples/s | efficiency | e2e (cache) samples/s | efficiency | e2e streaming |\n|---:|---:|---:|---:|---:|---:|---:|')
     for n, r in zip((1, 2, 4, 8), rows):

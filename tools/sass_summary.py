@@ -8,7 +8,7 @@ import sys
 
 so = sys.argv[1] if len(sys.argv) > 1 else 'calciumgan_b200/libcalciumgan_b200.so'
 txt = subprocess.run(['cuobjdump', '-sass', so], capture_output=True, text=True).stdout
-ops = ['UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UBLKCP', 'UTMAPF', 'SYNCS', 'HMMA', 'LDGSTS', 'REDG', 'ATOMG']
+ops = ['UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UBLKCP', 'UBLKRED', 'UTMAPF', 'SYNCS', 'HMMA', 'LDGSTS', 'REDG', 'ATOMG']
 per = collections.OrderedDict()
 cur = None
 for line in txt.splitlines():
@@ -27,7 +27,7 @@ for line in txt.splitlines():
     if op in ops:
       per[cur][op] += 1
 print('# SASS opcode summary of %s (sm_100a)\n' % so)
-print('`cuobjdump -sass`, instructions per kernel. UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG / UTMASTG / UBLKCP = TMA,')
+print('`cuobjdump -sass`, instructions per kernel. UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG / UTMASTG / UBLKCP = TMA, UBLKRED = bulk reduce-add (cp.reduce.async.bulk),')
 print('UTCBAR = tcgen05.commit, SYNCS = mbarrier ops, LDGSTS = cp.async, REDG / ATOMG = global reductions. No HMMA (legacy mma.sync) anywhere.\n')
 print('| kernel | instr | ' + ' | '.join(ops) + ' |')
 print('|---|---:|' + '---:|' * len(ops))
