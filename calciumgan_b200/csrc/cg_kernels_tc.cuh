@@ -1199,6 +1199,10 @@ struct Wg2Params {
   int swap;   // 1: operands exchanged (slab = output gradient with negated shifts, P tile = layer input at column g_acol):
               //    accumulator rows = output channels, columns = input channels, stored transposed
   long long* dbg;   // optional role cycle counters of CTA 0 (instrumented build, CG_TC_TIMING=1)
+  // CTA-pair variant (wgrad2p_tc_kernel): two work items of one (row split, n-tile) form a cluster; every item has
+  // pair_ntaps taps whose row offsets relative to the item's first tap are rel_pat[], so ONE descriptor set serves both CTAs
+  int pb_half, pair_ntaps, p_rows_total;
+  unsigned char rel_pat[16];
   int bulk;         // 1: the epilogue stages accumulator rows in the (then idle) stage ring and adds them to dW with one
                     //    bulk reduce per row segment (TMA engine) instead of red.global.v4 per 16 bytes, whose LSU issue rate
                     //    (~1.3 clk per lane-op) made the tail 12-15 % of the kernel
@@ -1216,12 +1220,113 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Epilogue of the weight-gradient kernels: accumulators (TMEM) -> gradient buffer, added to the other row splits' partial sums.
+__device__ __forceinline__ void wgrad2_epilogue(const Wg2Params& P, uint8_t* tiles, uint32_t tmem_base, int BN, int n_begin, int g,
+                                                int mb, int tap0, int ntaps, int nacc, int lq, int half, int r, int m, int lane) {
+  const WgParams& p = P.p;
+  const bool vec_ok = (p.n_real & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.dW) & 15) == 0);
+  (void)lane;
+  if (P.bulk && P.swap) {
+    // transposed store dW[seg][n][m]: stage each accumulator as [tap half][n][64 channels] (lanes = consecutive m, so
+    // the 4-byte stores are conflict-free), then one 256-byte bulk reduce-add per (tap, input channel) row
+    const uint32_t buf = smem_u32(tiles);
+    const int e = (int)threadIdx.x - 64;
+    int mcnt = p.m_real - mb * 64;
+    if (mcnt > 64) mcnt = 64;
+    for (int a = 0; a < nacc; ++a) {
+      if (a) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + a * BN + c0, v);
+        tmem_ld_wait();
+        const uint32_t dst_s = buf + (uint32_t)(((r >> 6) * BN + c0) * 256 + (r & 63) * 4);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst_s + j * 256), "r"(v[j]) : "memory");
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int idx = e; idx < 2 * BN; idx += 256) {
+        const int th = idx / BN, n = idx - th * BN;
+        const int ti = tap0 + 2 * a + th;
+        if (ti < tap0 + ntaps && n_begin + n < p.n_real && mcnt > 0) {
+          const int seg = P.g_seg[g][ti];
+          bulk_red_add_f32(p.dW + ((long long)seg * p.n_real + n_begin + n) * p.m_real + mb * 64,
+                           buf + (uint32_t)(th * BN + n) * 256u, (uint32_t)mcnt * 4u);
+        }
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  } else if (P.bulk) {
+    // row r of every accumulator: this thread's half of the columns -> padded row buffer (conflict-free 16-byte
+    // stores) -> one bulk reduce-add of the whole segment into dW
+    const int nch = BN >> 5, cb = half ? (nch + 1) >> 1 : 0, ce = half ? nch : (nch + 1) >> 1;
+    const uint32_t rowbuf = smem_u32(tiles) + (uint32_t)r * (uint32_t)(BN * 4 + 16);
+    const int n0 = n_begin + cb * 32;
+    int n1 = n_begin + ce * 32;
+    if (n1 > p.n_real) n1 = p.n_real;
+    for (int a = 0; a < nacc; ++a) {
+      const int ti = tap0 + 2 * a + (r >> 6);
+      const bool row_ok = ti < tap0 + ntaps && m < p.m_real;
+      const int seg = P.g_seg[g][ti < 32 ? ti : 0];
+      float* dst = p.dW + ((long long)seg * p.m_real + m) * p.n_real;
+      if (a) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // my previous segment has left shared memory
+      for (int c = cb; c < ce; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + a * BN + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) st_shared_v4(rowbuf + c * 128 + j * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      if (row_ok && n1 > n0) {
+        fence_proxy_async();
+        bulk_red_add_f32(dst + n0, rowbuf + cb * 128, (uint32_t)(n1 - n0) * 4u);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  } else
+  for (int a = 0; a < nacc; ++a) {
+    const int ti = tap0 + 2 * a + (r >> 6);
+    const bool row_ok = ti < tap0 + ntaps && m < p.m_real;
+    const int seg = P.g_seg[g][ti < 32 ? ti : 0];
+    float* dst = p.dW + ((long long)seg * p.m_real + m) * p.n_real;
+    for (int c0 = half * 32; c0 < BN; c0 += 64) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + a * BN + c0, v);
+      tmem_ld_wait();
+      if (row_ok && P.swap) {   // transposed store: element (m = output channel, n = input channel) -> dW[seg][n][m];
+                                // consecutive lanes hold consecutive m, so every warp instruction is one 128-byte line
+        const int n0 = n_begin + c0;
+        float* dcol = p.dW + ((long long)seg * p.n_real + n0) * p.m_real + m;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j < p.n_real) atomicAdd(dcol + (long long)j * p.m_real, __uint_as_float(v[j]));
+      } else if (row_ok) {
+        const int n0 = n_begin + c0;
+        if (vec_ok && n0 + 32 <= p.n_real) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4(dst + n0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                       __uint_as_float(v[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.n_real) atomicAdd(dst + n0 + j, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kWg2Threads, 1)
 wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmP,
                  const __grid_constant__ Wg2Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const WgParams& p = P.p;
   const int BN = P.BN;
   const int stages = P.stages;
   const int p_blocks = (BN + 63) >> 6;                  // 64-column MN-major blocks of the P tile (BN = 160 loads 3, uses 2.5)
@@ -1336,104 +1441,10 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
     const int r = lq * 32 + lane;       // accumulator row: tap (r / 64) of the pair, channel r % 64
     e_t0_w = CG_CLK();
     const int m = mb * 64 + (r & 63);
-    const bool vec_ok = (p.n_real & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.dW) & 15) == 0);
     mbar_wait(&tfull[0], 0);
     tc_fence_after();
     e_t1_w = CG_CLK();
-    if (P.bulk && P.swap) {
-      // transposed store dW[seg][n][m]: stage each accumulator as [tap half][n][64 channels] (lanes = consecutive m, so
-      // the 4-byte stores are conflict-free), then one 256-byte bulk reduce-add per (tap, input channel) row
-      const uint32_t buf = smem_u32(tiles);
-      const int e = (int)threadIdx.x - 64;
-      int mcnt = p.m_real - mb * 64;
-      if (mcnt > 64) mcnt = 64;
-      for (int a = 0; a < nacc; ++a) {
-        if (a) {
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-        }
-        for (int c0 = half * 32; c0 < BN; c0 += 64) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + a * BN + c0, v);
-          tmem_ld_wait();
-          const uint32_t dst_s = buf + (uint32_t)(((r >> 6) * BN + c0) * 256 + (r & 63) * 4);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst_s + j * 256), "r"(v[j]) : "memory");
-        }
-        fence_proxy_async();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int idx = e; idx < 2 * BN; idx += 256) {
-          const int th = idx / BN, n = idx - th * BN;
-          const int ti = tap0 + 2 * a + th;
-          if (ti < tap0 + ntaps && n_begin + n < p.n_real && mcnt > 0) {
-            const int seg = P.g_seg[g][ti];
-            bulk_red_add_f32(p.dW + ((long long)seg * p.n_real + n_begin + n) * p.m_real + mb * 64,
-                             buf + (uint32_t)(th * BN + n) * 256u, (uint32_t)mcnt * 4u);
-          }
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    } else if (P.bulk) {
-      // row r of every accumulator: this thread's half of the columns -> padded row buffer (conflict-free 16-byte
-      // stores) -> one bulk reduce-add of the whole segment into dW
-      const int nch = BN >> 5, cb = half ? (nch + 1) >> 1 : 0, ce = half ? nch : (nch + 1) >> 1;
-      const uint32_t rowbuf = smem_u32(tiles) + (uint32_t)r * (uint32_t)(BN * 4 + 16);
-      const int n0 = n_begin + cb * 32;
-      int n1 = n_begin + ce * 32;
-      if (n1 > p.n_real) n1 = p.n_real;
-      for (int a = 0; a < nacc; ++a) {
-        const int ti = tap0 + 2 * a + (r >> 6);
-        const bool row_ok = ti < tap0 + ntaps && m < p.m_real;
-        const int seg = P.g_seg[g][ti < 32 ? ti : 0];
-        float* dst = p.dW + ((long long)seg * p.m_real + m) * p.n_real;
-        if (a) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // my previous segment has left shared memory
-        for (int c = cb; c < ce; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + a * BN + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) st_shared_v4(rowbuf + c * 128 + j * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-        if (row_ok && n1 > n0) {
-          fence_proxy_async();
-          bulk_red_add_f32(dst + n0, rowbuf + cb * 128, (uint32_t)(n1 - n0) * 4u);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-      }
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    } else
-    for (int a = 0; a < nacc; ++a) {
-      const int ti = tap0 + 2 * a + (r >> 6);
-      const bool row_ok = ti < tap0 + ntaps && m < p.m_real;
-      const int seg = P.g_seg[g][ti < 32 ? ti : 0];
-      float* dst = p.dW + ((long long)seg * p.m_real + m) * p.n_real;
-      for (int c0 = half * 32; c0 < BN; c0 += 64) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + a * BN + c0, v);
-        tmem_ld_wait();
-        if (row_ok && P.swap) {   // transposed store: element (m = output channel, n = input channel) -> dW[seg][n][m];
-                                  // consecutive lanes hold consecutive m, so every warp instruction is one 128-byte line
-          const int n0 = n_begin + c0;
-          float* dcol = p.dW + ((long long)seg * p.n_real + n0) * p.m_real + m;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < p.n_real) atomicAdd(dcol + (long long)j * p.m_real, __uint_as_float(v[j]));
-        } else if (row_ok) {
-          const int n0 = n_begin + c0;
-          if (vec_ok && n0 + 32 <= p.n_real) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              red_add_v4(dst + n0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                         __uint_as_float(v[j + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.n_real) atomicAdd(dst + n0 + j, __uint_as_float(v[j]));
-          }
-        }
-      }
-    }
+    wgrad2_epilogue(P, tiles, tmem_base, BN, n_begin, g, mb, tap0, ntaps, nacc, lq, half, r, m, lane);
   }
   if (CG_DBG_ON && blockIdx.x == 0 && threadIdx.x == 64) { P.dbg[5] = CG_CLK() - e_t1_w; P.dbg[6] = e_t1_w - e_t0_w; }
   tc_fence_before();
@@ -1441,6 +1452,152 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// =============================================================================================
+// wgrad2p_tc: CTA-pair (cta_group::2) weight gradient. The single-CTA kernel is shared-memory bound: per M128 x N x K16 MMA
+// it reads A 4 KB + B 32*N B while TMA fills the stage ring, (reads + fills) / 128 B/clk per SM fits the measured loop
+// times of all four critic layers within 6 % (N = 128: 162 B/clk needed, N = 256: 137). Here two work items that share
+// the row split and the n-tile -- hence the P tile (output-gradient chunk) -- form a cluster: each CTA keeps its own slab,
+// accumulators and epilogue, but loads and reads only HALF of the P tile (BN/2 columns); the leader issues M = 256 MMAs.
+// Barriers as in rsgemm3: full on the leader (both CTAs' TMA loads complete_tx there), empty / accumulator-full
+// multicast-committed to both CTAs.
+// =============================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWg2Threads, 1)
+wgrad2p_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmP,
+                  const __grid_constant__ Wg2Params P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int BN = P.BN;
+  const int stages = P.stages;
+  const int stage_bytes = P.slab_bytes + P.pb_half * 8192;   // own slab + own half of the P tile
+  uint8_t* tiles = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* empty = full + stages;
+  uint64_t* tfull = empty + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  // ---- decode the work item: consecutive items of a split pair up; the pair shares (split, n-tile)
+  int w = blockIdx.x;
+  const int split = w / P.items_per_split;
+  w -= split * P.items_per_split;
+  const int pq = w >> 1;
+  const int nt = pq % P.n_tiles;
+  w = (pq / P.n_tiles) * 2 + (w & 1);
+  int g = 0;
+  if (w >= P.mblocks * P.nsub[0]) { g = 1; w -= P.mblocks * P.nsub[0]; }
+  const int sub = w % P.nsub[g];
+  const int mb = w / P.nsub[g];
+  const int tap0 = sub * P.taps_per_cta;
+  const int ntaps = P.pair_ntaps;
+  const int nacc = (ntaps + 1) / 2;
+  const int ch_begin = split * P.chunks_per_split;
+  int ch_end = ch_begin + P.chunks_per_split;
+  if (ch_end > P.total_chunks) ch_end = P.total_chunks;
+  const int nchunks = ch_end - ch_begin;
+  const int n_begin = P.n_origin + nt * BN;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmS);
+    prefetch_tmap(&tmP);
+    for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&tfull[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();          // barriers of both CTAs initialised before any remote arrive / TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  long long e_t0_w = 0, e_t1_w = 0;
+  griddep_wait();
+  griddep_launch();
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t ph = 0;
+    const int scol = (P.swap ? 0 : P.g_acol[g]) + mb * 64;
+    const int pcol = (P.swap ? P.g_acol[g] : 0) + n_begin + (int)rank * (BN / 2);
+    const int row0 = P.g_min_shift[g] + P.g_rel[g][tap0];      // the slab starts at this item's first tap
+    for (int ch = ch_begin; ch < ch_end; ++ch) {
+      const int b0 = ch / P.chunks_per_sample, q0 = (ch % P.chunks_per_sample) * 64;
+      mbar_wait(&empty[stage], ph ^ 1);
+      if (elect_one()) {
+        uint8_t* sa = tiles + (size_t)stage * stage_bytes;
+        if (rank == 0) mbar_expect_tx(&full[stage], (uint32_t)(2 * stage_bytes));
+        const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
+        tma2_load_3d(sa, &tmS, bar, scol, q0 + row0, b0);
+        for (int j = 0; j < P.pb_half; ++j)
+          tma2_load_3d(sa + P.slab_bytes + j * 8192, &tmP, bar, pcol + j * 64, q0, b0);
+      }
+      if (++stage == stages) { stage = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc(256, BN, 1, 1);
+      const uint32_t hi = desc_hi(1024);
+      const uint32_t lo0 = (smem_u32(tiles) >> 4) & 0x3FFF;
+      const uint32_t stage_step = (uint32_t)stage_bytes >> 4;
+      const uint32_t b_off = ((uint32_t)P.slab_bytes >> 4) | (512u << 16);   // P half tile: LBO = 8192 B between 64-channel blocks
+      uint32_t a_off[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const int ia = 2 * a, ib = (2 * a + 1 < ntaps) ? 2 * a + 1 : 2 * a;
+        const uint32_t ra = a < nacc ? P.rel_pat[ia] : 0, rb = a < nacc ? P.rel_pat[ib] : 0;
+        a_off[a] = ra * 8 + (((rb - ra) * 8) << 16);
+      }
+      int stage = 0;
+      uint32_t ph = 0;
+      long long w_wait = 0, w_issue = 0;
+      const long long w_t0 = CG_CLK();
+      for (int ci = 0; ci < nchunks; ++ci) {
+        const long long tq0 = CG_CLK();
+        mbar_wait(&full[stage], ph);
+        tc_fence_after();
+        const long long tq1 = CG_CLK();
+        w_wait += tq1 - tq0;
+        const uint32_t s_lo = lo0 + stage * stage_step;
+        if (elect_one()) {
+#pragma unroll
+          for (int a = 0; a < 8; ++a) {
+            if (a < nacc) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma2_bf16_lohi(tmem_base + a * BN, s_lo + a_off[a] + 128 * k, s_lo + b_off + 128 * k, hi, idesc,
+                                (uint32_t)(ci | k));
+            }
+          }
+          umma2_commit_mc(&empty[stage]);
+          if (ci == nchunks - 1) umma2_commit_mc(&tfull[0]);
+        }
+        __syncwarp();
+        w_issue += CG_CLK() - tq1;
+        if (++stage == stages) { stage = 0; ph ^= 1; }
+      }
+      if (CG_DBG_ON && blockIdx.x == 0 && lane == 0) {
+        P.dbg[0] = w_wait; P.dbg[1] = w_issue; P.dbg[2] = CG_CLK() - w_t0; P.dbg[3] = nchunks; P.dbg[4] = nacc;
+      }
+    }
+  } else {
+    const int lq = warp & 3, half = (warp - 2) >> 2;
+    const int r = lq * 32 + lane;       // accumulator row: tap (r / 64) of the pair, channel r % 64
+    e_t0_w = CG_CLK();
+    const int m = mb * 64 + (r & 63);
+    mbar_wait(&tfull[0], 0);
+    tc_fence_after();
+    e_t1_w = CG_CLK();
+    wgrad2_epilogue(P, tiles, tmem_base, BN, n_begin, g, mb, tap0, ntaps, nacc, lq, half, r, m, lane);
+  }
+  if (CG_DBG_ON && blockIdx.x == 0 && threadIdx.x == 64) { P.dbg[5] = CG_CLK() - e_t1_w; P.dbg[6] = e_t1_w - e_t0_w; }
+  tc_fence_before();
+  cluster_sync_all();          // nobody may exit (or free TMEM) while the peer can still signal / read
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, kTmemCols);
   }
 }
 
@@ -1498,7 +1655,8 @@ static inline int tc_init(TcState* s) {
 #undef CG_SET_SMEM
   if (!ok ||
       cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) != cudaSuccess ||
-      cudaFuncSetAttribute(tc::wgrad2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) != cudaSuccess)
+      cudaFuncSetAttribute(tc::wgrad2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(tc::wgrad2p_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->max_smem) != cudaSuccess)
     return cg_tc_set_err("cudaFuncSetAttribute(max dynamic smem) failed");
   return 0;
 }
@@ -1827,6 +1985,78 @@ static inline WgParams tc_wgrad2_swapped(const WgParams& p) {
   return w;
 }
 
+// CTA-pair launch of one pass of tc_wgrad2_launch (P holds the pass' tiling; items = work items per row split). Returns
+// false when the work items cannot be paired: odd count, tap subsets of different size or spacing, or (operand-swapped
+// mode, where the P tile depends on the tap group) a pair that would straddle the two groups.
+static inline bool tc_wgrad2_pair_launch(TcState* s, const tc::Wg2Params& P0, const WgParams& p, bool swap, int items,
+                                         cudaStream_t stream) {
+  if (getenv("CG_WG_NO_PAIR")) return false;
+  tc::Wg2Params P = P0;
+  const int combos = items / P.n_tiles;
+  if (combos % 2 || P.BN % 32 || P.BN > 256) return false;
+  if (swap && (P.mblocks * P.nsub[0]) % 2) return false;
+  int ntaps0 = -1, span = 0;
+  for (int g = 0; g < P.ngroups; ++g)
+    for (int sub = 0; sub < P.nsub[g]; ++sub) {
+      const int tap0 = sub * P.taps_per_cta;
+      int nt = P.g_nseg[g] - tap0;
+      if (nt > P.taps_per_cta) nt = P.taps_per_cta;
+      if (nt > 16) return false;
+      if (ntaps0 < 0) {
+        ntaps0 = nt;
+        for (int j = 0; j < nt; ++j) {
+          P.rel_pat[j] = (unsigned char)(P.g_rel[g][tap0 + j] - P.g_rel[g][tap0]);
+          if (P.rel_pat[j] > span) span = P.rel_pat[j];
+        }
+      } else {
+        if (nt != ntaps0) return false;
+        for (int j = 0; j < nt; ++j)
+          if (P.rel_pat[j] != (unsigned char)(P.g_rel[g][tap0 + j] - P.g_rel[g][tap0])) return false;
+      }
+    }
+  if (ntaps0 <= 0) return false;
+  P.pair_ntaps = ntaps0;
+  P.pb_half = (P.BN / 2 + 63) / 64;
+  P.box_rows = (64 + span + 7) / 8 * 8;
+  P.slab_bytes = P.box_rows * 128;
+  CUtensorMap tmS, tmP;
+  if (tc_get_map3(s, p.S, p.s_rs, p.s_rows, p.B, p.s_rs, p.s_bs, P.box_rows, 1, &tmS)) return false;
+  if (tc_get_map3(s, p.P, p.p_rs, P.p_rows_total, p.B, p.p_rs, p.p_bs, 64, 1, &tmP)) return false;
+  int splits = s->sm_count / items;
+  if (splits > P.total_chunks) splits = P.total_chunks;
+  if (splits < 1) return false;
+  P.items_per_split = items;
+  P.chunks_per_split = (P.total_chunks + splits - 1) / splits;
+  P.splits = (P.total_chunks + P.chunks_per_split - 1) / P.chunks_per_split;
+  const int stage_bytes = P.slab_bytes + P.pb_half * 8192;
+  int stages = (s->max_smem - 2048) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return false;
+  P.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  const bool dw_aligned = (reinterpret_cast<uintptr_t>(p.dW) & 15) == 0 && !getenv("CG_WG_NO_BULK");
+  if (swap)
+    P.bulk = (dw_aligned && P.BN % 64 == 0 && p.m_real % 4 == 0 && (size_t)2 * P.BN * 256 <= (size_t)stages * stage_bytes) ? 1 : 0;
+  else
+    P.bulk = (dw_aligned && p.n_real % 4 == 0 && P.n_origin % 4 == 0 &&
+              (size_t)128 * (P.BN * 4 + 16) <= (size_t)stages * stage_bytes) ? 1 : 0;
+  P.dbg = nullptr;
+  if (CG_TC_INSTRUMENTED && getenv("CG_TC_TIMING") != nullptr) {
+    if (!s->dbg_buf) cudaMalloc(&s->dbg_buf, 16 * sizeof(long long));
+    cudaMemsetAsync(s->dbg_buf, 0, 16 * sizeof(long long), stream);
+    P.dbg = s->dbg_buf;
+  }
+  tc_launch(tc::wgrad2p_tc_kernel, items * P.splits, tc::kWg2Threads, smem, stream, tmS, tmP, P);
+  if (P.dbg) {
+    long long h[16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, s->dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[wg2 timing] PAIR B=%d Q=%d M=%d N=%d swap=%d bulk=%d | BN=%d items=%d splits=%d stages=%d box_rows=%d | chunks %lld nacc %lld | mma: wait full %lld issue+commit %lld loop total %lld | epilogue: wait %lld work %lld\n",
+            p.B, p.Q, p.Mp, p.Np, P.swap, P.bulk, P.BN, items, P.splits, stages, P.box_rows, h[3], h[4], h[0], h[1], h[2], h[6], h[5]);
+  }
+  return true;
+}
+
 static inline int tc_wgrad2_launch(TcState* s, const WgParams& p_in, cudaStream_t stream) {
   tc::Wg2Params P;
   memset(&P, 0, sizeof(P));
@@ -1864,6 +2094,7 @@ static inline int tc_wgrad2_launch(TcState* s, const WgParams& p_in, cudaStream_
   CUtensorMap tmS, tmP;
   if (tc_get_map3(s, p.S, p.s_rs, p.s_rows, p.B, p.s_rs, p.s_bs, P.box_rows, 1, &tmS)) return 1;
   if (tc_get_map3(s, p.P, p.p_rs, swap ? p_in.s_rows : p.Q, p.B, p.p_rs, p.p_bs, 64, 1, &tmP)) return 1;
+  P.p_rows_total = swap ? p_in.s_rows : p.Q;
   // 256 < Np <= 512 with Np/2 a multiple of 32 (320 -> 2 x 160): two equal n-tiles in ONE launch instead of a 256-wide
   // launch plus a 64-wide remainder launch that runs shared-memory bound (measured 33% tensor-pipe activity)
   const bool halves = p.Np > 256 && p.Np <= 512 && (p.Np / 2) % 32 == 0 && !getenv("CG_WG_NO_HALVES");
@@ -1897,6 +2128,7 @@ static inline int tc_wgrad2_launch(TcState* s, const WgParams& p_in, cudaStream_
     if (splits < 1) splits = 1;
     P.chunks_per_split = (P.total_chunks + splits - 1) / splits;
     P.splits = (P.total_chunks + P.chunks_per_split - 1) / P.chunks_per_split;
+    if (tc_wgrad2_pair_launch(s, P, p, swap, items, stream)) continue;
     const int stage_bytes = P.slab_bytes + ((P.BN + 63) / 64) * 8192;
     int stages = (s->max_smem - 2048) / stage_bytes;
     if (stages > 8) stages = 8;
