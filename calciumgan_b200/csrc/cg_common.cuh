@@ -151,7 +151,7 @@ struct RsParams {
   int merged_phases;
   float flop_scale;                                // algorithmic / issued FLOPs (the shifted copies add zero taps); 0 = 1
   int dbg;                                         // timing experiments only
-  float* sumsq;                                    // optional: sumsq[b] += sum of squares of the fp32 results of sample b
+  double* sumsq;                                   // optional: sumsq[b] += sum of squares of the fp32 results of sample b
   int B, Q, N, n_real, Kc, k_real, epi;   // k_real: unpadded channels per tap (algorithmic FLOPs only)
   SegTable seg;
 };

@@ -114,7 +114,9 @@ struct cg_ctx {
   // critic activations (capacity 3*Bmax)
   void *X[NL + 1], *H[NL + 1], *DX[NL + 1], *DA[NL + 1];
   void* V5;                                // gradient penalty: linearised forward output of the last conv layer (Bmax samples)
-  float *scores, *coef, *sumsq, *ucoef, *norms;
+  float *scores, *coef, *ucoef, *norms;
+  double* sumsq;   // per-sample ||g||^2, accumulated in double: the sum of the fp32 partials is then exact, so the result
+                   // does not depend on the order in which the atomics of different CTAs arrive
   // generator activations (capacity Bmax)
   float* Z;
   void *HG[NL + 1], *AG[NL + 1], *DHG[NL + 1], *DAG[NL + 1], *DO;
@@ -552,7 +554,7 @@ extern "C" int cg_create(const cg_config* cfg, cg_ctx** out) {
     if (l < NL) { DA_(c->X[l], n); DA_(c->DX[l], n); } else { c->X[l] = c->H[l]; c->DX[l] = nullptr; }
   }
   DA_(c->V5, Bm * c->dl[NL] * c->dcp[NL] * es);
-  DA_(c->scores, Bt * 4); DA_(c->coef, Bt * 4); DA_(c->sumsq, Bm * 4); DA_(c->ucoef, Bm * 4); DA_(c->norms, Bm * 4);
+  DA_(c->scores, Bt * 4); DA_(c->coef, Bt * 4); DA_(c->sumsq, Bm * 8); DA_(c->ucoef, Bm * 4); DA_(c->norms, Bm * 4);
   DA_(c->Z, Bm * c->nd * 4);
   for (int i = 0; i <= NL; ++i) {
     const size_t n = Bm * c->gl[i] * c->gcp[i] * es;
@@ -1104,7 +1106,7 @@ static bool d_dgrad_ps_fusable(cg_ctx* c, int l, int Bt) {
   const RsParams p = d_dgrad_params(c, l, 0, Bt, nullptr);
   return tc_rsgemm_supported(p) && tc_rsgemm2_supported(p) && (p.seg.nphase == 2 || p.merged_phases);
 }
-static int d_dgrad_layer(cg_ctx* c, int l, int b0, int nb, void* out, float* sumsq = nullptr, const void* ps_mask = nullptr,
+static int d_dgrad_layer(cg_ctx* c, int l, int b0, int nb, void* out, double* sumsq = nullptr, const void* ps_mask = nullptr,
                          int group_b = 0, const int32_t* sh = nullptr, int groups = 0) {
   RsParams p = d_dgrad_params(c, l, b0, nb, out);
   p.sumsq = sumsq;
@@ -1145,7 +1147,7 @@ static RsParams d_dgrad_params(cg_ctx* c, int l, int b0, int nb, void* out) {
 
 // backward chain of sum_b coef[b]*D(x)_b down to DA[1] (and DX[0] for samples [dx0_b0, dx0_b0+dx0_nb))
 static int d_backward(cg_ctx* c, int Bt, int B, int groups, const int32_t* sh, int dx0_b0, int dx0_nb,
-                      float* sumsq = nullptr) {   // sumsq: per-sample squared norm of dX0, fused into the last GEMM
+                      double* sumsq = nullptr) {   // sumsq: per-sample squared norm of dX0, fused into the last GEMM
   CK(glue(c, 2.0 * Bt * c->dl[NL] * c->dcp[NL] * c->esz + 4.0 * c->dl[NL] * c->dc[NL]));
   DISPATCH_T(c, glue_launch(head_backward_kernel<T>, dim3(grid_for((long long)Bt * c->dl[NL] * c->dcp[NL] / (16 / c->esz))), dim3(256), 0, c->stream, 
                     (const T*)c->H[NL], dparam(c, 10), c->coef, (T*)c->DA[NL], Bt, c->dl[NL], c->dc[NL], c->dcp[NL]));
@@ -1371,7 +1373,7 @@ static int critic_forward_gp(cg_ctx* c, const float* real, int B, const float* n
   CK(d_forward(c, 3 * B, B, 3, sh));
   glue_launch(fill_coef_kernel, dim3((3 * B + 255) / 256), dim3(256), 0, c->stream, c->coef, B, 3, 0.f);
   CK(post_launch(c, "fill_coef"));
-  CU(cudaMemsetAsync(c->sumsq, 0, (size_t)B * 4, c->stream));
+  CU(cudaMemsetAsync(c->sumsq, 0, (size_t)B * 8, c->stream));
   // tensor-core path: ||g_b||^2 accumulates in the epilogue of the last data-gradient GEMM (fp32 accumulators)
   const bool fuse_norm = c->use_tc && c->dl[1] >= 128 && !c->tc.force_v1;
   CK(d_backward(c, 3 * B, B, 3, sh, 2 * B, B, fuse_norm ? c->sumsq : nullptr));
@@ -1708,10 +1710,11 @@ extern "C" int cg_debug_gp(cg_ctx* c, const float* xhat, int B, const int32_t* s
     CK(post_launch(c, "unpad"));
   }
   if (norms_dev) {
-    CU(cudaMemsetAsync(c->sumsq, 0, (size_t)B * 4, c->stream));
+    CU(cudaMemsetAsync(c->sumsq, 0, (size_t)B * 8, c->stream));
     DISPATCH_T(c, sumsq_kernel<T><<<B * 8, 256, 0, c->stream>>>((const T*)c->DX[0], c->sumsq, (long long)c->L * c->dcp[0], 8));
     CK(post_launch(c, "sumsq"));
-    CU(cudaMemcpyAsync(norms_dev, c->sumsq, (size_t)B * 4, cudaMemcpyDeviceToDevice, c->stream));   // squared norms
+    sumsq_to_float_kernel<<<(B + 255) / 256, 256, 0, c->stream>>>(c->sumsq, norms_dev, B);   // squared norms
+    CK(post_launch(c, "sumsq_to_float"));
   }
   CU(cudaStreamSynchronize(c->stream));
   return 0;
@@ -1734,7 +1737,7 @@ extern "C" int cg_gp_gradient(cg_ctx* c, const float* xhat, int B, const int32_t
   CK(d_forward(c, B, B, 1, sh));                                                    // pass 1: forward, slope masks
   glue_launch(fill_coef_kernel, dim3((B + 255) / 256), dim3(256), 0, c->stream, c->coef, B, 1, 1.f);
   CK(post_launch(c, "fill_coef"));
-  CU(cudaMemsetAsync(c->sumsq, 0, (size_t)B * 4, c->stream));
+  CU(cudaMemsetAsync(c->sumsq, 0, (size_t)B * 8, c->stream));
   const bool fuse_norm = c->use_tc && c->dl[1] >= 128 && !c->tc.force_v1;
   CK(d_backward(c, B, B, 1, sh, 0, B, fuse_norm ? c->sumsq : nullptr));             // pass 2: g and ||g||
   if (!fuse_norm) {

@@ -868,9 +868,10 @@ __global__ void sigmoid_backward_kernel(const T* __restrict__ DX0, const float* 
 // =============================================================================================
 // Gradient-penalty scalars (wgan_gp.py:49-50,58-62)
 // =============================================================================================
-// sumsq[b] = sum g[b,:]^2 ; one block per (sample, chunk), atomics into sumsq (zeroed before)
+// sumsq[b] = sum g[b,:]^2 ; one block per (sample, chunk), atomics into sumsq (zeroed before). The accumulator is a double:
+// adding a few hundred fp32 partial sums of similar magnitude in double is exact, hence independent of the arrival order
 template <typename T>
-__global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ G, float* __restrict__ sumsq,
+__global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ G, double* __restrict__ sumsq,
                                                     long long per_sample, int chunks) {
   __shared__ float red[8];
   const int b = blockIdx.x / chunks, ch = blockIdx.x % chunks;
@@ -890,13 +891,17 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const T* __restrict__ G, flo
   if (threadIdx.x < 32) {
     float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) atomicAdd(&sumsq[b], v);
+    if (threadIdx.x == 0) atomicAdd(&sumsq[b], (double)v);
   }
+}
+__global__ void sumsq_to_float_kernel(const double* __restrict__ sumsq, float* __restrict__ out, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) out[b] = (float)sumsq[b];
 }
 
 // single block: losses + per-sample coefficient of u = d(lambda*GP)/dg
 // scal[0]=dis_loss scal[1]=gp scal[2]=real_loss scal[3]=fake_loss ; norms[b] = ||g_b||
-__global__ void critic_scalars_kernel(const float* __restrict__ scores, const float* __restrict__ sumsq,
+__global__ void critic_scalars_kernel(const float* __restrict__ scores, const double* __restrict__ sumsq,
                                       float* __restrict__ ucoef, float* __restrict__ norms, float* __restrict__ scal,
                                       int B, float lambda) {
   pdl_enter();
@@ -905,7 +910,7 @@ __global__ void critic_scalars_kernel(const float* __restrict__ scores, const fl
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     sr += scores[b];
     sf += scores[B + b];
-    const float n = sqrtf(sumsq[b]);
+    const float n = sqrtf((float)sumsq[b]);
     norms[b] = n;
     sg += (n - 1.f) * (n - 1.f);
     ucoef[b] = lambda * (2.f / B) * (n - 1.f) / n;   // no epsilon: tf.norm (wgan_gp.py:49)

@@ -555,9 +555,9 @@ __device__ __forceinline__ void epilogue_block(const RsParams& p, uint32_t tmem_
   if (EPI == EPI_NONE && p.sumsq) {
     if (R.uniform) {   // all 32 rows of the warp belong to one sample
       ssq = warp_sum(R.my_ok ? ssq : 0.f);
-      if (lane == 0 && R.my_ok) atomicAdd(&p.sumsq[R.my_row / ((long long)p.Q * p.seg.nphase)], ssq);
+      if (lane == 0 && R.my_ok) atomicAdd(&p.sumsq[R.my_row / ((long long)p.Q * p.seg.nphase)], (double)ssq);
     } else if (R.my_ok) {
-      atomicAdd(&p.sumsq[R.my_row / ((long long)p.Q * p.seg.nphase)], ssq);
+      atomicAdd(&p.sumsq[R.my_row / ((long long)p.Q * p.seg.nphase)], (double)ssq);
     }
   }
 }
