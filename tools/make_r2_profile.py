@@ -50,7 +50,8 @@ if os.path.exists(p):
   out.append('## Launch list of one full step (`ncu --metrics gpu__time_duration.sum --clock-control none`, second step; `launches_%s.csv`)\n' % tag)
   out.append(subprocess.run([sys.executable, 'tools/launch_table.py', p], capture_output=True, text=True).stdout)
 
-p = os.path.join(G, '%s_full.ncu-rep' % tag)
+ntag = sys.argv[3] if len(sys.argv) > 3 else tag   # the 27-launch ncu --set full capture may carry an earlier tag
+p = os.path.join(G, '%s_full.ncu-rep' % ntag)
 if os.path.exists(p):
   raw = subprocess.run(['ncu', '-i', p, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
   rows = list(csv.reader(raw.splitlines()))
@@ -81,8 +82,25 @@ if os.path.exists(p):
   if gem_n:
     commit = subprocess.run(['git', 'rev-parse', '--short', 'HEAD'], capture_output=True, text=True).stdout.strip()
     json.dump({'conv_gemm_dram_bytes_per_launch': gem_bytes / gem_n, 'launches': gem_n, 'commit': commit,
-               'source': 'ncu --set full, %s_full.ncu-rep (dram__bytes_read.sum + dram__bytes_write.sum)' % tag},
+               'source': 'ncu --set full, %s_full.ncu-rep (dram__bytes_read.sum + dram__bytes_write.sum)' % ntag},
               open('profiles/r2_ncu_summary.json', 'w'), indent=1)
+
+p = os.path.join(G, '%s_wgrad.ncu-rep' % tag)
+if os.path.exists(p):
+  raw = subprocess.run(['ncu', '-i', p, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+  rows = list(csv.reader(raw.splitlines()))
+  hdr = rows[0]
+  c = {k: hdr.index(v) for k, v in {'k': 'Kernel Name', 'grid': 'Grid Size', 'dur': 'gpu__time_duration.sum', 'cyc': 'sm__cycles_elapsed.max',
+       'ops': 'sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed',
+       'dr': 'dram__bytes_read.sum', 'dw': 'dram__bytes_write.sum', 'regs': 'launch__registers_per_thread'}.items()}
+  out.append('## Weight-gradient kernel of the FINAL build (`wgrad2p_tc_kernel`, CTA pairs + bulk reduce-add epilogue): `ncu --set full -k regex:wgrad2p?_tc -c 6`\n')
+  out.append('The 27-launch table above was captured one build earlier (single-CTA `wgrad2_tc_kernel` with the bulk epilogue, rows 18 - 22); '
+             'these are the same five launches (critic conv5 ... conv1) of the final build. Before either change the five read 57.1 / 69.6 / 67.6 / 53.7 / 62.4 %.\n')
+  out.append('| # | kernel | grid | us | SM cycles | tensor % of peak (elapsed) | DRAM rd MB | DRAM wr MB | regs |\n|---|---|---|---:|---:|---:|---:|---:|---:|')
+  for i, r in enumerate(rows[2:]):
+    out.append('| %d | `%s` | %s | %.1f | %.0fk | %.1f | %.1f | %.1f | %s |' % (i, r[c['k']].split('(')[0], r[c['grid']], float(r[c['dur']]), float(r[c['cyc']].replace(',', '')) / 1e3,
+               float(r[c['ops']]), float(r[c['dr']]), float(r[c['dw']]), r[c['regs']]))
+  out.append('')
 
 p = os.path.join(G, '%s_layers.txt' % tag)
 if os.path.exists(p):
