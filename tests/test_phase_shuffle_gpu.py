@@ -131,3 +131,24 @@ def test_fused_adjoint_is_bit_exact_on_integers(layer):
     want = (acc.float() * slope).bfloat16().float()   # fp32 product, one rounding to bf16: the engine's storage
     assert torch.equal(a.cpu(), want), (layer, s, float((a.cpu() - want).abs().max()))
   assert fused.engine.tc_launch_count() > 0
+
+
+def test_gradient_penalty_activations_do_not_depend_on_atomic_order():
+  """v_0 = u(||g||) * g feeds the linearised pass, and ||g||^2 is accumulated with atomics from many CTAs. In fp32 its last
+  bit followed their arrival order, so two identical engines occasionally disagreed in thousands of activations
+  (profiles/r2_gp_reproducibility.txt); the double accumulator adds the fp32 partials exactly. Two identical engines must
+  now agree on every X[l] of every critic step, element for element."""
+  hp = O.HParams()
+  B = 5
+  real, noises, alphas, _ = O.synthetic_batch(hp, B, seed=B, n_critic=1)
+  a = build(hp, B)
+  b = build(hp, B)
+  b.generator.set_weights(a.generator.get_weights())
+  b.discriminator.set_weights(a.discriminator.get_weights())
+  for rep in range(3):
+    for s in (-10, -1, 4, 10):
+      sh = _group_shifts(s).reshape(-1)
+      a.engine.critic_step(real, noises[0], alphas[0], sh, update=False)
+      b.engine.critic_step(real, noises[0], alphas[0], sh, update=False)
+      for l in range(1, 6):
+        assert torch.equal(a.engine.debug_read(L.BUF_X, l, 3 * B), b.engine.debug_read(L.BUF_X, l, 3 * B)), (rep, s, l)
