@@ -5,8 +5,13 @@
 //              A tiles are tap-shifted 3-D TMA boxes (batch is its own dim -> per-sample zero fill),
 //              W tiles 2-D TMA boxes, both K-major SWIZZLE_128B; D (128 x BN fp32) lives in TMEM,
 //              double buffered; warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = epilogue (two per TMEM lane quarter).
+//  rsgemm3_tc: the same GEMM on CTA pairs (cta_group::2, M = 256), slab reuse through row-shifted descriptors, row-pair and
+//              merged-phase forms for 64-channel layers; serves every layer with >= 128 time rows per sample.
 //  wgrad_tc  : dW[tap][m][n] += sum_{b,q} S[b, q+shift(tap), scol(tap)+m] * P[b,q,n]
-//              both operands MN-major (reduction runs over time rows), split over rows, fp32 red.add.
+//              both operands MN-major (reduction runs over time rows), split over rows.
+//  wgrad2_tc : slab reuse (one slab per 64-row chunk serves all taps of a parity group through LBO-shifted descriptors);
+//              epilogue = accumulator rows staged in the idle stage ring + one bulk reduce-add per row segment.
+//  wgrad2p_tc: wgrad2 on CTA pairs: two work items share the P tile, each CTA loads / reads half of it (default).
 #pragma once
 #include <cuda.h>
 
