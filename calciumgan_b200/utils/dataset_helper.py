@@ -164,7 +164,14 @@ def get_dataset_info(hparams):
   if hparams.normalize:
     hparams.signals_min = float(info['signals_min'])
     hparams.signals_max = float(info['signals_max'])
+  set_generated_dir(hparams)
   return info
+
+
+def set_generated_dir(hparams):
+  """gan/utils/dataset_helper.py:139-141: generated signals go to output_dir/generated"""
+  hparams.generated_dir = os.path.join(hparams.output_dir, 'generated')
+  os.makedirs(hparams.generated_dir, exist_ok=True)
 
 
 def _load_split(pattern, signal_shape):

@@ -23,6 +23,43 @@ def denormalize(x, x_min, x_max):
   return x * (x_max - x_min) + x_min
 
 
+def reverse_preprocessing(hparams, x):
+  """gan/utils/utils.py:50-63: undo the dataset preprocessing so that generated signals match the raw recordings. Only the
+  1-D, non-FFT layout is in scope (conv2d / fft variants are not built)."""
+  if getattr(hparams, 'conv2d', False) or getattr(hparams, 'fft', False):
+    raise NotImplementedError('conv2d / fft datasets are out of scope of calciumgan_b200')
+  if hparams.normalize:
+    x = denormalize(x, x_min=hparams.signals_min, x_max=hparams.signals_max)
+  return x
+
+
+def save_fake_signals(hparams, epoch, signals):
+  """gan/utils/utils.py:93-113: append one validation batch of generated signals (de-normalised, float32, NWC) to
+  `generated_dir/epoch%03d_signals.h5` under the key 'signals', and record {epoch: {'global_step', 'filename'}} in
+  `generated_dir/info.pkl` the first time the epoch is seen. `signals` may be a device tensor (what `gan.validate` returns)."""
+  from . import h5_helper
+  if hasattr(signals, 'detach'):
+    signals = signals.detach().float().cpu().numpy()
+  signals = reverse_preprocessing(hparams, np.asarray(signals))
+  filename = os.path.join(hparams.generated_dir, 'epoch{:03d}_signals.h5'.format(epoch))
+  h5_helper.write(filename, {'signals': signals.astype(np.float32)})
+  info_filename = os.path.join(hparams.generated_dir, 'info.pkl')
+  info = {}
+  if os.path.exists(info_filename):
+    with open(info_filename, 'rb') as file:
+      info = pickle.load(file)
+  if epoch not in info:
+    info[epoch] = {'global_step': hparams.global_step, 'filename': filename}
+    with open(info_filename, 'wb') as file:
+      pickle.dump(info, file)
+
+
+def save_generated_at(hparams, epoch):
+  """main.py:81-84 of the reference: 'all' -> every 10th epoch and the last one, 'last' -> the last epoch only"""
+  last = epoch == hparams.epochs - 1
+  return (hparams.save_generated == 'all' and (epoch % 10 == 0 or last)) or (hparams.save_generated == 'last' and last)
+
+
 def get_current_git_hash():
   """gan/utils/utils.py:66-69; 'unknown' outside a git checkout instead of raising."""
   import subprocess

@@ -42,6 +42,8 @@ def get_dataset(hparams):
   hparams.noise_shape = (hparams.noise_dim,)
   hparams.train_steps = int(np.ceil(len(train) / hparams.batch_size))
   hparams.validation_steps = int(np.ceil(len(val) / hparams.batch_size))
+  from calciumgan_b200.utils.dataset_helper import set_generated_dir
+  set_generated_dir(hparams)
 
   def batches(x, shuffle):
     idx = np.random.permutation(len(x)) if shuffle else np.arange(len(x))
@@ -91,10 +93,14 @@ def train(hparams, train_ds, gan, summary, epoch, cache=None):
 
 
 def validate(hparams, validation_ds, gan, summary, epoch):
+  from calciumgan_b200.utils import utils
   start = time()
   gen_losses, dis_losses, gradient_penalties, results = [], [], [], {}
+  save_generated = utils.save_generated_at(hparams, epoch)      # main.py:81-84
   for signal, _ in validation_ds():
     fake, gen_loss, dis_loss, gradient_penalty, metrics = gan.validate(signal)
+    if save_generated:
+      utils.save_fake_signals(hparams, epoch, signals=fake)     # main.py:105-106
     gen_losses.append(gen_loss)
     dis_losses.append(dis_loss)
     gradient_penalties.append(gradient_penalty)

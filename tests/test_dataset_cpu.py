@@ -40,7 +40,7 @@ def test_dataset_layout_to_hparams(tmp_path):
   signals = rng.rand(11, 64, 6).astype(np.float32) * 3 - 1
   spikes = (rng.rand(11, 64, 6) > 0.9).astype(np.float32)
   D.write_dataset(str(tmp_path), signals, spikes, train_size=8, num_per_shard=3)
-  hp = argparse.Namespace(input_dir=str(tmp_path), batch_size=3, noise_dim=4)
+  hp = argparse.Namespace(input_dir=str(tmp_path), output_dir=str(tmp_path / 'runs'), batch_size=3, noise_dim=4)
   train_ds, val_ds = D.get_dataset(hp)
   assert hp.signal_shape == (64, 6) and hp.num_channels == 6 and hp.normalize and hp.noise_shape == (4,)
   assert hp.train_size == 8 and hp.validation_size == 3 and hp.train_steps == 3 and hp.num_train_shards == 3

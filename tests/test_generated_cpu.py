@@ -1,0 +1,107 @@
+"""`save_fake_signals` and its dataset store (gan/utils/utils.py:50-63,93-113, gan/utils/h5_helper.py,
+main.py:81-84): append semantics, selectors, bookkeeping in info.pkl, de-normalisation, and the epochs at which main.py
+saves. Runs on whichever backend the image offers (h5py when importable, else the .npy-parts fallback)."""
+import argparse
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from calciumgan_b200.utils import h5_helper, utils
+
+
+def test_write_appends_along_axis_0_and_selectors(tmp_path):
+  filename = str(tmp_path / 'x.h5')
+  rng = np.random.RandomState(0)
+  a, b = rng.rand(3, 16, 5).astype(np.float32), rng.rand(2, 16, 5).astype(np.float32)
+  assert not os.path.exists(filename) and not os.path.exists(h5_helper.parts_dir(filename))
+  h5_helper.write(filename, {'signals': a})
+  h5_helper.write(filename, {'signals': b, 'spikes': b.astype(np.int8)})
+  full = np.concatenate([a, b])
+  got = h5_helper.get(filename, 'signals')
+  assert got.dtype == np.float32
+  np.testing.assert_array_equal(got, full)
+  assert h5_helper.get_dataset_length(filename, 'signals') == 5 and h5_helper.get_dataset_length(filename, 'spikes') == 2
+  assert h5_helper.contains(filename, 'spikes') and not h5_helper.contains(filename, 'nothing')
+  np.testing.assert_array_equal(h5_helper.get(filename, 'signals', neuron=4), full[:, :, 4])
+  for t in (0, 2, 3, 4, -1):       # both blocks and the boundary between them
+    np.testing.assert_array_equal(h5_helper.get(filename, 'signals', trial=t), full[t])
+  with pytest.raises(KeyError):
+    h5_helper.get(filename, 'nothing')
+  with pytest.raises(AssertionError):
+    h5_helper.get(filename, 'signals', neuron=0, trial=0)
+  h5_helper.overwrite(filename, 'signals', a[:1])
+  np.testing.assert_array_equal(h5_helper.get(filename, 'signals'), a[:1])
+  with pytest.raises(KeyError):
+    h5_helper.overwrite(filename, 'nothing', a)
+
+
+def test_append_rejects_a_different_row_shape(tmp_path):
+  if h5_helper.backend() == 'h5py':
+    pytest.skip('h5py raises its own error type')
+  filename = str(tmp_path / 'x.h5')
+  h5_helper.write(filename, {'signals': np.zeros((2, 8, 3), np.float32)})
+  with pytest.raises(ValueError):
+    h5_helper.write(filename, {'signals': np.zeros((2, 8, 4), np.float32)})
+  with pytest.raises(ValueError):
+    h5_helper.write(filename, {'signals': np.zeros((2, 8, 3), np.float64)})
+
+
+def _hparams(tmp_path, **kw):
+  hp = argparse.Namespace(generated_dir=str(tmp_path), normalize=True, signals_min=-2.0, signals_max=6.0, fft=False,
+                          conv2d=False, global_step=17, epochs=25, save_generated='all')
+  hp.__dict__.update(kw)
+  return hp
+
+
+def test_save_fake_signals_denormalises_appends_and_records_the_epoch_once(tmp_path):
+  hp = _hparams(tmp_path)
+  rng = np.random.RandomState(1)
+  batches = [rng.rand(4, 32, 6).astype(np.float32), rng.rand(3, 32, 6).astype(np.float32)]    # ragged last batch
+  utils.save_fake_signals(hp, 3, batches[0])
+  hp.global_step = 99          # the epoch's entry keeps the step at which it was first written (utils.py:110-113)
+  utils.save_fake_signals(hp, 3, batches[1])
+  filename = os.path.join(str(tmp_path), 'epoch003_signals.h5')
+  got = h5_helper.get(filename, 'signals')
+  assert got.dtype == np.float32 and got.shape == (7, 32, 6)
+  np.testing.assert_allclose(got, np.concatenate(batches) * 8.0 - 2.0, rtol=1e-6)
+  utils.save_fake_signals(hp, 10, batches[1])
+  with open(os.path.join(str(tmp_path), 'info.pkl'), 'rb') as file:
+    info = pickle.load(file)
+  assert info == {3: {'global_step': 17, 'filename': filename},
+                  10: {'global_step': 99, 'filename': os.path.join(str(tmp_path), 'epoch010_signals.h5')}}
+
+
+def test_save_fake_signals_accepts_tensors_and_unnormalised_data(tmp_path):
+  torch = pytest.importorskip('torch')
+  hp = _hparams(tmp_path, normalize=False)
+  x = torch.rand(2, 8, 3, dtype=torch.float64, requires_grad=True)
+  utils.save_fake_signals(hp, 0, x)
+  got = h5_helper.get(os.path.join(str(tmp_path), 'epoch000_signals.h5'), 'signals')
+  assert got.dtype == np.float32
+  np.testing.assert_allclose(got, x.detach().numpy().astype(np.float32))
+  for flag in ('fft', 'conv2d'):     # out of scope: loud, not silently wrong
+    with pytest.raises(NotImplementedError):
+      utils.save_fake_signals(_hparams(tmp_path, **{flag: True}), 0, x)
+
+
+def test_epochs_at_which_main_saves_generated_signals(tmp_path):
+  """main.py:81-84: 'all' = every 10th epoch and the last, 'last' = only the last, '' = never"""
+  hp = _hparams(tmp_path)
+  assert [e for e in range(25) if utils.save_generated_at(hp, e)] == [0, 10, 20, 24]
+  hp.save_generated = 'last'
+  assert [e for e in range(25) if utils.save_generated_at(hp, e)] == [24]
+  hp.save_generated = ''
+  assert not any(utils.save_generated_at(hp, e) for e in range(25))
+
+
+def test_dataset_info_sets_the_generated_dir(tmp_path):
+  """gan/utils/dataset_helper.py:139-141"""
+  from calciumgan_b200.utils import dataset_helper
+  data_dir = str(tmp_path / 'tfrecords')
+  signals = np.random.RandomState(0).rand(4, 16, 3).astype(np.float32)
+  dataset_helper.write_dataset(data_dir, signals, np.zeros_like(signals), train_size=3)
+  hp = argparse.Namespace(input_dir=data_dir, output_dir=str(tmp_path / 'runs'))
+  dataset_helper.get_dataset_info(hp)
+  assert hp.generated_dir == os.path.join(hp.output_dir, 'generated') and os.path.isdir(hp.generated_dir)

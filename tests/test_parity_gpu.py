@@ -321,12 +321,22 @@ def test_main_end_to_end_on_tfrecords(tmp_path):
   assert hp.global_step == 4                                  # 2 epochs x ceil(7 / 4) batches
   assert os.path.exists(os.path.join(out_dir, 'checkpoints', 'epoch-001.pkl'))
   assert glob.glob(os.path.join(out_dir, 'events.out.tfevents.*'))
-  argv2 = list(argv)
+  assert not os.listdir(os.path.join(out_dir, 'generated'))   # --save_generated defaults to "": nothing is written
+  argv2 = list(argv) + ['--save_generated', 'last']
   argv2[argv2.index('--epochs') + 1] = '3'
   hp2 = driver.build_parser().parse_args(argv2)
   hp2.global_step, hp2.surrogate_ds = 0, False
   driver.main(hp2)
   assert hp2.start_epoch == 2 and hp2.global_step == 2        # resumed from epoch-001, one more epoch
+  # generated validation signals of the last epoch (main.py:81-84,105-106; utils.py:93-113): de-normalised float32 NWC
+  import pickle
+  from calciumgan_b200.utils import h5_helper
+  filename = os.path.join(out_dir, 'generated', 'epoch002_signals.h5')
+  fake = h5_helper.get(filename, 'signals')
+  assert fake.shape == (3, 256, 20) and fake.dtype == np.float32       # 10 - 7 validation signals in one batch
+  assert signals.min() <= fake.min() and fake.max() <= signals.max()     # sigmoid output mapped back to the data range
+  with open(os.path.join(out_dir, 'generated', 'info.pkl'), 'rb') as file:
+    assert pickle.load(file) == {2: {'global_step': 2, 'filename': filename}}
 
 
 def test_generator_head_kernel_modes_bf16(monkeypatch):
