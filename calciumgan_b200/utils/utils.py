@@ -60,6 +60,54 @@ def save_generated_at(hparams, epoch):
   return (hparams.save_generated == 'all' and (epoch % 10 == 0 or last)) or (hparams.save_generated == 'last' and last)
 
 
+def swap_neuron_major(hparams, array):
+  """gan/utils/utils.py:86-89: (validation_size, num_neurons, ...) -> neuron-major; anything else is returned as is"""
+  if tuple(array.shape[:2]) == (hparams.validation_size, hparams.num_neurons):
+    return np.swapaxes(array, 0, 1)
+  return array
+
+
+def get_array_format(shape, hparams):
+  """gan/utils/utils.py:154-165: one letter per axis -- W = sequence length, C = number of neurons, N = anything else"""
+  assert len(shape) <= 3
+  return ''.join('W' if s == hparams.sequence_length else 'C' if s == hparams.num_neurons else 'N' for s in shape)
+
+
+def set_array_format(array, data_format, hparams):
+  """gan/utils/utils.py:168-184: permute `array` (numpy or torch) to `data_format`, e.g. a (W, C) trace block to 'CW'"""
+  assert len(array.shape) == len(data_format)
+  current = get_array_format(array.shape, hparams)
+  assert set(current) == set(data_format)
+  if data_format == current:
+    return array
+  perm = [current.index(s) for s in data_format]
+  return array.permute(*perm) if hasattr(array, 'permute') else np.transpose(array, axes=perm)
+
+
+def remove_nan(array):
+  """gan/utils/utils.py:187-188"""
+  return array[np.logical_not(np.isnan(array))]
+
+
+def generate_dataset(hparams, gan, num_samples=1000, batch_size=100):
+  """gan/utils/utils.py:191-207: `num_samples` de-normalised generator outputs in batches of 100 ->
+  output_dir/generated.pkl {'signals': float32 (num_samples,) + signal_shape} (main.py:219-221 calls it with 2e6 samples
+  for surrogate datasets). The last batch is cut to size (the reference requires num_samples % 100 == 0)."""
+  generated = np.zeros((num_samples,) + tuple(hparams.signal_shape), dtype=np.float32)
+  for i in range(0, num_samples, batch_size):
+    n = min(batch_size, num_samples - i)
+    signals = gan.generate(gan.get_noise(n), denorm=True)
+    if hasattr(signals, 'detach'):
+      signals = signals.detach().float().cpu().numpy()
+    generated[i:i + n] = signals
+  filename = os.path.join(hparams.output_dir, 'generated.pkl')
+  with open(filename, 'wb') as file:
+    pickle.dump({'signals': generated}, file, protocol=4)      # protocol 4: arrays beyond 4 GiB
+  if getattr(hparams, 'verbose', 0):
+    print('save {} samples to {}'.format(num_samples, filename))
+  return filename
+
+
 def get_current_git_hash():
   """gan/utils/utils.py:66-69; 'unknown' outside a git checkout instead of raising."""
   import subprocess

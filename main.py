@@ -149,6 +149,8 @@ def main(hparams, return_metrics=False):
       utils.save_models(hparams, gan, epoch)
   summary.scalar('elapse/total', time() - start)
   summary.flush()
+  if getattr(hparams, 'surrogate_ds', False):    # main.py:219-221: samples for the surrogate metrics
+    utils.generate_dataset(hparams, gan=gan, num_samples=2 * 10**6)
   if hparams.verbose:
     print('elapse/total {:.2f}s'.format(time() - start))
   if return_metrics:

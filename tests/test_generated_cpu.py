@@ -105,3 +105,49 @@ def test_dataset_info_sets_the_generated_dir(tmp_path):
   hp = argparse.Namespace(input_dir=data_dir, output_dir=str(tmp_path / 'runs'))
   dataset_helper.get_dataset_info(hp)
   assert hp.generated_dir == os.path.join(hp.output_dir, 'generated') and os.path.isdir(hp.generated_dir)
+
+
+class _StubGan(object):
+  """get_noise / generate of gan/algorithms/gan.py:29-30,92-97 on the host: sample i is filled with its running index"""
+
+  def __init__(self, signal_shape):
+    self.signal_shape, self.count, self.batches = tuple(signal_shape), 0, []
+
+  def get_noise(self, batch_size):
+    return np.zeros((batch_size, 4), np.float32)
+
+  def generate(self, noise, denorm=False):
+    assert denorm
+    n = len(noise)
+    self.batches.append(n)
+    out = np.arange(self.count, self.count + n, dtype=np.float32).reshape((n,) + (1,) * len(self.signal_shape))
+    self.count += n
+    return np.broadcast_to(out, (n,) + self.signal_shape)
+
+
+def test_generate_dataset_writes_generated_pkl(tmp_path):
+  hp = argparse.Namespace(output_dir=str(tmp_path), signal_shape=(8, 3), verbose=0)
+  gan = _StubGan(hp.signal_shape)
+  filename = utils.generate_dataset(hp, gan, num_samples=250)
+  assert filename == os.path.join(str(tmp_path), 'generated.pkl') and gan.batches == [100, 100, 50]
+  with open(filename, 'rb') as file:
+    content = pickle.load(file)
+  assert list(content) == ['signals'] and content['signals'].dtype == np.float32 and content['signals'].shape == (250, 8, 3)
+  np.testing.assert_array_equal(content['signals'][:, 0, 0], np.arange(250))
+
+
+def test_array_format_helpers():
+  hp = argparse.Namespace(sequence_length=16, num_neurons=5, validation_size=7)
+  x = np.arange(7 * 16 * 5, dtype=np.float32).reshape(7, 16, 5)
+  assert utils.get_array_format(x.shape, hp) == 'NWC' and utils.get_array_format((5, 16), hp) == 'CW'
+  assert utils.set_array_format(x, 'NWC', hp) is x
+  np.testing.assert_array_equal(utils.set_array_format(x, 'NCW', hp), x.transpose(0, 2, 1))
+  np.testing.assert_array_equal(utils.set_array_format(x[0], 'CW', hp), x[0].T)      # what main.py:145-146 asks for
+  torch = pytest.importorskip('torch')
+  t = utils.set_array_format(torch.from_numpy(x), 'CWN', hp)
+  assert tuple(t.shape) == (5, 16, 7) and float(t[2, 3, 4]) == x[4, 3, 2]
+  with pytest.raises(AssertionError):
+    utils.set_array_format(x, 'NW', hp)
+  y = np.zeros((7, 5, 3))
+  assert utils.swap_neuron_major(hp, y).shape == (5, 7, 3) and utils.swap_neuron_major(hp, np.zeros((5, 7, 3))).shape == (5, 7, 3)
+  np.testing.assert_array_equal(utils.remove_nan(np.array([1.0, np.nan, 3.0])), [1.0, 3.0])
