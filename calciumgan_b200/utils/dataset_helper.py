@@ -172,44 +172,136 @@ def set_generated_dir(hparams):
   """gan/utils/dataset_helper.py:139-141: generated signals go to output_dir/generated"""
   hparams.generated_dir = os.path.join(hparams.output_dir, 'generated')
   os.makedirs(hparams.generated_dir, exist_ok=True)
+  hparams.validation_cache = os.path.join(hparams.generated_dir, 'validation.h5')
 
 
-def _load_split(pattern, signal_shape):
-  signals = []
+def _load_split(pattern, signal_shape, spike_shape=None):
+  """every record of the shards matching `pattern`, in file order: signals (N,) + signal_shape and, when `spike_shape`
+  is given, spikes (N,) + spike_shape (dataset_helper.py:157-164)"""
+  signals, spikes = [], []
   for path in sorted(glob(pattern)):
     for record in read_records(path):
       ex = parse_example(record)
       signals.append(np.frombuffer(ex['signal'], dtype=np.float32).reshape(signal_shape))
+      if spike_shape is not None:
+        spikes.append(np.frombuffer(ex['spike'], dtype=np.float32).reshape(spike_shape))
   if not signals:
     raise IOError('no records match %s' % pattern)
-  return np.stack(signals)
+  return np.stack(signals), (np.stack(spikes) if spike_shape is not None else None)
+
+
+def shuffle_buffer_order(n, buffer_size, rng):
+  """Order in which `tf.data.Dataset.shuffle(buffer_size)` (dataset_helper.py:172) emits n elements: a buffer of
+  `buffer_size` elements is filled in input order, a uniformly chosen slot is emitted and refilled with the next input
+  element. With buffer_size >= n this is a uniform permutation; with a smaller buffer element i cannot appear before
+  output position i - buffer_size + 1 (the locality a windowed shuffle has). Same algorithm, not the same random stream."""
+  buffer_size = max(1, int(buffer_size))
+  buf = list(range(min(buffer_size, n)))
+  nxt = len(buf)
+  order = np.empty(n, dtype=np.int64)
+  for k in range(n):
+    j = int(rng.randint(len(buf)))
+    order[k] = buf[j]
+    if nxt < n:
+      buf[j] = nxt
+      nxt += 1
+    else:
+      buf[j] = buf[-1]
+      buf.pop()
+  return order
+
+
+def shard_for_rank(n, rank, world_size):
+  """Indices of the samples rank `rank` trains on under batch-sharded data parallelism: a strided slice of the first
+  floor(n / world) * world samples, so every rank has the same number of samples -- hence the same number of batches and
+  the same (possibly ragged) last batch size, which the gradient exchange in every `gan.train` call requires."""
+  per = n // world_size
+  if per == 0:
+    raise ValueError('%d training samples cannot be split over %d ranks' % (n, world_size))
+  return np.arange(per * world_size)[rank::world_size]
 
 
 class _Batches(object):
-  """Re-iterable batch source: shuffle (train) + batch without drop_remainder (dataset_helper.py:171-181)."""
+  """Re-iterable batch source: shuffle(buffer_size) (train) + batch without drop_remainder (dataset_helper.py:171-181).
+  Yields (signals, spikes or None) like the reference's (signal, spike) pairs."""
 
-  def __init__(self, signals, batch_size, shuffle, seed=1234):
-    self.signals, self.batch_size, self.shuffle = signals, batch_size, shuffle
+  def __init__(self, signals, batch_size, shuffle, seed=1234, spikes=None, buffer_size=None):
+    self.signals, self.spikes, self.batch_size, self.shuffle = signals, spikes, batch_size, shuffle
+    self.buffer_size = len(signals) if buffer_size is None else buffer_size
     self.rng = np.random.RandomState(seed)
 
   def __len__(self):
     return int(np.ceil(len(self.signals) / self.batch_size))
 
   def __iter__(self):
-    idx = self.rng.permutation(len(self.signals)) if self.shuffle else np.arange(len(self.signals))
-    for i in range(0, len(idx), self.batch_size):
-      yield self.signals[idx[i:i + self.batch_size]], None
+    n = len(self.signals)
+    idx = shuffle_buffer_order(n, self.buffer_size, self.rng) if self.shuffle else np.arange(n)
+    for i in range(0, n, self.batch_size):
+      sel = idx[i:i + self.batch_size]
+      yield self.signals[sel], (None if self.spikes is None else self.spikes[sel])
+
+
+def cache_validation_set(hparams, validation_ds):
+  """dataset_helper.py:12-31: the de-normalised validation signals (float32) and spikes (int8) go to
+  generated_dir/validation.h5 once, next to the generated signals they are compared with."""
+  from . import h5_helper, utils
+  if h5_helper.exists(hparams.validation_cache):
+    return
+  for signal, spike in validation_ds:
+    signal = utils.reverse_preprocessing(hparams, np.asarray(signal))
+    h5_helper.write(hparams.validation_cache, {'signals': signal.astype(np.float32), 'spikes': np.asarray(spike).astype(np.int8)})
+
+
+def get_surrogate_dataset(hparams):
+  """dataset_helper.py:53-110: input_dir/training.pkl {'signals': (trials, neurons, time), 'spikes'} -> NWC signals scaled
+  to [0, 1] by the global min / max, the first 8192 trials train (shuffle buffer 2048), the rest validate."""
+  filename = os.path.join(hparams.input_dir, 'training.pkl')
+  if not os.path.exists(filename):
+    print('training dataset {} not found'.format(filename))
+    exit()
+  with open(filename, 'rb') as file:
+    data = pickle.load(file)
+  signals = np.transpose(np.asarray(data['signals'], np.float32), axes=[0, 2, 1])
+  spikes = np.asarray(data['spikes'])
+  hparams.signals_min, hparams.signals_max = float(np.min(signals)), float(np.max(signals))
+  signals = (signals - hparams.signals_min) / (hparams.signals_max - hparams.signals_min)
+  train_size = 8192
+  hparams.train_size, hparams.validation_size = len(signals[:train_size]), len(signals[train_size:])
+  hparams.signal_shape = tuple(signals.shape[1:])
+  hparams.spike_shape = tuple(spikes.shape[1:])
+  hparams.sequence_length, hparams.num_neurons, hparams.num_channels = signals.shape[1], signals.shape[-1], signals.shape[-1]
+  hparams.normalize, hparams.fft, hparams.conv2d = True, False, False
+  set_generated_dir(hparams)
+  return (_Batches(signals[:train_size], hparams.batch_size, True, spikes=spikes[:train_size], buffer_size=2048),
+          _Batches(signals[train_size:], hparams.batch_size, False, spikes=spikes[train_size:]))
 
 
 def get_dataset(hparams, summary=None):
-  """gan/utils/dataset_helper.py:185-206 for the TFRecord layout; returns re-iterable (train_ds, validation_ds)."""
+  """gan/utils/dataset_helper.py:185-206; returns re-iterable (train_ds, validation_ds) of (signal, spike) batches.
+  Under data parallelism (world_size > 1) the training split is sharded by `shard_for_rank`; validation is not."""
   hparams.noise_shape = (hparams.noise_dim,)
-  get_dataset_info(hparams)
-  train = _load_split(hparams.train_files, hparams.signal_shape)          # == ds.cache()
-  val = _load_split(hparams.validation_files, hparams.signal_shape)
+  rank, world = int(getattr(hparams, 'rank', 0)), int(getattr(hparams, 'world_size', 1))
+  if getattr(hparams, 'surrogate_ds', False):
+    train_ds, validation_ds = get_surrogate_dataset(hparams)
+  else:
+    if not os.path.exists(hparams.input_dir):
+      print('input directory {} cannot be found'.format(hparams.input_dir))
+      exit()
+    get_dataset_info(hparams)
+    train, train_spikes = _load_split(hparams.train_files, hparams.signal_shape, hparams.spike_shape)      # == ds.cache()
+    val, val_spikes = _load_split(hparams.validation_files, hparams.signal_shape, hparams.spike_shape)
+    train_ds = _Batches(train, hparams.batch_size, True, spikes=train_spikes, buffer_size=hparams.buffer_size)
+    validation_ds = _Batches(val, hparams.batch_size, False, spikes=val_spikes)
+    if getattr(hparams, 'save_generated', '') and rank == 0:
+      cache_validation_set(hparams, validation_ds)
+  if world > 1:
+    sel = shard_for_rank(len(train_ds.signals), rank, world)
+    train_ds = _Batches(train_ds.signals[sel], hparams.batch_size, True, seed=1234 + rank,
+                        spikes=None if train_ds.spikes is None else train_ds.spikes[sel], buffer_size=train_ds.buffer_size)
+    hparams.train_size = len(sel)
   hparams.train_steps = int(np.ceil(hparams.train_size / hparams.batch_size))
   hparams.validation_steps = int(np.ceil(hparams.validation_size / hparams.batch_size))
-  return _Batches(train, hparams.batch_size, True), _Batches(val, hparams.batch_size, False)
+  return train_ds, validation_ds
 
 
 def write_dataset(output_dir, signals, spikes, train_size, num_per_shard=1100, normalize=True):

@@ -28,6 +28,11 @@ def parts_dir(filename):
   return filename + '.parts'
 
 
+def exists(filename):
+  """the store `filename` has been written to (whichever backend holds it)"""
+  return os.path.exists(filename) or os.path.isdir(parts_dir(filename))
+
+
 def _blocks(filename, name):
   found = []
   for path in glob(os.path.join(parts_dir(filename), name + '.*.npy')):

@@ -19,10 +19,32 @@ if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
 
 
+def init_distributed(hparams):
+  """Batch-sharded data parallelism (no reference counterpart): under `torchrun --nproc-per-node N main.py ...`
+  every rank binds its GPU and joins the NCCL group before the engine is built, trains on its own shard of the training
+  split (`dataset_helper.shard_for_rank`) and exchanges gradients inside `gan.train`; rank 0 alone writes summaries,
+  checkpoints and generated signals. A plain `python main.py` leaves world_size = 1."""
+  hparams.world_size, hparams.rank = 1, 0
+  if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    if not dist.is_initialized():
+      dist.init_process_group('nccl')
+    hparams.world_size, hparams.rank = dist.get_world_size(), dist.get_rank()
+
+
+class NullSummary(object):
+  """what ranks other than 0 log to: every Summary method is accepted and dropped"""
+
+  def __getattr__(self, name):
+    return lambda *args, **kwargs: None
+
+
 def get_dataset(hparams):
   """Sets the hparams fields the models read (dataset_helper.py:84-91,120-136,186)."""
-  if not hparams.synthetic and os.path.exists(os.path.join(hparams.input_dir, 'info.pkl')):
-    from calciumgan_b200.utils import dataset_helper
+  from calciumgan_b200.utils import dataset_helper
+  if getattr(hparams, 'surrogate_ds', False) or (not hparams.synthetic and os.path.exists(os.path.join(hparams.input_dir, 'info.pkl'))):
     train_ds, validation_ds = dataset_helper.get_dataset(hparams)
     return (lambda: iter(train_ds)), (lambda: iter(validation_ds))
   path = os.path.join(hparams.input_dir, 'signals.npy')
@@ -33,6 +55,8 @@ def get_dataset(hparams):
     signals = np.load(path).astype(np.float32)
   n_train = int(len(signals) * 0.9) if len(signals) >= 10 else len(signals)
   train, val = signals[:n_train], signals[n_train:] if n_train < len(signals) else signals[:1]
+  if getattr(hparams, 'world_size', 1) > 1:
+    train = train[dataset_helper.shard_for_rank(len(train), hparams.rank, hparams.world_size)]
   hparams.train_size, hparams.validation_size = len(train), len(val)
   hparams.signal_shape = tuple(train.shape[1:])
   hparams.sequence_length, hparams.num_neurons = train.shape[1], train.shape[-1]
@@ -42,8 +66,7 @@ def get_dataset(hparams):
   hparams.noise_shape = (hparams.noise_dim,)
   hparams.train_steps = int(np.ceil(len(train) / hparams.batch_size))
   hparams.validation_steps = int(np.ceil(len(val) / hparams.batch_size))
-  from calciumgan_b200.utils.dataset_helper import set_generated_dir
-  set_generated_dir(hparams)
+  dataset_helper.set_generated_dir(hparams)
 
   def batches(x, shuffle):
     idx = np.random.permutation(len(x)) if shuffle else np.arange(len(x))
@@ -96,7 +119,7 @@ def validate(hparams, validation_ds, gan, summary, epoch):
   from calciumgan_b200.utils import utils
   start = time()
   gen_losses, dis_losses, gradient_penalties, results = [], [], [], {}
-  save_generated = utils.save_generated_at(hparams, epoch)      # main.py:81-84
+  save_generated = utils.save_generated_at(hparams, epoch) and getattr(hparams, 'rank', 0) == 0      # main.py:81-84
   for signal, _ in validation_ds():
     fake, gen_loss, dis_loss, gradient_penalty, metrics = gan.validate(signal)
     if save_generated:
@@ -121,18 +144,24 @@ def main(hparams, return_metrics=False):
   from calciumgan_b200.models.registry import get_models
   from calciumgan_b200.utils import utils
 
-  if hparams.clear_output_dir and os.path.exists(hparams.output_dir):
+  init_distributed(hparams)
+  chief = hparams.rank == 0
+  if chief and hparams.clear_output_dir and os.path.exists(hparams.output_dir):
     rmtree(hparams.output_dir)
   os.makedirs(hparams.output_dir, exist_ok=True)
-  np.random.seed(1234)
+  if hparams.world_size > 1:
+    import torch.distributed as dist
+    dist.barrier()                 # nobody reads output_dir (checkpoints to resume from) before rank 0 has cleared it
+  np.random.seed(1234 + hparams.rank)
 
   from calciumgan_b200.utils.summary_helper import Summary
-  summary = Summary(hparams)
+  summary = Summary(hparams) if chief else NullSummary()
   train_ds, validation_ds = get_dataset(hparams)
   generator, discriminator = get_models(hparams, summary)
   gan = get_algorithm(hparams, generator, discriminator, summary)
   utils.load_models(hparams, gan)
-  utils.save_hparams(hparams)       # main.py:184 of the reference
+  if chief:
+    utils.save_hparams(hparams)     # main.py:184 of the reference
 
   cache = None
   if not hparams.no_device_cache:
@@ -145,11 +174,11 @@ def main(hparams, return_metrics=False):
   for epoch in range(hparams.start_epoch, hparams.epochs):
     train(hparams, train_ds, gan, summary, epoch, cache)
     results = validate(hparams, validation_ds, gan, summary, epoch)
-    if not hparams.skip_checkpoints and (epoch % 10 == 0 or epoch == hparams.epochs - 1):
+    if chief and not hparams.skip_checkpoints and (epoch % 10 == 0 or epoch == hparams.epochs - 1):
       utils.save_models(hparams, gan, epoch)
   summary.scalar('elapse/total', time() - start)
   summary.flush()
-  if getattr(hparams, 'surrogate_ds', False):    # main.py:219-221: samples for the surrogate metrics
+  if chief and getattr(hparams, 'surrogate_ds', False):    # main.py:219-221: samples for the surrogate metrics
     utils.generate_dataset(hparams, gan=gan, num_samples=2 * 10**6)
   if hparams.verbose:
     print('elapse/total {:.2f}s'.format(time() - start))

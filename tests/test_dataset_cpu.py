@@ -1,9 +1,12 @@
 """TF-free TFRecord reader/writer for the reference's dataset layout (dataset/generate_tfrecords.py,
 gan/utils/dataset_helper.py): framing, protobuf payload, info.pkl -> hparams, batching without drop_remainder."""
 import argparse
+import os
+import pickle
 import struct
 
 import numpy as np
+import pytest
 
 from calciumgan_b200.utils import dataset_helper as D
 
@@ -126,3 +129,89 @@ def test_hand_assembled_example_known_answer():
   # masked crc of a known frame header (length 20): standard crc32c, rotated right by 15 and offset 0xa282ead8
   c = D.crc32c(struct.pack('<Q', 20))
   assert D.masked_crc32c(struct.pack('<Q', 20)) == ((((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF)
+
+
+def test_shuffle_buffer_order_is_a_windowed_permutation():
+  """tf.data's shuffle(buffer_size) (dataset_helper.py:172): element i cannot be emitted before position i - buffer + 1"""
+  rng = np.random.RandomState(0)
+  for n, buf in ((50, 8), (50, 1), (50, 50), (50, 500), (7, 3), (1, 4)):
+    order = D.shuffle_buffer_order(n, buf, rng)
+    assert sorted(order.tolist()) == list(range(n))
+    pos = np.empty(n, np.int64)
+    pos[order] = np.arange(n)
+    assert (pos >= np.arange(n) - buf + 1).all()
+    if buf == 1:
+      assert order.tolist() == list(range(n))
+  # a full-size buffer is a uniform shuffle: every element reaches the first position with probability 1 / n
+  first = np.bincount([D.shuffle_buffer_order(5, 5, rng)[0] for _ in range(4000)], minlength=5) / 4000.0
+  assert np.abs(first - 0.2).max() < 0.03
+  # a small buffer keeps the epoch roughly in file order
+  assert np.abs(D.shuffle_buffer_order(1000, 10, rng) - np.arange(1000)).max() < 200
+
+
+def test_rank_shards_are_disjoint_and_equal(tmp_path):
+  for n, world in ((10, 2), (11, 4), (8, 8), (1100, 8)):
+    shards = [D.shard_for_rank(n, r, world) for r in range(world)]
+    assert len({len(s) for s in shards}) == 1 and len(shards[0]) == n // world
+    allidx = np.concatenate(shards)
+    assert len(set(allidx.tolist())) == len(allidx) and allidx.max() < n
+  with pytest.raises(ValueError):
+    D.shard_for_rank(3, 0, 4)
+  # through get_dataset: two ranks, 9 training signals -> 4 each, the same number of steps, nothing shared
+  rng = np.random.RandomState(2)
+  signals = rng.rand(12, 32, 4).astype(np.float32)
+  D.write_dataset(str(tmp_path), signals, np.zeros_like(signals), train_size=9, num_per_shard=4)
+  seen = []
+  for rank in range(2):
+    hp = argparse.Namespace(input_dir=str(tmp_path), output_dir=str(tmp_path / 'runs'), batch_size=3, noise_dim=4,
+                            rank=rank, world_size=2)
+    train_ds, val_ds = D.get_dataset(hp)
+    assert hp.train_size == 4 and hp.train_steps == 2 and hp.validation_size == 3
+    assert [b.shape[0] for b, _ in train_ds] == [3, 1]
+    seen.append(np.concatenate([b for b, _ in train_ds]))
+    assert sum(b.shape[0] for b, _ in val_ds) == 3          # validation is not sharded
+  rows = {tuple(np.round(x.reshape(-1)[:6], 6)) for x in np.concatenate(seen)}
+  assert len(rows) == 8
+
+
+def test_validation_cache_written_once_with_raw_scale_signals_and_int8_spikes(tmp_path):
+  """dataset_helper.py:12-31,196-197: only with --save_generated"""
+  from calciumgan_b200.utils import h5_helper
+  rng = np.random.RandomState(3)
+  signals = rng.rand(9, 32, 4).astype(np.float32) * 5 - 2
+  spikes = (rng.rand(9, 32, 4) > 0.8).astype(np.float32)
+  data_dir = str(tmp_path / 'tfrecords')
+  D.write_dataset(data_dir, signals, spikes, train_size=5, num_per_shard=4)
+  hp = argparse.Namespace(input_dir=data_dir, output_dir=str(tmp_path / 'runs'), batch_size=3, noise_dim=4, save_generated='')
+  D.get_dataset(hp)
+  assert not h5_helper.exists(hp.validation_cache)
+  for _ in range(2):        # the second call finds the cache and leaves it alone
+    hp = argparse.Namespace(input_dir=data_dir, output_dir=str(tmp_path / 'runs'), batch_size=3, noise_dim=4, save_generated='last')
+    train_ds, val_ds = D.get_dataset(hp)
+    assert hp.validation_cache == os.path.join(hp.output_dir, 'generated', 'validation.h5')
+    got = h5_helper.get(hp.validation_cache, 'signals')
+    assert got.shape == (4, 32, 4) and got.dtype == np.float32
+    np.testing.assert_allclose(got, signals[5:], rtol=1e-5, atol=1e-5)
+    sp = h5_helper.get(hp.validation_cache, 'spikes')
+    assert sp.dtype == np.int8
+    np.testing.assert_array_equal(sp, spikes[5:].astype(np.int8))
+  # batches carry the spikes like the reference's (signal, spike) pairs
+  s0, k0 = next(iter(val_ds))
+  assert k0.shape == s0.shape and set(np.unique(k0)) <= {0.0, 1.0}
+
+
+def test_surrogate_dataset(tmp_path):
+  """dataset_helper.py:53-110: training.pkl holds (trials, neurons, time); 8192 train, the rest validate"""
+  rng = np.random.RandomState(4)
+  raw = (rng.rand(8200, 3, 16) * 4 - 1).astype(np.float32)
+  spikes = (rng.rand(8200, 16, 3) > 0.9).astype(np.int8)
+  with open(str(tmp_path / 'training.pkl'), 'wb') as file:
+    pickle.dump({'signals': raw, 'spikes': spikes}, file)
+  hp = argparse.Namespace(input_dir=str(tmp_path), output_dir=str(tmp_path / 'runs'), batch_size=1024, noise_dim=4, surrogate_ds=True)
+  train_ds, val_ds = D.get_dataset(hp)
+  assert hp.signal_shape == (16, 3) and hp.spike_shape == (16, 3) and hp.num_neurons == 3 and hp.sequence_length == 16
+  assert hp.train_size == 8192 and hp.validation_size == 8 and hp.train_steps == 8 and hp.validation_steps == 1
+  assert hp.normalize and abs(hp.signals_min - raw.min()) < 1e-6 and abs(hp.signals_max - raw.max()) < 1e-6
+  val = np.concatenate([b for b, _ in val_ds])
+  np.testing.assert_allclose(val, (raw[8192:].transpose(0, 2, 1) - raw.min()) / (raw.max() - raw.min()), rtol=1e-5, atol=1e-6)
+  assert train_ds.buffer_size == 2048 and sum(b.shape[0] for b, _ in train_ds) == 8192
