@@ -1,19 +1,10 @@
-"""Algorithm registry — same surface as the reference's gan/algorithms/registry.py:4-19."""
-_ALGORITHMS = dict()
+"""Algorithm plugins: `@register(name)` on a class constructed as `cls(hparams, generator, discriminator, summary)` and
+`get_algorithm`, the surface of the reference's gan/algorithms/registry.py:4-19 (unknown name: message + exit)."""
+from ..plugin_registry import PluginTable
 
-
-def register(name):
-
-  def add_to_dict(fn):
-    global _ALGORITHMS
-    _ALGORITHMS[name] = fn
-    return fn
-
-  return add_to_dict
+_table = PluginTable('Algorithm {} not found')
+register = _table.register
 
 
 def get_algorithm(hparams, generator, discriminator, summary=None):
-  if hparams.algorithm not in _ALGORITHMS:
-    print('Algorithm {} not found'.format(hparams.algorithm))
-    exit()
-  return _ALGORITHMS[hparams.algorithm](hparams, generator, discriminator, summary)
+  return _table.resolve(hparams.algorithm)(hparams, generator, discriminator, summary)
