@@ -151,3 +151,88 @@ def test_array_format_helpers():
   y = np.zeros((7, 5, 3))
   assert utils.swap_neuron_major(hp, y).shape == (5, 7, 3) and utils.swap_neuron_major(hp, np.zeros((5, 7, 3))).shape == (5, 7, 3)
   np.testing.assert_array_equal(utils.remove_nan(np.array([1.0, np.nan, 3.0])), [1.0, 3.0])
+
+
+class _StubModel(object):
+
+  def __init__(self, weights):
+    self.weights = [w.copy() for w in weights]
+
+  def get_weights(self):
+    return [w.copy() for w in self.weights]
+
+  def set_weights(self, weights):
+    self.weights = [np.asarray(w).copy() for w in weights]
+
+
+class _StubEngine(object):
+
+  def __init__(self):
+    self.state = {0: (np.full(3, 1.0, np.float32), np.full(3, 2.0, np.float32)),
+                  1: (np.full(2, 3.0, np.float32), np.full(2, 4.0, np.float32))}
+
+  def get_opt_state(self, which):
+    m, v = self.state[which]
+    return m.copy(), v.copy(), 0
+
+  def set_opt_state(self, which, m, v, steps):
+    self.state[which] = (np.asarray(m).copy(), np.asarray(v).copy())
+
+
+def _stub_gan(seed):
+  rng = np.random.RandomState(seed)
+  return argparse.Namespace(generator=_StubModel([rng.rand(4, 3).astype(np.float32), rng.rand(3).astype(np.float32)]),
+                            discriminator=_StubModel([rng.rand(2, 2).astype(np.float32)]),
+                            gen_optimizer=argparse.Namespace(iterations=seed), dis_optimizer=argparse.Namespace(iterations=5 * seed),
+                            engine=_StubEngine())
+
+
+def test_checkpoint_layout_and_resume(tmp_path):
+  """utils.py:116-152: output_dir/checkpoints/epoch-%03d.pkl with the reference's five keys; the newest epoch is resumed"""
+  hp = argparse.Namespace(output_dir=str(tmp_path), verbose=0)
+  a = _stub_gan(7)
+  utils.save_models(hp, a, 9)
+  a.gen_optimizer.iterations, a.dis_optimizer.iterations = 70, 350
+  a.generator.weights[0] += 1.0
+  a.engine.state[0] = (np.full(3, 9.0, np.float32), np.full(3, 8.0, np.float32))
+  utils.save_models(hp, a, 10)
+  assert sorted(os.listdir(hp.ckpt_dir)) == ['epoch-009.pkl', 'epoch-010.pkl'] and hp.ckpt_dir == os.path.join(str(tmp_path), 'checkpoints')
+  with open(os.path.join(hp.ckpt_dir, 'epoch-010.pkl'), 'rb') as file:
+    content = pickle.load(file)
+  assert set(content) == {'epoch', 'gen_weights', 'dis_weights', 'gen_steps', 'dis_steps', 'b200_adam'}
+  assert content['epoch'] == 10 and content['gen_steps'] == 70 and content['dis_steps'] == 350
+  assert [w.dtype for w in content['gen_weights']] == [np.float32, np.float32]
+  b = _stub_gan(1)
+  hp2 = argparse.Namespace(output_dir=str(tmp_path), verbose=0)
+  utils.load_models(hp2, b)
+  assert hp2.start_epoch == 11 and b.gen_optimizer.iterations == 70 and b.dis_optimizer.iterations == 350
+  for x, y in zip(b.generator.get_weights() + b.discriminator.get_weights(), a.generator.get_weights() + a.discriminator.get_weights()):
+    np.testing.assert_array_equal(x, y)
+  np.testing.assert_array_equal(b.engine.state[0][0], np.full(3, 9.0, np.float32))
+  # a checkpoint written by the reference: no Adam moments, epoch numbers past the zero padding still order numerically
+  with open(os.path.join(hp.ckpt_dir, 'epoch-1000.pkl'), 'wb') as file:
+    pickle.dump({'epoch': 1000, 'gen_weights': a.generator.get_weights(), 'dis_weights': a.discriminator.get_weights(),
+                 'gen_steps': 1, 'dis_steps': 2}, file)
+  c = _stub_gan(2)
+  before = c.engine.state[1][0].copy()
+  hp3 = argparse.Namespace(output_dir=str(tmp_path), verbose=0)
+  utils.load_models(hp3, c)
+  assert hp3.start_epoch == 1001 and c.gen_optimizer.iterations == 1
+  np.testing.assert_array_equal(c.engine.state[1][0], before)      # moments untouched
+  # nothing to resume from
+  hp4 = argparse.Namespace(output_dir=str(tmp_path / 'fresh'), verbose=0)
+  utils.load_models(hp4, c)
+  assert hp4.start_epoch == 0
+
+
+def test_hparams_json_roundtrip(tmp_path):
+  """utils.py:72-85"""
+  import json
+  hp = argparse.Namespace(output_dir=str(tmp_path), num_units=64, signal_shape=(2048, 102), lr=np.float32(1e-4), steps=np.int64(3))
+  utils.save_hparams(hp)
+  stored = json.load(open(os.path.join(str(tmp_path), 'hparams.json')))
+  assert stored['signal_shape'] == [2048, 102] and stored['num_units'] == 64 and stored['steps'] == 3 and 'git_hash' in stored
+  fresh = argparse.Namespace(output_dir=str(tmp_path), num_units=99)
+  utils.load_hparams(fresh)
+  assert fresh.num_units == 99 and fresh.signal_shape == [2048, 102] and abs(fresh.lr - 1e-4) < 1e-9
+  assert abs(utils.denormalize(utils.normalize(3.0, -2.0, 6.0), -2.0, 6.0) - 3.0) < 1e-12
