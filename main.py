@@ -186,46 +186,58 @@ def main(hparams, return_metrics=False):
     return results
 
 
+# The reference's command line (main.py:229-261): (flag, default, help). A bool default makes a store_true switch, any other
+# default fixes the value type; `choices` are listed separately.
+REFERENCE_FLAGS = (
+    ('input_dir', 'dataset/tfrecords', 'TFRecord shards + info.pkl'),
+    ('output_dir', 'runs', 'TensorBoard events, hparams.json, checkpoints/, generated/'),
+    ('batch_size', 64, None),
+    ('num_units', 32, 'channel multiplier of both networks'),
+    ('kernel_size', 24, None),
+    ('strides', 2, None),
+    ('m', 2, 'phase shuffle m'),
+    ('n', 2, 'phase shuffle n'),
+    ('epochs', 20, None),
+    ('dropout', 0.2, 'unused by the calciumgan model'),
+    ('learning_rate', 0.0001, None),
+    ('noise_dim', 32, None),
+    ('gradient_penalty', 10.0, 'WGAN-GP lambda'),
+    ('model', 'wavegan', None),
+    ('activation', 'leakyrelu', None),
+    ('batch_norm', False, None),
+    ('layer_norm', False, None),
+    ('algorithm', 'wgan-gp', None),
+    ('n_critic', 5, 'number of steps between each generator update'),
+    ('clear_output_dir', False, None),
+    ('save_generated', '', 'save the generated validation signals: after the last epoch, or after every 10th as well'),
+    ('plot_weights', False, 'accepted for compatibility; plotting is out of scope'),
+    ('skip_checkpoints', False, None),
+    ('mixed_precision', False, 'bf16 tensor-core path'),
+    ('profile', False, 'open a cudaProfilerStart/Stop + NVTX window around batches 2-6 of the 2nd epoch'),
+    ('dpi', 120, 'accepted for compatibility; plotting is out of scope'),
+    ('verbose', 1, None),
+)
+# additions (not in the reference): data source when no TFRecord pipeline is available, and the dataset cache switch
+EXTRA_FLAGS = (
+    ('synthetic', False, 'uniform [0,1) signals of shape (N, 2048, 102)'),
+    ('synthetic_size', 512, None),
+    ('no_device_cache', False, 'stream every batch from host memory instead of caching the training set in HBM'),
+)
+FLAG_CHOICES = {'save_generated': ['', 'last', 'all']}
+
+
 def build_parser():
   parser = argparse.ArgumentParser()
-  parser.add_argument('--input_dir', default='dataset/tfrecords')
-  parser.add_argument('--output_dir', default='runs')
-  parser.add_argument('--batch_size', default=64, type=int)
-  parser.add_argument('--num_units', default=32, type=int)
-  parser.add_argument('--kernel_size', default=24, type=int)
-  parser.add_argument('--strides', default=2, type=int)
-  parser.add_argument('--m', default=2, type=int, help='phase shuffle m')
-  parser.add_argument('--n', default=2, type=int, help='phase shuffle n')
-  parser.add_argument('--epochs', default=20, type=int)
-  parser.add_argument('--dropout', default=0.2, type=float)
-  parser.add_argument('--learning_rate', default=0.0001, type=float)
-  parser.add_argument('--noise_dim', default=32, type=int)
-  parser.add_argument('--gradient_penalty', default=10.0, type=float)
-  parser.add_argument('--model', default='wavegan', type=str)
-  parser.add_argument('--activation', default='leakyrelu', type=str)
-  parser.add_argument('--batch_norm', action='store_true')
-  parser.add_argument('--layer_norm', action='store_true')
-  parser.add_argument('--algorithm', default='wgan-gp', type=str)
-  parser.add_argument('--n_critic', default=5, type=int, help='number of steps between each generator update')
-  parser.add_argument('--clear_output_dir', action='store_true')
-  parser.add_argument('--save_generated', default="", choices=["", "last", "all"], type=str)
-  parser.add_argument('--plot_weights', action='store_true')
-  parser.add_argument('--skip_checkpoints', action='store_true')
-  parser.add_argument('--mixed_precision', action='store_true')
-  parser.add_argument('--profile', action='store_true',
-                      help='open a cudaProfilerStart/Stop + NVTX window around batches 2-6 of the 2nd epoch')
-  parser.add_argument('--dpi', default=120, type=int)
-  parser.add_argument('--verbose', default=1, type=int)
-  # additions (not in the reference): data source when no TFRecord pipeline is available
-  parser.add_argument('--synthetic', action='store_true', help='uniform [0,1) signals of shape (N, 2048, 102)')
-  parser.add_argument('--synthetic_size', default=512, type=int)
-  parser.add_argument('--no_device_cache', action='store_true',
-                      help='stream every batch from host memory instead of caching the training set in HBM')
+  for name, default, text in REFERENCE_FLAGS + EXTRA_FLAGS:
+    if isinstance(default, bool):
+      parser.add_argument('--' + name, action='store_true', help=text)
+    else:
+      parser.add_argument('--' + name, default=default, type=type(default), choices=FLAG_CHOICES.get(name), help=text)
   return parser
 
 
 if __name__ == '__main__':
   params = build_parser().parse_args()
   params.global_step = 0
-  params.surrogate_ds = True if 'surrogate' in params.input_dir else False
+  params.surrogate_ds = 'surrogate' in params.input_dir      # main.py:265 of the reference
   main(params)
