@@ -25,18 +25,17 @@ class Summary(object):
     self._writer(training).add_scalar(tag, float(value), global_step=step)
 
   def log(self, gen_loss, dis_loss, gradient_penalty, metrics=None, elapse=None, gan=None, step=0, training=True):
-    """summary_helper.py:559-588."""
-    self.scalar('loss/generator', gen_loss, step=step, training=training)
-    self.scalar('loss/discriminator', dis_loss, step=step, training=training)
-    if gradient_penalty is not None:
-      self.scalar('loss/gradient_penalty', gradient_penalty, step=step, training=training)
-    if metrics is not None:
-      for tag, value in metrics.items():
-        self.scalar(tag, value, step=step, training=training)
-    if elapse is not None:
-      self.scalar('elapse', elapse, step=step, training=training)
+    """One epoch's scalars under the reference's tags (summary_helper.py:559-588): loss/generator, loss/discriminator,
+    loss/gradient_penalty (WGAN-GP only), the signal metrics under their own tags, elapse, and -- validation with mixed
+    precision -- model/loss_scale."""
+    entries = [('loss/generator', gen_loss), ('loss/discriminator', dis_loss), ('loss/gradient_penalty', gradient_penalty)]
+    entries += list((metrics or {}).items())
+    entries.append(('elapse', elapse))
     if not training and gan is not None and getattr(self._hparams, 'mixed_precision', False):
-      self.scalar('model/loss_scale', gan.gen_optimizer.loss_scale, step=step, training=training)
+      entries.append(('model/loss_scale', gan.gen_optimizer.loss_scale))
+    for tag, value in entries:
+      if value is not None:
+        self.scalar(tag, value, step=step, training=training)
 
   def profiler_trace(self):
     """summary_helper.py:115-116 (tf.summary.trace_on): start of the profiled window."""

@@ -52,3 +52,31 @@ def test_null_summary_accepts_everything():
   s.scalar('elapse/total', 1.0)
   s.flush()
   s.profiler_trace()
+
+
+def test_summary_writes_the_reference_scalar_tags(tmp_path):
+  """summary_helper.py:559-588: tags and writers (train events in output_dir, validation events in output_dir/validation)"""
+  import argparse
+  import glob
+  from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+  from calciumgan_b200.utils.summary_helper import Summary
+  hp = argparse.Namespace(output_dir=str(tmp_path), mixed_precision=True)
+  s = Summary(hp)
+  s.log(1.0, 2.0, None, metrics={'signals_metrics/min': 0.5}, elapse=3.0, step=4, training=True)
+  gan = argparse.Namespace(gen_optimizer=argparse.Namespace(loss_scale=1.0))
+  s.log(1.5, 2.5, 0.25, gan=gan, step=5, training=False)
+  s.scalar('elapse/total', 9.0)
+  s.flush()
+
+  def scalars(directory):
+    acc = EventAccumulator(directory)
+    acc.Reload()
+    return {tag: [(e.step, e.value) for e in acc.Scalars(tag)] for tag in acc.Tags()['scalars']}
+
+  train = scalars(str(tmp_path))
+  assert set(train) == {'loss/generator', 'loss/discriminator', 'signals_metrics/min', 'elapse', 'elapse/total'}
+  assert train['loss/discriminator'] == [(4, 2.0)] and train['elapse'] == [(4, 3.0)]
+  val = scalars(os.path.join(str(tmp_path), 'validation'))
+  assert set(val) == {'loss/generator', 'loss/discriminator', 'loss/gradient_penalty', 'model/loss_scale'}
+  assert val['loss/gradient_penalty'] == [(5, 0.25)]
+  assert glob.glob(os.path.join(str(tmp_path), 'events.out.tfevents.*'))
